@@ -1,0 +1,145 @@
+/* sat_b200.h — C ABI of libsat_b200.so: the soft-attention LSTM decode path of
+ * Cheng-Lin-Li/show-attend-and-tell on NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI: its boundary is the Python attribute surface of
+ * CaptionGenerator consumed through tf.Session.run feeds/fetches.  Each entry point
+ * below names the reference interface it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *   - return 0 (SAT_OK) on success, a negative SAT_ERR_* code otherwise; nothing is
+ *     thrown or aborted across the boundary; sat_last_error() describes the failure
+ *     (thread local).
+ *   - every tensor argument is a DEVICE pointer unless the name ends in _host;
+ *     the caller owns every tensor buffer; the library owns its workspace and its
+ *     repacked copies of the weights.
+ *   - all tensors are dense row-major fp32 (model.py:205-213) except word ids, which
+ *     are int32 (model.py:214-216).
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation except in *_host entry points, which return after the results
+ *     are in host memory, and in sat_set_weight (one-time repack).
+ *   - a handle is bound to the CUDA device current at sat_create and is not thread
+ *     safe (the reference's driver loop is single threaded: base_model.py:184-212).
+ */
+#ifndef SAT_B200_H_
+#define SAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAT_OK 0
+#define SAT_ERR_INVALID (-1)     /* bad argument / shape mismatch (TF InvalidArgumentError) */
+#define SAT_ERR_CUDA (-2)        /* a CUDA runtime / driver call failed */
+#define SAT_ERR_STATE (-3)       /* weights missing, contexts not prepared, ... */
+#define SAT_ERR_UNSUPPORTED (-4) /* shape outside what the kernels implement */
+#define SAT_ERR_NOMEM (-5)
+
+typedef struct sat_handle sat_handle;
+
+/* Static shape of the decoder graph.  Field names follow config.py:9-17,67 (including the
+ * `initalize` spelling); L and D are num_ctx / dim_ctx of model.py:54-59,103-108. */
+typedef struct sat_dims {
+    int32_t max_batch;            /* max rows per step = images x beam            */
+    int32_t num_ctx;              /* L                                            */
+    int32_t dim_ctx;              /* D                                            */
+    int32_t num_lstm_units;       /* H                                            */
+    int32_t dim_embedding;        /* E                                            */
+    int32_t dim_attend_layer;     /* A                                            */
+    int32_t dim_decode_layer;     /* Dd                                           */
+    int32_t dim_initalize_layer;  /* I                                            */
+    int32_t vocabulary_size;      /* V                                            */
+    int32_t num_attend_layers;    /* 1 or 2                                       */
+    int32_t num_decode_layers;    /* 1 or 2                                       */
+    int32_t num_initalize_layers; /* 1 or 2                                       */
+    int32_t max_caption_length;   /* max steps of a loop / beam search            */
+    int32_t max_beam;             /* max beam_size (<= 4); 0 or 1 = no beam search */
+} sat_dims;
+
+/* replaces CaptionGenerator(config) (main.py:48,61,69; model.py:7-13, build_rnn :190-356) */
+int sat_create(const sat_dims* dims, sat_handle** out);
+void sat_destroy(sat_handle* h);
+const char* sat_last_error(void);
+int sat_version(void);
+
+/* integer knobs: "gemm" (1 = tcgen05 [default], 0 = CUDA-core bring-up kernels),
+ * "umma_layout" (0 = interleaved, 1 = 128B swizzle; must be set before sat_set_weight),
+ * "graphs" (1 = replay CUDA graphs in loops [default]), "hoist" (1 = project the contexts
+ * once per image batch [default]; 0 = recompute every step like model.py:259-262),
+ * "coop" (1 = cooperative launch of the attention kernel [default]). */
+int sat_set_option(sat_handle* h, const char* key, int64_t value);
+int sat_get_info(sat_handle* h, const char* key, int64_t* value);
+
+/* replaces BaseModel.load's per-variable assign (base_model.py:257-278).  `tf_var_name` is
+ * the TF variable name with or without ":0" (e.g. "lstm/lstm_cell/kernel"); `dev` holds the
+ * variable in the reference's layout: dense kernels [in, units] (rows=in, cols=units), biases
+ * [units] (rows=1), the LSTM kernel [D+E+H, 4H] with column blocks i,j,f,o, the embedding [V,E].
+ * The data is repacked into the library's own storage before the call returns. */
+int sat_set_weight(sat_handle* h, const char* tf_var_name, const float* dev, int64_t rows, int64_t cols,
+                   void* stream);
+/* number of variables still missing (0 = ready) */
+int sat_weights_missing(sat_handle* h);
+
+/* replaces sess.run([conv_feats, initial_memory, initial_output], {images})
+ * (base_model.py:168-170) minus the CNN: projects the contexts (attend fc_1a, model.py:417-420,
+ * hoisted out of the step loop) and runs initialize (model.py:239-242, 358-393).
+ * contexts [n_img, L, D]; initial_memory / initial_output [n_img, H] may be NULL. */
+int sat_prepare_contexts(sat_handle* h, const float* contexts, int32_t n_img, float* initial_memory,
+                         float* initial_output, void* stream);
+
+/* replaces sess.run([memory, output, probs], {contexts, last_word, last_memory, last_output})
+ * (base_model.py:207-212; graph model.py:258-290).  All of memory/output [B,H] are required;
+ * logits / probs [B,V] and alpha [B,L] may be NULL.  `contexts` must be the buffer last given
+ * to sat_prepare_contexts with n_img == B (otherwise the projection is redone here). */
+int sat_decode_step(sat_handle* h, const float* contexts, const int32_t* last_word, const float* last_memory,
+                    const float* last_output, float* memory, float* output, float* logits, float* probs,
+                    float* alpha, int32_t B, void* stream);
+
+/* T steps on the device without host round trips: prepare + initialize + T x step, the word fed
+ * to step t+1 being argmax of step t (model.py:289) or forced_words[b, t] (teacher forcing,
+ * model.py:310).  tokens [B,T] receives the argmax words; logits_all [T,B,V] may be NULL. */
+int sat_decode_loop(sat_handle* h, const float* contexts, int32_t B, int32_t T, const int32_t* forced_words,
+                    int32_t* tokens, float* logits_all, void* stream);
+
+/* replaces BaseModel.beam_search (base_model.py:163-240) with TopN/CaptionData semantics of
+ * utils/misc.py:38-87; `eos_id` stands for vocabulary.words[w] == '.' (base_model.py:229).
+ * Outputs per image, sorted by descending score: sentences [n_img, beam, T] (-1 padded),
+ * lengths [n_img, beam], scores [n_img, beam] (fp64 products of probabilities,
+ * base_model.py:224), n_results [n_img], is_complete [n_img]. */
+int sat_beam_search(sat_handle* h, const float* contexts, int32_t n_img, int32_t beam_size, int32_t T,
+                    int32_t eos_id, int32_t* sentences, int32_t* lengths, double* scores, int32_t* n_results,
+                    int32_t* is_complete, void* stream);
+
+/* host-buffer forms: copy in, run, copy out, synchronise (what a sess.run caller sees) */
+int sat_decode_step_host(sat_handle* h, const float* contexts_host, int32_t contexts_changed,
+                         const int32_t* last_word_host, const float* last_memory_host,
+                         const float* last_output_host, float* memory_host, float* output_host,
+                         float* probs_host, int32_t B, void* stream);
+int sat_decode_loop_host(sat_handle* h, const float* contexts_host, int32_t B, int32_t T,
+                         const int32_t* forced_words_host, int32_t* tokens_host, void* stream);
+int sat_beam_search_host(sat_handle* h, const float* contexts_host, int32_t n_img, int32_t beam_size, int32_t T,
+                         int32_t eos_id, int32_t* sentences_host, int32_t* lengths_host, double* scores_host,
+                         int32_t* n_results_host, int32_t* is_complete_host, void* stream);
+
+/* individually callable kernels of one step (profiling / unit tests).  Rows = n_img * group;
+ * `group` rows of one image share its contexts (beams).
+ *   sat_attention_fwd : attend + context vector (model.py:262-264) given the state h [rows,H]
+ *   sat_lstm_fwd      : embedding lookup + LSTMCell (model.py:272-279)
+ *   sat_vocab_gemm    : decode (model.py:282-287) -> logits [rows,V]                         */
+int sat_attention_fwd(sat_handle* h, const float* contexts, const float* output, float* alpha, float* context,
+                      int32_t n_img, int32_t group, void* stream);
+int sat_lstm_fwd(sat_handle* h, const float* context, const int32_t* last_word, const float* last_memory,
+                 const float* last_output, float* memory, float* output, int32_t rows, void* stream);
+int sat_vocab_gemm(sat_handle* h, const float* output, const float* context, const int32_t* last_word,
+                   float* logits, int32_t rows, void* stream);
+/* generic dense layer y = act(x W + b) through the same tensor-core kernel (tests):
+ * x [rows,K], w_tf [K,n_out] (TF layout), b [n_out] or NULL, act 0 none / 1 tanh. */
+int sat_dense_fwd(sat_handle* h, const float* x, const float* w_tf, const float* b, float* y, int32_t rows,
+                  int32_t K, int32_t n_out, int32_t act, int32_t splits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAT_B200_H_ */

@@ -1,0 +1,973 @@
+// sat_api.cu — the C ABI of libsat_b200.so (include/sat_b200.h): handle, weight
+// ingestion (TF variable names/layouts, base_model.py:242-278), workspace, and the
+// kernel sequences of prepare / decode step / decode loop / beam search.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sat_b200.h"
+#include "sat_attention.cuh"
+#include "sat_linear.cuh"
+#include "sat_rows.cuh"
+
+using namespace sat;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) return fail(SAT_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define RET(x)                 \
+    do {                       \
+        int r_ = (x);          \
+        if (r_ != SAT_OK) return r_; \
+    } while (0)
+
+// ------------------------------------------------------------------ handle
+struct Layer {
+    std::string name;  // TF scope, e.g. "decode/fc_1"
+    int K = 0, n_out = 0;
+    bool lstm = false, has_bias = true;
+    int k_blocks = 0, n_tiles = 0;
+    uint8_t* wpack = nullptr;
+    float* bias = nullptr;  // packed order, n_tiles*128
+    bool w_set = false, b_set = false;
+    float* ws = nullptr;
+    size_t ws_floats = 0;
+    unsigned* counters = nullptr;
+    size_t n_counters = 0;
+};
+
+struct VecParam {  // a kernel of shape [n,1] kept as a plain fp32 vector
+    std::string name;
+    int n = 0;
+    float* dev = nullptr;
+    bool set = false;
+};
+
+struct GraphEntry {
+    std::vector<long long> key;
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+};
+
+struct sat_handle {
+    sat_dims d;
+    int dev = 0, num_sms = 0, smem_optin = 0;
+    int opt_gemm = 1, opt_layout = 0, opt_graphs = 1, opt_hoist = 1, opt_coop = 1;
+    bool weights_locked = false;
+
+    Layer init_a1, init_a2, init_b1, init_b2;  // 1-layer mode uses init_a1 / init_b1 as fc_a / fc_b
+    Layer att_1a, att_1b;                      // 1-layer mode: att_1b is fc_b [H, L], att_1a unused
+    VecParam att_vec;                          // attend/fc_2 [A] or attend/fc_a [D]
+    Layer lstm;
+    Layer dec_1, dec_2;                        // 1-layer mode uses dec_2 as decode/fc
+    float* embedding = nullptr;
+    bool emb_set = false;
+    std::vector<Layer*> layers;
+
+    // workspace
+    int max_rows = 0;
+    float *T1 = nullptr, *q = nullptr, *e = nullptr, *alpha = nullptr, *z = nullptr, *mean = nullptr;
+    float *tmp_a = nullptr, *tmp_b = nullptr, *t_dec = nullptr, *logits = nullptr;
+    float* st_c[2] = {nullptr, nullptr};
+    float* st_h[2] = {nullptr, nullptr};
+    int32_t *word = nullptr, *zero_word = nullptr;
+    unsigned* rowcnt = nullptr;
+    // beam
+    int32_t *topk_idx = nullptr, *part_n = nullptr, *comp_n = nullptr, *comp_sent = nullptr;
+    int32_t* sent[2] = {nullptr, nullptr};
+    float* topk_p = nullptr;
+    double* part_score = nullptr;
+    void* comp_heap = nullptr;
+    // host-form staging
+    float* stage_ctx = nullptr;
+    void* stage_misc = nullptr;
+    size_t stage_misc_bytes = 0;
+
+    // contexts state
+    const float* prep_ctx = nullptr;
+    int prep_ni = 0;
+    const float* map_ctx = nullptr;
+    int map_ni = 0;
+    CUtensorMap ctx_map;
+
+    std::vector<GraphEntry> graphs;
+};
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled g_encode = nullptr;
+
+static int get_encoder() {
+    if (g_encode) return SAT_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SAT_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = (PFN_tmapEncodeTiled)fn;
+    return SAT_OK;
+}
+
+template <typename T>
+static int dmalloc(T** p, size_t n) {
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(SAT_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    return SAT_OK;
+}
+
+static int layer_setup(sat_handle* h, Layer& ly, const char* name, int K, int n_out, bool lstm, bool has_bias) {
+    ly.name = name;
+    ly.K = K;
+    ly.n_out = n_out;
+    ly.lstm = lstm;
+    ly.has_bias = has_bias;
+    ly.k_blocks = (K + kBK - 1) / kBK;
+    ly.n_tiles = (n_out + kTileN - 1) / kTileN;
+    if (K % 8) return fail(SAT_ERR_UNSUPPORTED, "%s: input width %d must be a multiple of 8", name, K);
+    RET(dmalloc(&ly.wpack, (size_t)ly.n_tiles * ly.k_blocks * kWStageBytes));
+    RET(dmalloc(&ly.bias, (size_t)ly.n_tiles * kTileN));
+    CK(cudaMemset(ly.bias, 0, (size_t)ly.n_tiles * kTileN * sizeof(float)));
+    ly.b_set = !has_bias;
+    h->layers.push_back(&ly);
+    return SAT_OK;
+}
+
+static void layer_free(Layer& ly) {
+    cudaFree(ly.wpack);
+    cudaFree(ly.bias);
+    cudaFree(ly.ws);
+    cudaFree(ly.counters);
+    ly = Layer();
+}
+
+extern "C" int sat_version(void) { return 100; }
+extern "C" const char* sat_last_error(void) { return g_err; }
+
+extern "C" void sat_destroy(sat_handle* h) {
+    if (!h) return;
+    cudaDeviceSynchronize();
+    for (auto& g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (Layer* ly : h->layers) layer_free(*ly);
+    void* bufs[] = {h->att_vec.dev, h->embedding, h->T1, h->q, h->e, h->alpha, h->z, h->mean, h->tmp_a, h->tmp_b,
+                    h->t_dec, h->logits, h->st_c[0], h->st_c[1], h->st_h[0], h->st_h[1], h->word, h->zero_word,
+                    h->rowcnt, h->topk_idx, h->part_n, h->comp_n, h->comp_sent, h->sent[0], h->sent[1], h->topk_p,
+                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc};
+    for (void* b : bufs) cudaFree(b);
+    delete h;
+}
+
+extern "C" int sat_create(const sat_dims* dims, sat_handle** out) {
+    if (!dims || !out) return fail(SAT_ERR_INVALID, "sat_create: null argument");
+    *out = nullptr;
+    const sat_dims& d = *dims;
+    if (d.max_batch < 1 || d.num_ctx < 1 || d.dim_ctx < 1 || d.num_lstm_units < 1 || d.vocabulary_size < 2)
+        return fail(SAT_ERR_INVALID, "sat_create: non-positive dimension");
+    if (d.num_ctx > 256) return fail(SAT_ERR_UNSUPPORTED, "num_ctx %d > 256", d.num_ctx);
+    if (d.dim_ctx % 32 || d.num_lstm_units % 32 || d.dim_embedding % 8 || d.dim_attend_layer % 8 ||
+        d.dim_decode_layer % 8 || d.dim_initalize_layer % 8)
+        return fail(SAT_ERR_UNSUPPORTED, "dim_ctx and num_lstm_units must be multiples of 32, the other widths of 8");
+    if (d.max_beam > 4) return fail(SAT_ERR_UNSUPPORTED, "max_beam %d > 4", d.max_beam);
+    for (int v : {d.num_attend_layers, d.num_decode_layers, d.num_initalize_layers})
+        if (v != 1 && v != 2) return fail(SAT_ERR_INVALID, "num_*_layers must be 1 or 2");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(SAT_ERR_CUDA, "no CUDA device (%s): sat_b200 has no CPU path", cudaGetErrorString(ce));
+
+    sat_handle* h = new sat_handle();
+    h->d = d;
+    int rc = SAT_OK;
+    auto body = [&]() -> int {
+        CK(cudaGetDevice(&h->dev));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, h->dev));
+        if (prop.major != 10) return fail(SAT_ERR_UNSUPPORTED, "device sm_%d%d is not sm_100", prop.major, prop.minor);
+        h->num_sms = prop.multiProcessorCount;
+        CK(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->dev));
+        CK(lin_init_attrs());
+        RET(get_encoder());
+        const int D = d.dim_ctx, E = d.dim_embedding, H = d.num_lstm_units, A = d.dim_attend_layer,
+                  Dd = d.dim_decode_layer, I = d.dim_initalize_layer, V = d.vocabulary_size, L = d.num_ctx;
+        if (d.num_initalize_layers == 2) {
+            RET(layer_setup(h, h->init_a1, "initialize/fc_a1", D, I, false, true));
+            RET(layer_setup(h, h->init_a2, "initialize/fc_a2", I, H, false, true));
+            RET(layer_setup(h, h->init_b1, "initialize/fc_b1", D, I, false, true));
+            RET(layer_setup(h, h->init_b2, "initialize/fc_b2", I, H, false, true));
+        } else {
+            RET(layer_setup(h, h->init_a1, "initialize/fc_a", D, H, false, true));
+            RET(layer_setup(h, h->init_b1, "initialize/fc_b", D, H, false, true));
+        }
+        if (d.num_attend_layers == 2) {
+            RET(layer_setup(h, h->att_1a, "attend/fc_1a", D, A, false, true));
+            RET(layer_setup(h, h->att_1b, "attend/fc_1b", H, A, false, true));
+            h->att_vec.name = "attend/fc_2";
+            h->att_vec.n = A;
+        } else {
+            RET(layer_setup(h, h->att_1b, "attend/fc_b", H, L, false, false));
+            h->att_vec.name = "attend/fc_a";
+            h->att_vec.n = D;
+        }
+        RET(dmalloc(&h->att_vec.dev, (size_t)h->att_vec.n));
+        RET(layer_setup(h, h->lstm, "lstm/lstm_cell", D + E + H, 4 * H, true, true));
+        if (d.num_decode_layers == 2) {
+            RET(layer_setup(h, h->dec_1, "decode/fc_1", H + D + E, Dd, false, true));
+            RET(layer_setup(h, h->dec_2, "decode/fc_2", Dd, V, false, true));
+        } else {
+            RET(layer_setup(h, h->dec_2, "decode/fc", H + D + E, V, false, true));
+        }
+        RET(dmalloc(&h->embedding, (size_t)V * E));
+
+        const size_t R = (size_t)d.max_batch;
+        h->max_rows = d.max_batch;
+        const int RL = d.num_attend_layers == 2 ? A : D;
+        if (d.num_attend_layers == 2) RET(dmalloc(&h->T1, R * L * A));
+        RET(dmalloc(&h->q, R * (size_t)(d.num_attend_layers == 2 ? A : L)));
+        (void)RL;
+        RET(dmalloc(&h->e, R * L));
+        RET(dmalloc(&h->alpha, R * L));
+        RET(dmalloc(&h->z, R * D));
+        RET(dmalloc(&h->mean, R * D));
+        RET(dmalloc(&h->tmp_a, R * (size_t)(I > H ? I : H)));
+        RET(dmalloc(&h->tmp_b, R * (size_t)(I > H ? I : H)));
+        RET(dmalloc(&h->t_dec, R * Dd));
+        RET(dmalloc(&h->logits, R * V));
+        for (int i = 0; i < 2; ++i) {
+            RET(dmalloc(&h->st_c[i], R * H));
+            RET(dmalloc(&h->st_h[i], R * H));
+        }
+        RET(dmalloc(&h->word, R));
+        RET(dmalloc(&h->zero_word, R));
+        CK(cudaMemset(h->zero_word, 0, R * sizeof(int32_t)));
+        RET(dmalloc(&h->rowcnt, R));
+        const int T = d.max_caption_length > 0 ? d.max_caption_length : 1;
+        if (d.max_beam >= 1) {
+            const size_t K = (size_t)d.max_beam + 1;
+            RET(dmalloc(&h->topk_idx, R * K));
+            RET(dmalloc(&h->topk_p, R * K));
+            RET(dmalloc(&h->part_score, R));
+            RET(dmalloc(&h->part_n, R));
+            RET(dmalloc(&h->comp_n, R));
+            RET(dmalloc(&h->comp_sent, R * T));
+            RET(dmalloc(&h->sent[0], R * T));
+            RET(dmalloc(&h->sent[1], R * T));
+            RET(dmalloc((uint8_t**)&h->comp_heap, R * beam_citem_bytes()));
+        }
+        return SAT_OK;
+    };
+    rc = body();
+    if (rc != SAT_OK) {
+        sat_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return SAT_OK;
+}
+
+extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
+    if (!h || !key) return fail(SAT_ERR_INVALID, "sat_set_option: null argument");
+    std::string k(key);
+    if (k == "gemm") h->opt_gemm = (int)value;
+    else if (k == "umma_layout") {
+        if (h->weights_locked && (int)value != h->opt_layout)
+            return fail(SAT_ERR_STATE, "umma_layout must be chosen before the first sat_set_weight");
+        if (value != 0 && value != 1) return fail(SAT_ERR_INVALID, "umma_layout must be 0 or 1");
+        h->opt_layout = (int)value;
+    } else if (k == "graphs") h->opt_graphs = (int)value;
+    else if (k == "hoist") { h->opt_hoist = (int)value; h->prep_ctx = nullptr; }
+    else if (k == "coop") h->opt_coop = (int)value;
+    else return fail(SAT_ERR_INVALID, "unknown option '%s'", key);
+    for (auto& g : h->graphs) {  // options change the captured work
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    }
+    h->graphs.clear();
+    return SAT_OK;
+}
+
+extern "C" int sat_get_info(sat_handle* h, const char* key, int64_t* value) {
+    if (!h || !key || !value) return fail(SAT_ERR_INVALID, "sat_get_info: null argument");
+    std::string k(key);
+    if (k == "num_sms") *value = h->num_sms;
+    else if (k == "smem_optin") *value = h->smem_optin;
+    else if (k == "gemm") *value = h->opt_gemm;
+    else if (k == "umma_layout") *value = h->opt_layout;
+    else if (k == "weight_bytes") {
+        size_t b = 0;
+        for (Layer* ly : h->layers) b += (size_t)ly->n_tiles * ly->k_blocks * kWStageBytes;
+        *value = (int64_t)b;
+    } else return fail(SAT_ERR_INVALID, "unknown info key '%s'", key);
+    return SAT_OK;
+}
+
+// ------------------------------------------------------------------ weights
+extern "C" int sat_set_weight(sat_handle* h, const char* tf_var_name, const float* dev, int64_t rows, int64_t cols,
+                              void* stream) {
+    if (!h || !tf_var_name || !dev) return fail(SAT_ERR_INVALID, "sat_set_weight: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::string name(tf_var_name);
+    if (name.size() > 2 && name.compare(name.size() - 2, 2, ":0") == 0) name.resize(name.size() - 2);
+    h->weights_locked = true;
+    h->prep_ctx = nullptr;
+    if (name == "word_embedding/weights") {
+        if (rows != h->d.vocabulary_size || cols != h->d.dim_embedding)
+            return fail(SAT_ERR_INVALID, "%s: expected [%d,%d], got [%lld,%lld]", name.c_str(), h->d.vocabulary_size,
+                        h->d.dim_embedding, (long long)rows, (long long)cols);
+        CK(cudaMemcpyAsync(h->embedding, dev, (size_t)rows * cols * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        h->emb_set = true;
+        return SAT_OK;
+    }
+    if (name == h->att_vec.name + "/kernel") {
+        if (rows * cols != h->att_vec.n)
+            return fail(SAT_ERR_INVALID, "%s: expected %d elements, got [%lld,%lld]", name.c_str(), h->att_vec.n,
+                        (long long)rows, (long long)cols);
+        CK(cudaMemcpyAsync(h->att_vec.dev, dev, (size_t)h->att_vec.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        h->att_vec.set = true;
+        return SAT_OK;
+    }
+    for (Layer* ly : h->layers) {
+        if (name == ly->name + "/kernel") {
+            if (rows != ly->K || cols != ly->n_out)
+                return fail(SAT_ERR_INVALID, "%s: expected [%d,%d], got [%lld,%lld]", name.c_str(), ly->K, ly->n_out,
+                            (long long)rows, (long long)cols);
+            CK(lin_repack_weight(dev, ly->K, ly->n_out, ly->lstm ? ly->n_out / 4 : 0, ly->wpack, h->opt_layout, st));
+            CK(cudaStreamSynchronize(st));
+            ly->w_set = true;
+            return SAT_OK;
+        }
+        if (name == ly->name + "/bias") {
+            if (!ly->has_bias) return fail(SAT_ERR_INVALID, "%s: layer has no bias (use_bias=False)", name.c_str());
+            if (rows * cols != ly->n_out)
+                return fail(SAT_ERR_INVALID, "%s: expected %d elements, got [%lld,%lld]", name.c_str(), ly->n_out,
+                            (long long)rows, (long long)cols);
+            CK(lin_repack_bias(dev, ly->n_out, ly->lstm ? ly->n_out / 4 : 0, ly->bias, st));
+            CK(cudaStreamSynchronize(st));
+            ly->b_set = true;
+            return SAT_OK;
+        }
+    }
+    return fail(SAT_ERR_INVALID, "unknown variable '%s'", name.c_str());
+}
+
+extern "C" int sat_weights_missing(sat_handle* h) {
+    if (!h) return fail(SAT_ERR_INVALID, "null handle");
+    int missing = 0;
+    for (Layer* ly : h->layers) missing += (ly->w_set ? 0 : 1) + (ly->b_set ? 0 : 1);
+    missing += h->emb_set ? 0 : 1;
+    missing += h->att_vec.set ? 0 : 1;
+    return missing;
+}
+
+static int require_ready(sat_handle* h) {
+    if (!h) return fail(SAT_ERR_INVALID, "null handle");
+    for (Layer* ly : h->layers) {
+        if (!ly->w_set) return fail(SAT_ERR_STATE, "variable %s/kernel was never set", ly->name.c_str());
+        if (!ly->b_set) return fail(SAT_ERR_STATE, "variable %s/bias was never set", ly->name.c_str());
+    }
+    if (!h->emb_set) return fail(SAT_ERR_STATE, "variable word_embedding/weights was never set");
+    if (!h->att_vec.set) return fail(SAT_ERR_STATE, "variable %s/kernel was never set", h->att_vec.name.c_str());
+    return SAT_OK;
+}
+
+// ------------------------------------------------------------ dense planning
+static LinSeg seg(const float* p, int ld, int width, const int32_t* gather = nullptr) {
+    LinSeg s;
+    s.ptr = p;
+    s.gather = gather;
+    s.ld = ld;
+    s.width = width;
+    s.row_div = 1;
+    return s;
+}
+
+static bool stream_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) return false;
+    return cs != cudaStreamCaptureStatusNone;
+}
+
+static int plan(sat_handle* h, Layer& ly, LinProblem& P, std::initializer_list<LinSeg> segs, int rows, int epi,
+                float* out, int ldo, cudaStream_t st, int force_splits = 0) {
+    memset(&P, 0, sizeof(P));
+    int k = 0, ns = 0;
+    for (const LinSeg& s : segs) {
+        if (s.width % 8 || s.ld % 4) return fail(SAT_ERR_UNSUPPORTED, "%s: segment width/ld alignment", ly.name.c_str());
+        P.seg[ns++] = s;
+        k += s.width;
+    }
+    if (k != ly.K) return fail(SAT_ERR_INVALID, "%s: operand width %d != %d", ly.name.c_str(), k, ly.K);
+    P.nseg = ns;
+    P.K = ly.K;
+    P.k_blocks = ly.k_blocks;
+    P.rows = rows;
+    P.n_row_tiles = (rows + 255) / 256;
+    int per = (rows + P.n_row_tiles - 1) / P.n_row_tiles;
+    P.row_tile = ((per + 15) / 16) * 16;
+    P.n_out = ly.n_out;
+    P.n_tiles = ly.n_tiles;
+    P.wpack = ly.wpack;
+    P.bias = ly.bias;
+    P.epi = epi;
+    P.out = out;
+    P.ldo = ldo;
+    // split-K: fill the SMs; cost model in units of K-blocks (fixed per-CTA overhead ~4)
+    const int tiles = P.n_tiles * P.n_row_tiles;
+    int best = 1;
+    if (force_splits > 0) best = force_splits < P.k_blocks ? force_splits : P.k_blocks;
+    else {
+        double bc = 1e30;
+        const int smax = P.k_blocks < 16 ? P.k_blocks : 16;
+        for (int s = 1; s <= smax; ++s) {
+            const int waves = (tiles * s + h->num_sms - 1) / h->num_sms;
+            const double c = waves * ((P.k_blocks + s - 1) / s + 4.0) + (s > 1 ? 0.25 * s : 0.0);
+            if (c < bc - 1e-9) { bc = c; best = s; }
+        }
+    }
+    P.splits = best;
+    const bool direct = best == 1 && epi != kEpiLstm;
+    if (!direct) {
+        const size_t need = (size_t)best * P.n_row_tiles * P.row_tile * P.n_tiles * kTileN;
+        if (need > ly.ws_floats) {
+            if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: workspace growth during graph capture", ly.name.c_str());
+            CK(cudaDeviceSynchronize());
+            cudaFree(ly.ws);
+            ly.ws = nullptr;
+            ly.ws_floats = 0;
+            RET(dmalloc(&ly.ws, need));
+            ly.ws_floats = need;
+        }
+        if ((size_t)tiles > ly.n_counters) {
+            if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: counter growth during graph capture", ly.name.c_str());
+            CK(cudaDeviceSynchronize());
+            cudaFree(ly.counters);
+            ly.counters = nullptr;
+            RET(dmalloc(&ly.counters, (size_t)tiles));
+            CK(cudaMemset(ly.counters, 0, (size_t)tiles * sizeof(unsigned)));
+            ly.n_counters = tiles;
+        }
+    }
+    P.ws = ly.ws;
+    P.counters = ly.counters;
+    P.cta_count = tiles * best;
+    return SAT_OK;
+}
+
+static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
+    LinLaunch L;
+    memset(&L, 0, sizeof(L));
+    int begin = 0, max_rt = 16;
+    for (int i = 0; i < n; ++i) {
+        L.p[i] = probs[i];
+        L.p[i].cta_begin = begin;
+        begin += probs[i].cta_count;
+        if (probs[i].row_tile > max_rt) max_rt = probs[i].row_tile;
+    }
+    L.nprob = n;
+    L.layout_mode = h->opt_layout;
+    L.stages = lin_pick_stages(max_rt);
+    if (L.stages < 1) return fail(SAT_ERR_UNSUPPORTED, "row tile %d does not fit in shared memory", max_rt);
+    CK(lin_launch(L, st, h->opt_gemm == 0));
+    return SAT_OK;
+}
+
+// --------------------------------------------------------------- contexts
+static int ensure_ctx_map(sat_handle* h, const float* ctx, int n_img) {
+    if (h->map_ctx == ctx && h->map_ni == n_img) return SAT_OK;
+    const int L = h->d.num_ctx, D = h->d.dim_ctx;
+    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)n_img * L};
+    cuuint64_t gstr[1] = {(cuuint64_t)D * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)L};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = g_encode(&h->ctx_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ctx, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SAT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    h->map_ctx = ctx;
+    h->map_ni = n_img;
+    return SAT_OK;
+}
+
+// attend fc_1a over every location (model.py:417-420): T1 = tanh(ctx2d * W1a + b1a)
+static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStream_t st) {
+    if (h->d.num_attend_layers != 2) return SAT_OK;
+    LinProblem P;
+    RET(plan(h, h->att_1a, P, {seg(ctx, h->d.dim_ctx, h->d.dim_ctx)}, n_img * h->d.num_ctx, kEpiBiasTanh, h->T1,
+             h->d.dim_attend_layer, st));
+    return launch(h, &P, 1, st);
+}
+
+// initialize (model.py:239-242, 358-393)
+static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st) {
+    const sat_dims& d = h->d;
+    CK(ctx_mean_launch(ctx, h->mean, n_img, d.num_ctx, d.dim_ctx, st));
+    LinProblem P[2];
+    if (d.num_initalize_layers == 1) {
+        RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, c0, d.num_lstm_units, st));
+        RET(plan(h, h->init_b1, P[1], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, h0, d.num_lstm_units, st));
+        return launch(h, P, 2, st);
+    }
+    const int I = d.dim_initalize_layer;
+    RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBiasTanh, h->tmp_a, I, st));
+    RET(plan(h, h->init_b1, P[1], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBiasTanh, h->tmp_b, I, st));
+    RET(launch(h, P, 2, st));
+    RET(plan(h, h->init_a2, P[0], {seg(h->tmp_a, I, I)}, n_img, kEpiBias, c0, d.num_lstm_units, st));
+    RET(plan(h, h->init_b2, P[1], {seg(h->tmp_b, I, I)}, n_img, kEpiBias, h0, d.num_lstm_units, st));
+    return launch(h, P, 2, st);
+}
+
+static int prepare_impl(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st) {
+    if (n_img < 1 || n_img > h->max_rows) return fail(SAT_ERR_INVALID, "n_img %d outside [1, %d]", n_img, h->max_rows);
+    RET(ensure_ctx_map(h, ctx, n_img));
+    if (h->opt_hoist) {
+        RET(project_contexts(h, ctx, n_img, st));
+        h->prep_ctx = ctx;
+        h->prep_ni = n_img;
+    }
+    if (c0 && h0) RET(run_initialize(h, ctx, n_img, c0, h0, st));
+    return SAT_OK;
+}
+
+extern "C" int sat_prepare_contexts(sat_handle* h, const float* contexts, int32_t n_img, float* initial_memory,
+                                    float* initial_output, void* stream) {
+    RET(require_ready(h));
+    if (!contexts) return fail(SAT_ERR_INVALID, "contexts is null");
+    if ((initial_memory == nullptr) != (initial_output == nullptr))
+        return fail(SAT_ERR_INVALID, "initial_memory and initial_output must both be given or both be null");
+    return prepare_impl(h, contexts, n_img, initial_memory, initial_output, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------- step
+struct StepIO {
+    const float* ctx;
+    int n_img, group;
+    const int32_t* last_word;
+    const float *c_in, *h_in;
+    float *c_out, *h_out, *logits, *probs, *alpha;
+    RowsParams rows;  // softmax-stage extras (tokens / next_word / topk); logits/probs/V filled here
+    bool want_rows;
+};
+
+static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, const float* h_in, float* alpha, float* z,
+                          cudaStream_t st) {
+    const sat_dims& d = h->d;
+    const int rows = n_img * G;
+    RET(ensure_ctx_map(h, ctx, n_img));
+    AttParams ap;
+    memset(&ap, 0, sizeof(ap));
+    LinProblem P;
+    if (d.num_attend_layers == 2) {
+        if (!(h->opt_hoist && h->prep_ctx == ctx && h->prep_ni == n_img)) RET(project_contexts(h, ctx, n_img, st));
+        // state branch: q = tanh(h * W1b + b1b)   (model.py:421-424)
+        RET(plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiBiasTanh, h->q,
+                 d.dim_attend_layer, st));
+        RET(launch(h, &P, 1, st));
+        ap.T = h->T1;
+        ap.RL = d.dim_attend_layer;
+        ap.q = h->q;
+        ap.eadd = nullptr;
+    } else {
+        // logits2 = h * fc_b   (model.py:409-413), added to ctx . fc_a inside the kernel
+        RET(plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiNone, h->q, d.num_ctx, st));
+        RET(launch(h, &P, 1, st));
+        ap.T = ctx;
+        ap.RL = d.dim_ctx;
+        ap.q = nullptr;
+        ap.eadd = h->q;
+    }
+    ap.vec = h->att_vec.dev;
+    ap.e = h->e;
+    ap.rowcnt = h->rowcnt;
+    ap.target = (unsigned)d.num_ctx;
+    ap.alpha = alpha ? alpha : h->alpha;
+    ap.z = z;
+    ap.NI = n_img;
+    ap.G = G;
+    ap.L = d.num_ctx;
+    ap.D = d.dim_ctx;
+    if (!att_plan(ap, h->smem_optin)) return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
+    CK(cudaMemsetAsync(h->rowcnt, 0, (size_t)n_img * sizeof(unsigned), st));
+    CK(att_launch(h->ctx_map, ap, h->num_sms, st, h->opt_coop != 0));
+    return SAT_OK;
+}
+
+static int lstm_impl(sat_handle* h, const float* z, const int32_t* last_word, const float* c_in, const float* h_in,
+                     float* c_out, float* h_out, int rows, cudaStream_t st) {
+    const sat_dims& d = h->d;
+    LinProblem P;
+    // current_input = concat([context, word_embed]) (model.py:277); LSTMCell concat([x, h]) (TF)
+    RET(plan(h, h->lstm, P,
+             {seg(z, d.dim_ctx, d.dim_ctx), seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word),
+              seg(h_in, d.num_lstm_units, d.num_lstm_units)},
+             rows, kEpiLstm, nullptr, 0, st));
+    P.c_in = c_in;
+    P.c_out = c_out;
+    P.h_out = h_out;
+    P.H = d.num_lstm_units;
+    return launch(h, &P, 1, st);
+}
+
+static int decode_impl(sat_handle* h, const float* h_out, const float* z, const int32_t* last_word, float* logits,
+                       int rows, cudaStream_t st) {
+    const sat_dims& d = h->d;
+    LinProblem P;
+    // expanded_output = concat([output, context, word_embed]) (model.py:283-286)
+    if (d.num_decode_layers == 2) {
+        RET(plan(h, h->dec_1, P,
+                 {seg(h_out, d.num_lstm_units, d.num_lstm_units), seg(z, d.dim_ctx, d.dim_ctx),
+                  seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word)},
+                 rows, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st));
+        RET(launch(h, &P, 1, st));
+        RET(plan(h, h->dec_2, P, {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer)}, rows, kEpiBias, logits,
+                 d.vocabulary_size, st));
+        return launch(h, &P, 1, st);
+    }
+    RET(plan(h, h->dec_2, P,
+             {seg(h_out, d.num_lstm_units, d.num_lstm_units), seg(z, d.dim_ctx, d.dim_ctx),
+              seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word)},
+             rows, kEpiBias, logits, d.vocabulary_size, st));
+    return launch(h, &P, 1, st);
+}
+
+static int step_impl(sat_handle* h, StepIO& io, cudaStream_t st) {
+    const int rows = io.n_img * io.group;
+    if (rows > h->max_rows) return fail(SAT_ERR_INVALID, "rows %d > max_batch %d", rows, h->max_rows);
+    RET(attention_impl(h, io.ctx, io.n_img, io.group, io.h_in, io.alpha, h->z, st));
+    RET(lstm_impl(h, h->z, io.last_word, io.c_in, io.h_in, io.c_out, io.h_out, rows, st));
+    float* logits = io.logits ? io.logits : h->logits;
+    RET(decode_impl(h, io.h_out, h->z, io.last_word, logits, rows, st));
+    if (io.probs || io.want_rows) {
+        RowsParams rp = io.rows;
+        rp.logits = logits;
+        rp.V = h->d.vocabulary_size;
+        rp.probs = io.probs;
+        CK(rows_softmax_launch(rp, rows, st));
+    }
+    return SAT_OK;
+}
+
+extern "C" int sat_decode_step(sat_handle* h, const float* contexts, const int32_t* last_word,
+                               const float* last_memory, const float* last_output, float* memory, float* output,
+                               float* logits, float* probs, float* alpha, int32_t B, void* stream) {
+    RET(require_ready(h));
+    if (!contexts || !last_word || !last_memory || !last_output || !memory || !output)
+        return fail(SAT_ERR_INVALID, "sat_decode_step: null tensor");
+    if (B < 1 || B > h->max_rows) return fail(SAT_ERR_INVALID, "batch %d outside [1, %d]", B, h->max_rows);
+    if (memory == last_memory || output == last_output)
+        return fail(SAT_ERR_INVALID, "sat_decode_step: state outputs must not alias the inputs");
+    StepIO io;
+    memset(&io, 0, sizeof(io));
+    io.ctx = contexts; io.n_img = B; io.group = 1; io.last_word = last_word;
+    io.c_in = last_memory; io.h_in = last_output; io.c_out = memory; io.h_out = output;
+    io.logits = logits; io.probs = probs; io.alpha = alpha;
+    return step_impl(h, io, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------ CUDA graphs
+template <typename F>
+static int run_graphed(sat_handle* h, const std::vector<long long>& key, cudaStream_t st, F&& enqueue) {
+    if (!h->opt_graphs || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return enqueue();
+    GraphEntry* ent = nullptr;
+    for (auto& g : h->graphs)
+        if (g.key == key) ent = &g;
+    if (!ent) {
+        if (h->graphs.size() >= 16) {
+            if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec);
+            h->graphs.erase(h->graphs.begin());
+        }
+        h->graphs.push_back(GraphEntry());
+        ent = &h->graphs.back();
+        ent->key = key;
+    }
+    if (ent->exec) {
+        CK(cudaGraphLaunch(ent->exec, st));
+        return SAT_OK;
+    }
+    if (ent->seen == 0) {  // first use: run eagerly so that every workspace exists
+        ent->seen = 1;
+        return enqueue();
+    }
+    // contexts-dependent caches are part of the key, so replays stay valid
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != SAT_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (ce != cudaSuccess) return fail(SAT_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&ent->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        ent->exec = nullptr;
+        return fail(SAT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    }
+    CK(cudaGraphLaunch(ent->exec, st));
+    return SAT_OK;
+}
+
+// ------------------------------------------------------------------- loop
+static int loop_enqueue(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
+                        float* logits_all, cudaStream_t st) {
+    RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st));
+    CK(cudaMemsetAsync(h->word, 0, (size_t)B * sizeof(int32_t), st));  // <start> = 0 (model.py:254)
+    for (int t = 0; t < T; ++t) {
+        StepIO io;
+        memset(&io, 0, sizeof(io));
+        io.ctx = ctx; io.n_img = B; io.group = 1; io.last_word = h->word;
+        io.c_in = h->st_c[t & 1]; io.h_in = h->st_h[t & 1];
+        io.c_out = h->st_c[(t + 1) & 1]; io.h_out = h->st_h[(t + 1) & 1];
+        io.logits = logits_all ? logits_all + (size_t)t * B * h->d.vocabulary_size : nullptr;
+        io.want_rows = true;
+        io.rows.tokens = tokens; io.rows.tokens_ld = T; io.rows.step = t;
+        io.rows.next_word = h->word; io.rows.forced = forced; io.rows.forced_ld = T;
+        RET(step_impl(h, io, st));
+    }
+    return SAT_OK;
+}
+
+extern "C" int sat_decode_loop(sat_handle* h, const float* contexts, int32_t B, int32_t T, const int32_t* forced_words,
+                               int32_t* tokens, float* logits_all, void* stream) {
+    RET(require_ready(h));
+    if (!contexts || !tokens) return fail(SAT_ERR_INVALID, "sat_decode_loop: null tensor");
+    if (B < 1 || B > h->max_rows) return fail(SAT_ERR_INVALID, "batch %d outside [1, %d]", B, h->max_rows);
+    if (T < 1) return fail(SAT_ERR_INVALID, "T must be >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<long long> key = {1, (long long)contexts, B, T, (long long)forced_words, (long long)tokens,
+                                  (long long)logits_all};
+    // the graph bakes in the tensor map and T1 validity: force a fresh encode inside the captured work
+    return run_graphed(h, key, st, [&]() -> int {
+        return loop_enqueue(h, contexts, B, T, forced_words, tokens, logits_all, st);
+    });
+}
+
+// ------------------------------------------------------------ beam search
+static int beam_enqueue(sat_handle* h, const float* ctx, int NI, int beam, int T, int eos, int32_t* sentences,
+                        int32_t* lengths, double* scores, int32_t* n_results, int32_t* is_complete, cudaStream_t st) {
+    const sat_dims& d = h->d;
+    const int H = d.num_lstm_units;
+    // states: st_*[0] = inputs of the current step, st_*[1] = outputs
+    RET(prepare_impl(h, ctx, NI, h->st_c[0], h->st_h[0], st));               // base_model.py:168-170
+    CK(cudaMemsetAsync(h->comp_n, 0, (size_t)NI * sizeof(int32_t), st));
+    BeamParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.NI = NI; bp.beam = beam; bp.T = T; bp.eos_id = eos; bp.H = H;
+    bp.topk_idx = h->topk_idx; bp.topk_p = h->topk_p;
+    bp.part_score = h->part_score; bp.part_n = h->part_n;
+    bp.sent[0] = h->sent[0]; bp.sent[1] = h->sent[1];
+    bp.comp_heap = (CItem*)h->comp_heap; bp.comp_n = h->comp_n; bp.comp_sent = h->comp_sent;
+    bp.c_out = h->st_c[1]; bp.h_out = h->st_h[1]; bp.c_next = h->st_c[0]; bp.h_next = h->st_h[0];
+    bp.next_word = h->word;
+    bp.res_sent = sentences; bp.res_len = lengths; bp.res_score = scores; bp.res_n = n_results;
+    bp.res_complete = is_complete;
+    for (int idx = 0; idx < T; ++idx) {                                       // base_model.py:184
+        const int G = idx == 0 ? 1 : beam;                                    // base_model.py:191
+        StepIO io;
+        memset(&io, 0, sizeof(io));
+        io.ctx = ctx; io.n_img = NI; io.group = G;
+        io.last_word = idx == 0 ? h->zero_word : h->word;                     // base_model.py:193-198
+        io.c_in = h->st_c[0]; io.h_in = h->st_h[0]; io.c_out = h->st_c[1]; io.h_out = h->st_h[1];
+        io.want_rows = true;
+        io.rows.topk = beam + 1; io.rows.topk_idx = h->topk_idx; io.rows.topk_p = h->topk_p;
+        RET(step_impl(h, io, st));
+        bp.nlive = G; bp.step = idx;
+        CK(beam_update_launch(bp, st));
+    }
+    bp.step = T;
+    CK(beam_finalize_launch(bp, st));
+    return SAT_OK;
+}
+
+extern "C" int sat_beam_search(sat_handle* h, const float* contexts, int32_t n_img, int32_t beam_size, int32_t T,
+                               int32_t eos_id, int32_t* sentences, int32_t* lengths, double* scores,
+                               int32_t* n_results, int32_t* is_complete, void* stream) {
+    RET(require_ready(h));
+    if (!contexts || !sentences || !lengths || !scores || !n_results || !is_complete)
+        return fail(SAT_ERR_INVALID, "sat_beam_search: null tensor");
+    if (beam_size < 1 || beam_size > h->d.max_beam) return fail(SAT_ERR_INVALID, "beam_size %d outside [1, %d]", beam_size, h->d.max_beam);
+    if (T < 1 || T > h->d.max_caption_length) return fail(SAT_ERR_INVALID, "T %d outside [1, %d]", T, h->d.max_caption_length);
+    if (n_img < 1 || (long long)n_img * beam_size > h->max_rows)
+        return fail(SAT_ERR_INVALID, "n_img*beam %lld > max_batch %d", (long long)n_img * beam_size, h->max_rows);
+    if (h->d.vocabulary_size < beam_size + 2) return fail(SAT_ERR_INVALID, "vocabulary too small for beam %d", beam_size);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<long long> key = {2, (long long)contexts, n_img, beam_size, T, eos_id, (long long)sentences,
+                                  (long long)lengths, (long long)scores, (long long)n_results, (long long)is_complete};
+    return run_graphed(h, key, st, [&]() -> int {
+        return beam_enqueue(h, contexts, n_img, beam_size, T, eos_id, sentences, lengths, scores, n_results,
+                            is_complete, st);
+    });
+}
+
+// ---------------------------------------------------------- host-buffer forms
+static int ensure_stage(sat_handle* h, size_t misc_bytes) {
+    const sat_dims& d = h->d;
+    if (!h->stage_ctx) RET(dmalloc(&h->stage_ctx, (size_t)h->max_rows * d.num_ctx * d.dim_ctx));
+    if (misc_bytes > h->stage_misc_bytes) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(h->stage_misc);
+        h->stage_misc = nullptr;
+        h->stage_misc_bytes = 0;
+        RET(dmalloc((uint8_t**)&h->stage_misc, misc_bytes));
+        h->stage_misc_bytes = misc_bytes;
+    }
+    return SAT_OK;
+}
+
+extern "C" int sat_decode_step_host(sat_handle* h, const float* contexts_host, int32_t contexts_changed,
+                                    const int32_t* last_word_host, const float* last_memory_host,
+                                    const float* last_output_host, float* memory_host, float* output_host,
+                                    float* probs_host, int32_t B, void* stream) {
+    RET(require_ready(h));
+    if (!contexts_host || !last_word_host || !last_memory_host || !last_output_host || !memory_host || !output_host ||
+        !probs_host)
+        return fail(SAT_ERR_INVALID, "sat_decode_step_host: null buffer");
+    if (B < 1 || B > h->max_rows) return fail(SAT_ERR_INVALID, "batch %d outside [1, %d]", B, h->max_rows);
+    const sat_dims& d = h->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t HB = (size_t)B * d.num_lstm_units * sizeof(float), VB = (size_t)B * d.vocabulary_size * sizeof(float);
+    RET(ensure_stage(h, 4 * HB + VB + (size_t)B * sizeof(int32_t)));
+    uint8_t* m = (uint8_t*)h->stage_misc;
+    float *c_in = (float*)m, *h_in = (float*)(m + HB), *c_out = (float*)(m + 2 * HB), *h_out = (float*)(m + 3 * HB);
+    float* probs = (float*)(m + 4 * HB);
+    int32_t* lw = (int32_t*)(m + 4 * HB + VB);
+    if (contexts_changed || h->prep_ctx != h->stage_ctx || h->prep_ni != B) {
+        CK(cudaMemcpyAsync(h->stage_ctx, contexts_host, (size_t)B * d.num_ctx * d.dim_ctx * sizeof(float),
+                           cudaMemcpyHostToDevice, st));
+        RET(prepare_impl(h, h->stage_ctx, B, nullptr, nullptr, st));
+    }
+    CK(cudaMemcpyAsync(lw, last_word_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c_in, last_memory_host, HB, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h_in, last_output_host, HB, cudaMemcpyHostToDevice, st));
+    StepIO io;
+    memset(&io, 0, sizeof(io));
+    io.ctx = h->stage_ctx; io.n_img = B; io.group = 1; io.last_word = lw;
+    io.c_in = c_in; io.h_in = h_in; io.c_out = c_out; io.h_out = h_out; io.probs = probs;
+    RET(step_impl(h, io, st));
+    CK(cudaMemcpyAsync(memory_host, c_out, HB, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(output_host, h_out, HB, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(probs_host, probs, VB, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SAT_OK;
+}
+
+extern "C" int sat_decode_loop_host(sat_handle* h, const float* contexts_host, int32_t B, int32_t T,
+                                    const int32_t* forced_words_host, int32_t* tokens_host, void* stream) {
+    RET(require_ready(h));
+    if (!contexts_host || !tokens_host) return fail(SAT_ERR_INVALID, "sat_decode_loop_host: null buffer");
+    if (B < 1 || B > h->max_rows || T < 1) return fail(SAT_ERR_INVALID, "bad B/T");
+    const sat_dims& d = h->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t TB = (size_t)B * T * sizeof(int32_t);
+    RET(ensure_stage(h, 2 * TB));
+    int32_t* tok = (int32_t*)h->stage_misc;
+    int32_t* forced = forced_words_host ? (int32_t*)((uint8_t*)h->stage_misc + TB) : nullptr;
+    CK(cudaMemcpyAsync(h->stage_ctx, contexts_host, (size_t)B * d.num_ctx * d.dim_ctx * sizeof(float),
+                       cudaMemcpyHostToDevice, st));
+    if (forced) CK(cudaMemcpyAsync(forced, forced_words_host, TB, cudaMemcpyHostToDevice, st));
+    RET(sat_decode_loop(h, h->stage_ctx, B, T, forced, tok, nullptr, stream));
+    CK(cudaMemcpyAsync(tokens_host, tok, TB, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SAT_OK;
+}
+
+extern "C" int sat_beam_search_host(sat_handle* h, const float* contexts_host, int32_t n_img, int32_t beam_size,
+                                    int32_t T, int32_t eos_id, int32_t* sentences_host, int32_t* lengths_host,
+                                    double* scores_host, int32_t* n_results_host, int32_t* is_complete_host,
+                                    void* stream) {
+    RET(require_ready(h));
+    if (!contexts_host || !sentences_host || !lengths_host || !scores_host || !n_results_host || !is_complete_host)
+        return fail(SAT_ERR_INVALID, "sat_beam_search_host: null buffer");
+    if (n_img < 1 || beam_size < 1 || T < 1 || (long long)n_img * beam_size > h->max_rows)
+        return fail(SAT_ERR_INVALID, "bad n_img/beam/T");
+    const sat_dims& d = h->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nb = (size_t)n_img * beam_size;
+    const size_t o_sc = 0, o_sent = nb * 8, o_len = o_sent + nb * T * 4, o_n = o_len + nb * 4, o_c = o_n + n_img * 4,
+                 total = o_c + n_img * 4;
+    RET(ensure_stage(h, total));
+    uint8_t* m = (uint8_t*)h->stage_misc;
+    CK(cudaMemcpyAsync(h->stage_ctx, contexts_host, (size_t)n_img * d.num_ctx * d.dim_ctx * sizeof(float),
+                       cudaMemcpyHostToDevice, st));
+    RET(sat_beam_search(h, h->stage_ctx, n_img, beam_size, T, eos_id, (int32_t*)(m + o_sent), (int32_t*)(m + o_len),
+                        (double*)(m + o_sc), (int32_t*)(m + o_n), (int32_t*)(m + o_c), stream));
+    CK(cudaMemcpyAsync(scores_host, m + o_sc, nb * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sentences_host, m + o_sent, nb * T * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(lengths_host, m + o_len, nb * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_results_host, m + o_n, (size_t)n_img * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(is_complete_host, m + o_c, (size_t)n_img * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SAT_OK;
+}
+
+// ------------------------------------------------- individually callable kernels
+extern "C" int sat_attention_fwd(sat_handle* h, const float* contexts, const float* output, float* alpha,
+                                 float* context, int32_t n_img, int32_t group, void* stream) {
+    RET(require_ready(h));
+    if (!contexts || !output || !context) return fail(SAT_ERR_INVALID, "sat_attention_fwd: null tensor");
+    if (n_img < 1 || group < 1 || (long long)n_img * group > h->max_rows)
+        return fail(SAT_ERR_INVALID, "n_img*group outside [1, %d]", h->max_rows);
+    return attention_impl(h, contexts, n_img, group, output, alpha, context, (cudaStream_t)stream);
+}
+
+extern "C" int sat_lstm_fwd(sat_handle* h, const float* context, const int32_t* last_word, const float* last_memory,
+                            const float* last_output, float* memory, float* output, int32_t rows, void* stream) {
+    RET(require_ready(h));
+    if (!context || !last_word || !last_memory || !last_output || !memory || !output)
+        return fail(SAT_ERR_INVALID, "sat_lstm_fwd: null tensor");
+    if (rows < 1 || rows > h->max_rows) return fail(SAT_ERR_INVALID, "rows outside [1, %d]", h->max_rows);
+    return lstm_impl(h, context, last_word, last_memory, last_output, memory, output, rows, (cudaStream_t)stream);
+}
+
+extern "C" int sat_vocab_gemm(sat_handle* h, const float* output, const float* context, const int32_t* last_word,
+                              float* logits, int32_t rows, void* stream) {
+    RET(require_ready(h));
+    if (!output || !context || !last_word || !logits) return fail(SAT_ERR_INVALID, "sat_vocab_gemm: null tensor");
+    if (rows < 1 || rows > h->max_rows) return fail(SAT_ERR_INVALID, "rows outside [1, %d]", h->max_rows);
+    return decode_impl(h, output, context, last_word, logits, rows, (cudaStream_t)stream);
+}
+
+extern "C" int sat_dense_fwd(sat_handle* h, const float* x, const float* w_tf, const float* b, float* y, int32_t rows,
+                             int32_t K, int32_t n_out, int32_t act, int32_t splits, void* stream) {
+    if (!h || !x || !w_tf || !y) return fail(SAT_ERR_INVALID, "sat_dense_fwd: null argument");
+    if (rows < 1 || K < 8 || K % 8 || n_out < 1) return fail(SAT_ERR_INVALID, "sat_dense_fwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    Layer ly;
+    std::vector<Layer*> keep = h->layers;  // layer_setup registers the layer; undo below
+    int rc = layer_setup(h, ly, "dense_fwd", K, n_out, false, true);
+    h->layers = keep;
+    if (rc == SAT_OK) {
+        auto body = [&]() -> int {
+            CK(lin_repack_weight(w_tf, K, n_out, 0, ly.wpack, h->opt_layout, st));
+            CK(lin_repack_bias(b, n_out, 0, ly.bias, st));
+            LinProblem P;
+            RET(plan(h, ly, P, {seg(x, K, K)}, rows, act ? kEpiBiasTanh : kEpiBias, y, n_out, st, splits));
+            RET(launch(h, &P, 1, st));
+            CK(cudaStreamSynchronize(st));
+            return SAT_OK;
+        };
+        rc = body();
+    }
+    layer_free(ly);
+    return rc;
+}

@@ -1,0 +1,461 @@
+// sat_linear.cu — small-batch dense layers on tcgen05 tensor cores.
+//
+// Computes, for up to 4 grouped problems per launch,
+//     out[b, n] = epilogue( sum_k X[b, k] * W[k, n] + bias[n] )
+// which is tf.layers.dense (utils/nn.py:85-105) and the LSTMCell matmul
+// (model.py:276-279) of the reference.  The batch is small (4..384) and the
+// weights are large, so every problem is bound by streaming W once from HBM.
+//
+// Formulation ("swap-AB"): the weight matrix is the UMMA M operand — a CTA owns
+// 128 output features x a K-range — and the batch rows are the UMMA N operand
+// (16..256).  fp32 parity (1e-3 vs the fp32 reference) is kept with a
+// split-precision product: W and X are each held as bf16 hi + bf16 lo
+// (w = hi + lo to 16 mantissa bits) and three MMAs are issued per K-step,
+//     acc += Whi*Xhi + Wlo*Xhi + Whi*Xlo        (fp32 accumulation in TMEM).
+// W is repacked once at sat_set_weight() into the exact shared-memory image of
+// the UMMA K-major operand (hi and lo halves adjacent: 4 bytes per weight, the
+// same HBM traffic as the fp32 original), so a pipeline stage is filled by ONE
+// 32 KB cp.async.bulk (TMA) per CTA.  X (tiny) is converted fp32 -> bf16 hi/lo
+// by four producer warps straight from its fp32 sources (context vector, word
+// embedding row gather, hidden state: the concat of model.py:277,283-286 is
+// never materialised).  Split-K partials meet in an L2-resident workspace; the
+// last-arriving CTA of a tile reduces them in fixed order (deterministic) and
+// applies the fused epilogue (bias / tanh / LSTM gates).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM
+// allocator + MMA issuer (one lane), warps 2..5 = X producers, then epilogue.
+#include "sat_common.cuh"
+#include "sat_linear.cuh"
+
+namespace sat {
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ void split_bf16x8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+    float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]);
+        __nv_bfloat16 h1 = __float2bfloat16_rn(x[2 * i + 1]);
+        __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+        __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// fp32 source of the 8 consecutive K elements starting at k0 of activation row b (zeros outside).
+__device__ __forceinline__ void load_x8(const LinProblem& P, int b, int k0, float4& a, float4& c) {
+    a = make_float4(0.f, 0.f, 0.f, 0.f);
+    c = a;
+    if (b >= P.rows || k0 >= P.K) return;
+    int start = 0;
+#pragma unroll
+    for (int s = 0; s < kMaxSeg; ++s) {
+        if (s < P.nseg) {
+            const LinSeg& sg = P.seg[s];
+            if (k0 >= start && k0 < start + sg.width) {
+                const int row = sg.gather ? sg.gather[b] : b / sg.row_div;
+                const float4* p = reinterpret_cast<const float4*>(sg.ptr + (size_t)row * sg.ld + (k0 - start));
+                a = p[0];
+                c = p[1];
+            }
+            start += sg.width;
+        }
+    }
+}
+
+struct EpiCtx {
+    const LinProblem* P;
+    int n_tile, row0, rows_here;
+};
+
+// generic epilogues on one value
+__device__ __forceinline__ float epi_scalar(const LinProblem& P, float acc, int n) {
+    if (P.epi == kEpiNone) return acc;
+    acc += P.bias[n];
+    return P.epi == kEpiBiasTanh ? tanhf(acc) : acc;
+}
+
+// TF LSTMCell (un-vendored TF 1.7 dependency; gate order i, j, f, o and forget_bias 1.0
+// confirmed on the reference's recorded GraphDef, tests/golden/graph_fixture.json):
+//   c = sigmoid(f + 1) * c_prev + sigmoid(i) * tanh(j);  h = sigmoid(o) * tanh(c)
+__device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, int b, int unit) {
+    const float cp = P.c_in[(size_t)b * P.H + unit];
+    const float c = sigmoidf_acc(g.z + 1.0f) * cp + sigmoidf_acc(g.x) * tanhf(g.y);
+    const float h = sigmoidf_acc(g.w) * tanhf(c);
+    P.c_out[(size_t)b * P.H + unit] = c;
+    P.h_out[(size_t)b * P.H + unit] = h;
+}
+
+// ------------------------------------------------------------- UMMA kernel
+__global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_constant__ LinLaunch L) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // control block: barriers etc. live in the first 1024 bytes
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(smem_raw);  // [stages]
+    uint64_t* full_x = full_w + 8;
+    uint64_t* empty = full_x + 8;
+    uint64_t* tmem_full = empty + 8;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint32_t* last_flag = tmem_ptr + 1;
+    uint8_t* stage_base = smem_raw + 1024;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- which problem / tile / split am I?
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxProb; ++i)
+        if (i < L.nprob && (int)blockIdx.x >= L.p[i].cta_begin) pi = i;
+    const LinProblem& P = L.p[pi];
+    const int local = blockIdx.x - P.cta_begin;
+    const int split = local % P.splits;
+    const int t = local / P.splits;
+    const int n_tile = t % P.n_tiles;
+    const int rt = t / P.n_tiles;
+    const int row0 = rt * P.row_tile;
+    const int N = P.row_tile;
+    const int kb0 = (int)(((long long)P.k_blocks * split) / P.splits);
+    const int kb1 = (int)(((long long)P.k_blocks * (split + 1)) / P.splits);
+    const int nkb = kb1 - kb0;
+    const int S = L.stages;
+    const int mode = L.layout_mode;
+    const uint32_t x_half_bytes = (uint32_t)N * kBK * 2;
+    const uint32_t stage_bytes = kWStageBytes + 2 * x_half_bytes;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < N) tmem_cols <<= 1;
+
+    // ---- one-time setup
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_w[s], 1);
+            mbar_init(&full_x[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer: one 32 KB bulk copy per stage =====================
+        if (lane == 0) {
+            const uint8_t* src = P.wpack + ((size_t)n_tile * P.k_blocks + kb0) * kWStageBytes;
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_w[s], kWStageBytes);
+                tma_bulk_g2s(stage_base + (size_t)s * stage_bytes, src + (size_t)it * kWStageBytes, kWStageBytes,
+                             &full_w[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kTileN, N);
+            const uint32_t lbo = mode == 0 ? 128u : 16u;
+            const uint32_t layout = mode == 0 ? 0u : 2u;
+            const uint32_t kstep = mode == 0 ? 256u : 32u;  // bytes per UMMA K (=16 bf16) inside a stage tile
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(&full_w[s], ph);
+                mbar_wait(&full_x[s], ph);
+                tc_fence_after();
+                const uint32_t wb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t xb = wb + kWStageBytes;
+#pragma unroll
+                for (int kk = 0; kk < kBK / 16; ++kk) {
+                    const uint64_t a_hi = umma_smem_desc(wb + kk * kstep, lbo, 1024, layout);
+                    const uint64_t a_lo = umma_smem_desc(wb + kWHalfBytes + kk * kstep, lbo, 1024, layout);
+                    const uint64_t b_hi = umma_smem_desc(xb + kk * kstep, lbo, 1024, layout);
+                    const uint64_t b_lo = umma_smem_desc(xb + x_half_bytes + kk * kstep, lbo, 1024, layout);
+                    umma_f16(tmem_d, a_hi, b_hi, idesc, (it | kk) != 0 ? 1u : 0u);
+                    umma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
+                    umma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
+                }
+                umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // ===================== X producers (warps 2..5), then epilogue =====================
+        const int pt = threadIdx.x - 64;  // 0..127
+        for (int it = 0; it < nkb; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t* xh = stage_base + (size_t)s * stage_bytes + kWStageBytes;
+            uint8_t* xl = xh + x_half_bytes;
+            const int kbase = (kb0 + it) * kBK;
+            for (int u = pt; u < N * 8; u += 128) {
+                const int kg = u / N, r = u - kg * N;
+                float4 a, c;
+                load_x8(P, row0 + r, kbase + kg * 8, a, c);
+                uint4 hi, lo;
+                split_bf16x8(a, c, hi, lo);
+                const uint32_t off = umma_tile_off(mode, r, kg);
+                *reinterpret_cast<uint4*>(xh + off) = hi;
+                *reinterpret_cast<uint4*>(xl + off) = lo;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&full_x[s]);
+        }
+
+        // ---- epilogue: TMEM -> registers
+        const int q = warp & 3;               // TMEM lane quadrant this warp may access
+        const int nl = q * 32 + lane;          // output feature within the tile (TMEM lane)
+        const int n = n_tile * kTileN + nl;    // packed output index
+        const int rows_here = min(N, P.rows - row0);
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+        const bool direct = (P.splits == 1) && (P.epi != kEpiLstm);
+        const int npad = P.n_tiles * kTileN;
+        const int rpad = P.n_row_tiles * P.row_tile;
+        float* wsp = P.ws + ((size_t)split * rpad + row0) * npad + n;
+        for (int c0 = 0; c0 < N; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)c0, v);
+            if (direct) {
+                if (n < P.n_out) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < rows_here) P.out[(size_t)(row0 + c0 + j) * P.ldo + n] = epi_scalar(P, v[j], n);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < rows_here) wsp[(size_t)(c0 + j) * npad] = v[j];
+            }
+        }
+        tc_fence_before();
+
+        if (!direct) {
+            // ---- split-K rendezvous: last CTA of this tile reduces + applies the epilogue
+            __threadfence();
+            named_bar_sync(1, 128);
+            unsigned* ctr = P.counters + (rt * P.n_tiles + n_tile);
+            if (pt == 0) {
+                const unsigned old = atomicAdd(ctr, 1u);
+                *last_flag = (old == (unsigned)(P.splits - 1)) ? 1u : 0u;
+            }
+            named_bar_sync(1, 128);
+            if (*last_flag) {
+                __threadfence();
+                const float* ws0 = P.ws + (size_t)row0 * npad + (size_t)n_tile * kTileN;
+                const size_t sstride = (size_t)rpad * npad;
+                if (P.epi == kEpiLstm) {
+                    for (int idx = pt; idx < rows_here * 32; idx += 128) {
+                        const int b = idx >> 5, u = idx & 31;
+                        const float4* p = reinterpret_cast<const float4*>(ws0 + (size_t)b * npad + 4 * u);
+                        float4 g = __ldcg(p);
+                        for (int s2 = 1; s2 < P.splits; ++s2) {
+                            const float4 w =
+                                __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + s2 * sstride));
+                            g.x += w.x; g.y += w.y; g.z += w.z; g.w += w.w;
+                        }
+                        const int unit = n_tile * 32 + u;
+                        if (unit < P.H) {
+                            const float4 bb = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
+                            g.x += bb.x; g.y += bb.y; g.z += bb.z; g.w += bb.w;
+                            lstm_gates(P, g, row0 + b, unit);
+                        }
+                    }
+                } else {
+                    for (int idx = pt; idx < rows_here * kTileN; idx += 128) {
+                        const int b = idx >> 7, nn = idx & 127;
+                        const float* p = ws0 + (size_t)b * npad + nn;
+                        float acc = __ldcg(p);
+                        for (int s2 = 1; s2 < P.splits; ++s2) acc += __ldcg(p + s2 * sstride);
+                        const int ng = n_tile * kTileN + nn;
+                        if (ng < P.n_out) P.out[(size_t)(row0 + b) * P.ldo + ng] = epi_scalar(P, acc, ng);
+                    }
+                }
+                if (pt == 0) *ctr = 0u;  // ready for the next launch
+            }
+        }
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, tmem_cols);
+    }
+}
+
+// -------------------------------------------------- SIMT bring-up kernel
+// Same math on CUDA cores from the same packed weights (w = hi + lo).  Used by
+// the tests to cross-check the tcgen05 path and its packing; selected with
+// sat_set_option("gemm", 0).  Grid: one CTA per (n_tile, 16-row group).
+__global__ void __launch_bounds__(128) lin_simt_kernel(const __grid_constant__ LinLaunch L) {
+    __shared__ float xs[16][kBK + 1];
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxProb; ++i)
+        if (i < L.nprob && (int)blockIdx.x >= L.p[i].cta_begin) pi = i;
+    const LinProblem& P = L.p[pi];
+    const int local = blockIdx.x - P.cta_begin;
+    const int n_tile = local % P.n_tiles;
+    const int rg = local / P.n_tiles;
+    const int row0 = rg * 16;
+    const int r = threadIdx.x;  // output feature within tile
+    const int mode = L.layout_mode;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int kb = 0; kb < P.k_blocks; ++kb) {
+        __syncthreads();
+        {   // 16 rows x 8 k-groups = 128 groups, one per thread
+            const int b = threadIdx.x >> 3, kg = threadIdx.x & 7;
+            float4 a, c;
+            load_x8(P, row0 + b, kb * kBK + kg * 8, a, c);
+            float* d = &xs[b][kg * 8];
+            d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = c.x; d[5] = c.y; d[6] = c.z; d[7] = c.w;
+        }
+        __syncthreads();
+        const uint8_t* tile = P.wpack + ((size_t)n_tile * P.k_blocks + kb) * kWStageBytes;
+        for (int kg = 0; kg < 8; ++kg) {
+            const uint32_t off = umma_tile_off(mode, r, kg);
+            const uint4 hi = *reinterpret_cast<const uint4*>(tile + off);
+            const uint4 lo = *reinterpret_cast<const uint4*>(tile + kWHalfBytes + off);
+            const uint32_t hh[4] = {hi.x, hi.y, hi.z, hi.w}, ll[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t hv = (e & 1) ? (hh[e >> 1] >> 16) : (hh[e >> 1] & 0xffffu);
+                const uint32_t lv = (e & 1) ? (ll[e >> 1] >> 16) : (ll[e >> 1] & 0xffffu);
+                const float w = __uint_as_float(hv << 16) + __uint_as_float(lv << 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fmaf(xs[j][kg * 8 + e], w, acc[j]);
+            }
+        }
+    }
+    const int n = n_tile * kTileN + r;
+    if (P.epi == kEpiLstm) {
+        const int lane = threadIdx.x & 31, base = lane & ~3;
+        for (int j = 0; j < 16; ++j) {
+            const float v = acc[j] + P.bias[n];
+            float4 g;
+            g.x = __shfl_sync(0xffffffffu, v, base + 0);
+            g.y = __shfl_sync(0xffffffffu, v, base + 1);
+            g.z = __shfl_sync(0xffffffffu, v, base + 2);
+            g.w = __shfl_sync(0xffffffffu, v, base + 3);
+            const int unit = n >> 2;
+            if ((lane & 3) == 0 && row0 + j < P.rows && unit < P.H) lstm_gates(P, g, row0 + j, unit);
+        }
+    } else if (n < P.n_out) {
+        for (int j = 0; j < 16; ++j)
+            if (row0 + j < P.rows) P.out[(size_t)(row0 + j) * P.ldo + n] = epi_scalar(P, acc[j], n);
+    }
+}
+
+// ---------------------------------------------------- one-time weight repack
+// TF kernel [K, n_out] fp32 row-major (tf.layers.dense, utils/nn.py:96-105) ->
+// packed bf16 hi/lo UMMA tiles.  perm_H > 0 selects the LSTM gate interleave:
+// packed output p = unit*4 + gate  <->  TF column gate*H + unit (split order i,j,f,o).
+__global__ void repack_weight_kernel(const float* __restrict__ w, int K, int n_out, int perm_H, uint8_t* wpack,
+                                     int k_blocks, int n_tiles, int mode) {
+    const size_t total = (size_t)n_tiles * k_blocks * kTileN * 8;  // 16-byte groups
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(g % kTileN);
+        size_t t = g / kTileN;
+        const int kg = (int)(t % 8);
+        t /= 8;
+        const int kb = (int)(t % k_blocks);
+        const int nt = (int)(t / k_blocks);
+        const int p = nt * kTileN + r;
+        int col = -1;
+        if (p < n_out) col = perm_H > 0 ? (p & 3) * perm_H + (p >> 2) : p;
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = kb * kBK + kg * 8 + e;
+            x[e] = (col >= 0 && k < K) ? w[(size_t)k * n_out + col] : 0.f;
+        }
+        uint4 hi, lo;
+        split_bf16x8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), hi, lo);
+        uint8_t* tile = wpack + ((size_t)nt * k_blocks + kb) * kWStageBytes;
+        const uint32_t off = umma_tile_off(mode, r, kg);
+        *reinterpret_cast<uint4*>(tile + off) = hi;
+        *reinterpret_cast<uint4*>(tile + kWHalfBytes + off) = lo;
+    }
+}
+
+__global__ void repack_bias_kernel(const float* __restrict__ b, int n_out, int perm_H, float* out, int npad) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npad; p += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (p < n_out && b) v = b[perm_H > 0 ? (p & 3) * perm_H + (p >> 2) : p];
+        out[p] = v;
+    }
+}
+
+// ------------------------------------------------------------ host side
+static int g_smem_optin = 0;
+
+cudaError_t lin_init_attrs() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+}
+
+size_t lin_smem_bytes(int row_tile, int stages) {
+    return 1024 + (size_t)stages * (kWStageBytes + 2 * (size_t)row_tile * kBK * 2);
+}
+
+int lin_pick_stages(int row_tile) {
+    const size_t budget = (size_t)(g_smem_optin > 0 ? g_smem_optin : 232448) - 1024;
+    const size_t per = kWStageBytes + 2 * (size_t)row_tile * kBK * 2;
+    int s = (int)(budget / per);
+    if (s > 8) s = 8;
+    return s;
+}
+
+cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt) {
+    int total = 0;
+    if (use_simt) {
+        LinLaunch M = L;
+        for (int i = 0; i < M.nprob; ++i) {
+            M.p[i].cta_begin = total;
+            M.p[i].cta_count = M.p[i].n_tiles * ((M.p[i].rows + 15) / 16);
+            total += M.p[i].cta_count;
+        }
+        lin_simt_kernel<<<total, 128, 0, st>>>(M);
+        return cudaGetLastError();
+    }
+    int max_rt = 16;
+    for (int i = 0; i < L.nprob; ++i) {
+        total += L.p[i].cta_count;
+        if (L.p[i].row_tile > max_rt) max_rt = L.p[i].row_tile;
+    }
+    const size_t smem = lin_smem_bytes(max_rt, L.stages);
+    lin_umma_kernel<<<total, kLinThreads, smem, st>>>(L);
+    return cudaGetLastError();
+}
+
+cudaError_t lin_repack_weight(const float* w_tf, int K, int n_out, int perm_H, uint8_t* wpack, int layout_mode,
+                              cudaStream_t st) {
+    const int k_blocks = (K + kBK - 1) / kBK, n_tiles = (n_out + kTileN - 1) / kTileN;
+    repack_weight_kernel<<<1184, 256, 0, st>>>(w_tf, K, n_out, perm_H, wpack, k_blocks, n_tiles, layout_mode);
+    return cudaGetLastError();
+}
+
+cudaError_t lin_repack_bias(const float* b_tf, int n_out, int perm_H, float* bias_packed, cudaStream_t st) {
+    const int npad = ((n_out + kTileN - 1) / kTileN) * kTileN;
+    repack_bias_kernel<<<(npad + 255) / 256, 256, 0, st>>>(b_tf, n_out, perm_H, bias_packed, npad);
+    return cudaGetLastError();
+}
+
+}  // namespace sat

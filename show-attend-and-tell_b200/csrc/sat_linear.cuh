@@ -1,0 +1,83 @@
+// sat_linear.cuh — descriptors of the small-batch dense layer kernels
+// (tf.layers.dense / LSTMCell matmul of the reference: utils/nn.py:85-105,
+// model.py:276-279, 438-459) as executed on sm_100a.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace sat {
+
+constexpr int kBK = 64;                                  // K elements per pipeline stage
+constexpr int kTileN = 128;                              // outputs per CTA tile (UMMA M)
+constexpr int kWHalfBytes = kTileN * kBK * 2;            // one bf16 half (hi or lo) of a W tile
+constexpr int kWStageBytes = 2 * kWHalfBytes;            // hi + lo, contiguous in the packed image
+constexpr int kLinThreads = 192;                         // warp0 TMA, warp1 MMA, warps2-5 X-producer/epilogue
+constexpr int kMaxSeg = 3;
+constexpr int kMaxProb = 4;
+
+enum LinEpilogue : int {
+    kEpiBias = 0,      // out = acc + bias                      (decode fc_2 / fc, initialize fc_*2)
+    kEpiBiasTanh = 1,  // out = tanh(acc + bias)                (attend fc_1a/fc_1b, decode fc_1, initialize fc_*1)
+    kEpiLstm = 2,      // TF LSTMCell gates i,j,f,o -> (c, h)   (model.py:278)
+    kEpiNone = 3       // out = acc (bias-free dense: attend fc_a / fc_b, model.py:403-413)
+};
+
+// One K-segment of the activation operand: X[b, k0 + j] = ptr[row(b) * ld + j],
+// row(b) = gather ? gather[b] (embedding lookup, model.py:273) : b / row_div.
+struct LinSeg {
+    const float* ptr;
+    const int32_t* gather;
+    int ld;
+    int width;   // multiple of 8
+    int row_div; // >= 1; b / row_div selects the source row (beams sharing one image row)
+};
+
+struct LinProblem {
+    LinSeg seg[kMaxSeg];
+    int nseg;
+    int K;          // sum of widths
+    int k_blocks;   // ceil(K / kBK)
+    int rows;       // valid activation rows (batch)
+    int row_tile;   // activation rows per CTA = UMMA N, multiple of 16, <= 256
+    int n_row_tiles;
+    int n_out;      // valid outputs
+    int n_tiles;    // ceil(n_out / 128)
+    int splits;     // split-K factor
+    const uint8_t* wpack;  // [n_tiles][k_blocks][hi|lo][128 x 64 bf16, canonical UMMA K-major layout]
+    const float* bias;     // packed output order, n_tiles*128 entries (zero padded); may be null for kEpiNone
+    float* ws;             // split-K partials [splits][n_row_tiles*row_tile][n_tiles*128]
+    unsigned* counters;    // [n_row_tiles * n_tiles], zero between launches
+    int epi;
+    float* out;            // [rows, ldo]
+    int ldo;
+    const float* c_in;     // LSTM: [rows, H]
+    float* c_out;
+    float* h_out;
+    int H;
+    int cta_begin;         // first CTA of this problem in the grouped grid
+    int cta_count;
+};
+
+struct LinLaunch {
+    LinProblem p[kMaxProb];
+    int nprob;
+    int layout_mode;  // 0 = no-swizzle (interleaved 8x16B core matrices), 1 = 128B swizzle
+    int stages;
+};
+
+// byte offset of the 16-byte group (row r, k-group kg in [0,8)) inside a [rows x 64] bf16
+// K-major operand tile.  Both modes place 8-row groups 1024 B apart.
+__host__ __device__ __forceinline__ uint32_t umma_tile_off(int mode, int r, int kg) {
+    return mode == 0 ? (uint32_t)((r >> 3) * 1024 + kg * 128 + (r & 7) * 16)
+                     : (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kg ^ (r & 7)) * 16));
+}
+
+size_t lin_smem_bytes(int row_tile, int stages);
+int lin_pick_stages(int row_tile);
+cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt);
+cudaError_t lin_repack_weight(const float* w_tf, int K, int n_out, int perm_H, uint8_t* wpack, int layout_mode,
+                              cudaStream_t st);
+cudaError_t lin_repack_bias(const float* b_tf, int n_out, int perm_H, float* bias_packed, cudaStream_t st);
+cudaError_t lin_init_attrs();
+
+}  // namespace sat

@@ -1,0 +1,326 @@
+"""CaptionGenerator — the reference's model/driver call surface for the decode path
+(model.py:190-356 build_rnn, base_model.py:163-240 beam_search, :257-278 load) on top of
+libsat_b200.so.
+
+Mapping to the reference:
+  CaptionGenerator(config)                         main.py:48,61,69
+  .load(sess, model_file) / .set_weights(dict)     base_model.py:257-278
+  .initialize(contexts) -> (memory, output)        sess.run([initial_memory, initial_output]) base_model.py:168-170
+  .decode_step(contexts, last_word, last_memory, last_output) -> (memory, output, probs)
+                                                   sess.run([memory, output, probs], ...)     base_model.py:207-212
+  .beam_search(contexts, ...) -> per image list of CaptionData(sentence, score)
+                                                   base_model.py:163-240
+  .decode_loop(contexts, T, forced_words)          the unrolled loop of model.py:258-312 (greedy / teacher forced)
+The one intentional deviation: precomputed contexts (conv features) take the place of
+image files, because the CNN is out of scope.  `sess` arguments are accepted and ignored.
+
+numpy in -> numpy out goes through the *_host C entry points (host<->device copies
+inside the call, like a sess.run).  torch CUDA tensors in -> torch CUDA tensors out stays
+on the device and is asynchronous on `self.stream`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .lib import Dims, check, load_library
+
+
+def weight_shapes(config):
+    """TF variable names (without ':0') and shapes of the decoder, as tf.layers.dense /
+    LSTMCell / get_variable create them (utils/nn.py:96-105, model.py:219-230)."""
+    D, E, H, V = config.dim_ctx, config.dim_embedding, config.num_lstm_units, config.vocabulary_size
+    A, Dd, I, L = (config.dim_attend_layer, config.dim_decode_layer, config.dim_initalize_layer,
+                   config.num_ctx)
+    s = {"word_embedding/weights": (V, E)}
+    if config.num_initalize_layers == 1:
+        for n in ("a", "b"):
+            s["initialize/fc_%s/kernel" % n] = (D, H)
+            s["initialize/fc_%s/bias" % n] = (H,)
+    else:
+        for n in ("a", "b"):
+            s["initialize/fc_%s1/kernel" % n] = (D, I)
+            s["initialize/fc_%s1/bias" % n] = (I,)
+            s["initialize/fc_%s2/kernel" % n] = (I, H)
+            s["initialize/fc_%s2/bias" % n] = (H,)
+    if config.num_attend_layers == 1:
+        s["attend/fc_a/kernel"] = (D, 1)
+        s["attend/fc_b/kernel"] = (H, L)
+    else:
+        s["attend/fc_1a/kernel"] = (D, A)
+        s["attend/fc_1a/bias"] = (A,)
+        s["attend/fc_1b/kernel"] = (H, A)
+        s["attend/fc_1b/bias"] = (A,)
+        s["attend/fc_2/kernel"] = (A, 1)
+    s["lstm/lstm_cell/kernel"] = (D + E + H, 4 * H)
+    s["lstm/lstm_cell/bias"] = (4 * H,)
+    if config.num_decode_layers == 1:
+        s["decode/fc/kernel"] = (H + D + E, V)
+        s["decode/fc/bias"] = (V,)
+    else:
+        s["decode/fc_1/kernel"] = (H + D + E, Dd)
+        s["decode/fc_1/bias"] = (Dd,)
+        s["decode/fc_2/kernel"] = (Dd, V)
+        s["decode/fc_2/bias"] = (V,)
+    return s
+
+
+class CaptionData(object):
+    """utils/misc.py:38-60 (memory/output are not returned to the host)."""
+    __slots__ = ("sentence", "score", "complete")
+
+    def __init__(self, sentence, score, complete):
+        self.sentence, self.score, self.complete = sentence, score, complete
+
+    def __repr__(self):
+        return "CaptionData(score=%.6g, sentence=%s)" % (self.score, self.sentence)
+
+
+class CaptionGenerator(object):
+    def __init__(self, config, max_batch=None, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("sat_b200 needs an NVIDIA B200 (sm_100a): no CUDA device visible, no CPU path")
+        self.torch = torch
+        self.config = config
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.lib = load_library()
+        beam = max(1, int(getattr(config, "beam_size", 1)))
+        if max_batch is None:
+            max_batch = int(config.batch_size) * beam
+        self.max_batch = int(max_batch)
+        d = Dims(self.max_batch, config.num_ctx, config.dim_ctx, config.num_lstm_units, config.dim_embedding,
+                 config.dim_attend_layer, config.dim_decode_layer, config.dim_initalize_layer,
+                 config.vocabulary_size, config.num_attend_layers, config.num_decode_layers,
+                 config.num_initalize_layers, config.max_caption_length, beam)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib, self.lib.sat_create(C.byref(d), C.byref(self._h)))
+            self.stream = torch.cuda.Stream(self.device)
+        self._shapes = weight_shapes(config)
+        self._keep = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self.lib.sat_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    close = __del__
+
+    def _st(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def _check(self, rc):
+        check(self.lib, rc)
+
+    def set_option(self, key, value):
+        self._check(self.lib.sat_set_option(self._h, key.encode(), int(value)))
+
+    def info(self, key):
+        v = C.c_int64()
+        self._check(self.lib.sat_get_info(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    def _dev(self, x, dtype):
+        """torch CUDA tensor (contiguous, right dtype) from numpy / torch input."""
+        torch = self.torch
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        return x.to(device=self.device, dtype=dtype).contiguous()
+
+    def _sync_in(self):
+        # make work queued on the caller's current stream visible to ours
+        self.stream.wait_stream(self.torch.cuda.current_stream(self.device))
+
+    def _sync_out(self):
+        self.torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    # ------------------------------------------------------------------ weights
+    def variable_names(self):
+        return list(self._shapes)
+
+    def set_weights(self, weights):
+        """weights: {tf_variable_name[:0]: ndarray/tensor} in the reference layouts."""
+        torch = self.torch
+        given = {(k[:-2] if k.endswith(":0") else k): v for k, v in weights.items()}
+        for name, shp in self._shapes.items():
+            if name not in given:
+                continue
+            w = self._dev(given[name], torch.float32)
+            if tuple(w.shape) != tuple(shp) and int(np.prod(w.shape)) != int(np.prod(shp)):
+                raise ValueError("%s: expected shape %s, got %s" % (name, shp, tuple(w.shape)))
+            rows, cols = (shp[0], shp[1]) if len(shp) == 2 else (1, shp[0])
+            torch.cuda.synchronize(self.device)
+            self._check(self.lib.sat_set_weight(self._h, name.encode(), self._p(w), rows, cols, self._st()))
+        return self.lib.sat_weights_missing(self._h)
+
+    def load(self, sess=None, model_file=None):
+        """base_model.py:257-278: np.load of the pickled {var.name: ndarray} dict."""
+        data = np.load(model_file, encoding="latin1", allow_pickle=True).item()
+        missing = self.set_weights(data)
+        return len(self._shapes) - missing
+
+    # ------------------------------------------------------------------ device API
+    def prepare(self, contexts, want_state=True):
+        """Project the contexts once per image batch and run `initialize`.  contexts: CUDA tensor
+        [B, L, D].  Returns (initial_memory, initial_output) CUDA tensors [B, H]."""
+        torch = self.torch
+        B = contexts.shape[0]
+        c0 = torch.empty(B, self.config.num_lstm_units, device=self.device) if want_state else None
+        h0 = torch.empty_like(c0) if want_state else None
+        self._sync_in()
+        self._check(self.lib.sat_prepare_contexts(self._h, self._p(contexts), B, self._p(c0), self._p(h0), self._st()))
+        self._sync_out()
+        self._keep["ctx"] = contexts
+        return c0, h0
+
+    def step_device(self, contexts, last_word, last_memory, last_output, want=("probs",)):
+        torch = self.torch
+        cfg = self.config
+        B = contexts.shape[0]
+        mem = torch.empty(B, cfg.num_lstm_units, device=self.device)
+        out = torch.empty_like(mem)
+        logits = torch.empty(B, cfg.vocabulary_size, device=self.device) if "logits" in want else None
+        probs = torch.empty(B, cfg.vocabulary_size, device=self.device) if "probs" in want else None
+        alpha = torch.empty(B, cfg.num_ctx, device=self.device) if "alpha" in want else None
+        self._sync_in()
+        self._check(self.lib.sat_decode_step(self._h, self._p(contexts), self._p(last_word), self._p(last_memory),
+                                             self._p(last_output), self._p(mem), self._p(out), self._p(logits),
+                                             self._p(probs), self._p(alpha), B, self._st()))
+        self._sync_out()
+        return dict(memory=mem, output=out, logits=logits, probs=probs, alpha=alpha)
+
+    def loop_device(self, contexts, num_steps, forced_words=None, want_logits=False):
+        torch = self.torch
+        B = contexts.shape[0]
+        tokens = torch.empty(B, num_steps, dtype=torch.int32, device=self.device)
+        logits = (torch.empty(num_steps, B, self.config.vocabulary_size, device=self.device)
+                  if want_logits else None)
+        self._sync_in()
+        self._check(self.lib.sat_decode_loop(self._h, self._p(contexts), B, num_steps, self._p(forced_words),
+                                             self._p(tokens), self._p(logits), self._st()))
+        self._sync_out()
+        self._keep["loop"] = (contexts, forced_words, tokens, logits)
+        return tokens, logits
+
+    def beam_device(self, contexts, beam_size, num_steps, eos_id):
+        torch = self.torch
+        n = contexts.shape[0]
+        sent = torch.empty(n, beam_size, num_steps, dtype=torch.int32, device=self.device)
+        lens = torch.empty(n, beam_size, dtype=torch.int32, device=self.device)
+        scores = torch.empty(n, beam_size, dtype=torch.float64, device=self.device)
+        nres = torch.empty(n, dtype=torch.int32, device=self.device)
+        comp = torch.empty(n, dtype=torch.int32, device=self.device)
+        self._sync_in()
+        self._check(self.lib.sat_beam_search(self._h, self._p(contexts), n, beam_size, num_steps, eos_id,
+                                             self._p(sent), self._p(lens), self._p(scores), self._p(nres),
+                                             self._p(comp), self._st()))
+        self._sync_out()
+        self._keep["beam"] = (contexts, sent, lens, scores, nres, comp)
+        return sent, lens, scores, nres, comp
+
+    # ------------------------------------------------------------------ reference-shaped API
+    def initialize(self, contexts, sess=None):
+        """(initial_memory, initial_output) for a batch of contexts (base_model.py:168-170)."""
+        is_np = isinstance(contexts, np.ndarray)
+        ctx = self._dev(contexts, self.torch.float32)
+        c0, h0 = self.prepare(ctx)
+        if is_np:
+            self.torch.cuda.synchronize(self.device)
+            return c0.cpu().numpy(), h0.cpu().numpy()
+        return c0, h0
+
+    def decode_step(self, contexts, last_word, last_memory, last_output, sess=None, contexts_changed=True,
+                    extras=False):
+        """One sess.run([memory, output, probs], feed_dict=...) (base_model.py:207-212).
+
+        numpy inputs: host path; `contexts_changed=False` tells the library the contexts are
+        the ones of the previous call (the reference re-feeds them every call).
+        torch CUDA inputs: device path.  `extras=True` also returns logits and alpha."""
+        cfg = self.config
+        if isinstance(contexts, np.ndarray) and not extras:
+            B = contexts.shape[0]
+            ctx = np.ascontiguousarray(contexts, np.float32)
+            lw = np.ascontiguousarray(last_word, np.int32)
+            lm = np.ascontiguousarray(last_memory, np.float32)
+            lo = np.ascontiguousarray(last_output, np.float32)
+            mem = np.empty((B, cfg.num_lstm_units), np.float32)
+            out = np.empty_like(mem)
+            probs = np.empty((B, cfg.vocabulary_size), np.float32)
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+            self._check(self.lib.sat_decode_step_host(self._h, vp(ctx), 1 if contexts_changed else 0, vp(lw), vp(lm),
+                                                      vp(lo), vp(mem), vp(out), vp(probs), B, self._st()))
+            return mem, out, probs
+        is_np = isinstance(contexts, np.ndarray)
+        torch = self.torch
+        ctx = self._dev(contexts, torch.float32)
+        if contexts_changed or self._keep.get("ctx") is not ctx:
+            self.prepare(ctx, want_state=False)
+        r = self.step_device(ctx, self._dev(last_word, torch.int32), self._dev(last_memory, torch.float32),
+                             self._dev(last_output, torch.float32),
+                             want=("probs", "logits", "alpha") if extras else ("probs",))
+        if is_np:
+            torch.cuda.synchronize(self.device)
+            r = {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
+        if extras:
+            return r
+        return r["memory"], r["output"], r["probs"]
+
+    def decode_loop(self, contexts, num_steps=None, forced_words=None, want_logits=False):
+        """initialize + num_steps decode steps without host round trips; returns tokens [B,T]
+        (argmax of every step, model.py:289) and optionally logits [T,B,V]."""
+        cfg = self.config
+        T = int(num_steps or cfg.max_caption_length)
+        if isinstance(contexts, np.ndarray) and not want_logits:
+            B = contexts.shape[0]
+            ctx = np.ascontiguousarray(contexts, np.float32)
+            fw = None if forced_words is None else np.ascontiguousarray(forced_words, np.int32)
+            tokens = np.empty((B, T), np.int32)
+            vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+            self._check(self.lib.sat_decode_loop_host(self._h, vp(ctx), B, T, vp(fw), vp(tokens), self._st()))
+            return tokens
+        is_np = isinstance(contexts, np.ndarray)
+        torch = self.torch
+        ctx = self._dev(contexts, torch.float32)
+        fw = None if forced_words is None else self._dev(forced_words, torch.int32)
+        tokens, logits = self.loop_device(ctx, T, fw, want_logits)
+        if is_np:
+            torch.cuda.synchronize(self.device)
+            tokens = tokens.cpu().numpy()
+            logits = logits.cpu().numpy() if logits is not None else None
+        return (tokens, logits) if want_logits else tokens
+
+    def beam_search(self, contexts, sess=None, vocabulary=None, eos_id=None, beam_size=None, num_steps=None):
+        """base_model.py:163-240.  Returns, per image, the captions sorted by descending score
+        (complete captions if any were completed, else the partial ones)."""
+        cfg = self.config
+        beam = int(beam_size or cfg.beam_size)
+        T = int(num_steps or cfg.max_caption_length)
+        eos = int(cfg.eos_id if eos_id is None else eos_id)
+        n = contexts.shape[0]
+        if isinstance(contexts, np.ndarray):
+            ctx = np.ascontiguousarray(contexts, np.float32)
+            sent = np.empty((n, beam, T), np.int32)
+            lens = np.empty((n, beam), np.int32)
+            scores = np.empty((n, beam), np.float64)
+            nres = np.empty((n,), np.int32)
+            comp = np.empty((n,), np.int32)
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+            self._check(self.lib.sat_beam_search_host(self._h, vp(ctx), n, beam, T, eos, vp(sent), vp(lens),
+                                                      vp(scores), vp(nres), vp(comp), self._st()))
+        else:
+            ts = self.beam_device(contexts, beam, T, eos)
+            self.torch.cuda.synchronize(self.device)
+            sent, lens, scores, nres, comp = [t.cpu().numpy() for t in ts]
+        results = []
+        for k in range(n):
+            results.append([CaptionData([int(w) for w in sent[k, j, :lens[k, j]]], float(scores[k, j]),
+                                        bool(comp[k])) for j in range(int(nres[k]))])
+        return results

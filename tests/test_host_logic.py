@@ -1,0 +1,104 @@
+"""Host-side logic that needs no GPU: config mirror, variable naming, batch sharding, and the
+world_size-2 gloo path of the multi-GPU plumbing."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import sat_b200
+from oracle import ref_step as R
+from sat_b200 import parallel
+
+
+def test_config_field_names_follow_the_reference():
+    c = sat_b200.Config()
+    for f in ("max_caption_length", "dim_embedding", "num_lstm_units", "num_initalize_layers",
+              "dim_initalize_layer", "num_attend_layers", "dim_attend_layer", "num_decode_layers",
+              "dim_decode_layer", "vocabulary_size", "batch_size", "beam_size", "fc_drop_rate", "lstm_drop_rate"):
+        assert hasattr(c, f)
+    assert (c.num_ctx, c.dim_ctx) == (196, 512)
+    r = sat_b200.Config(cnn="resnet50")
+    assert (r.num_ctx, r.dim_ctx) == (49, 2048)          # model.py:103-108
+    with pytest.raises(AttributeError):
+        sat_b200.Config(nonsense=1)
+
+
+@pytest.mark.parametrize("layers", [1, 2])
+def test_facade_variable_table_equals_oracle(layers):
+    c = sat_b200.Config(num_attend_layers=layers, num_decode_layers=layers, num_initalize_layers=layers)
+    o = R.OracleConfig(num_attend_layers=layers, num_decode_layers=layers, num_initalize_layers=layers)
+    assert sat_b200.weight_shapes(c) == R.weight_shapes(o)
+
+
+def test_shard_range_partitions_exactly():
+    for n in (1, 7, 64, 512):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    parallel.init_process_group("gloo")
+    lo, hi = parallel.shard_range(n, rank, world)
+    # each rank "decodes" its shard of images: token = image id * 10 + t (stands in for the GPU step)
+    local = torch.tensor([[i * 10 + t for t in range(4)] for i in range(lo, hi)], dtype=torch.int32)
+    full = parallel.gather_shards(local, n)
+    tmax = parallel.max_over_ranks(1.0 + rank)
+    q.put((rank, full.numpy().tolist(), tmax))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_gather_and_max():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n = 7
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [[i * 10 + t for t in range(4)] for i in range(n)]
+    for rank, full, tmax in outs:
+        assert full == expect
+        assert tmax == 2.0
+
+
+def test_golden_fixtures_match_current_oracle():
+    """tests/golden/step_*.npz were produced by the fp64 oracle; guard against silent drift."""
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    for tag, layers in (("2layer", 2), ("1layer", 1)):
+        z = np.load(os.path.join(here, "step_%s.npz" % tag))
+        cfg = R.OracleConfig(num_ctx=49, dim_ctx=64, dim_embedding=32, num_lstm_units=64, dim_initalize_layer=32,
+                             dim_attend_layer=32, dim_decode_layer=64, vocabulary_size=300, batch_size=3,
+                             max_caption_length=6, num_attend_layers=layers, num_decode_layers=layers,
+                             num_initalize_layers=layers)
+        w = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+        r = R.decode_step(cfg, w, z["ctx"], z["last_word"], z["last_memory"], z["last_output"], np.float64)
+        for k in ("memory", "output", "probs", "logits", "alpha", "context"):
+            np.testing.assert_allclose(r[k], z["step_" + k], rtol=1e-12, atol=1e-14)
+        toks, _ = R.decode_loop(cfg, w, z["ctx"], 6, z["forced"], np.float64)
+        assert (toks == z["tokens"]).all()
