@@ -65,6 +65,7 @@ struct GraphEntry {
     std::vector<long long> key;
     int seen = 0;
     cudaGraphExec_t exec = nullptr;
+    long long kernels = 0;  // kernel launches one replay stands for
 };
 
 struct sat_handle {
@@ -109,6 +110,29 @@ struct sat_handle {
     CUtensorMap ctx_map;
 
     std::vector<GraphEntry> graphs;
+
+    // launch accounting / optional per-kernel-family timing (eager launches only)
+    long long launches = 0;
+    int opt_profile = 0;
+    int cur_tag = 0;
+    struct ProfRec { int tag; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+};
+
+enum ProfTag { kTagAtt = 0, kTagAttState, kTagLstm, kTagDec1, kTagDec2, kTagProj, kTagInit, kTagRows, kTagBeam, kNumTags };
+static const char* kTagNames[kNumTags] = {"att", "att_state", "lstm", "dec1", "dec2", "proj", "init", "rows", "beam"};
+
+struct ProfScope {
+    sat_handle* h; cudaStream_t st; bool on; cudaEvent_t a = nullptr, b = nullptr; int tag;
+    ProfScope(sat_handle* h_, int tag_, cudaStream_t st_) : h(h_), st(st_), tag(tag_) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        on = h->opt_profile && cs == cudaStreamCaptureStatusNone;
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(b, st); h->prof.push_back({tag, a, b}); }
+    }
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -296,6 +320,12 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     } else if (k == "graphs") h->opt_graphs = (int)value;
     else if (k == "hoist") { h->opt_hoist = (int)value; h->prep_ctx = nullptr; }
     else if (k == "coop") h->opt_coop = (int)value;
+    else if (k == "profile") {
+        h->opt_profile = (int)value;
+        for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        h->prof.clear();
+        return SAT_OK;
+    } else if (k == "reset_counters") { h->launches = 0; return SAT_OK; }
     else return fail(SAT_ERR_INVALID, "unknown option '%s'", key);
     for (auto& g : h->graphs) {  // options change the captured work
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -311,6 +341,18 @@ extern "C" int sat_get_info(sat_handle* h, const char* key, int64_t* value) {
     else if (k == "smem_optin") *value = h->smem_optin;
     else if (k == "gemm") *value = h->opt_gemm;
     else if (k == "umma_layout") *value = h->opt_layout;
+    else if (k == "launches") *value = h->launches;
+    else if (k.rfind("prof_ns_", 0) == 0 || k.rfind("prof_n_", 0) == 0) {
+        const bool want_n = k.rfind("prof_n_", 0) == 0;
+        const std::string t = k.substr(want_n ? 7 : 8);
+        int tag = -1;
+        for (int i = 0; i < kNumTags; ++i) if (t == kTagNames[i]) tag = i;
+        if (tag < 0) return fail(SAT_ERR_INVALID, "unknown profile tag '%s'", t.c_str());
+        CK(cudaDeviceSynchronize());
+        double ns = 0; long long n = 0;
+        for (auto& r : h->prof) if (r.tag == tag) { float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b); ns += ms * 1e6; ++n; }
+        *value = want_n ? n : (int64_t)ns;
+    }
     else if (k == "weight_bytes") {
         size_t b = 0;
         for (Layer* ly : h->layers) b += (size_t)ly->n_tiles * ly->k_blocks * kWStageBytes;
@@ -487,7 +529,11 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.layout_mode = h->opt_layout;
     L.stages = lin_pick_stages(max_rt);
     if (L.stages < 1) return fail(SAT_ERR_UNSUPPORTED, "row tile %d does not fit in shared memory", max_rt);
-    CK(lin_launch(L, st, h->opt_gemm == 0));
+    {
+        ProfScope ps(h, h->cur_tag, st);
+        CK(lin_launch(L, st, h->opt_gemm == 0));
+    }
+    h->launches += 1;
     return SAT_OK;
 }
 
@@ -511,6 +557,7 @@ static int ensure_ctx_map(sat_handle* h, const float* ctx, int n_img) {
 // attend fc_1a over every location (model.py:417-420): T1 = tanh(ctx2d * W1a + b1a)
 static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStream_t st) {
     if (h->d.num_attend_layers != 2) return SAT_OK;
+    h->cur_tag = kTagProj;
     LinProblem P;
     RET(plan(h, h->att_1a, P, {seg(ctx, h->d.dim_ctx, h->d.dim_ctx)}, n_img * h->d.num_ctx, kEpiBiasTanh, h->T1,
              h->d.dim_attend_layer, st));
@@ -520,7 +567,9 @@ static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStre
 // initialize (model.py:239-242, 358-393)
 static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st) {
     const sat_dims& d = h->d;
+    h->cur_tag = kTagInit;
     CK(ctx_mean_launch(ctx, h->mean, n_img, d.num_ctx, d.dim_ctx, st));
+    h->launches += 1;
     LinProblem P[2];
     if (d.num_initalize_layers == 1) {
         RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, c0, d.num_lstm_units, st));
@@ -578,6 +627,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     LinProblem P;
     if (d.num_attend_layers == 2) {
         if (!(h->opt_hoist && h->prep_ctx == ctx && h->prep_ni == n_img)) RET(project_contexts(h, ctx, n_img, st));
+        h->cur_tag = kTagAttState;
         // state branch: q = tanh(h * W1b + b1b)   (model.py:421-424)
         RET(plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiBiasTanh, h->q,
                  d.dim_attend_layer, st));
@@ -588,6 +638,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         ap.eadd = nullptr;
     } else {
         // logits2 = h * fc_b   (model.py:409-413), added to ctx . fc_a inside the kernel
+        h->cur_tag = kTagAttState;
         RET(plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiNone, h->q, d.num_ctx, st));
         RET(launch(h, &P, 1, st));
         ap.T = ctx;
@@ -607,13 +658,18 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     ap.D = d.dim_ctx;
     if (!att_plan(ap, h->smem_optin)) return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
     CK(cudaMemsetAsync(h->rowcnt, 0, (size_t)n_img * sizeof(unsigned), st));
-    CK(att_launch(h->ctx_map, ap, h->num_sms, st, h->opt_coop != 0));
+    {
+        ProfScope ps(h, kTagAtt, st);
+        CK(att_launch(h->ctx_map, ap, h->num_sms, st, h->opt_coop != 0));
+    }
+    h->launches += 1;
     return SAT_OK;
 }
 
 static int lstm_impl(sat_handle* h, const float* z, const int32_t* last_word, const float* c_in, const float* h_in,
                      float* c_out, float* h_out, int rows, cudaStream_t st) {
     const sat_dims& d = h->d;
+    h->cur_tag = kTagLstm;
     LinProblem P;
     // current_input = concat([context, word_embed]) (model.py:277); LSTMCell concat([x, h]) (TF)
     RET(plan(h, h->lstm, P,
@@ -632,16 +688,19 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
     const sat_dims& d = h->d;
     LinProblem P;
     // expanded_output = concat([output, context, word_embed]) (model.py:283-286)
+    h->cur_tag = kTagDec1;
     if (d.num_decode_layers == 2) {
         RET(plan(h, h->dec_1, P,
                  {seg(h_out, d.num_lstm_units, d.num_lstm_units), seg(z, d.dim_ctx, d.dim_ctx),
                   seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word)},
                  rows, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st));
         RET(launch(h, &P, 1, st));
+        h->cur_tag = kTagDec2;
         RET(plan(h, h->dec_2, P, {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer)}, rows, kEpiBias, logits,
                  d.vocabulary_size, st));
         return launch(h, &P, 1, st);
     }
+    h->cur_tag = kTagDec2;
     RET(plan(h, h->dec_2, P,
              {seg(h_out, d.num_lstm_units, d.num_lstm_units), seg(z, d.dim_ctx, d.dim_ctx),
               seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word)},
@@ -661,7 +720,11 @@ static int step_impl(sat_handle* h, StepIO& io, cudaStream_t st) {
         rp.logits = logits;
         rp.V = h->d.vocabulary_size;
         rp.probs = io.probs;
-        CK(rows_softmax_launch(rp, rows, st));
+        {
+            ProfScope ps(h, kTagRows, st);
+            CK(rows_softmax_launch(rp, rows, st));
+        }
+        h->launches += 1;
     }
     return SAT_OK;
 }
@@ -701,6 +764,7 @@ static int run_graphed(sat_handle* h, const std::vector<long long>& key, cudaStr
     }
     if (ent->exec) {
         CK(cudaGraphLaunch(ent->exec, st));
+        h->launches += ent->kernels;
         return SAT_OK;
     }
     if (ent->seen == 0) {  // first use: run eagerly so that every workspace exists
@@ -709,7 +773,10 @@ static int run_graphed(sat_handle* h, const std::vector<long long>& key, cudaStr
     }
     // contexts-dependent caches are part of the key, so replays stay valid
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const long long before = h->launches;
     int rc = enqueue();
+    ent->kernels = h->launches - before;
+    h->launches = before;
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != SAT_OK) {
@@ -724,6 +791,7 @@ static int run_graphed(sat_handle* h, const std::vector<long long>& key, cudaStr
         return fail(SAT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
     }
     CK(cudaGraphLaunch(ent->exec, st));
+    h->launches += ent->kernels;
     return SAT_OK;
 }
 
@@ -792,10 +860,15 @@ static int beam_enqueue(sat_handle* h, const float* ctx, int NI, int beam, int T
         io.rows.topk = beam + 1; io.rows.topk_idx = h->topk_idx; io.rows.topk_p = h->topk_p;
         RET(step_impl(h, io, st));
         bp.nlive = G; bp.step = idx;
-        CK(beam_update_launch(bp, st));
+        {
+            ProfScope ps(h, kTagBeam, st);
+            CK(beam_update_launch(bp, st));
+        }
+        h->launches += 1;
     }
     bp.step = T;
     CK(beam_finalize_launch(bp, st));
+    h->launches += 1;
     return SAT_OK;
 }
 

@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
 
     __syncthreads();
     if (warp == 1) {
+        __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_d, tmem_cols);
     }

@@ -135,6 +135,16 @@ class CaptionGenerator(object):
             x = torch.from_numpy(np.ascontiguousarray(x))
         return x.to(device=self.device, dtype=dtype).contiguous()
 
+    def _buf(self, name, shape, dtype):
+        """Persistent device buffer (stable address, so loop/beam CUDA graphs are replayed, not rebuilt).
+        The returned tensor is overwritten by the next call of the same kind."""
+        key = (name, tuple(shape), dtype)
+        t = self._keep.get(key)
+        if t is None:
+            t = self.torch.empty(*shape, dtype=dtype, device=self.device)
+            self._keep[key] = t
+        return t
+
     def _sync_in(self):
         # make work queued on the caller's current stream visible to ours
         self.stream.wait_stream(self.torch.cuda.current_stream(self.device))
@@ -200,8 +210,8 @@ class CaptionGenerator(object):
     def loop_device(self, contexts, num_steps, forced_words=None, want_logits=False):
         torch = self.torch
         B = contexts.shape[0]
-        tokens = torch.empty(B, num_steps, dtype=torch.int32, device=self.device)
-        logits = (torch.empty(num_steps, B, self.config.vocabulary_size, device=self.device)
+        tokens = self._buf("tokens", (B, num_steps), torch.int32)
+        logits = (self._buf("loop_logits", (num_steps, B, self.config.vocabulary_size), torch.float32)
                   if want_logits else None)
         self._sync_in()
         self._check(self.lib.sat_decode_loop(self._h, self._p(contexts), B, num_steps, self._p(forced_words),
@@ -213,11 +223,11 @@ class CaptionGenerator(object):
     def beam_device(self, contexts, beam_size, num_steps, eos_id):
         torch = self.torch
         n = contexts.shape[0]
-        sent = torch.empty(n, beam_size, num_steps, dtype=torch.int32, device=self.device)
-        lens = torch.empty(n, beam_size, dtype=torch.int32, device=self.device)
-        scores = torch.empty(n, beam_size, dtype=torch.float64, device=self.device)
-        nres = torch.empty(n, dtype=torch.int32, device=self.device)
-        comp = torch.empty(n, dtype=torch.int32, device=self.device)
+        sent = self._buf("b_sent", (n, beam_size, num_steps), torch.int32)
+        lens = self._buf("b_lens", (n, beam_size), torch.int32)
+        scores = self._buf("b_scores", (n, beam_size), torch.float64)
+        nres = self._buf("b_nres", (n,), torch.int32)
+        comp = self._buf("b_comp", (n,), torch.int32)
         self._sync_in()
         self._check(self.lib.sat_beam_search(self._h, self._p(contexts), n, beam_size, num_steps, eos_id,
                                              self._p(sent), self._p(lens), self._p(scores), self._p(nres),
