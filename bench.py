@@ -252,23 +252,25 @@ def main():
         model.set_option("profile", 1)
         reps = 20
         for i in range(reps + 3):
-            flush.zero_()                                  # evict L2 between launches
             if i == 3:
                 torch.cuda.synchronize(); model.set_option("profile", 1)   # drop warm-up records
             with torch.cuda.stream(st):
-                st.wait_stream(torch.cuda.current_stream())
+                # the L2 flush runs on the SAME stream just before: it evicts L2 and keeps the GPU busy
+                # while the host enqueues event / kernel / event, so no host latency is inside the interval
+                flush.zero_()
                 rc = model.lib.sat_attention_fwd(model._h, hp(ctx_dev[0]), hp(hstate), hp(alpha), hp(z), B, 1,
                                                  model._st())
                 assert rc == 0, model.lib.sat_last_error()
-            torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
         att_ns = model.info("prof_ns_att") / max(1, model.info("prof_n_att"))
         # per-family times of one eager step (cold L2), for the breakdown
         model.set_option("profile", 1)
         lw = torch.zeros(B, dtype=torch.int32, device=dev)
         c_in = torch.rand(B, H, device=dev) - 0.5
-        for i in range(5):
-            flush.zero_()
-            model.step_device(ctx_dev[0], lw, c_in, hstate, want=())
+        with torch.cuda.stream(st):
+            for i in range(5):
+                flush.zero_()
+                model.step_device(ctx_dev[0], lw, c_in, hstate, want=())
         torch.cuda.synchronize()
         fam = {t: model.info("prof_ns_" + t) / max(1, model.info("prof_n_" + t)) / 1e3
                for t in ("att_state", "att", "lstm", "dec1", "dec2")}

@@ -450,7 +450,7 @@ static bool stream_capturing(cudaStream_t st) {
 }
 
 static int plan(sat_handle* h, Layer& ly, LinProblem& P, std::initializer_list<LinSeg> segs, int rows, int epi,
-                float* out, int ldo, cudaStream_t st, int force_splits = 0) {
+                float* out, int ldo, cudaStream_t st, int force_splits = 0, int group = 1) {
     memset(&P, 0, sizeof(P));
     int k = 0, ns = 0;
     for (const LinSeg& s : segs) {
@@ -475,14 +475,21 @@ static int plan(sat_handle* h, Layer& ly, LinProblem& P, std::initializer_list<L
     P.ldo = ldo;
     // split-K: fill the SMs; cost model in units of K-blocks (fixed per-CTA overhead ~4)
     const int tiles = P.n_tiles * P.n_row_tiles;
+    // split-K CTAs rendezvous inside the kernel, so a split launch must fit on the GPU in one wave
+    // (`group` problems share the grid).  Cost model in units of K blocks: a CTA costs its K range plus
+    // a fixed ~4 blocks (pipeline fill + epilogue), a split costs a rendezvous.
+    const int budget = h->num_sms / (group > 0 ? group : 1);
     int best = 1;
-    if (force_splits > 0) best = force_splits < P.k_blocks ? force_splits : P.k_blocks;
-    else {
+    if (force_splits > 0) {
+        best = force_splits < P.k_blocks ? force_splits : P.k_blocks;
+        while (best > 1 && tiles * best > budget) --best;
+    } else {
         double bc = 1e30;
         const int smax = P.k_blocks < 16 ? P.k_blocks : 16;
         for (int s = 1; s <= smax; ++s) {
+            if (s > 1 && tiles * s > budget) break;
             const int waves = (tiles * s + h->num_sms - 1) / h->num_sms;
-            const double c = waves * ((P.k_blocks + s - 1) / s + 4.0) + (s > 1 ? 0.25 * s : 0.0);
+            const double c = waves * ((P.k_blocks + s - 1) / s + 4.0) + (s > 1 ? 2.0 : 0.0);
             if (c < bc - 1e-9) { bc = c; best = s; }
         }
     }
@@ -499,14 +506,14 @@ static int plan(sat_handle* h, Layer& ly, LinProblem& P, std::initializer_list<L
             RET(dmalloc(&ly.ws, need));
             ly.ws_floats = need;
         }
-        if ((size_t)tiles > ly.n_counters) {
+        if ((size_t)2 * tiles > ly.n_counters) {
             if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: counter growth during graph capture", ly.name.c_str());
             CK(cudaDeviceSynchronize());
             cudaFree(ly.counters);
             ly.counters = nullptr;
-            RET(dmalloc(&ly.counters, (size_t)tiles));
-            CK(cudaMemset(ly.counters, 0, (size_t)tiles * sizeof(unsigned)));
-            ly.n_counters = tiles;
+            RET(dmalloc(&ly.counters, (size_t)2 * tiles));
+            CK(cudaMemset(ly.counters, 0, (size_t)2 * tiles * sizeof(unsigned)));
+            ly.n_counters = (size_t)2 * tiles;
         }
     }
     P.ws = ly.ws;
@@ -572,16 +579,16 @@ static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0,
     h->launches += 1;
     LinProblem P[2];
     if (d.num_initalize_layers == 1) {
-        RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, c0, d.num_lstm_units, st));
-        RET(plan(h, h->init_b1, P[1], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, h0, d.num_lstm_units, st));
+        RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, c0, d.num_lstm_units, st, 0, 2));
+        RET(plan(h, h->init_b1, P[1], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, h0, d.num_lstm_units, st, 0, 2));
         return launch(h, P, 2, st);
     }
     const int I = d.dim_initalize_layer;
-    RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBiasTanh, h->tmp_a, I, st));
-    RET(plan(h, h->init_b1, P[1], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBiasTanh, h->tmp_b, I, st));
+    RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBiasTanh, h->tmp_a, I, st, 0, 2));
+    RET(plan(h, h->init_b1, P[1], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBiasTanh, h->tmp_b, I, st, 0, 2));
     RET(launch(h, P, 2, st));
-    RET(plan(h, h->init_a2, P[0], {seg(h->tmp_a, I, I)}, n_img, kEpiBias, c0, d.num_lstm_units, st));
-    RET(plan(h, h->init_b2, P[1], {seg(h->tmp_b, I, I)}, n_img, kEpiBias, h0, d.num_lstm_units, st));
+    RET(plan(h, h->init_a2, P[0], {seg(h->tmp_a, I, I)}, n_img, kEpiBias, c0, d.num_lstm_units, st, 0, 2));
+    RET(plan(h, h->init_b2, P[1], {seg(h->tmp_b, I, I)}, n_img, kEpiBias, h0, d.num_lstm_units, st, 0, 2));
     return launch(h, P, 2, st);
 }
 

@@ -91,6 +91,10 @@ __device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, int b,
 }
 
 // ------------------------------------------------------------- UMMA kernel
+struct XChunk {
+    float4 a[2], c[2];
+};
+
 __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_constant__ LinLaunch L) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // control block: barriers etc. live in the first 1024 bytes
@@ -99,7 +103,6 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     uint64_t* empty = full_x + 8;
     uint64_t* tmem_full = empty + 8;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    uint32_t* last_flag = tmem_ptr + 1;
     uint8_t* stage_base = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_w[s], 1);
-            mbar_init(&full_x[s], 128);
+            mbar_init(&full_x[s], kLinProducers);
             mbar_init(&empty[s], 1);
         }
         mbar_init(tmem_full, 1);
@@ -189,31 +192,56 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             umma_commit(tmem_full);
         }
     } else {
-        // ===================== X producers (warps 2..5), then epilogue =====================
-        const int pt = threadIdx.x - 64;  // 0..127
-        for (int it = 0; it < nkb; ++it) {
+        // ===================== X producers (warps 2..9), then epilogue =====================
+        // The fp32 sources of X are L2 resident; their latency is hidden by keeping the loads of the
+        // NEXT chunk in flight while the current one is converted and stored.
+        const int pt = threadIdx.x - 64;  // 0..255
+        const int units = N * 8;          // 16-byte groups per K block
+        const int JC = (units + 2 * kLinProducers - 1) / (2 * kLinProducers);  // chunks (2 units/thread) per block
+        const int total = nkb * JC;
+        auto load_chunk = [&](int g, XChunk& ch) {
+            const int it = g / JC, jc = g - it * JC;
+            const int kbase = (kb0 + it) * kBK;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int u = pt + kLinProducers * (jc * 2 + e);
+                if (u < units) {
+                    const int kg = u / N, r = u - kg * N;
+                    load_x8(P, row0 + r, kbase + kg * 8, ch.a[e], ch.c[e]);
+                }
+            }
+        };
+        XChunk cur, nxt;
+        if (total > 0) load_chunk(0, cur);
+        for (int g = 0; g < total; ++g) {
+            const int it = g / JC, jc = g - it * JC;
             const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            mbar_wait(&empty[s], ph ^ 1u);
+            if (g + 1 < total) load_chunk(g + 1, nxt);
+            if (jc == 0) mbar_wait(&empty[s], ((uint32_t)(it / S) & 1u) ^ 1u);
             uint8_t* xh = stage_base + (size_t)s * stage_bytes + kWStageBytes;
             uint8_t* xl = xh + x_half_bytes;
-            const int kbase = (kb0 + it) * kBK;
-            for (int u = pt; u < N * 8; u += 128) {
-                const int kg = u / N, r = u - kg * N;
-                float4 a, c;
-                load_x8(P, row0 + r, kbase + kg * 8, a, c);
-                uint4 hi, lo;
-                split_bf16x8(a, c, hi, lo);
-                const uint32_t off = umma_tile_off(mode, r, kg);
-                *reinterpret_cast<uint4*>(xh + off) = hi;
-                *reinterpret_cast<uint4*>(xl + off) = lo;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int u = pt + kLinProducers * (jc * 2 + e);
+                if (u < units) {
+                    const int kg = u / N, r = u - kg * N;
+                    uint4 hi, lo;
+                    split_bf16x8(cur.a[e], cur.c[e], hi, lo);
+                    const uint32_t off = umma_tile_off(mode, r, kg);
+                    *reinterpret_cast<uint4*>(xh + off) = hi;
+                    *reinterpret_cast<uint4*>(xl + off) = lo;
+                }
             }
-            fence_proxy_async_smem();
-            mbar_arrive(&full_x[s]);
+            if (jc == JC - 1) {
+                fence_proxy_async_smem();
+                mbar_arrive(&full_x[s]);
+            }
+            cur = nxt;
         }
 
-        // ---- epilogue: TMEM -> registers
+        // ---- epilogue: TMEM -> registers (two warps per TMEM lane quadrant, alternating column chunks)
         const int q = warp & 3;               // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;     // 0 or 1
         const int nl = q * 32 + lane;          // output feature within the tile (TMEM lane)
         const int n = n_tile * kTileN + nl;    // packed output index
         const int rows_here = min(N, P.rows - row0);
@@ -224,7 +252,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         const int npad = P.n_tiles * kTileN;
         const int rpad = P.n_row_tiles * P.row_tile;
         float* wsp = P.ws + ((size_t)split * rpad + row0) * npad + n;
-        for (int c0 = 0; c0 < N; c0 += 16) {
+        for (int c0 = half * 16; c0 < N; c0 += 32) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);
             if (direct) {
@@ -242,47 +270,65 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         tc_fence_before();
 
         if (!direct) {
-            // ---- split-K rendezvous: last CTA of this tile reduces + applies the epilogue
+            // ---- split-K rendezvous.  Every CTA of the tile publishes its partial, waits until all
+            // `splits` partials are visible (all CTAs are co-resident: cooperative launch), then reduces
+            // ITS 1/splits share of the tile in fixed split order (bit-reproducible) and applies the
+            // fused epilogue.  ctr[0] counts arrivals, ctr[1] departures; the last one out resets both.
+            unsigned* ctr = P.counters + 2 * (rt * P.n_tiles + n_tile);
             __threadfence();
-            named_bar_sync(1, 128);
-            unsigned* ctr = P.counters + (rt * P.n_tiles + n_tile);
+            named_bar_sync(1, kLinProducers);
             if (pt == 0) {
-                const unsigned old = atomicAdd(ctr, 1u);
-                *last_flag = (old == (unsigned)(P.splits - 1)) ? 1u : 0u;
-            }
-            named_bar_sync(1, 128);
-            if (*last_flag) {
-                __threadfence();
-                const float* ws0 = P.ws + (size_t)row0 * npad + (size_t)n_tile * kTileN;
-                const size_t sstride = (size_t)rpad * npad;
-                if (P.epi == kEpiLstm) {
-                    for (int idx = pt; idx < rows_here * 32; idx += 128) {
-                        const int b = idx >> 5, u = idx & 31;
-                        const float4* p = reinterpret_cast<const float4*>(ws0 + (size_t)b * npad + 4 * u);
-                        float4 g = __ldcg(p);
-                        for (int s2 = 1; s2 < P.splits; ++s2) {
-                            const float4 w =
-                                __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + s2 * sstride));
-                            g.x += w.x; g.y += w.y; g.z += w.z; g.w += w.w;
-                        }
-                        const int unit = n_tile * 32 + u;
-                        if (unit < P.H) {
-                            const float4 bb = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
-                            g.x += bb.x; g.y += bb.y; g.z += bb.z; g.w += bb.w;
-                            lstm_gates(P, g, row0 + b, unit);
-                        }
-                    }
-                } else {
-                    for (int idx = pt; idx < rows_here * kTileN; idx += 128) {
-                        const int b = idx >> 7, nn = idx & 127;
-                        const float* p = ws0 + (size_t)b * npad + nn;
-                        float acc = __ldcg(p);
-                        for (int s2 = 1; s2 < P.splits; ++s2) acc += __ldcg(p + s2 * sstride);
-                        const int ng = n_tile * kTileN + nn;
-                        if (ng < P.n_out) P.out[(size_t)(row0 + b) * P.ldo + ng] = epi_scalar(P, acc, ng);
+                atomicAdd(ctr, 1u);
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(ctr) < (unsigned)P.splits) {
+                    if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
+                        printf("sat_b200: split-K rendezvous timed out (block %d)\n", (int)blockIdx.x);
+                        __trap();
                     }
                 }
-                if (pt == 0) *ctr = 0u;  // ready for the next launch
+            }
+            named_bar_sync(1, kLinProducers);
+            const float* ws0 = P.ws + (size_t)row0 * npad + (size_t)n_tile * kTileN;
+            const size_t sstride = (size_t)rpad * npad;
+            const int cnt = rows_here * 32;  // float4 groups (row b, 4 consecutive outputs) in the tile
+            const int lo = (int)(((long long)cnt * split) / P.splits);
+            const int hi = (int)(((long long)cnt * (split + 1)) / P.splits);
+            for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
+                const int b = idx >> 5, u = idx & 31;
+                const float* p = ws0 + (size_t)b * npad + 4 * u;
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s2 = 0; s2 < P.splits; s2 += 4) {
+                    float4 part[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (s2 + j < P.splits) part[j] = __ldcg(reinterpret_cast<const float4*>(p + (s2 + j) * sstride));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (s2 + j < P.splits) { g.x += part[j].x; g.y += part[j].y; g.z += part[j].z; g.w += part[j].w; }
+                }
+                if (P.epi == kEpiLstm) {
+                    const int unit = n_tile * 32 + u;
+                    if (unit < P.H) {
+                        const float4 bb = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
+                        g.x += bb.x; g.y += bb.y; g.z += bb.z; g.w += bb.w;
+                        lstm_gates(P, g, row0 + b, unit);
+                    }
+                } else {
+                    const int ng = n_tile * kTileN + 4 * u;
+                    float* o = P.out + (size_t)(row0 + b) * P.ldo + ng;
+                    if (ng + 0 < P.n_out) o[0] = epi_scalar(P, g.x, ng + 0);
+                    if (ng + 1 < P.n_out) o[1] = epi_scalar(P, g.y, ng + 1);
+                    if (ng + 2 < P.n_out) o[2] = epi_scalar(P, g.z, ng + 2);
+                    if (ng + 3 < P.n_out) o[3] = epi_scalar(P, g.w, ng + 3);
+                }
+            }
+            named_bar_sync(1, kLinProducers);
+            if (pt == 0) {
+                const unsigned old = atomicAdd(ctr + 1, 1u);
+                if (old == (unsigned)(P.splits - 1)) {  // everyone has passed the wait and finished reading
+                    ctr[0] = 0u;
+                    ctr[1] = 0u;
+                }
             }
         }
     }
@@ -442,8 +488,19 @@ cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt) {
         if (L.p[i].row_tile > max_rt) max_rt = L.p[i].row_tile;
     }
     const size_t smem = lin_smem_bytes(max_rt, L.stages);
-    lin_umma_kernel<<<total, kLinThreads, smem, st>>>(L);
-    return cudaGetLastError();
+    bool coop = false;
+    for (int i = 0; i < L.nprob; ++i) coop = coop || L.p[i].splits > 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(total);
+    cfg.blockDim = dim3(kLinThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = coop ? 1 : 0;   // split-K CTAs wait for each other: they must be co-resident
+    return cudaLaunchKernelEx(&cfg, lin_umma_kernel, L);
 }
 
 cudaError_t lin_repack_weight(const float* w_tf, int K, int n_out, int perm_H, uint8_t* wpack, int layout_mode,

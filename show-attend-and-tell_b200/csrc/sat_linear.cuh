@@ -11,7 +11,8 @@ constexpr int kBK = 64;                                  // K elements per pipel
 constexpr int kTileN = 128;                              // outputs per CTA tile (UMMA M)
 constexpr int kWHalfBytes = kTileN * kBK * 2;            // one bf16 half (hi or lo) of a W tile
 constexpr int kWStageBytes = 2 * kWHalfBytes;            // hi + lo, contiguous in the packed image
-constexpr int kLinThreads = 192;                         // warp0 TMA, warp1 MMA, warps2-5 X-producer/epilogue
+constexpr int kLinThreads = 320;                         // warp0 TMA, warp1 MMA, warps2-9 X-producer/epilogue
+constexpr int kLinProducers = 256;
 constexpr int kMaxSeg = 3;
 constexpr int kMaxProb = 4;
 
@@ -46,7 +47,7 @@ struct LinProblem {
     const uint8_t* wpack;  // [n_tiles][k_blocks][hi|lo][128 x 64 bf16, canonical UMMA K-major layout]
     const float* bias;     // packed output order, n_tiles*128 entries (zero padded); may be null for kEpiNone
     float* ws;             // split-K partials [splits][n_row_tiles*row_tile][n_tiles*128]
-    unsigned* counters;    // [n_row_tiles * n_tiles], zero between launches
+    unsigned* counters;    // [2 * n_row_tiles * n_tiles] (arrivals, departures), zero between launches
     int epi;
     float* out;            // [rows, ldo]
     int ldo;
