@@ -96,12 +96,28 @@ def time_cpu_oracle(wl, steps, warmup, budget_s=25.0):
     import numpy as np
     R, ocfg, w = oracle_setup(wl)
     ctx = R.synth_contexts(ocfg, wl["B"])
-    # a sample = T_s decode steps of the full batch (same per-token work as the full loop)
-    t0 = time.perf_counter()
     c, h = R.initialize(ocfg, w, ctx)
     word = np.zeros(wl["B"], np.int32)
-    r = R.decode_step(ocfg, w, ctx, word, c, h)           # warm-up step, also calibrates
-    per_step = time.perf_counter() - t0
+    R.decode_step(ocfg, w, ctx, word, c, h)               # warm-up (BLAS thread pool, page faults)
+    # give the CPU its best case: pick the BLAS thread count that runs one step fastest
+    ncpu = os.cpu_count() or 1
+    best_t, per_step, limiter = ncpu, None, None
+    try:
+        from threadpoolctl import threadpool_limits
+        cands = sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu})
+        for t in cands:
+            with threadpool_limits(limits=t):
+                R.decode_step(ocfg, w, ctx, word, c, h)
+                t0 = time.perf_counter()
+                R.decode_step(ocfg, w, ctx, word, c, h)
+                dt = time.perf_counter() - t0
+            if per_step is None or dt < per_step:
+                best_t, per_step = t, dt
+        limiter = threadpool_limits(limits=best_t)
+    except Exception:
+        t0 = time.perf_counter()
+        R.decode_step(ocfg, w, ctx, word, c, h)
+        per_step = time.perf_counter() - t0
     T_s = max(1, min(wl["T"], int(budget_s / max(per_step, 1e-3) / max(steps + warmup, 1))))
     times = []
     for it in range(warmup + steps):
@@ -116,9 +132,12 @@ def time_cpu_oracle(wl, steps, warmup, budget_s=25.0):
             times.append(time.perf_counter() - t0)
     total = sum(times)
     toks = wl["B"] * T_s * len(times)
-    return dict(value=toks / total, unit="tokens/s", cores=os.cpu_count(), kind="port",
+    if limiter is not None:
+        limiter.restore_original_limits()
+    return dict(value=toks / total, unit="tokens/s", cores=best_t, kind="port",
                 sample="%d x (initialize + %d of %d decode steps) at B=%d, numpy/BLAS fp32 oracle restating "
-                       "model.py (not TensorFlow: not installable here)" % (len(times), T_s, wl["T"], wl["B"]),
+                       "model.py (not TensorFlow: not installable here); %d BLAS threads (fastest of the counts "
+                       "tried on %d host cores)" % (len(times), T_s, wl["T"], wl["B"], best_t, ncpu),
                 ms_per_step=1e3 * total / len(times) * (wl["T"] / T_s), steps_sampled=T_s)
 
 
