@@ -68,7 +68,10 @@ int sat_version(void);
  * "umma_layout" (0 = interleaved, 1 = 128B swizzle; must be set before sat_set_weight),
  * "graphs" (1 = replay CUDA graphs in loops [default]), "hoist" (1 = project the contexts
  * once per image batch [default]; 0 = recompute every step like model.py:259-262),
- * "coop" (1 = cooperative launch of the attention kernel [default]). */
+ * "coop" (1 = cooperative launch of the attention kernel [default]), "xpack" (1 = dense layers
+ * convert their activations once in a cooperative pre-pass and fetch them by TMA [default];
+ * 0 = per-stage conversion by producer warps), "profile" (1 = record CUDA events around every
+ * eager kernel launch; read back with sat_get_info "prof_ns_<family>" / "prof_n_<family>"). */
 int sat_set_option(sat_handle* h, const char* key, int64_t value);
 int sat_get_info(sat_handle* h, const char* key, int64_t* value);
 

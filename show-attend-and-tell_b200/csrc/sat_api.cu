@@ -52,6 +52,9 @@ struct Layer {
     size_t ws_floats = 0;
     unsigned* counters = nullptr;
     size_t n_counters = 0;
+    uint8_t* xpack = nullptr;  // packed activations (x_mode 1)
+    size_t xpack_bytes = 0;
+    unsigned* xbar = nullptr;  // {count, generation}
 };
 
 struct VecParam {  // a kernel of shape [n,1] kept as a plain fp32 vector
@@ -71,7 +74,7 @@ struct GraphEntry {
 struct sat_handle {
     sat_dims d;
     int dev = 0, num_sms = 0, smem_optin = 0;
-    int opt_gemm = 1, opt_layout = 0, opt_graphs = 1, opt_hoist = 1, opt_coop = 1;
+    int opt_gemm = 1, opt_layout = 0, opt_graphs = 1, opt_hoist = 1, opt_coop = 1, opt_xpack = 1;
     bool weights_locked = false;
 
     Layer init_a1, init_a2, init_b1, init_b2;  // 1-layer mode uses init_a1 / init_b1 as fc_a / fc_b
@@ -181,6 +184,8 @@ static void layer_free(Layer& ly) {
     cudaFree(ly.bias);
     cudaFree(ly.ws);
     cudaFree(ly.counters);
+    cudaFree(ly.xpack);
+    cudaFree(ly.xbar);
     ly = Layer();
 }
 
@@ -320,6 +325,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     } else if (k == "graphs") h->opt_graphs = (int)value;
     else if (k == "hoist") { h->opt_hoist = (int)value; h->prep_ctx = nullptr; }
     else if (k == "coop") h->opt_coop = (int)value;
+    else if (k == "xpack") h->opt_xpack = (int)value;
     else if (k == "profile") {
         h->opt_profile = (int)value;
         for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -519,6 +525,23 @@ static int plan(sat_handle* h, Layer& ly, LinProblem& P, std::initializer_list<L
     P.ws = ly.ws;
     P.counters = ly.counters;
     P.cta_count = tiles * best;
+    // packed-activation scratch for the cooperative pre-pass (used when the launch fits one wave)
+    const size_t xneed = (size_t)P.n_row_tiles * P.k_blocks * 2 * P.row_tile * kBK * 2;
+    if (xneed > ly.xpack_bytes || !ly.xbar) {
+        if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: scratch growth during graph capture", ly.name.c_str());
+        CK(cudaDeviceSynchronize());
+        cudaFree(ly.xpack);
+        ly.xpack = nullptr;
+        ly.xpack_bytes = 0;
+        RET(dmalloc(&ly.xpack, xneed));
+        ly.xpack_bytes = xneed;
+        if (!ly.xbar) {
+            RET(dmalloc(&ly.xbar, (size_t)2));
+            CK(cudaMemset(ly.xbar, 0, 2 * sizeof(unsigned)));
+        }
+    }
+    P.xpack = ly.xpack;
+    P.xbar = ly.xbar;
     return SAT_OK;
 }
 
@@ -535,6 +558,7 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.nprob = n;
     L.layout_mode = h->opt_layout;
     L.stages = lin_pick_stages(max_rt);
+    L.x_mode = (h->opt_xpack && begin <= h->num_sms) ? 1 : 0;  // the pre-pass needs every CTA co-resident
     if (L.stages < 1) return fail(SAT_ERR_UNSUPPORTED, "row tile %d does not fit in shared memory", max_rt);
     {
         ProfScope ps(h, h->cur_tag, st);

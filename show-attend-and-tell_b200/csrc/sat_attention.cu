@@ -31,7 +31,7 @@ namespace sat {
 constexpr int kAttConsumerWarps = 8;
 constexpr int kAttThreads = (kAttConsumerWarps + 1) * 32;
 
-template <int G>
+template <int G, int RV>
 __global__ void __launch_bounds__(kAttThreads, 1)
 att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_constant__ AttParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -95,11 +95,18 @@ att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_const
 
     // ============================== consumers ==============================
     const int ct = threadIdx.x;  // 0..255
-    for (int j = ct; j < RL; j += kAttConsumerWarps * 32) vec_s[j] = p.vec[j];
+    constexpr int NT = kAttConsumerWarps * 32;
+    for (int j = ct; j < RL; j += NT) vec_s[j] = p.vec[j];
     int cur_q_img = -1, cur_a_img = -1;
     int idx = 0;
+    int img_lo = -1, img_hi = -1;   // images whose rows this CTA scored (for the release at the end of phase 1)
+    int cnt_lo = 0, cnt_mid_first = 0;
+    (void)cnt_lo; (void)cnt_mid_first;
 
     // ---------------- phase 1: attention logits ----------------
+    // RV > 0: the row length is RV*128 floats and w2 / q live in registers (one float4 per lane per 128 floats)
+    float4 wreg[RV > 0 ? RV : 1];
+    float4 qreg[G][RV > 0 ? RV : 1];
     for (int r = r_begin; r < r_end;) {
         const int img = r / L;
         int n = min(p.rch, r_end - r);
@@ -107,41 +114,67 @@ att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_const
         const int s = idx % p.nslots;
         const uint32_t ph = (uint32_t)(idx / p.nslots) & 1u;
         if (img != cur_q_img) {
-            named_bar_sync(1, kAttConsumerWarps * 32);
-            if (p.q) {
-                const float4* src = reinterpret_cast<const float4*>(p.q + (size_t)img * G * RL);
-                float4* dst = reinterpret_cast<float4*>(q_s);
-                for (int j = ct; j < G * RL / 4; j += kAttConsumerWarps * 32) dst[j] = src[j];
+            if (cur_q_img < 0) {
+                named_bar_sync(1, NT);  // vec_s visible
+                if (RV > 0) {
+#pragma unroll
+                    for (int k = 0; k < (RV > 0 ? RV : 1); ++k) wreg[k] = reinterpret_cast<const float4*>(vec_s)[lane + 32 * k];
+                }
+                img_lo = img;
+            }
+            if (RV > 0) {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+#pragma unroll
+                    for (int k = 0; k < (RV > 0 ? RV : 1); ++k)
+                        qreg[g][k] = p.q ? __ldg(reinterpret_cast<const float4*>(p.q + ((size_t)img * G + g) * RL) + lane + 32 * k)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                if (cur_q_img >= 0) named_bar_sync(1, NT);  // everyone done with the previous image's q_s
+                if (p.q) {
+                    const float4* src = reinterpret_cast<const float4*>(p.q + (size_t)img * G * RL);
+                    float4* dst = reinterpret_cast<float4*>(q_s);
+                    for (int j = ct; j < G * RL / 4; j += NT) dst[j] = src[j];
+                }
+                named_bar_sync(1, NT);
             }
             cur_q_img = img;
-            named_bar_sync(1, kAttConsumerWarps * 32);
-        } else if (idx == 0) {
-            named_bar_sync(1, kAttConsumerWarps * 32);  // vec_s visible
+            img_hi = img;
         }
         mbar_wait(&full[s], ph);
         const float* buf = reinterpret_cast<const float*>(slots + (size_t)s * p.slot_bytes);
-        int done = 0;
         for (int row = warp; row < n; row += kAttConsumerWarps) {
             float acc[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) acc[g] = 0.f;
             const float4* trow = reinterpret_cast<const float4*>(buf + (size_t)row * RL);
-            for (int j = lane; j < RL / 4; j += 32) {
-                const float4 t = trow[j];
-                const float4 w = reinterpret_cast<const float4*>(vec_s)[j];
-                if (p.q) {
+            if (RV > 0) {
+#pragma unroll
+                for (int k = 0; k < (RV > 0 ? RV : 1); ++k) {
+                    const float4 t = trow[lane + 32 * k];
+                    const float4 w = wreg[k];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        const float4 qq = reinterpret_cast<const float4*>(q_s + (size_t)g * RL)[j];
+                        const float4 qq = qreg[g][k];
                         acc[g] = fmaf(w.x, t.x + qq.x, acc[g]);
                         acc[g] = fmaf(w.y, t.y + qq.y, acc[g]);
                         acc[g] = fmaf(w.z, t.z + qq.z, acc[g]);
                         acc[g] = fmaf(w.w, t.w + qq.w, acc[g]);
                     }
-                } else {
-                    float a0 = fmaf(w.x, t.x, fmaf(w.y, t.y, fmaf(w.z, t.z, w.w * t.w)));
+                }
+            } else {
+                for (int j = lane; j < RL / 4; j += 32) {
+                    const float4 t = trow[j];
+                    const float4 w = reinterpret_cast<const float4*>(vec_s)[j];
 #pragma unroll
-                    for (int g = 0; g < G; ++g) acc[g] += a0;
+                    for (int g = 0; g < G; ++g) {
+                        float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.q) qq = reinterpret_cast<const float4*>(q_s + (size_t)g * RL)[j];
+                        acc[g] = fmaf(w.x, t.x + qq.x, acc[g]);
+                        acc[g] = fmaf(w.y, t.y + qq.y, acc[g]);
+                        acc[g] = fmaf(w.z, t.z + qq.z, acc[g]);
+                        acc[g] = fmaf(w.w, t.w + qq.w, acc[g]);
+                    }
                 }
             }
             const int l = r + row - img * L;
@@ -154,21 +187,27 @@ att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_const
                     p.e[o] = sum;
                 }
             }
-            ++done;
-        }
-        if (lane == 0) {
-            if (done) {
-                __threadfence();
-                atomicAdd(p.rowcnt + img, (unsigned)done);
-            }
-            mbar_arrive(&empty[s]);
         }
         __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
         r += n;
         ++idx;
     }
+    // release the logits: ONE gpu-scope fence per CTA (not per chunk), then per-image row counts
+    if (r_begin < r_end) {
+        named_bar_sync(1, NT);
+        if (ct == 0) {
+            __threadfence();
+            for (int img = img_lo; img <= img_hi; ++img) {
+                const int a = max(r_begin, img * L), b = min(r_end, (img + 1) * L);
+                if (b > a) atomicAdd(p.rowcnt + img, (unsigned)(b - a));
+            }
+        }
+    }
 
     // ---------------- phase 2: softmax + context vector ----------------
+    // item = [L x 32] floats; lanes 0-7 / 8-15 / 16-23 / 24-31 read four consecutive rows as float4
+    const int sub = lane >> 3, l4 = lane & 7;
     int parity = 0;
     for (int it = i_begin; it < i_end; ++it, ++idx) {
         const int img = it / nds, ds = it - img * nds;
@@ -184,7 +223,7 @@ att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_const
                     }
                 }
             }
-            named_bar_sync(1, kAttConsumerWarps * 32);
+            named_bar_sync(1, NT);
             for (int g = warp; g < G; g += kAttConsumerWarps) {
                 const float* er = p.e + ((size_t)img * G + g) * L;
                 float m = -INFINITY;
@@ -205,24 +244,41 @@ att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_const
                 }
             }
             cur_a_img = img;
-            named_bar_sync(1, kAttConsumerWarps * 32);
+            named_bar_sync(1, NT);
         }
         mbar_wait(&full[s], ph);
-        const float* buf = reinterpret_cast<const float*>(slots + (size_t)s * p.slot_bytes);
-        float acc[G];
+        const float4* buf4 = reinterpret_cast<const float4*>(slots + (size_t)s * p.slot_bytes);
+        float4 acc[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] = 0.f;
-        for (int l = warp; l < L; l += kAttConsumerWarps) {
-            const float x = buf[l * 32 + lane];
+        for (int g = 0; g < G; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = warp * 4 + sub; l < L; l += kAttConsumerWarps * 4) {
+            const float4 x = buf4[l * 8 + l4];
 #pragma unroll
-            for (int g = 0; g < G; ++g) acc[g] = fmaf(alpha_s[g * Lp + l], x, acc[g]);
+            for (int g = 0; g < G; ++g) {
+                const float a = alpha_s[g * Lp + l];
+                acc[g].x = fmaf(a, x.x, acc[g].x);
+                acc[g].y = fmaf(a, x.y, acc[g].y);
+                acc[g].z = fmaf(a, x.z, acc[g].z);
+                acc[g].w = fmaf(a, x.w, acc[g].w);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        float* rp = red + (size_t)parity * kAttConsumerWarps * G * 32;
+        float4* rp4 = reinterpret_cast<float4*>(red + (size_t)parity * kAttConsumerWarps * G * 32);
 #pragma unroll
-        for (int g = 0; g < G; ++g) rp[(warp * G + g) * 32 + lane] = acc[g];
-        named_bar_sync(1, kAttConsumerWarps * 32);
+        for (int g = 0; g < G; ++g) {
+            float4 v = acc[g];
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+                v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+                v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+            }
+            if (sub == 0) rp4[(warp * G + g) * 8 + l4] = v;
+        }
+        named_bar_sync(1, NT);
+        const float* rp = reinterpret_cast<const float*>(rp4);
         for (int g = warp; g < G; g += kAttConsumerWarps) {
             float sum = 0.f;
 #pragma unroll
@@ -260,10 +316,10 @@ bool att_plan(AttParams& p, int smem_optin) {
     return n >= 2;
 }
 
-template <int G>
-static cudaError_t att_launch_g(const CUtensorMap& map, const AttParams& p, int grid, cudaStream_t st, bool coop) {
+template <int G, int RV>
+static cudaError_t att_launch_gr(const CUtensorMap& map, const AttParams& p, int grid, cudaStream_t st, bool coop) {
     const size_t smem = att_smem_bytes(p);
-    cudaError_t e = cudaFuncSetAttribute(att_fused_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(att_fused_kernel<G, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -275,7 +331,14 @@ static cudaError_t att_launch_g(const CUtensorMap& map, const AttParams& p, int 
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = coop ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, att_fused_kernel<G>, map, p);
+    return cudaLaunchKernelEx(&cfg, att_fused_kernel<G, RV>, map, p);
+}
+
+template <int G>
+static cudaError_t att_launch_g(const CUtensorMap& map, const AttParams& p, int grid, cudaStream_t st, bool coop) {
+    // register-resident w2/q when a row is exactly 512 floats (dim_attend_layer = 512, the reference default)
+    if (p.RL == 512) return att_launch_gr<G, 4>(map, p, grid, st, coop);
+    return att_launch_gr<G, 0>(map, p, grid, st, coop);
 }
 
 cudaError_t att_launch(const CUtensorMap& map, const AttParams& p, int num_sms, cudaStream_t st, bool coop) {

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     uint64_t* tmem_full = empty + 8;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
     uint8_t* stage_base = smem_raw + 1024;
+    const bool xtma = L.x_mode == 1;  // activations pre-packed by all CTAs, then fetched by TMA
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_w[s], 1);
-            mbar_init(&full_x[s], kLinProducers);
+            mbar_init(&full_x[s], xtma ? 1 : kLinProducers);
             mbar_init(&empty[s], 1);
         }
         mbar_init(tmem_full, 1);
@@ -144,22 +145,53 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         tmem_alloc(tmem_ptr, tmem_cols);
         tmem_relinquish();
     }
+    // grid-barrier generation must be sampled before this CTA can possibly arrive on it
+    unsigned gen0 = 0;
+    if (xtma && threadIdx.x == 0) gen0 = ld_acquire_gpu(P.xbar + 1);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
+    const uint32_t x_stage_bytes = 2 * x_half_bytes;
 
     if (warp == 0) {
         // ===================== TMA producer: one 32 KB bulk copy per stage =====================
         if (lane == 0) {
             const uint8_t* src = P.wpack + ((size_t)n_tile * P.k_blocks + kb0) * kWStageBytes;
-            for (int it = 0; it < nkb; ++it) {
+            const uint8_t* xsrc = P.xpack + ((size_t)rt * P.k_blocks + kb0) * x_stage_bytes;
+            auto load_w = [&](int it) {
                 const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_w[s], kWStageBytes);
                 tma_bulk_g2s(stage_base + (size_t)s * stage_bytes, src + (size_t)it * kWStageBytes, kWStageBytes,
                              &full_w[s]);
+            };
+            auto load_x = [&](int it) {
+                const int s = it % S;
+                mbar_arrive_expect_tx(&full_x[s], x_stage_bytes);
+                tma_bulk_g2s(stage_base + (size_t)s * stage_bytes + kWStageBytes, xsrc + (size_t)it * x_stage_bytes,
+                             x_stage_bytes, &full_x[s]);
+            };
+            const int pre = nkb < S ? nkb : S;
+            if (xtma) {
+                // weights do not depend on the activation pre-pass: fill the pipeline with W first, then
+                // wait for the grid-wide pack to complete and fetch the X halves of the same stages
+                for (int it = 0; it < pre; ++it) load_w(it);
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(P.xbar + 1) == gen0) {
+                    if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
+                        printf("sat_b200: activation pack barrier timed out (block %d)\n", (int)blockIdx.x);
+                        __trap();
+                    }
+                }
+                fence_proxy_async_global();
+                for (int it = 0; it < pre; ++it) load_x(it);
+            }
+            for (int it = xtma ? pre : 0; it < nkb; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                load_w(it);
+                if (xtma) load_x(it);
             }
         }
     } else if (warp == 1) {
@@ -196,9 +228,38 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         // The fp32 sources of X are L2 resident; their latency is hidden by keeping the loads of the
         // NEXT chunk in flight while the current one is converted and stored.
         const int pt = threadIdx.x - 64;  // 0..255
-        const int units = N * 8;          // 16-byte groups per K block
+        if (xtma) {
+            // ---- cooperative pre-pass: this problem's CTAs convert X (fp32 -> bf16 hi/lo UMMA tiles) ONCE
+            // into global scratch; consecutive threads take consecutive 8-element groups of a row (coalesced).
+            const int kgroups = P.k_blocks * 8;
+            const int utot = P.n_row_tiles * N * kgroups;
+            for (int u = local * kLinProducers + pt; u < utot; u += P.cta_count * kLinProducers) {
+                const int rr = u / kgroups, kgk = u - rr * kgroups;
+                const int rt2 = rr / N, r = rr - rt2 * N;
+                float4 a, c;
+                load_x8(P, rt2 * N + r, kgk * 8, a, c);
+                uint4 hi, lo;
+                split_bf16x8(a, c, hi, lo);
+                uint8_t* dst = P.xpack + ((size_t)rt2 * P.k_blocks + (kgk >> 3)) * x_stage_bytes +
+                               umma_tile_off(mode, r, kgk & 7);
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + x_half_bytes) = lo;
+            }
+            __threadfence();
+            fence_proxy_async_global();
+            named_bar_sync(1, kLinProducers);
+            if (pt == 0) {  // grid barrier arrive: the last CTA opens the next generation
+                const unsigned old = atomicAdd(P.xbar, 1u);
+                if (old == (unsigned)(P.cta_count - 1)) {
+                    P.xbar[0] = 0u;
+                    __threadfence();
+                    atomicAdd(P.xbar + 1, 1u);
+                }
+            }
+        }
+        const int units = xtma ? 0 : N * 8;  // 16-byte groups per K block (in-kernel producer mode)
         const int JC = (units + 2 * kLinProducers - 1) / (2 * kLinProducers);  // chunks (2 units/thread) per block
-        const int total = nkb * JC;
+        const int total = xtma ? 0 : nkb * JC;
         auto load_chunk = [&](int g, XChunk& ch) {
             const int it = g / JC, jc = g - it * JC;
             const int kbase = (kb0 + it) * kBK;
@@ -490,6 +551,7 @@ cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt) {
     const size_t smem = lin_smem_bytes(max_rt, L.stages);
     bool coop = false;
     for (int i = 0; i < L.nprob; ++i) coop = coop || L.p[i].splits > 1;
+    coop = coop || L.x_mode == 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(total);
     cfg.blockDim = dim3(kLinThreads);

@@ -48,6 +48,8 @@ struct LinProblem {
     const float* bias;     // packed output order, n_tiles*128 entries (zero padded); may be null for kEpiNone
     float* ws;             // split-K partials [splits][n_row_tiles*row_tile][n_tiles*128]
     unsigned* counters;    // [2 * n_row_tiles * n_tiles] (arrivals, departures), zero between launches
+    uint8_t* xpack;        // x_mode 1: packed activations [n_row_tiles][k_blocks][hi|lo][row_tile x 64 bf16]
+    unsigned* xbar;        // x_mode 1: grid barrier {count, generation}
     int epi;
     float* out;            // [rows, ldo]
     int ldo;
@@ -64,6 +66,7 @@ struct LinLaunch {
     int nprob;
     int layout_mode;  // 0 = no-swizzle (interleaved 8x16B core matrices), 1 = 128B swizzle
     int stages;
+    int x_mode;       // 0 = producer warps convert X per stage; 1 = cooperative pre-pack + TMA (grid <= #SMs)
 };
 
 // byte offset of the 16-byte group (row r, k-group kg in [0,8)) inside a [rows x 64] bf16
