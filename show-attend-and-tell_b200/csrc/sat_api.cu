@@ -55,6 +55,10 @@ struct Layer {
     uint8_t* xpack = nullptr;  // packed activations (x_mode 1)
     size_t xpack_bytes = 0;
     unsigned* xbar = nullptr;  // {count, generation}
+    float* am_val = nullptr;   // fused-argmax tile candidates
+    int32_t* am_idx = nullptr;
+    unsigned* am_ctr = nullptr;
+    size_t am_n = 0;
 };
 
 struct VecParam {  // a kernel of shape [n,1] kept as a plain fp32 vector
@@ -75,6 +79,7 @@ struct sat_handle {
     sat_dims d;
     int dev = 0, num_sms = 0, smem_optin = 0;
     int opt_gemm = 1, opt_layout = 0, opt_graphs = 1, opt_hoist = 1, opt_coop = 1, opt_xpack = 1;
+    int opt_l2_w = 2, opt_l2_t = 1, opt_l2_ctx = 0;  // weights evict_last, projected contexts evict_first
     bool weights_locked = false;
 
     Layer init_a1, init_a2, init_b1, init_b2;  // 1-layer mode uses init_a1 / init_b1 as fc_a / fc_b
@@ -186,6 +191,9 @@ static void layer_free(Layer& ly) {
     cudaFree(ly.counters);
     cudaFree(ly.xpack);
     cudaFree(ly.xbar);
+    cudaFree(ly.am_val);
+    cudaFree(ly.am_idx);
+    cudaFree(ly.am_ctr);
     ly = Layer();
 }
 
@@ -326,6 +334,9 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "hoist") { h->opt_hoist = (int)value; h->prep_ctx = nullptr; }
     else if (k == "coop") h->opt_coop = (int)value;
     else if (k == "xpack") h->opt_xpack = (int)value;
+    else if (k == "l2_w") h->opt_l2_w = (int)value;
+    else if (k == "l2_t") h->opt_l2_t = (int)value;
+    else if (k == "l2_ctx") h->opt_l2_ctx = (int)value;
     else if (k == "profile") {
         h->opt_profile = (int)value;
         for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -558,6 +569,7 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.nprob = n;
     L.layout_mode = h->opt_layout;
     L.stages = lin_pick_stages(max_rt);
+    L.l2_w = h->opt_l2_w;
     L.x_mode = (h->opt_xpack && begin <= h->num_sms) ? 1 : 0;  // the pre-pass needs every CTA co-resident
     if (L.stages < 1) return fail(SAT_ERR_UNSUPPORTED, "row tile %d does not fit in shared memory", max_rt);
     {
@@ -646,10 +658,22 @@ struct StepIO {
     float *c_out, *h_out, *logits, *probs, *alpha;
     RowsParams rows;  // softmax-stage extras (tokens / next_word / topk); logits/probs/V filled here
     bool want_rows;
+    bool q_ready;      // the state branch q for this step was produced by the previous step's grouped launch
+    bool make_next_q;  // also compute q of the NEXT step (from this step's output) alongside decode fc_1
 };
 
+// state branch of attend: q = tanh(h*W1b + b1b) (model.py:421-424) or, 1-layer, h*fc_b (model.py:409-413)
+static int plan_att_state(sat_handle* h, LinProblem& P, const float* h_in, int rows, cudaStream_t st, int group) {
+    const sat_dims& d = h->d;
+    if (d.num_attend_layers == 2)
+        return plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiBiasTanh, h->q,
+                    d.dim_attend_layer, st, 0, group);
+    return plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiNone, h->q, d.num_ctx, st, 0,
+                group);
+}
+
 static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, const float* h_in, float* alpha, float* z,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool q_ready = false) {
     const sat_dims& d = h->d;
     const int rows = n_img * G;
     RET(ensure_ctx_map(h, ctx, n_img));
@@ -659,10 +683,10 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     if (d.num_attend_layers == 2) {
         if (!(h->opt_hoist && h->prep_ctx == ctx && h->prep_ni == n_img)) RET(project_contexts(h, ctx, n_img, st));
         h->cur_tag = kTagAttState;
-        // state branch: q = tanh(h * W1b + b1b)   (model.py:421-424)
-        RET(plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiBiasTanh, h->q,
-                 d.dim_attend_layer, st));
-        RET(launch(h, &P, 1, st));
+        if (!q_ready) {
+            RET(plan_att_state(h, P, h_in, rows, st, 1));
+            RET(launch(h, &P, 1, st));
+        }
         ap.T = h->T1;
         ap.RL = d.dim_attend_layer;
         ap.q = h->q;
@@ -670,8 +694,10 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     } else {
         // logits2 = h * fc_b   (model.py:409-413), added to ctx . fc_a inside the kernel
         h->cur_tag = kTagAttState;
-        RET(plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiNone, h->q, d.num_ctx, st));
-        RET(launch(h, &P, 1, st));
+        if (!q_ready) {
+            RET(plan_att_state(h, P, h_in, rows, st, 1));
+            RET(launch(h, &P, 1, st));
+        }
         ap.T = ctx;
         ap.RL = d.dim_ctx;
         ap.q = nullptr;
@@ -687,6 +713,8 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     ap.G = G;
     ap.L = d.num_ctx;
     ap.D = d.dim_ctx;
+    ap.l2_t = h->opt_l2_t;
+    ap.l2_ctx = h->opt_l2_ctx;
     if (!att_plan(ap, h->smem_optin)) return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
     CK(cudaMemsetAsync(h->rowcnt, 0, (size_t)n_img * sizeof(unsigned), st));
     {
@@ -714,39 +742,88 @@ static int lstm_impl(sat_handle* h, const float* z, const int32_t* last_word, co
     return launch(h, &P, 1, st);
 }
 
+// fused greedy argmax on the vocabulary layer: only when it runs un-split in one wave
+static int attach_argmax(sat_handle* h, Layer& ly, LinProblem& P, const RowsParams* am, cudaStream_t st) {
+    if (!am || P.splits != 1 || h->opt_gemm == 0) return 0;
+    const size_t need = (size_t)P.n_row_tiles * P.n_tiles * P.row_tile;
+    if (need > ly.am_n) {
+        if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: scratch growth during graph capture", ly.name.c_str());
+        CK(cudaDeviceSynchronize());
+        cudaFree(ly.am_val); cudaFree(ly.am_idx);
+        ly.am_val = nullptr; ly.am_idx = nullptr; ly.am_n = 0;
+        RET(dmalloc(&ly.am_val, need));
+        RET(dmalloc(&ly.am_idx, need));
+        ly.am_n = need;
+        if (!ly.am_ctr) {
+            RET(dmalloc(&ly.am_ctr, (size_t)1));
+            CK(cudaMemset(ly.am_ctr, 0, sizeof(unsigned)));
+        }
+    }
+    P.am_val = ly.am_val; P.am_idx = ly.am_idx; P.am_ctr = ly.am_ctr;
+    P.am_tokens = am->tokens; P.am_tokens_ld = am->tokens_ld; P.am_step = am->step;
+    P.am_next_word = am->next_word; P.am_forced = am->forced; P.am_forced_ld = am->forced_ld;
+    return 1;
+}
+
+// returns 1 in *argmax_done if the prediction / next word were produced by the vocabulary layer itself
 static int decode_impl(sat_handle* h, const float* h_out, const float* z, const int32_t* last_word, float* logits,
-                       int rows, cudaStream_t st) {
+                       int rows, cudaStream_t st, bool make_next_q = false, const RowsParams* am = nullptr,
+                       int* argmax_done = nullptr) {
     const sat_dims& d = h->d;
-    LinProblem P;
+    LinProblem P[2];
+    int used = 0;
+    if (argmax_done) *argmax_done = 0;
     // expanded_output = concat([output, context, word_embed]) (model.py:283-286)
     h->cur_tag = kTagDec1;
     if (d.num_decode_layers == 2) {
-        RET(plan(h, h->dec_1, P,
+        const int group = make_next_q ? 2 : 1;
+        RET(plan(h, h->dec_1, P[0],
                  {seg(h_out, d.num_lstm_units, d.num_lstm_units), seg(z, d.dim_ctx, d.dim_ctx),
                   seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word)},
-                 rows, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st));
-        RET(launch(h, &P, 1, st));
+                 rows, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st, 0, group));
+        int np = 1;
+        if (make_next_q) {  // q of the next step depends on the same h_out: share the launch
+            RET(plan_att_state(h, P[1], h_out, rows, st, 2));
+            np = 2;
+        }
+        RET(launch(h, P, np, st));
         h->cur_tag = kTagDec2;
-        RET(plan(h, h->dec_2, P, {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer)}, rows, kEpiBias, logits,
+        RET(plan(h, h->dec_2, P[0], {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer)}, rows, kEpiBias, logits,
                  d.vocabulary_size, st));
-        return launch(h, &P, 1, st);
+        used = attach_argmax(h, h->dec_2, P[0], am, st);
+        if (used < 0) return used;
+        RET(launch(h, P, 1, st));
+        if (argmax_done) *argmax_done = used;
+        return SAT_OK;
     }
     h->cur_tag = kTagDec2;
-    RET(plan(h, h->dec_2, P,
+    const int group = make_next_q ? 2 : 1;
+    RET(plan(h, h->dec_2, P[0],
              {seg(h_out, d.num_lstm_units, d.num_lstm_units), seg(z, d.dim_ctx, d.dim_ctx),
               seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word)},
-             rows, kEpiBias, logits, d.vocabulary_size, st));
-    return launch(h, &P, 1, st);
+             rows, kEpiBias, logits, d.vocabulary_size, st, 0, group));
+    int np = 1;
+    if (make_next_q) {
+        RET(plan_att_state(h, P[1], h_out, rows, st, 2));
+        np = 2;
+    }
+    // the fused argmax overwrites next_word, which this very launch still gathers embeddings with:
+    // only safe when the embedding rows are not an operand of the vocabulary layer (2-layer decode)
+    RET(launch(h, P, np, st));
+    return SAT_OK;
 }
 
 static int step_impl(sat_handle* h, StepIO& io, cudaStream_t st) {
     const int rows = io.n_img * io.group;
     if (rows > h->max_rows) return fail(SAT_ERR_INVALID, "rows %d > max_batch %d", rows, h->max_rows);
-    RET(attention_impl(h, io.ctx, io.n_img, io.group, io.h_in, io.alpha, h->z, st));
+    RET(attention_impl(h, io.ctx, io.n_img, io.group, io.h_in, io.alpha, h->z, st, io.q_ready));
     RET(lstm_impl(h, h->z, io.last_word, io.c_in, io.h_in, io.c_out, io.h_out, rows, st));
     float* logits = io.logits ? io.logits : h->logits;
-    RET(decode_impl(h, io.h_out, h->z, io.last_word, logits, rows, st));
-    if (io.probs || io.want_rows) {
+    const bool argmax_only = io.want_rows && !io.probs && io.rows.topk == 0 && !io.rows.argmax;
+    int fused = 0;
+    RET(decode_impl(h, io.h_out, h->z, io.last_word, logits, rows, st, io.make_next_q,
+                    argmax_only ? &io.rows : nullptr, &fused));
+    if ((io.probs || io.want_rows) && !fused) {
         RowsParams rp = io.rows;
         rp.logits = logits;
         rp.V = h->d.vocabulary_size;
@@ -841,6 +918,8 @@ static int loop_enqueue(sat_handle* h, const float* ctx, int B, int T, const int
         io.want_rows = true;
         io.rows.tokens = tokens; io.rows.tokens_ld = T; io.rows.step = t;
         io.rows.next_word = h->word; io.rows.forced = forced; io.rows.forced_ld = T;
+        io.q_ready = t > 0;
+        io.make_next_q = t + 1 < T;
         RET(step_impl(h, io, st));
     }
     return SAT_OK;

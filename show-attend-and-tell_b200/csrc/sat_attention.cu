@@ -67,6 +67,7 @@ att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_const
         // ============================ producer ============================
         if (lane == 0) {
             tma_prefetch_desc(&ctx_map);
+            const uint64_t pol_t = l2_policy(p.l2_t), pol_c = l2_policy(p.l2_ctx);
             int idx = 0;
             for (int r = r_begin; r < r_end;) {
                 const int img = r / L;
@@ -77,7 +78,7 @@ att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_const
                 mbar_wait(&empty[s], ph ^ 1u);
                 const uint32_t bytes = (uint32_t)n * RL * 4u;
                 mbar_arrive_expect_tx(&full[s], bytes);
-                tma_bulk_g2s(slots + (size_t)s * p.slot_bytes, p.T + (size_t)r * RL, bytes, &full[s]);
+                tma_bulk_g2s_hint(slots + (size_t)s * p.slot_bytes, p.T + (size_t)r * RL, bytes, &full[s], p.l2_t, pol_t);
                 r += n;
                 ++idx;
             }
@@ -87,7 +88,8 @@ att_fused_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_const
                 const uint32_t ph = (uint32_t)(idx / p.nslots) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full[s], (uint32_t)L * 128u);
-                tma_tensor2d_g2s(slots + (size_t)s * p.slot_bytes, &ctx_map, ds * 32, img * L, &full[s]);
+                tma_tensor2d_g2s_hint(slots + (size_t)s * p.slot_bytes, &ctx_map, ds * 32, img * L, &full[s], p.l2_ctx,
+                                      pol_c);
             }
         }
         return;

@@ -20,6 +20,7 @@ struct AttParams {
     int rch;             // phase-1 rows per TMA chunk
     int slot_bytes;
     int nslots;
+    int l2_t, l2_ctx;    // L2 eviction policies of the two streams (see l2_policy)
 };
 
 bool att_plan(AttParams& p, int smem_optin);

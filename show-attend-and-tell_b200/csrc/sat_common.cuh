@@ -64,12 +64,48 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 eviction-priority policies for TMA loads: 0 = none, 1 = evict_first (streamed once per step),
+// 2 = evict_last (weights: keep resident in the 126 MB L2 across decode steps), 3 = evict_normal.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+    uint64_t pol = 0;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 3) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                  int kind, uint64_t pol) {
+    if (kind == 0) {
+        tma_bulk_g2s(dst_smem, src_gmem, bytes, bar);
+        return;
+    }
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_tensor2d_g2s_hint(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar,
+                                                      int kind, uint64_t pol);
+
 // 2-D tiled tensor copy global -> shared through a CUtensorMap (UTMALDG).
 __device__ __forceinline__ void tma_tensor2d_g2s(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
             "r"(smem_u32(dst_smem)),
         "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_tensor2d_g2s_hint(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar,
+                                                      int kind, uint64_t pol) {
+    if (kind == 0) {
+        tma_tensor2d_g2s(dst_smem, tmap, c0, c1, bar);
+        return;
+    }
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {

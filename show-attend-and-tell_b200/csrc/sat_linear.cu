@@ -159,11 +159,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         if (lane == 0) {
             const uint8_t* src = P.wpack + ((size_t)n_tile * P.k_blocks + kb0) * kWStageBytes;
             const uint8_t* xsrc = P.xpack + ((size_t)rt * P.k_blocks + kb0) * x_stage_bytes;
+            const uint64_t wpol = l2_policy(L.l2_w);
             auto load_w = [&](int it) {
                 const int s = it % S;
                 mbar_arrive_expect_tx(&full_w[s], kWStageBytes);
-                tma_bulk_g2s(stage_base + (size_t)s * stage_bytes, src + (size_t)it * kWStageBytes, kWStageBytes,
-                             &full_w[s]);
+                tma_bulk_g2s_hint(stage_base + (size_t)s * stage_bytes, src + (size_t)it * kWStageBytes, kWStageBytes,
+                                  &full_w[s], L.l2_w, wpol);
             };
             auto load_x = [&](int it) {
                 const int s = it % S;
@@ -313,19 +314,78 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         const int npad = P.n_tiles * kTileN;
         const int rpad = P.n_row_tiles * P.row_tile;
         float* wsp = P.ws + ((size_t)split * rpad + row0) * npad + n;
+        const bool do_am = direct && P.am_val != nullptr;
+        float* am_s_val = reinterpret_cast<float*>(stage_base);            // [4][256] pipeline smem is idle now
+        int* am_s_idx = reinterpret_cast<int*>(stage_base + 4 * 256 * 4);
         for (int c0 = half * 16; c0 < N; c0 += 32) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);
             if (direct) {
                 if (n < P.n_out) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < rows_here) P.out[(size_t)(row0 + c0 + j) * P.ldo + n] = epi_scalar(P, v[j], n);
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] = epi_scalar(P, v[j], n);
+                        if (c0 + j < rows_here) P.out[(size_t)(row0 + c0 + j) * P.ldo + n] = v[j];
+                    }
+                }
+                if (do_am) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float bv = n < P.n_out ? v[j] : -INFINITY;
+                        int bi = n;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                        }
+                        if (lane == 0) { am_s_val[q * 256 + c0 + j] = bv; am_s_idx[q * 256 + c0 + j] = bi; }
+                    }
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (c0 + j < rows_here) wsp[(size_t)(c0 + j) * npad] = v[j];
+            }
+        }
+        if (do_am) {
+            // tile candidates -> global; the last CTA of the problem reduces them per row (first maximum wins,
+            // like tf.argmax) and emits the prediction / the word fed to the next step
+            named_bar_sync(1, kLinProducers);
+            const int tile_id = rt * P.n_tiles + n_tile;
+            if (pt < N) {
+                float bv = am_s_val[pt];
+                int bi = am_s_idx[pt];
+#pragma unroll
+                for (int qq = 1; qq < 4; ++qq) {
+                    const float ov = am_s_val[qq * 256 + pt];
+                    const int oi = am_s_idx[qq * 256 + pt];
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                P.am_val[(size_t)tile_id * N + pt] = bv;
+                P.am_idx[(size_t)tile_id * N + pt] = bi;
+            }
+            __threadfence();
+            named_bar_sync(1, kLinProducers);
+            unsigned* flag = reinterpret_cast<unsigned*>(stage_base + 8192);
+            if (pt == 0) *flag = atomicAdd(P.am_ctr, 1u) == (unsigned)(P.cta_count - 1) ? 1u : 0u;
+            named_bar_sync(1, kLinProducers);
+            if (*flag) {
+                __threadfence();
+                for (int b = pt; b < P.rows; b += kLinProducers) {
+                    const int rt2 = b / N, c = b - rt2 * N;
+                    float bv = -INFINITY;
+                    int bi = 0x7fffffff;
+                    for (int tl = 0; tl < P.n_tiles; ++tl) {
+                        const float ov = __ldcg(P.am_val + (size_t)(rt2 * P.n_tiles + tl) * N + c);
+                        const int oi = __ldcg(P.am_idx + (size_t)(rt2 * P.n_tiles + tl) * N + c);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (P.am_tokens) P.am_tokens[(size_t)b * P.am_tokens_ld + P.am_step] = bi;
+                    if (P.am_next_word)
+                        P.am_next_word[b] = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi;
+                }
+                if (pt == 0) *P.am_ctr = 0u;
             }
         }
         tc_fence_before();

@@ -57,6 +57,17 @@ struct LinProblem {
     float* c_out;
     float* h_out;
     int H;
+    // optional fused greedy argmax over the outputs (decode fc_2 -> prediction, model.py:289):
+    // per-tile candidates, then the last CTA of the problem picks the word of every row
+    float* am_val;         // [n_row_tiles * n_tiles * row_tile]
+    int32_t* am_idx;
+    unsigned* am_ctr;      // zero between launches
+    int32_t* am_tokens;    // [rows, am_tokens_ld] or null
+    int am_tokens_ld;
+    int am_step;
+    int32_t* am_next_word; // [rows] or null
+    const int32_t* am_forced;  // teacher-forced next words [rows, am_forced_ld] or null
+    int am_forced_ld;
     int cta_begin;         // first CTA of this problem in the grouped grid
     int cta_count;
 };
@@ -66,6 +77,7 @@ struct LinLaunch {
     int nprob;
     int layout_mode;  // 0 = no-swizzle (interleaved 8x16B core matrices), 1 = 128B swizzle
     int stages;
+    int l2_w;         // L2 eviction policy of the weight stream (see l2_policy)
     int x_mode;       // 0 = producer warps convert X per stage; 1 = cooperative pre-pack + TMA (grid <= #SMs)
 };
 
