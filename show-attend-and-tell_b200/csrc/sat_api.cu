@@ -1,7 +1,6 @@
 // sat_api.cu — the C ABI of libsat_b200.so (include/sat_b200.h): handle, weight
 // ingestion (TF variable names/layouts, base_model.py:242-278), workspace, and the
 // kernel sequences of prepare / decode step / decode loop / beam search.
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -113,9 +112,8 @@ struct sat_handle {
     // contexts state
     const float* prep_ctx = nullptr;
     int prep_ni = 0;
-    const float* map_ctx = nullptr;
-    int map_ni = 0;
-    CUtensorMap ctx_map;
+    float* att_part = nullptr;
+    size_t att_part_floats = 0;
 
     std::vector<GraphEntry> graphs;
 
@@ -142,22 +140,6 @@ struct ProfScope {
         if (on) { cudaEventRecord(b, st); h->prof.push_back({tag, a, b}); }
     }
 };
-
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-static PFN_tmapEncodeTiled g_encode = nullptr;
-
-static int get_encoder() {
-    if (g_encode) return SAT_OK;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SAT_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-    g_encode = (PFN_tmapEncodeTiled)fn;
-    return SAT_OK;
-}
 
 template <typename T>
 static int dmalloc(T** p, size_t n) {
@@ -209,7 +191,7 @@ extern "C" void sat_destroy(sat_handle* h) {
     void* bufs[] = {h->att_vec.dev, h->embedding, h->T1, h->q, h->e, h->alpha, h->z, h->mean, h->tmp_a, h->tmp_b,
                     h->t_dec, h->logits, h->st_c[0], h->st_c[1], h->st_h[0], h->st_h[1], h->word, h->zero_word,
                     h->rowcnt, h->topk_idx, h->part_n, h->comp_n, h->comp_sent, h->sent[0], h->sent[1], h->topk_p,
-                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc};
+                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part};
     for (void* b : bufs) cudaFree(b);
     delete h;
 }
@@ -243,7 +225,6 @@ extern "C" int sat_create(const sat_dims* dims, sat_handle** out) {
         h->num_sms = prop.multiProcessorCount;
         CK(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->dev));
         CK(lin_init_attrs());
-        RET(get_encoder());
         const int D = d.dim_ctx, E = d.dim_embedding, H = d.num_lstm_units, A = d.dim_attend_layer,
                   Dd = d.dim_decode_layer, I = d.dim_initalize_layer, V = d.vocabulary_size, L = d.num_ctx;
         if (d.num_initalize_layers == 2) {
@@ -297,6 +278,7 @@ extern "C" int sat_create(const sat_dims* dims, sat_handle** out) {
         RET(dmalloc(&h->zero_word, R));
         CK(cudaMemset(h->zero_word, 0, R * sizeof(int32_t)));
         RET(dmalloc(&h->rowcnt, R));
+        CK(cudaMemset(h->rowcnt, 0, R * sizeof(unsigned)));
         const int T = d.max_caption_length > 0 ? d.max_caption_length : 1;
         if (d.max_beam >= 1) {
             const size_t K = (size_t)d.max_beam + 1;
@@ -581,22 +563,6 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
 }
 
 // --------------------------------------------------------------- contexts
-static int ensure_ctx_map(sat_handle* h, const float* ctx, int n_img) {
-    if (h->map_ctx == ctx && h->map_ni == n_img) return SAT_OK;
-    const int L = h->d.num_ctx, D = h->d.dim_ctx;
-    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)n_img * L};
-    cuuint64_t gstr[1] = {(cuuint64_t)D * sizeof(float)};
-    cuuint32_t box[2] = {32u, (cuuint32_t)L};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = g_encode(&h->ctx_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ctx, gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(SAT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    h->map_ctx = ctx;
-    h->map_ni = n_img;
-    return SAT_OK;
-}
-
 // attend fc_1a over every location (model.py:417-420): T1 = tanh(ctx2d * W1a + b1a)
 static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStream_t st) {
     if (h->d.num_attend_layers != 2) return SAT_OK;
@@ -630,7 +596,6 @@ static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0,
 
 static int prepare_impl(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st) {
     if (n_img < 1 || n_img > h->max_rows) return fail(SAT_ERR_INVALID, "n_img %d outside [1, %d]", n_img, h->max_rows);
-    RET(ensure_ctx_map(h, ctx, n_img));
     if (h->opt_hoist) {
         RET(project_contexts(h, ctx, n_img, st));
         h->prep_ctx = ctx;
@@ -676,7 +641,6 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
                           cudaStream_t st, bool q_ready = false) {
     const sat_dims& d = h->d;
     const int rows = n_img * G;
-    RET(ensure_ctx_map(h, ctx, n_img));
     AttParams ap;
     memset(&ap, 0, sizeof(ap));
     LinProblem P;
@@ -704,9 +668,9 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         ap.eadd = h->q;
     }
     ap.vec = h->att_vec.dev;
+    ap.ctx = ctx;
     ap.e = h->e;
     ap.rowcnt = h->rowcnt;
-    ap.target = (unsigned)d.num_ctx;
     ap.alpha = alpha ? alpha : h->alpha;
     ap.z = z;
     ap.NI = n_img;
@@ -715,11 +679,22 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     ap.D = d.dim_ctx;
     ap.l2_t = h->opt_l2_t;
     ap.l2_ctx = h->opt_l2_ctx;
-    if (!att_plan(ap, h->smem_optin)) return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
-    CK(cudaMemsetAsync(h->rowcnt, 0, (size_t)n_img * sizeof(unsigned), st));
+    if (!att_plan(ap, h->smem_optin, h->num_sms))
+        return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
+    const size_t pneed = att_part_floats(ap);
+    if (pneed > h->att_part_floats) {
+        if (stream_capturing(st)) return fail(SAT_ERR_STATE, "attention scratch growth during graph capture");
+        CK(cudaDeviceSynchronize());
+        cudaFree(h->att_part);
+        h->att_part = nullptr;
+        h->att_part_floats = 0;
+        RET(dmalloc(&h->att_part, pneed));
+        h->att_part_floats = pneed;
+    }
+    ap.part = h->att_part;
     {
         ProfScope ps(h, kTagAtt, st);
-        CK(att_launch(h->ctx_map, ap, h->num_sms, st, h->opt_coop != 0));
+        CK(att_launch(ap, st));
     }
     h->launches += 1;
     return SAT_OK;

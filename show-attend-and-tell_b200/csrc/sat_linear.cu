@@ -372,18 +372,42 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             named_bar_sync(1, kLinProducers);
             if (*flag) {
                 __threadfence();
-                for (int b = pt; b < P.rows; b += kLinProducers) {
-                    const int rt2 = b / N, c = b - rt2 * N;
+                // 4 lanes per row, each scanning every 4th tile with the loads batched (the candidates sit in
+                // L2: a dependent-load loop would cost one L2 round trip per tile)
+                const int part = pt & 3;
+                for (int b0 = 0; b0 < P.rows; b0 += kLinProducers / 4) {
+                    const int b = b0 + (pt >> 2);
+                    const bool live = b < P.rows;
+                    const int rt2 = live ? b / N : 0, c = live ? b - rt2 * N : 0;
+                    const float* pv = P.am_val + (size_t)rt2 * P.n_tiles * N + c;
+                    const int32_t* pi2 = P.am_idx + (size_t)rt2 * P.n_tiles * N + c;
                     float bv = -INFINITY;
                     int bi = 0x7fffffff;
-                    for (int tl = 0; tl < P.n_tiles; ++tl) {
-                        const float ov = __ldcg(P.am_val + (size_t)(rt2 * P.n_tiles + tl) * N + c);
-                        const int oi = __ldcg(P.am_idx + (size_t)(rt2 * P.n_tiles + tl) * N + c);
+                    for (int tl = part; tl < P.n_tiles; tl += 32) {
+                        float ov[8];
+                        int oi[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int tt = tl + 4 * u;
+                            const bool ok = live && tt < P.n_tiles;
+                            ov[u] = ok ? __ldcg(pv + (size_t)tt * N) : -INFINITY;
+                            oi[u] = ok ? __ldcg(pi2 + (size_t)tt * N) : 0x7fffffff;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (ov[u] > bv || (ov[u] == bv && oi[u] < bi)) { bv = ov[u]; bi = oi[u]; }
+                    }
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                     }
-                    if (P.am_tokens) P.am_tokens[(size_t)b * P.am_tokens_ld + P.am_step] = bi;
-                    if (P.am_next_word)
-                        P.am_next_word[b] = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi;
+                    if (live && part == 0) {
+                        if (P.am_tokens) P.am_tokens[(size_t)b * P.am_tokens_ld + P.am_step] = bi;
+                        if (P.am_next_word)
+                            P.am_next_word[b] = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi;
+                    }
                 }
                 if (pt == 0) *P.am_ctr = 0u;
             }
