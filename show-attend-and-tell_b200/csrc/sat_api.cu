@@ -114,6 +114,8 @@ struct sat_handle {
     int prep_ni = 0;
     float* att_part = nullptr;
     size_t att_part_floats = 0;
+    unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
+    int opt_trace = 0;
 
     std::vector<GraphEntry> graphs;
 
@@ -191,7 +193,7 @@ extern "C" void sat_destroy(sat_handle* h) {
     void* bufs[] = {h->att_vec.dev, h->embedding, h->T1, h->q, h->e, h->alpha, h->z, h->mean, h->tmp_a, h->tmp_b,
                     h->t_dec, h->logits, h->st_c[0], h->st_c[1], h->st_h[0], h->st_h[1], h->word, h->zero_word,
                     h->rowcnt, h->topk_idx, h->part_n, h->comp_n, h->comp_sent, h->sent[0], h->sent[1], h->topk_p,
-                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part};
+                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part, h->trace};
     for (void* b : bufs) cudaFree(b);
     delete h;
 }
@@ -316,7 +318,12 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "hoist") { h->opt_hoist = (int)value; h->prep_ctx = nullptr; }
     else if (k == "coop") h->opt_coop = (int)value;
     else if (k == "xpack") h->opt_xpack = (int)value;
-    else if (k == "l2_w") h->opt_l2_w = (int)value;
+    else if (k == "trace") {
+        h->opt_trace = (int)value;
+        if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
+        if (h->trace) CK(cudaMemset(h->trace, 0, 1024 * 16 * sizeof(unsigned long long)));
+        return SAT_OK;
+    } else if (k == "l2_w") h->opt_l2_w = (int)value;
     else if (k == "l2_t") h->opt_l2_t = (int)value;
     else if (k == "l2_ctx") h->opt_l2_ctx = (int)value;
     else if (k == "profile") {
@@ -352,6 +359,7 @@ extern "C" int sat_get_info(sat_handle* h, const char* key, int64_t* value) {
         for (auto& r : h->prof) if (r.tag == tag) { float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b); ns += ms * 1e6; ++n; }
         *value = want_n ? n : (int64_t)ns;
     }
+    else if (k == "trace_ptr") *value = (int64_t)(uintptr_t)h->trace;
     else if (k == "weight_bytes") {
         size_t b = 0;
         for (Layer* ly : h->layers) b += (size_t)ly->n_tiles * ly->k_blocks * kWStageBytes;
@@ -552,6 +560,7 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.layout_mode = h->opt_layout;
     L.stages = lin_pick_stages(max_rt);
     L.l2_w = h->opt_l2_w;
+    L.dbg = (h->opt_trace == 1 && begin <= 1024) ? h->trace : nullptr;
     L.x_mode = (h->opt_xpack && begin <= h->num_sms) ? 1 : 0;  // the pre-pass needs every CTA co-resident
     if (L.stages < 1) return fail(SAT_ERR_UNSUPPORTED, "row tile %d does not fit in shared memory", max_rt);
     {
@@ -692,6 +701,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         h->att_part_floats = pneed;
     }
     ap.part = h->att_part;
+    ap.dbg = h->opt_trace == 2 ? h->trace : nullptr;
     {
         ProfScope ps(h, kTagAtt, st);
         CK(att_launch(ap, st));

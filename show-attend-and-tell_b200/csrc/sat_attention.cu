@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
     const int r_begin = att_rbegin(NR, P, c), r_end = att_rbegin(NR, P, c + 1);
 
     if (threadIdx.x == 0) {
+        trace_stamp(p.dbg, 0);
         for (int s = 0; s < p.nslots; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kAttConsumerWarps);
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
     const int nper = (D + NT - 1) / NT;   // context features per thread (d = ct + NT*k)
     int idx = 0;
     bool first_seg = true;
+    if (ct == 0) trace_stamp(p.dbg, 1);
 
     for (int seg0 = r_begin; seg0 < r_end;) {
         const int img = seg0 / L;
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
             const int n = min(p.rch, seg1 - r);
             const int s = idx % p.nslots;
             mbar_wait(&full[s], (uint32_t)(idx / p.nslots) & 1u);
+            if (ct == 0 && r == r_begin) trace_stamp(p.dbg, 2);
             const float* buf = reinterpret_cast<const float*>(slots + (size_t)s * p.slot_bytes);
             for (int row = warp; row < n; row += kAttConsumerWarps) {
                 float acc[G];
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
             if (lane == 0) mbar_arrive(&empty[s]);
         }
         named_bar_sync(1, NT);
+        if (ct == 0 && seg0 == r_begin) trace_stamp(p.dbg, 3);
 
         // ---- segment-local softmax statistics: m = max e, w = exp(e - m), s = sum w
         for (int g = warp; g < G; g += kAttConsumerWarps) {
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
             const int n = min(p.cch, seg1 - r);
             const int s = idx % p.nslots;
             mbar_wait(&full[s], (uint32_t)(idx / p.nslots) & 1u);
+            if (ct == 0 && r == r_begin) trace_stamp(p.dbg, 4);
             const float* buf = reinterpret_cast<const float*>(slots + (size_t)s * p.slot_bytes);
             for (int row = 0; row < n; ++row) {
                 const int ll = r + row - seg0;
@@ -237,6 +242,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
+        if (ct == 0 && seg0 == r_begin) trace_stamp(p.dbg, 5);
         // ---- publish the partial, last CTA of the image merges
         const int slot_id = img - r_begin / L;                // ordinal of this segment within the CTA
         float* part = p.part + ((size_t)c * p.segmax + slot_id) * G * (D + 2);
@@ -261,6 +267,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         unsigned* flag = reinterpret_cast<unsigned*>(misc + 2 * G);
         if (ct == 0) *flag = atomicAdd(p.rowcnt + img, 1u) == (unsigned)(c_hi - c_lo) ? 1u : 0u;
         named_bar_sync(1, NT);
+        if (ct == 0 && seg0 == r_begin) trace_stamp(p.dbg, 6);
         if (*flag) {
             __threadfence();
             if (ct == 0) p.rowcnt[img] = 0u;                  // ready for the next launch
@@ -299,6 +306,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         }
         seg0 = seg1;
     }
+    if (ct == 0) trace_stamp(p.dbg, 7);
 }
 
 size_t att_smem_bytes(const AttParams& p) {

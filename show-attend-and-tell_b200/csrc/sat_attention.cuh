@@ -22,6 +22,7 @@ struct AttParams {
     int nslots;
     int grid, segmax;
     int l2_t, l2_ctx;    // L2 eviction policies of the two streams (see l2_policy)
+    unsigned long long* dbg;  // optional [grid][16] timeline stamps
 };
 
 bool att_plan(AttParams& p, int smem_optin, int num_sms);

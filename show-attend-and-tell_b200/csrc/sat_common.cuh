@@ -187,6 +187,16 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// in-kernel timeline stamps (debug option "trace"): ns since an arbitrary origin, one row of 16 per CTA
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_stamp(unsigned long long* dbg, int slot) {
+    if (dbg) dbg[(size_t)blockIdx.x * 16 + slot] = globaltimer_ns();
+}
+
 // --------------------------------------------------------------- misc math
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
+        trace_stamp(L.dbg, 0);
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_w[s], 1);
             mbar_init(&full_x[s], xtma ? 1 : kLinProducers);
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                     }
                 }
                 fence_proxy_async_global();
+                trace_stamp(L.dbg, 3);
                 for (int it = 0; it < pre; ++it) load_x(it);
             }
             for (int it = xtma ? pre : 0; it < nkb; ++it) {
@@ -206,7 +208,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(&full_w[s], ph);
+                if (it == 0) trace_stamp(L.dbg, 4);
                 mbar_wait(&full_x[s], ph);
+                if (it == 0) trace_stamp(L.dbg, 5);
                 tc_fence_after();
                 const uint32_t wb = smem_u32(stage_base + (size_t)s * stage_bytes);
                 const uint32_t xb = wb + kWStageBytes;
@@ -223,12 +227,14 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
             }
             umma_commit(tmem_full);
+            trace_stamp(L.dbg, 6);
         }
     } else {
         // ===================== X producers (warps 2..9), then epilogue =====================
         // The fp32 sources of X are L2 resident; their latency is hidden by keeping the loads of the
         // NEXT chunk in flight while the current one is converted and stored.
         const int pt = threadIdx.x - 64;  // 0..255
+        if (pt == 0) trace_stamp(L.dbg, 1);
         if (xtma) {
             // ---- cooperative pre-pass: this problem's CTAs convert X (fp32 -> bf16 hi/lo UMMA tiles) ONCE
             // into global scratch; consecutive threads take consecutive 8-element groups of a row (coalesced).
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             fence_proxy_async_global();
             named_bar_sync(1, kLinProducers);
             if (pt == 0) {  // grid barrier arrive: the last CTA opens the next generation
+                trace_stamp(L.dbg, 2);
                 const unsigned old = atomicAdd(P.xbar, 1u);
                 if (old == (unsigned)(P.cta_count - 1)) {
                     P.xbar[0] = 0u;
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         const int rows_here = min(N, P.rows - row0);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        if (pt == 0) trace_stamp(L.dbg, 7);
         const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
         const bool direct = (P.splits == 1) && (P.epi != kEpiLstm);
         const int npad = P.n_tiles * kTileN;
@@ -423,6 +431,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             __threadfence();
             named_bar_sync(1, kLinProducers);
             if (pt == 0) {
+                trace_stamp(L.dbg, 8);
                 atomicAdd(ctr, 1u);
                 const long long t0 = clock64();
                 while (ld_acquire_gpu(ctr) < (unsigned)P.splits) {
@@ -433,6 +442,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 }
             }
             named_bar_sync(1, kLinProducers);
+            if (pt == 0) trace_stamp(L.dbg, 9);
             const float* ws0 = P.ws + (size_t)row0 * npad + (size_t)n_tile * kTileN;
             const size_t sstride = (size_t)rpad * npad;
             const int cnt = rows_here * 32;  // float4 groups (row b, 4 consecutive outputs) in the tile
@@ -479,6 +489,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     }
 
     __syncthreads();
+    if (threadIdx.x == 0) trace_stamp(L.dbg, 10);
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();

@@ -78,6 +78,7 @@ struct LinLaunch {
     int layout_mode;  // 0 = no-swizzle (interleaved 8x16B core matrices), 1 = 128B swizzle
     int stages;
     int l2_w;         // L2 eviction policy of the weight stream (see l2_policy)
+    unsigned long long* dbg;  // optional [grid][16] timeline stamps
     int x_mode;       // 0 = producer warps convert X per stage; 1 = cooperative pre-pack + TMA (grid <= #SMs)
 };
 

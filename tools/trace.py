@@ -1,0 +1,77 @@
+"""In-kernel timelines (globaltimer stamps) of the attention and dense kernels at config 2.
+    python tools/trace.py > gpurun_out/trace.log
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sat_b200
+
+B, L, D, H, V, T = 64, 196, 512, 1024, 10000, 20
+cfg = sat_b200.Config(batch_size=B, beam_size=1, num_ctx=L, dim_ctx=D, num_lstm_units=H, vocabulary_size=V,
+                      max_caption_length=T)
+m = sat_b200.CaptionGenerator(cfg)
+g = torch.Generator().manual_seed(1)
+m.set_weights({n: torch.rand(*s, generator=g) * 0.16 - 0.08 for n, s in sat_b200.weight_shapes(cfg).items()})
+ctx = torch.relu(torch.randn(B, L, D, generator=g)).cuda()
+hstate = (torch.rand(B, H, generator=g) - 0.5).cuda()
+cstate = (torch.rand(B, H, generator=g) - 0.5).cuda()
+lw = torch.zeros(B, dtype=torch.int32).cuda()
+flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+m.prepare(ctx, want_state=False)
+p = lambda t: C.c_void_p(t.data_ptr())
+alpha = torch.empty(B, L, device="cuda"); z = torch.empty(B, D, device="cuda")
+c2 = torch.empty_like(cstate); h2 = torch.empty_like(hstate); logits = torch.empty(B, V, device="cuda")
+
+
+def read_trace(n):
+    import cuda.bindings.runtime as cr
+    torch.cuda.synchronize()
+    host = np.zeros(1024 * 16, np.int64)
+    err, = cr.cudaMemcpy(host.ctypes.data, m.info("trace_ptr"), host.nbytes, cr.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0, err
+    return host.reshape(1024, 16)[:n]
+
+
+def show(name, tr, labels):
+    t0 = tr[:, 0].min()
+    print("== %s  (us after the first CTA started; mean / max over %d CTAs)" % (name, len(tr)))
+    for i, lab in enumerate(labels):
+        col = tr[:, i]
+        ok = col > 0
+        if ok.any():
+            v = (col[ok] - t0) / 1e3
+            print("  %-34s mean %7.2f  min %7.2f  max %7.2f   (n=%d)" % (lab, v.mean(), v.min(), v.max(), ok.sum()))
+
+
+def run(kind, fn, grid, labels, trace_mode, cold):
+    for rep in range(3):
+        if cold:
+            flush.zero_()
+        m.set_option("trace", trace_mode)
+        torch.cuda.synchronize()
+        fn()
+        torch.cuda.synchronize()
+    show(kind + (" cold-L2" if cold else " warm-L2"), read_trace(grid), labels)
+    m.set_option("trace", 0)
+
+
+att_labels = ["start", "consumers ready", "first T1 chunk landed", "pass-1 done (seg 0)", "first ctx chunk landed",
+              "pass-2 done (seg 0)", "published (seg 0)", "end"]
+lin_labels = ["start", "producers start", "pack done -> arrive", "TMA thread: barrier passed", "MMA: first W stage",
+              "MMA: first X stage", "MMA: all issued", "epilogue: accumulator ready", "partials written",
+              "rendezvous passed", "end"]
+
+with torch.cuda.stream(m.stream):
+    for cold in (True, False):
+        run("attention", lambda: m.lib.sat_attention_fwd(m._h, p(ctx), p(hstate), p(alpha), p(z), B, 1, m._st()), 148,
+            att_labels, 2, cold)
+        # note: sat_attention_fwd also launches the state-branch dense layer first (traced only in mode 1)
+        run("lstm", lambda: m.lib.sat_lstm_fwd(m._h, p(z), p(lw), p(cstate), p(hstate), p(c2), p(h2), B, m._st()), 128,
+            lin_labels, 1, cold)
+        run("decode (fc_1 then fc_2; last launch = fc_2, 79 CTAs)",
+            lambda: m.lib.sat_vocab_gemm(m._h, p(h2), p(z), p(lw), p(logits), B, m._st()), 79, lin_labels, 1, cold)
