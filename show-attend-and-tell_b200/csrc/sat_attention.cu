@@ -210,37 +210,87 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         }
         named_bar_sync(1, NT);
 
-        // ---- pass 2: un-normalised partial context over the SAME rows (thread per feature)
+        // ---- pass 2: un-normalised partial context over the SAME rows.  Thread ct owns the features
+        // d = 2*ct + 512*k (+1) when D % 512 == 0 (float2 per 512 features), else d = ct + 256*k.
         float zacc[G][kAttMaxDPerThread];
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int k = 0; k < kAttMaxDPerThread; ++k) zacc[g][k] = 0.f;
+        const bool vec2 = (D % 512) == 0;
+        const int nk2 = D / 512;
         for (int r = seg0; r < seg1; r += p.cch, ++idx) {
             const int n = min(p.cch, seg1 - r);
             const int s = idx % p.nslots;
             mbar_wait(&full[s], (uint32_t)(idx / p.nslots) & 1u);
             if (ct == 0 && r == r_begin) trace_stamp(p.dbg, 4);
             const float* buf = reinterpret_cast<const float*>(slots + (size_t)s * p.slot_bytes);
-            for (int row = 0; row < n; ++row) {
-                const int ll = r + row - seg0;
-                float wv[G];
+            if (vec2) {
+                const float2* b2 = reinterpret_cast<const float2*>(buf) + ct;
+                const int rowstride = D / 2;   // float2 per row
+                int row = 0;
+                for (; row + 4 <= n; row += 4) {
+                    const int ll = r + row - seg0;
+                    float wv[G][4];
 #pragma unroll
-                for (int g = 0; g < G; ++g) wv[g] = w_s[g * Lp + ll];
-                const float* xrow = buf + (size_t)row * D;
+                    for (int g = 0; g < G; ++g)
 #pragma unroll
-                for (int k = 0; k < kAttMaxDPerThread; ++k) {
-                    if (k < nper) {
-                        const int d = ct + NT * k;
-                        const float x = d < D ? xrow[d] : 0.f;
+                        for (int j = 0; j < 4; ++j) wv[g][j] = w_s[g * Lp + ll + j];
 #pragma unroll
-                        for (int g = 0; g < G; ++g) zacc[g][k] = fmaf(wv[g], x, zacc[g][k]);
+                    for (int k = 0; k < kAttMaxDPerThread / 2; ++k) {
+                        if (k < nk2) {
+                            float2 x[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) x[j] = b2[(size_t)(row + j) * rowstride + 256 * k];
+#pragma unroll
+                            for (int g = 0; g < G; ++g)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    zacc[g][2 * k] = fmaf(wv[g][j], x[j].x, zacc[g][2 * k]);
+                                    zacc[g][2 * k + 1] = fmaf(wv[g][j], x[j].y, zacc[g][2 * k + 1]);
+                                }
+                        }
+                    }
+                }
+                for (; row < n; ++row) {
+                    const int ll = r + row - seg0;
+#pragma unroll
+                    for (int k = 0; k < kAttMaxDPerThread / 2; ++k) {
+                        if (k < nk2) {
+                            const float2 x = b2[(size_t)row * rowstride + 256 * k];
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                const float wv = w_s[g * Lp + ll];
+                                zacc[g][2 * k] = fmaf(wv, x.x, zacc[g][2 * k]);
+                                zacc[g][2 * k + 1] = fmaf(wv, x.y, zacc[g][2 * k + 1]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int row = 0; row < n; ++row) {
+                    const int ll = r + row - seg0;
+                    float wv[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) wv[g] = w_s[g * Lp + ll];
+                    const float* xrow = buf + (size_t)row * D;
+#pragma unroll
+                    for (int k = 0; k < kAttMaxDPerThread; ++k) {
+                        if (k < nper) {
+                            const int d = ct + NT * k;
+                            const float x = d < D ? xrow[d] : 0.f;
+#pragma unroll
+                            for (int g = 0; g < G; ++g) zacc[g][k] = fmaf(wv[g], x, zacc[g][k]);
+                        }
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
+        // feature index of accumulator k of this thread
+        auto feat = [&](int k) { return vec2 ? 2 * ct + 512 * (k >> 1) + (k & 1) : ct + NT * k; };
+        const int nacc = vec2 ? 2 * nk2 : nper;
 
         if (ct == 0 && seg0 == r_begin) trace_stamp(p.dbg, 5);
         // ---- publish the partial, last CTA of the image merges
@@ -250,8 +300,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         for (int g = 0; g < G; ++g) {
 #pragma unroll
             for (int k = 0; k < kAttMaxDPerThread; ++k) {
-                const int d = ct + NT * k;
-                if (k < nper && d < D) part[(size_t)g * (D + 2) + d] = zacc[g][k];
+                const int d = feat(k);
+                if (k < nacc && d < D) part[(size_t)g * (D + 2) + d] = zacc[g][k];
             }
             if (ct == 0) { part[(size_t)g * (D + 2) + D] = misc[g]; part[(size_t)g * (D + 2) + D + 1] = misc[G + g]; }
         }
@@ -271,38 +321,64 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         if (*flag) {
             __threadfence();
             if (ct == 0) p.rowcnt[img] = 0u;                  // ready for the next launch
+            // statistics of every contributor -> smem (one L2 round trip), then scales
+            const int nc = c_hi - c_lo + 1;
+            float* st_m = q_s;                                // q_s / vec_s are free to reuse only in the RV path;
+            float* st_sc = w_s;                               // w_s of this segment is consumed: reuse it for scales
+            (void)st_m;
+            for (int i = ct; i < nc * G; i += NT) {
+                const int cc = c_lo + i / G, g = i - (i / G) * G;
+                const int sid = img - att_rbegin(NR, P, cc) / L;
+                const float* pp = p.part + (((size_t)cc * p.segmax + sid) * G + g) * (D + 2);
+                st_sc[2 * i] = __ldcg(pp + D);
+                st_sc[2 * i + 1] = __ldcg(pp + D + 1);
+            }
+            named_bar_sync(1, NT);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                // merge statistics (every thread redundantly; <= a handful of partials)
                 float M = -INFINITY;
-                for (int cc = c_lo; cc <= c_hi; ++cc) {
-                    const int sid = img - att_rbegin(NR, P, cc) / L;
-                    M = fmaxf(M, __ldcg(p.part + (((size_t)cc * p.segmax + sid) * G + g) * (D + 2) + D));
-                }
+                for (int j = 0; j < nc; ++j) M = fmaxf(M, st_sc[2 * (j * G + g)]);
                 float S = 0.f;
+                for (int j = 0; j < nc; ++j) S = fmaf(st_sc[2 * (j * G + g) + 1], expf(st_sc[2 * (j * G + g)] - M), S);
+                const float inv = 1.0f / S;
                 float zz[kAttMaxDPerThread];
 #pragma unroll
                 for (int k = 0; k < kAttMaxDPerThread; ++k) zz[k] = 0.f;
-                for (int cc = c_lo; cc <= c_hi; ++cc) {
-                    const int sid = img - att_rbegin(NR, P, cc) / L;
-                    const float* pp = p.part + (((size_t)cc * p.segmax + sid) * G + g) * (D + 2);
-                    const float sc = expf(__ldcg(pp + D) - M);
-                    S = fmaf(__ldcg(pp + D + 1), sc, S);
+                for (int j0 = 0; j0 < nc; j0 += 4) {           // partials of up to 4 contributors in flight
+                    float v[4][kAttMaxDPerThread];
 #pragma unroll
-                    for (int k = 0; k < kAttMaxDPerThread; ++k) {
-                        const int d = ct + NT * k;
-                        if (k < nper && d < D) zz[k] = fmaf(__ldcg(pp + d), sc, zz[k]);
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j0 + jj;
+                        if (j < nc) {
+                            const int cc = c_lo + j;
+                            const int sid = img - att_rbegin(NR, P, cc) / L;
+                            const float* pp = p.part + (((size_t)cc * p.segmax + sid) * G + g) * (D + 2);
+#pragma unroll
+                            for (int k = 0; k < kAttMaxDPerThread; ++k) {
+                                const int d = feat(k);
+                                v[jj][k] = (k < nacc && d < D) ? __ldcg(pp + d) : 0.f;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j0 + jj;
+                        if (j < nc) {
+                            const float sc = expf(st_sc[2 * (j * G + g)] - M);
+#pragma unroll
+                            for (int k = 0; k < kAttMaxDPerThread; ++k) zz[k] = fmaf(v[jj][k], sc, zz[k]);
+                        }
                     }
                 }
-                const float inv = 1.0f / S;
 #pragma unroll
                 for (int k = 0; k < kAttMaxDPerThread; ++k) {
-                    const int d = ct + NT * k;
-                    if (k < nper && d < D) p.z[((size_t)img * G + g) * D + d] = zz[k] * inv;
+                    const int d = feat(k);
+                    if (k < nacc && d < D) p.z[((size_t)img * G + g) * D + d] = zz[k] * inv;
                 }
                 const float* er = p.e + ((size_t)img * G + g) * L;
                 for (int l = ct; l < L; l += NT) p.alpha[((size_t)img * G + g) * L + l] = expf(__ldcg(er + l) - M) * inv;
             }
+            named_bar_sync(1, NT);                            // st_sc (= w_s) is rewritten by the next segment
         }
         seg0 = seg1;
     }
