@@ -114,6 +114,14 @@ struct sat_handle {
     int prep_ni = 0;
     float* att_part = nullptr;
     size_t att_part_floats = 0;
+    // packed activations (bf16 hi/lo UMMA tiles written by the producer kernels)
+    bool pa_ok = false;            // every operand width is a multiple of 64
+    int opt_pa = 1;
+    uint8_t* pa_h[2] = {nullptr, nullptr};
+    uint8_t *pa_z = nullptr, *pa_emb = nullptr, *pa_t = nullptr;
+    // valid for the duration of one step_impl call
+    bool pa_on = false;
+    uint8_t *pa_cur_h_in = nullptr, *pa_cur_h_out = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
     int opt_trace = 0;
 
@@ -193,7 +201,7 @@ extern "C" void sat_destroy(sat_handle* h) {
     void* bufs[] = {h->att_vec.dev, h->embedding, h->T1, h->q, h->e, h->alpha, h->z, h->mean, h->tmp_a, h->tmp_b,
                     h->t_dec, h->logits, h->st_c[0], h->st_c[1], h->st_h[0], h->st_h[1], h->word, h->zero_word,
                     h->rowcnt, h->topk_idx, h->part_n, h->comp_n, h->comp_sent, h->sent[0], h->sent[1], h->topk_p,
-                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part, h->trace};
+                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part, h->trace, h->pa_h[0], h->pa_h[1], h->pa_z, h->pa_emb, h->pa_t};
     for (void* b : bufs) cudaFree(b);
     delete h;
 }
@@ -281,6 +289,15 @@ extern "C" int sat_create(const sat_dims* dims, sat_handle** out) {
         CK(cudaMemset(h->zero_word, 0, R * sizeof(int32_t)));
         RET(dmalloc(&h->rowcnt, R));
         CK(cudaMemset(h->rowcnt, 0, R * sizeof(unsigned)));
+        h->pa_ok = (D % 64 == 0) && (E % 64 == 0) && (H % 64 == 0) && (d.num_decode_layers == 1 || Dd % 64 == 0);
+        if (h->pa_ok) {
+            const size_t RP = R + 272;   // rows padded to whole row tiles
+            RET(dmalloc(&h->pa_h[0], RP * H * 4));
+            RET(dmalloc(&h->pa_h[1], RP * H * 4));
+            RET(dmalloc(&h->pa_z, RP * D * 4));
+            RET(dmalloc(&h->pa_emb, RP * E * 4));
+            RET(dmalloc(&h->pa_t, RP * Dd * 4));
+        }
         const int T = d.max_caption_length > 0 ? d.max_caption_length : 1;
         if (d.max_beam >= 1) {
             const size_t K = (size_t)d.max_beam + 1;
@@ -318,6 +335,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "hoist") { h->opt_hoist = (int)value; h->prep_ctx = nullptr; }
     else if (k == "coop") h->opt_coop = (int)value;
     else if (k == "xpack") h->opt_xpack = (int)value;
+    else if (k == "pa") h->opt_pa = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -440,14 +458,21 @@ static int require_ready(sat_handle* h) {
 }
 
 // ------------------------------------------------------------ dense planning
-static LinSeg seg(const float* p, int ld, int width, const int32_t* gather = nullptr) {
+static LinSeg seg(const float* p, int ld, int width, const int32_t* gather = nullptr, const uint8_t* pa = nullptr) {
     LinSeg s;
     s.ptr = p;
     s.gather = gather;
     s.ld = ld;
     s.width = width;
     s.row_div = 1;
+    s.pa = pa;
     return s;
+}
+
+static int row_tile_for(int rows) {
+    const int nrt = (rows + 255) / 256;
+    const int per = (rows + nrt - 1) / nrt;
+    return ((per + 15) / 16) * 16;
 }
 
 static bool stream_capturing(cudaStream_t st) {
@@ -561,7 +586,11 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.stages = lin_pick_stages(max_rt);
     L.l2_w = h->opt_l2_w;
     L.dbg = (h->opt_trace == 1 && begin <= 1024) ? h->trace : nullptr;
-    L.x_mode = (h->opt_xpack && begin <= h->num_sms) ? 1 : 0;  // the pre-pass needs every CTA co-resident
+    bool all_pa = true;
+    for (int i = 0; i < n; ++i)
+        for (int sgi = 0; sgi < probs[i].nseg; ++sgi) all_pa = all_pa && probs[i].seg[sgi].pa != nullptr;
+    if (all_pa) L.x_mode = 2;   // operands were packed by their producers: nothing to convert, nothing to wait for
+    else L.x_mode = (h->opt_xpack && begin <= h->num_sms) ? 1 : 0;  // the pre-pass needs every CTA co-resident
     if (L.stages < 1) return fail(SAT_ERR_UNSUPPORTED, "row tile %d does not fit in shared memory", max_rt);
     {
         ProfScope ps(h, h->cur_tag, st);
@@ -583,7 +612,8 @@ static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStre
 }
 
 // initialize (model.py:239-242, 358-393)
-static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st) {
+static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st,
+                          uint8_t* h0_pa = nullptr) {
     const sat_dims& d = h->d;
     h->cur_tag = kTagInit;
     CK(ctx_mean_launch(ctx, h->mean, n_img, d.num_ctx, d.dim_ctx, st));
@@ -592,6 +622,7 @@ static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0,
     if (d.num_initalize_layers == 1) {
         RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, c0, d.num_lstm_units, st, 0, 2));
         RET(plan(h, h->init_b1, P[1], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, h0, d.num_lstm_units, st, 0, 2));
+        P[1].out_pa = h0_pa;
         return launch(h, P, 2, st);
     }
     const int I = d.dim_initalize_layer;
@@ -600,17 +631,19 @@ static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0,
     RET(launch(h, P, 2, st));
     RET(plan(h, h->init_a2, P[0], {seg(h->tmp_a, I, I)}, n_img, kEpiBias, c0, d.num_lstm_units, st, 0, 2));
     RET(plan(h, h->init_b2, P[1], {seg(h->tmp_b, I, I)}, n_img, kEpiBias, h0, d.num_lstm_units, st, 0, 2));
+    P[1].out_pa = h0_pa;
     return launch(h, P, 2, st);
 }
 
-static int prepare_impl(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st) {
+static int prepare_impl(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st,
+                        uint8_t* h0_pa = nullptr) {
     if (n_img < 1 || n_img > h->max_rows) return fail(SAT_ERR_INVALID, "n_img %d outside [1, %d]", n_img, h->max_rows);
     if (h->opt_hoist) {
         RET(project_contexts(h, ctx, n_img, st));
         h->prep_ctx = ctx;
         h->prep_ni = n_img;
     }
-    if (c0 && h0) RET(run_initialize(h, ctx, n_img, c0, h0, st));
+    if (c0 && h0) RET(run_initialize(h, ctx, n_img, c0, h0, st, h0_pa));
     return SAT_OK;
 }
 
@@ -634,16 +667,20 @@ struct StepIO {
     bool want_rows;
     bool q_ready;      // the state branch q for this step was produced by the previous step's grouped launch
     bool make_next_q;  // also compute q of the NEXT step (from this step's output) alongside decode fc_1
+    int pa_slot;       // packed h of this step's input lives in pa_h[pa_slot], the output goes to pa_h[pa_slot ^ 1]
+    bool pa_h_valid;   // pa_h[pa_slot] was written by the producer of h_in (initialize / previous LSTM)
+    bool pa_emb_valid; // pa_emb holds the embedding rows of last_word (previous step's fused argmax)
 };
 
 // state branch of attend: q = tanh(h*W1b + b1b) (model.py:421-424) or, 1-layer, h*fc_b (model.py:409-413)
-static int plan_att_state(sat_handle* h, LinProblem& P, const float* h_in, int rows, cudaStream_t st, int group) {
+static int plan_att_state(sat_handle* h, LinProblem& P, const float* h_in, int rows, cudaStream_t st, int group,
+                          const uint8_t* h_pa = nullptr) {
     const sat_dims& d = h->d;
     if (d.num_attend_layers == 2)
-        return plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiBiasTanh, h->q,
-                    d.dim_attend_layer, st, 0, group);
-    return plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units)}, rows, kEpiNone, h->q, d.num_ctx, st, 0,
-                group);
+        return plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units, nullptr, h_pa)}, rows, kEpiBiasTanh,
+                    h->q, d.dim_attend_layer, st, 0, group);
+    return plan(h, h->att_1b, P, {seg(h_in, d.num_lstm_units, d.num_lstm_units, nullptr, h_pa)}, rows, kEpiNone, h->q,
+                d.num_ctx, st, 0, group);
 }
 
 static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, const float* h_in, float* alpha, float* z,
@@ -657,7 +694,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         if (!(h->opt_hoist && h->prep_ctx == ctx && h->prep_ni == n_img)) RET(project_contexts(h, ctx, n_img, st));
         h->cur_tag = kTagAttState;
         if (!q_ready) {
-            RET(plan_att_state(h, P, h_in, rows, st, 1));
+            RET(plan_att_state(h, P, h_in, rows, st, 1, h->pa_on ? h->pa_cur_h_in : nullptr));
             RET(launch(h, &P, 1, st));
         }
         ap.T = h->T1;
@@ -668,7 +705,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         // logits2 = h * fc_b   (model.py:409-413), added to ctx . fc_a inside the kernel
         h->cur_tag = kTagAttState;
         if (!q_ready) {
-            RET(plan_att_state(h, P, h_in, rows, st, 1));
+            RET(plan_att_state(h, P, h_in, rows, st, 1, h->pa_on ? h->pa_cur_h_in : nullptr));
             RET(launch(h, &P, 1, st));
         }
         ap.T = ctx;
@@ -701,6 +738,11 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         h->att_part_floats = pneed;
     }
     ap.part = h->att_part;
+    if (h->pa_on) {
+        ap.pa_z = h->pa_z;
+        ap.pa_row_tile = row_tile_for(rows);
+        ap.pa_mode = h->opt_layout;
+    }
     ap.dbg = h->opt_trace == 2 ? h->trace : nullptr;
     {
         ProfScope ps(h, kTagAtt, st);
@@ -716,10 +758,13 @@ static int lstm_impl(sat_handle* h, const float* z, const int32_t* last_word, co
     h->cur_tag = kTagLstm;
     LinProblem P;
     // current_input = concat([context, word_embed]) (model.py:277); LSTMCell concat([x, h]) (TF)
+    const bool pa = h->pa_on;
     RET(plan(h, h->lstm, P,
-             {seg(z, d.dim_ctx, d.dim_ctx), seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word),
-              seg(h_in, d.num_lstm_units, d.num_lstm_units)},
+             {seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? h->pa_z : nullptr),
+              seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word, pa ? h->pa_emb : nullptr),
+              seg(h_in, d.num_lstm_units, d.num_lstm_units, nullptr, pa ? h->pa_cur_h_in : nullptr)},
              rows, kEpiLstm, nullptr, 0, st));
+    P.out_pa = pa ? h->pa_cur_h_out : nullptr;
     P.c_in = c_in;
     P.c_out = c_out;
     P.h_out = h_out;
@@ -762,34 +807,44 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
     h->cur_tag = kTagDec1;
     if (d.num_decode_layers == 2) {
         const int group = make_next_q ? 2 : 1;
+        const bool pa = h->pa_on;
         RET(plan(h, h->dec_1, P[0],
-                 {seg(h_out, d.num_lstm_units, d.num_lstm_units), seg(z, d.dim_ctx, d.dim_ctx),
-                  seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word)},
+                 {seg(h_out, d.num_lstm_units, d.num_lstm_units, nullptr, pa ? h->pa_cur_h_out : nullptr),
+                  seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? h->pa_z : nullptr),
+                  seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word, pa ? h->pa_emb : nullptr)},
                  rows, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st, 0, group));
+        P[0].out_pa = pa ? h->pa_t : nullptr;
         int np = 1;
         if (make_next_q) {  // q of the next step depends on the same h_out: share the launch
-            RET(plan_att_state(h, P[1], h_out, rows, st, 2));
+            RET(plan_att_state(h, P[1], h_out, rows, st, 2, pa ? h->pa_cur_h_out : nullptr));
             np = 2;
         }
         RET(launch(h, P, np, st));
         h->cur_tag = kTagDec2;
-        RET(plan(h, h->dec_2, P[0], {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer)}, rows, kEpiBias, logits,
-                 d.vocabulary_size, st));
+        RET(plan(h, h->dec_2, P[0], {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer, nullptr, pa ? h->pa_t : nullptr)},
+                 rows, kEpiBias, logits, d.vocabulary_size, st));
         used = attach_argmax(h, h->dec_2, P[0], am, st);
         if (used < 0) return used;
+        if (used && pa) {   // the vocabulary layer also packs the embedding row of the word it just chose
+            P[0].am_emb = h->embedding;
+            P[0].am_E = d.dim_embedding;
+            P[0].am_emb_pa = h->pa_emb;
+        }
         RET(launch(h, P, 1, st));
         if (argmax_done) *argmax_done = used;
         return SAT_OK;
     }
     h->cur_tag = kTagDec2;
     const int group = make_next_q ? 2 : 1;
+    const bool pa = h->pa_on;
     RET(plan(h, h->dec_2, P[0],
-             {seg(h_out, d.num_lstm_units, d.num_lstm_units), seg(z, d.dim_ctx, d.dim_ctx),
-              seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word)},
+             {seg(h_out, d.num_lstm_units, d.num_lstm_units, nullptr, pa ? h->pa_cur_h_out : nullptr),
+              seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? h->pa_z : nullptr),
+              seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word, pa ? h->pa_emb : nullptr)},
              rows, kEpiBias, logits, d.vocabulary_size, st, 0, group));
     int np = 1;
     if (make_next_q) {
-        RET(plan_att_state(h, P[1], h_out, rows, st, 2));
+        RET(plan_att_state(h, P[1], h_out, rows, st, 2, pa ? h->pa_cur_h_out : nullptr));
         np = 2;
     }
     // the fused argmax overwrites next_word, which this very launch still gathers embeddings with:
@@ -801,6 +856,20 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
 static int step_impl(sat_handle* h, StepIO& io, cudaStream_t st) {
     const int rows = io.n_img * io.group;
     if (rows > h->max_rows) return fail(SAT_ERR_INVALID, "rows %d > max_batch %d", rows, h->max_rows);
+    h->pa_on = h->pa_ok && h->opt_pa && h->opt_gemm != 0;
+    if (h->pa_on) {
+        h->pa_cur_h_in = h->pa_h[io.pa_slot & 1];
+        h->pa_cur_h_out = h->pa_h[(io.pa_slot & 1) ^ 1];
+        PackJob jobs[2];
+        int nj = 0;
+        const int rtile = row_tile_for(rows);
+        if (!io.pa_h_valid) jobs[nj++] = PackJob{io.h_in, nullptr, h->d.num_lstm_units, h->d.num_lstm_units, rows, rtile, h->pa_cur_h_in};
+        if (!io.pa_emb_valid) jobs[nj++] = PackJob{h->embedding, io.last_word, h->d.dim_embedding, h->d.dim_embedding, rows, rtile, h->pa_emb};
+        if (nj) {
+            CK(pack_rows_launch(jobs, nj, h->opt_layout, st));
+            h->launches += 1;
+        }
+    }
     RET(attention_impl(h, io.ctx, io.n_img, io.group, io.h_in, io.alpha, h->z, st, io.q_ready));
     RET(lstm_impl(h, h->z, io.last_word, io.c_in, io.h_in, io.c_out, io.h_out, rows, st));
     float* logits = io.logits ? io.logits : h->logits;
@@ -819,6 +888,8 @@ static int step_impl(sat_handle* h, StepIO& io, cudaStream_t st) {
         }
         h->launches += 1;
     }
+    io.pa_emb_valid = h->pa_on && fused != 0;   // tells the caller whether the next step's embedding is packed
+    h->pa_on = false;
     return SAT_OK;
 }
 
@@ -891,8 +962,10 @@ static int run_graphed(sat_handle* h, const std::vector<long long>& key, cudaStr
 // ------------------------------------------------------------------- loop
 static int loop_enqueue(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
                         float* logits_all, cudaStream_t st) {
-    RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st));
+    const bool pa = h->pa_ok && h->opt_pa && h->opt_gemm != 0;
+    RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st, pa ? h->pa_h[0] : nullptr));
     CK(cudaMemsetAsync(h->word, 0, (size_t)B * sizeof(int32_t), st));  // <start> = 0 (model.py:254)
+    bool emb_valid = false;
     for (int t = 0; t < T; ++t) {
         StepIO io;
         memset(&io, 0, sizeof(io));
@@ -905,7 +978,11 @@ static int loop_enqueue(sat_handle* h, const float* ctx, int B, int T, const int
         io.rows.next_word = h->word; io.rows.forced = forced; io.rows.forced_ld = T;
         io.q_ready = t > 0;
         io.make_next_q = t + 1 < T;
+        io.pa_slot = t & 1;          // initialize / the previous LSTM wrote the packed h into this slot
+        io.pa_h_valid = pa;
+        io.pa_emb_valid = emb_valid;
         RET(step_impl(h, io, st));
+        emb_valid = io.pa_emb_valid;
     }
     return SAT_OK;
 }

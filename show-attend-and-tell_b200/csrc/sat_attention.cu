@@ -25,6 +25,7 @@
 // G rows (beams) of one image share the image's T1/ctx traffic.
 #include "sat_common.cuh"
 #include "sat_attention.cuh"
+#include "sat_linear.cuh"
 
 namespace sat {
 
@@ -373,7 +374,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
 #pragma unroll
                 for (int k = 0; k < kAttMaxDPerThread; ++k) {
                     const int d = feat(k);
-                    if (k < nacc && d < D) p.z[((size_t)img * G + g) * D + d] = zz[k] * inv;
+                    if (k < nacc && d < D) {
+                        const float zv = zz[k] * inv;
+                        p.z[((size_t)img * G + g) * D + d] = zv;
+                        if (p.pa_z) pa_store(p.pa_z, p.pa_mode, p.pa_row_tile, D >> 6, img * G + g, d, zv);
+                    }
                 }
                 const float* er = p.e + ((size_t)img * G + g) * L;
                 for (int l = ct; l < L; l += NT) p.alpha[((size_t)img * G + g) * L + l] = expf(__ldcg(er + l) - M) * inv;

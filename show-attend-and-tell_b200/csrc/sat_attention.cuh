@@ -22,6 +22,8 @@ struct AttParams {
     int nslots;
     int grid, segmax;
     int l2_t, l2_ctx;    // L2 eviction policies of the two streams (see l2_policy)
+    uint8_t* pa_z;       // optional packed copy of z for the dense layers that consume it
+    int pa_row_tile, pa_mode;
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
 };
 

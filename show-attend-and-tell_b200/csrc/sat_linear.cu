@@ -82,12 +82,13 @@ __device__ __forceinline__ float epi_scalar(const LinProblem& P, float acc, int 
 // TF LSTMCell (un-vendored TF 1.7 dependency; gate order i, j, f, o and forget_bias 1.0
 // confirmed on the reference's recorded GraphDef, tests/golden/graph_fixture.json):
 //   c = sigmoid(f + 1) * c_prev + sigmoid(i) * tanh(j);  h = sigmoid(o) * tanh(c)
-__device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, int b, int unit) {
+__device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, int b, int unit, int mode) {
     const float cp = P.c_in[(size_t)b * P.H + unit];
     const float c = sigmoidf_acc(g.z + 1.0f) * cp + sigmoidf_acc(g.x) * tanhf(g.y);
     const float h = sigmoidf_acc(g.w) * tanhf(c);
     P.c_out[(size_t)b * P.H + unit] = c;
     P.h_out[(size_t)b * P.H + unit] = h;
+    if (P.out_pa) pa_store(P.out_pa, mode, P.row_tile, P.H >> 6, b, unit, h);   // h feeds the next dense layers
 }
 
 // ------------------------------------------------------------- UMMA kernel
@@ -104,7 +105,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     uint64_t* tmem_full = empty + 8;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
     uint8_t* stage_base = smem_raw + 1024;
-    const bool xtma = L.x_mode == 1;  // activations pre-packed by all CTAs, then fetched by TMA
+    const bool xpa = L.x_mode == 2;   // every X segment was packed by its producer kernel
+    const bool xpre = L.x_mode == 1;  // activations packed by a cooperative pre-pass of this launch
+    const bool xtma = xpa || xpre;    // X stages are fetched by TMA
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     }
     // grid-barrier generation must be sampled before this CTA can possibly arrive on it
     unsigned gen0 = 0;
-    if (xtma && threadIdx.x == 0) gen0 = ld_acquire_gpu(P.xbar + 1);
+    if (xpre && threadIdx.x == 0) gen0 = ld_acquire_gpu(P.xbar + 1);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -169,12 +172,19 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             };
             auto load_x = [&](int it) {
                 const int s = it % S;
+                const uint8_t* xs = xsrc + (size_t)it * x_stage_bytes;
+                if (xpa) {  // K block kb0+it lives in the packed activation of the segment that covers it
+                    int kb = kb0 + it, sg = 0;
+                    while (sg + 1 < P.nseg && kb >= (P.seg[sg].width >> 6)) { kb -= P.seg[sg].width >> 6; ++sg; }
+                    xs = P.seg[sg].pa + ((size_t)rt * (P.seg[sg].width >> 6) + kb) * x_stage_bytes;
+                }
                 mbar_arrive_expect_tx(&full_x[s], x_stage_bytes);
-                tma_bulk_g2s(stage_base + (size_t)s * stage_bytes + kWStageBytes, xsrc + (size_t)it * x_stage_bytes,
-                             x_stage_bytes, &full_x[s]);
+                tma_bulk_g2s(stage_base + (size_t)s * stage_bytes + kWStageBytes, xs, x_stage_bytes, &full_x[s]);
             };
             const int pre = nkb < S ? nkb : S;
-            if (xtma) {
+            if (xpa) {
+                for (int it = 0; it < pre; ++it) { load_w(it); load_x(it); }
+            } else if (xpre) {
                 // weights do not depend on the activation pre-pass: fill the pipeline with W first, then
                 // wait for the grid-wide pack to complete and fetch the X halves of the same stages
                 for (int it = 0; it < pre; ++it) load_w(it);
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         // NEXT chunk in flight while the current one is converted and stored.
         const int pt = threadIdx.x - 64;  // 0..255
         if (pt == 0) trace_stamp(L.dbg, 1);
-        if (xtma) {
+        if (xpre) {
             // ---- cooperative pre-pass: this problem's CTAs convert X (fp32 -> bf16 hi/lo UMMA tiles) ONCE
             // into global scratch; consecutive threads take consecutive 8-element groups of a row (coalesced).
             const int kgroups = P.k_blocks * 8;
@@ -333,7 +343,10 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         v[j] = epi_scalar(P, v[j], n);
-                        if (c0 + j < rows_here) P.out[(size_t)(row0 + c0 + j) * P.ldo + n] = v[j];
+                        if (c0 + j < rows_here) {
+                            if (P.out) P.out[(size_t)(row0 + c0 + j) * P.ldo + n] = v[j];
+                            if (P.out_pa) pa_store(P.out_pa, mode, N, P.n_out >> 6, row0 + c0 + j, n, v[j]);
+                        }
                     }
                 }
                 if (do_am) {
@@ -417,6 +430,43 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             P.am_next_word[b] = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi;
                     }
                 }
+                if (P.am_emb_pa) {
+                    // the word fed to the next step is known now: hand its embedding row to the next LSTM /
+                    // decode layers already packed (model.py:272-274 lookup + operand conversion)
+                    named_bar_sync(1, kLinProducers);   // next_word[] written by this CTA is visible to it
+                    const int groups = P.am_E >> 3;
+                    const int total = P.rows * groups;
+                    const size_t half = (size_t)N * kBK * 2;
+                    for (int u0 = pt; u0 < total; u0 += kLinProducers * 4) {
+                        float4 a[4], c4[4];
+                        int bb[4], gg[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int u = u0 + j * kLinProducers;
+                            bb[j] = -1;
+                            if (u < total) {
+                                bb[j] = u / groups;
+                                gg[j] = u - bb[j] * groups;
+                                const int w = P.am_next_word[bb[j]];
+                                const float4* src = reinterpret_cast<const float4*>(P.am_emb + (size_t)w * P.am_E + gg[j] * 8);
+                                a[j] = src[0];
+                                c4[j] = src[1];
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (bb[j] >= 0) {
+                                uint4 hi, lo;
+                                split_bf16x8(a[j], c4[j], hi, lo);
+                                const int rt2 = bb[j] / N, r = bb[j] - rt2 * N;
+                                uint8_t* dst = P.am_emb_pa + ((size_t)rt2 * (P.am_E >> 6) + (gg[j] >> 3)) * 2 * half +
+                                               umma_tile_off(mode, r, gg[j] & 7);
+                                *reinterpret_cast<uint4*>(dst) = hi;
+                                *reinterpret_cast<uint4*>(dst + half) = lo;
+                            }
+                        }
+                    }
+                }
                 if (pt == 0) *P.am_ctr = 0u;
             }
         }
@@ -466,15 +516,19 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                     if (unit < P.H) {
                         const float4 bb = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
                         g.x += bb.x; g.y += bb.y; g.z += bb.z; g.w += bb.w;
-                        lstm_gates(P, g, row0 + b, unit);
+                        lstm_gates(P, g, row0 + b, unit, mode);
                     }
                 } else {
                     const int ng = n_tile * kTileN + 4 * u;
-                    float* o = P.out + (size_t)(row0 + b) * P.ldo + ng;
-                    if (ng + 0 < P.n_out) o[0] = epi_scalar(P, g.x, ng + 0);
-                    if (ng + 1 < P.n_out) o[1] = epi_scalar(P, g.y, ng + 1);
-                    if (ng + 2 < P.n_out) o[2] = epi_scalar(P, g.z, ng + 2);
-                    if (ng + 3 < P.n_out) o[3] = epi_scalar(P, g.w, ng + 3);
+                    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (ng + j < P.n_out) {
+                            const float y = epi_scalar(P, gv[j], ng + j);
+                            if (P.out) P.out[(size_t)(row0 + b) * P.ldo + ng + j] = y;
+                            if (P.out_pa) pa_store(P.out_pa, mode, N, P.n_out >> 6, row0 + b, ng + j, y);
+                        }
+                    }
                 }
             }
             named_bar_sync(1, kLinProducers);
@@ -554,11 +608,15 @@ __global__ void __launch_bounds__(128) lin_simt_kernel(const __grid_constant__ L
             g.z = __shfl_sync(0xffffffffu, v, base + 2);
             g.w = __shfl_sync(0xffffffffu, v, base + 3);
             const int unit = n >> 2;
-            if ((lane & 3) == 0 && row0 + j < P.rows && unit < P.H) lstm_gates(P, g, row0 + j, unit);
+            if ((lane & 3) == 0 && row0 + j < P.rows && unit < P.H) lstm_gates(P, g, row0 + j, unit, mode);
         }
     } else if (n < P.n_out) {
         for (int j = 0; j < 16; ++j)
-            if (row0 + j < P.rows) P.out[(size_t)(row0 + j) * P.ldo + n] = epi_scalar(P, acc[j], n);
+            if (row0 + j < P.rows) {
+                const float y = epi_scalar(P, acc[j], n);
+                if (P.out) P.out[(size_t)(row0 + j) * P.ldo + n] = y;
+                if (P.out_pa) pa_store(P.out_pa, mode, P.row_tile, P.n_out >> 6, row0 + j, n, y);
+            }
     }
 }
 
@@ -600,6 +658,54 @@ __global__ void repack_bias_kernel(const float* __restrict__ b, int n_out, int p
         if (p < n_out && b) v = b[perm_H > 0 ? (p & 3) * perm_H + (p >> 2) : p];
         out[p] = v;
     }
+}
+
+// fp32 rows (optionally gathered: embedding lookup) -> packed activation; up to 2 jobs per launch
+struct PackJobs {
+    PackJob j[2];
+    int n, mode;
+};
+__global__ void pack_rows_kernel(const PackJobs J) {
+    for (int q = 0; q < J.n; ++q) {
+        const PackJob& jb = J.j[q];
+        const int groups = jb.width >> 3;
+        const int nrt = (jb.rows + jb.row_tile - 1) / jb.row_tile;
+        const int total = nrt * jb.row_tile * groups;   // padded rows are zero filled
+        const size_t half = (size_t)jb.row_tile * kBK * 2;
+        for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+            const int b = u / groups, g = u - b * groups;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+            if (b < jb.rows) {
+                const int row = jb.gather ? jb.gather[b] : b;
+                const float4* src = reinterpret_cast<const float4*>(jb.src + (size_t)row * jb.ld + g * 8);
+                a = src[0];
+                c = src[1];
+            }
+            uint4 hi, lo;
+            split_bf16x8(a, c, hi, lo);
+            const int rt = b / jb.row_tile, r = b - rt * jb.row_tile;
+            uint8_t* dst = jb.pa + ((size_t)rt * (jb.width >> 6) + (g >> 3)) * 2 * half + umma_tile_off(J.mode, r, g & 7);
+            *reinterpret_cast<uint4*>(dst) = hi;
+            *reinterpret_cast<uint4*>(dst + half) = lo;
+        }
+    }
+}
+
+cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st) {
+    PackJobs J;
+    J.n = njobs;
+    J.mode = layout_mode;
+    int total = 0;
+    for (int i = 0; i < njobs; ++i) {
+        J.j[i] = jobs[i];
+        const int nrt = (jobs[i].rows + jobs[i].row_tile - 1) / jobs[i].row_tile;
+        total = max(total, nrt * jobs[i].row_tile * (jobs[i].width >> 3));
+    }
+    int grid = (total + 255) / 256;
+    if (grid > 148) grid = 148;
+    if (grid < 1) grid = 1;
+    pack_rows_kernel<<<grid, 256, 0, st>>>(J);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------ host side

@@ -4,6 +4,7 @@
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 
 namespace sat {
 
@@ -31,7 +32,13 @@ struct LinSeg {
     int ld;
     int width;   // multiple of 8
     int row_div; // >= 1; b / row_div selects the source row (beams sharing one image row)
+    const uint8_t* pa;  // same operand already packed by its producer (see PackedAct), or null
 };
+
+// A "packed activation": an fp32 [rows, width] tensor (width % 64 == 0) kept by its PRODUCER kernel in
+// the bf16 hi/lo UMMA operand image  [n_row_tiles][width/64][hi|lo][row_tile x 64 bf16]  so that the
+// consuming dense layer fetches its X stages by TMA with no conversion pass.
+__host__ __device__ __forceinline__ size_t pa_stage_bytes(int row_tile) { return (size_t)row_tile * kBK * 2 * 2; }
 
 struct LinProblem {
     LinSeg seg[kMaxSeg];
@@ -68,6 +75,11 @@ struct LinProblem {
     int32_t* am_next_word; // [rows] or null
     const int32_t* am_forced;  // teacher-forced next words [rows, am_forced_ld] or null
     int am_forced_ld;
+    uint8_t* out_pa;       // optional packed copy of the output for the next dense layer (width n_out)
+    // fused epilogue of the vocabulary layer in loops: pack the embedding row of the chosen next word
+    const float* am_emb;   // [V, E] embedding matrix or null
+    int am_E;
+    uint8_t* am_emb_pa;    // packed [rows, E]
     int cta_begin;         // first CTA of this problem in the grouped grid
     int cta_count;
 };
@@ -79,7 +91,8 @@ struct LinLaunch {
     int stages;
     int l2_w;         // L2 eviction policy of the weight stream (see l2_policy)
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
-    int x_mode;       // 0 = producer warps convert X per stage; 1 = cooperative pre-pack + TMA (grid <= #SMs)
+    int x_mode;       // 0 = producer warps convert X per stage; 1 = cooperative pre-pack + TMA (grid <= #SMs);
+                      // 2 = every operand segment arrives packed from its producer (TMA from t = 0)
 };
 
 // byte offset of the 16-byte group (row r, k-group kg in [0,8)) inside a [rows x 64] bf16
@@ -88,6 +101,28 @@ __host__ __device__ __forceinline__ uint32_t umma_tile_off(int mode, int r, int 
     return mode == 0 ? (uint32_t)((r >> 3) * 1024 + kg * 128 + (r & 7) * 16)
                      : (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kg ^ (r & 7)) * 16));
 }
+
+// store one fp32 value into a packed activation (2-byte hi and lo stores)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pa_store(uint8_t* pa, int mode, int row_tile, int kblocks, int b, int col, float v) {
+    const int rt = b / row_tile, r = b - rt * row_tile;
+    const int kb = col >> 6, kg = (col & 63) >> 3, e = col & 7;
+    const size_t half = (size_t)row_tile * kBK * 2;
+    uint8_t* dst = pa + ((size_t)rt * kblocks + kb) * 2 * half + umma_tile_off(mode, r, kg) + e * 2;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    *reinterpret_cast<__nv_bfloat16*>(dst) = h;
+    *reinterpret_cast<__nv_bfloat16*>(dst + half) = l;
+}
+#endif
+
+struct PackJob {           // fp32 rows (optionally gathered) -> packed activation
+    const float* src;
+    const int32_t* gather;
+    int ld, width, rows, row_tile;
+    uint8_t* pa;
+};
+cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st);
 
 size_t lin_smem_bytes(int row_tile, int stages);
 int lin_pick_stages(int row_tile);

@@ -108,6 +108,22 @@ def test_hoisted_and_per_step_projection_agree():
     assert np.array_equal(a, b)
 
 
+def test_packed_activation_and_prepass_paths_agree():
+    """Operands packed by their producer kernels (default) vs the cooperative pre-pass vs per-stage producer
+    warps: the same bf16 hi/lo split feeds the same MMAs, so the three paths must agree bit for bit."""
+    ocfg, w, m = make_pair(4)
+    ctx = R.synth_contexts(ocfg, 4)
+    toks = {}
+    for name, opts in (("pa", dict(pa=1, xpack=1)), ("prepass", dict(pa=0, xpack=1)), ("warps", dict(pa=0, xpack=0))):
+        for k, v in opts.items():
+            m.set_option(k, v)
+        toks[name] = m.decode_loop(ctx, 6, None, want_logits=True)
+    m.set_option("pa", 1); m.set_option("xpack", 1)
+    for name in ("prepass", "warps"):
+        assert np.array_equal(toks["pa"][0], toks[name][0])
+        assert np.array_equal(toks["pa"][1], toks[name][1]), name
+
+
 def test_error_behaviour():
     import sat_b200
     cfg = sat_b200.Config(batch_size=2, beam_size=1, **SMALL)
