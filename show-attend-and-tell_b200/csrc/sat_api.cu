@@ -124,6 +124,7 @@ struct sat_handle {
     uint8_t *pa_cur_h_in = nullptr, *pa_cur_h_out = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
     int opt_trace = 0;
+    int trace_at = 0;      // with trace == 1: index of the dense launch (counted from the option call) to stamp
 
     std::vector<GraphEntry> graphs;
 
@@ -341,7 +342,8 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
         if (h->trace) CK(cudaMemset(h->trace, 0, 1024 * 16 * sizeof(unsigned long long)));
         return SAT_OK;
-    } else if (k == "l2_w") h->opt_l2_w = (int)value;
+    } else if (k == "trace_at") { h->trace_at = (int)value; return SAT_OK; }
+    else if (k == "l2_w") h->opt_l2_w = (int)value;
     else if (k == "l2_t") h->opt_l2_t = (int)value;
     else if (k == "l2_ctx") h->opt_l2_ctx = (int)value;
     else if (k == "profile") {
@@ -585,7 +587,8 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.layout_mode = h->opt_layout;
     L.stages = lin_pick_stages(max_rt);
     L.l2_w = h->opt_l2_w;
-    L.dbg = (h->opt_trace == 1 && begin <= 1024) ? h->trace : nullptr;
+    L.dbg = nullptr;
+    if (h->opt_trace == 1 && begin <= 1024 && h->trace_at-- == 0) L.dbg = h->trace;
     bool all_pa = true;
     for (int i = 0; i < n; ++i)
         for (int sgi = 0; sgi < probs[i].nseg; ++sgi) all_pa = all_pa && probs[i].seg[sgi].pa != nullptr;
@@ -684,7 +687,7 @@ static int plan_att_state(sat_handle* h, LinProblem& P, const float* h_in, int r
 }
 
 static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, const float* h_in, float* alpha, float* z,
-                          cudaStream_t st, bool q_ready = false) {
+                          cudaStream_t st, bool q_ready = false, const int32_t* last_word = nullptr) {
     const sat_dims& d = h->d;
     const int rows = n_img * G;
     AttParams ap;
@@ -742,6 +745,12 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         ap.pa_z = h->pa_z;
         ap.pa_row_tile = row_tile_for(rows);
         ap.pa_mode = h->opt_layout;
+        if (last_word) {   // the embedding rows of this step's words are packed on the side
+            ap.emb = h->embedding;
+            ap.emb_word = last_word;
+            ap.emb_pa = h->pa_emb;
+            ap.emb_E = h->d.dim_embedding;
+        }
     }
     ap.dbg = h->opt_trace == 2 ? h->trace : nullptr;
     {
@@ -825,11 +834,8 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
                  rows, kEpiBias, logits, d.vocabulary_size, st));
         used = attach_argmax(h, h->dec_2, P[0], am, st);
         if (used < 0) return used;
-        if (used && pa) {   // the vocabulary layer also packs the embedding row of the word it just chose
-            P[0].am_emb = h->embedding;
-            P[0].am_E = d.dim_embedding;
-            P[0].am_emb_pa = h->pa_emb;
-        }
+        // (the embedding row of the chosen word is packed by the next step's attention kernel, off the
+        //  critical path; the in-epilogue variant P.am_emb_pa serialised 4096 gathers on one CTA)
         RET(launch(h, P, 1, st));
         if (argmax_done) *argmax_done = used;
         return SAT_OK;
@@ -864,13 +870,12 @@ static int step_impl(sat_handle* h, StepIO& io, cudaStream_t st) {
         int nj = 0;
         const int rtile = row_tile_for(rows);
         if (!io.pa_h_valid) jobs[nj++] = PackJob{io.h_in, nullptr, h->d.num_lstm_units, h->d.num_lstm_units, rows, rtile, h->pa_cur_h_in};
-        if (!io.pa_emb_valid) jobs[nj++] = PackJob{h->embedding, io.last_word, h->d.dim_embedding, h->d.dim_embedding, rows, rtile, h->pa_emb};
         if (nj) {
             CK(pack_rows_launch(jobs, nj, h->opt_layout, st));
             h->launches += 1;
         }
     }
-    RET(attention_impl(h, io.ctx, io.n_img, io.group, io.h_in, io.alpha, h->z, st, io.q_ready));
+    RET(attention_impl(h, io.ctx, io.n_img, io.group, io.h_in, io.alpha, h->z, st, io.q_ready, io.last_word));
     RET(lstm_impl(h, h->z, io.last_word, io.c_in, io.h_in, io.c_out, io.h_out, rows, st));
     float* logits = io.logits ? io.logits : h->logits;
     const bool argmax_only = io.want_rows && !io.probs && io.rows.topk == 0 && !io.rows.argmax;

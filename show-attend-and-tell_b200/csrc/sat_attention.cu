@@ -109,6 +109,33 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
     const int nper = (D + NT - 1) / NT;   // context features per thread (d = ct + NT*k)
     int idx = 0;
     bool first_seg = true;
+    if (p.emb_pa) {
+        // embedding rows of the words fed to this step -> packed operand tiles (a few 16-byte groups per CTA)
+        const int groups = p.emb_E >> 3;
+        const int total = p.NI * G * groups;
+        const size_t half = (size_t)p.pa_row_tile * kBK * 2;
+        for (int u = c * NT + ct; u < total; u += P * NT) {
+            const int b = u / groups, gi = u - b * groups;
+            const int w = p.emb_word[b];
+            const float4* src = reinterpret_cast<const float4*>(p.emb + (size_t)w * p.emb_E + gi * 8);
+            const float4 a = __ldg(src), a2 = __ldg(src + 1);
+            const float x[8] = {a.x, a.y, a.z, a.w, a2.x, a2.y, a2.z, a2.w};
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+                hh[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                ll[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            const int rt = b / p.pa_row_tile, r = b - rt * p.pa_row_tile;
+            uint8_t* dst = p.emb_pa + ((size_t)rt * (p.emb_E >> 6) + (gi >> 3)) * 2 * half +
+                           umma_tile_off(p.pa_mode, r, gi & 7);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(dst + half) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
+    }
     if (ct == 0) trace_stamp(p.dbg, 1);
 
     for (int seg0 = r_begin; seg0 < r_end;) {

@@ -24,6 +24,12 @@ struct AttParams {
     int l2_t, l2_ctx;    // L2 eviction policies of the two streams (see l2_policy)
     uint8_t* pa_z;       // optional packed copy of z for the dense layers that consume it
     int pa_row_tile, pa_mode;
+    // side job while the first TMA chunks are in flight: embedding lookup of this step's words
+    // (model.py:272-274), packed for the LSTM / decode layers that follow
+    const float* emb;    // [V, E] or null
+    const int32_t* emb_word;  // [NI*G]
+    uint8_t* emb_pa;
+    int emb_E;
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
 };
 

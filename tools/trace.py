@@ -66,7 +66,21 @@ lin_labels = ["start", "producers start", "pack done -> arrive", "TMA thread: ba
               "MMA: first X stage", "MMA: all issued", "epilogue: accumulator ready", "partials written",
               "rendezvous passed", "end"]
 
+def step_traced(k):
+    """one full decode step through step_impl (packed-activation path); stamp the k-th dense launch"""
+    def fn():
+        m.set_option("trace_at", k)
+        m.step_device(ctx, lw, cstate, hstate, want=())
+    return fn
+
+
 with torch.cuda.stream(m.stream):
+    m.step_device(ctx, lw, cstate, hstate, want=())     # allocate everything once
+    torch.cuda.synchronize()
+    # dense launches of one step: 0 = state branch q, 1 = LSTM, 2 = decode fc_1, 3 = decode fc_2
+    for k, (name, grid) in enumerate([("step: att state (q)", 64), ("step: LSTM [packed operands]", 128),
+                                      ("step: decode fc_1 [packed operands]", 128), ("step: decode fc_2 [packed]", 79)]):
+        run(name, step_traced(k), grid, lin_labels, 1, False)
     for cold in (True, False):
         run("attention", lambda: m.lib.sat_attention_fwd(m._h, p(ctx), p(hstate), p(alpha), p(z), B, 1, m._st()), 148,
             att_labels, 2, cold)
