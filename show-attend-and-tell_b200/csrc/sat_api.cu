@@ -47,10 +47,6 @@ struct Layer {
     uint8_t* wpack = nullptr;
     float* bias = nullptr;  // packed order, n_tiles*128
     bool w_set = false, b_set = false;
-    float* ws = nullptr;
-    size_t ws_floats = 0;
-    unsigned* counters = nullptr;
-    size_t n_counters = 0;
     uint8_t* xpack = nullptr;  // packed activations (x_mode 1)
     size_t xpack_bytes = 0;
     unsigned* xbar = nullptr;  // {count, generation}
@@ -180,8 +176,6 @@ static int layer_setup(sat_handle* h, Layer& ly, const char* name, int K, int n_
 static void layer_free(Layer& ly) {
     cudaFree(ly.wpack);
     cudaFree(ly.bias);
-    cudaFree(ly.ws);
-    cudaFree(ly.counters);
     cudaFree(ly.xpack);
     cudaFree(ly.xbar);
     cudaFree(ly.am_val);
@@ -509,49 +503,25 @@ static int plan(sat_handle* h, Layer& ly, LinProblem& P, std::initializer_list<L
     P.ldo = ldo;
     // split-K: fill the SMs; cost model in units of K-blocks (fixed per-CTA overhead ~4)
     const int tiles = P.n_tiles * P.n_row_tiles;
-    // split-K CTAs rendezvous inside the kernel, so a split launch must fit on the GPU in one wave
-    // (`group` problems share the grid).  Cost model in units of K blocks: a CTA costs its K range plus
-    // a fixed ~4 blocks (pipeline fill + epilogue), a split costs a rendezvous.
+    // split-K: the `splits` CTAs of a tile form one thread-block cluster (partials meet in DSMEM), so the
+    // factor is a portable cluster size.  Cost model in units of K blocks: a CTA costs its K range plus a
+    // fixed ~4 blocks (pipeline fill + epilogue); a split adds a cluster barrier.
     const int budget = h->num_sms / (group > 0 ? group : 1);
     int best = 1;
     if (force_splits > 0) {
-        best = force_splits < P.k_blocks ? force_splits : P.k_blocks;
-        while (best > 1 && tiles * best > budget) --best;
+        best = 1;
+        while (best * 2 <= force_splits && best * 2 <= 8 && best * 2 <= P.k_blocks) best *= 2;
     } else {
         double bc = 1e30;
-        const int smax = P.k_blocks < 16 ? P.k_blocks : 16;
-        for (int s = 1; s <= smax; ++s) {
-            if (s > 1 && tiles * s > budget) break;
-            const int waves = (tiles * s + h->num_sms - 1) / h->num_sms;
-            const double c = waves * ((P.k_blocks + s - 1) / s + 4.0) + (s > 1 ? 2.0 : 0.0);
+        for (int s = 1; s <= 8 && s <= P.k_blocks; s *= 2) {
+            const int waves = (tiles * s + budget - 1) / budget;
+            const double c = waves * ((P.k_blocks + s - 1) / s + 4.0) + (s > 1 ? 1.0 : 0.0);
             if (c < bc - 1e-9) { bc = c; best = s; }
         }
     }
     P.splits = best;
-    const bool direct = best == 1 && epi != kEpiLstm;
-    if (!direct) {
-        const size_t need = (size_t)best * P.n_row_tiles * P.row_tile * P.n_tiles * kTileN;
-        if (need > ly.ws_floats) {
-            if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: workspace growth during graph capture", ly.name.c_str());
-            CK(cudaDeviceSynchronize());
-            cudaFree(ly.ws);
-            ly.ws = nullptr;
-            ly.ws_floats = 0;
-            RET(dmalloc(&ly.ws, need));
-            ly.ws_floats = need;
-        }
-        if ((size_t)2 * tiles > ly.n_counters) {
-            if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: counter growth during graph capture", ly.name.c_str());
-            CK(cudaDeviceSynchronize());
-            cudaFree(ly.counters);
-            ly.counters = nullptr;
-            RET(dmalloc(&ly.counters, (size_t)2 * tiles));
-            CK(cudaMemset(ly.counters, 0, (size_t)2 * tiles * sizeof(unsigned)));
-            ly.n_counters = (size_t)2 * tiles;
-        }
-    }
-    P.ws = ly.ws;
-    P.counters = ly.counters;
+    P.ws = nullptr;
+    P.counters = nullptr;
     P.cta_count = tiles * best;
     // packed-activation scratch for the cooperative pre-pass (used when the launch fits one wave)
     const size_t xneed = (size_t)P.n_row_tiles * P.k_blocks * 2 * P.row_tile * kBK * 2;
@@ -577,6 +547,12 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     LinLaunch L;
     memset(&L, 0, sizeof(L));
     int begin = 0, max_rt = 16;
+    int smin = probs[0].splits;
+    for (int i = 1; i < n; ++i) smin = probs[i].splits < smin ? probs[i].splits : smin;
+    for (int i = 0; i < n; ++i) {   // one cluster shape per launch: grouped problems share the split factor
+        probs[i].splits = smin;
+        probs[i].cta_count = probs[i].n_tiles * probs[i].n_row_tiles * smin;
+    }
     for (int i = 0; i < n; ++i) {
         L.p[i] = probs[i];
         L.p[i].cta_begin = begin;
@@ -593,7 +569,7 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     for (int i = 0; i < n; ++i)
         for (int sgi = 0; sgi < probs[i].nseg; ++sgi) all_pa = all_pa && probs[i].seg[sgi].pa != nullptr;
     if (all_pa) L.x_mode = 2;   // operands were packed by their producers: nothing to convert, nothing to wait for
-    else L.x_mode = (h->opt_xpack && begin <= h->num_sms) ? 1 : 0;  // the pre-pass needs every CTA co-resident
+    else L.x_mode = (h->opt_xpack && smin == 1 && begin <= h->num_sms) ? 1 : 0;  // pre-pass: grid barrier, no clusters
     if (L.stages < 1) return fail(SAT_ERR_UNSUPPORTED, "row tile %d does not fit in shared memory", max_rt);
     {
         ProfScope ps(h, h->cur_tag, st);

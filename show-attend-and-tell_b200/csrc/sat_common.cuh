@@ -187,6 +187,24 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ------------------------------------------------ thread-block clusters / distributed shared memory
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_map(uint32_t local_smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(cluster_addr)
+                 : "memory");
+    return v;
+}
+
 // in-kernel timeline stamps (debug option "trace"): ns since an arbitrary origin, one row of 16 per CTA
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;

@@ -318,84 +318,126 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             cur = nxt;
         }
 
-        // ---- epilogue: TMEM -> registers (two warps per TMEM lane quadrant, alternating column chunks)
+        // ---- epilogue part 1: accumulator tile TMEM -> shared memory (two warps per TMEM lane quadrant).
+        // tile_s[col][n] (fp32, n fastest) lives in the idle pipeline stages: every TMA write has landed and
+        // every MMA has read its operands once tmem_full fires.
         const int q = warp & 3;               // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;     // 0 or 1
         const int nl = q * 32 + lane;          // output feature within the tile (TMEM lane)
-        const int n = n_tile * kTileN + nl;    // packed output index
-        const int rows_here = min(N, P.rows - row0);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         if (pt == 0) trace_stamp(L.dbg, 7);
         const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-        const bool direct = (P.splits == 1) && (P.epi != kEpiLstm);
-        const int npad = P.n_tiles * kTileN;
-        const int rpad = P.n_row_tiles * P.row_tile;
-        float* wsp = P.ws + ((size_t)split * rpad + row0) * npad + n;
-        const bool do_am = direct && P.am_val != nullptr;
-        float* am_s_val = reinterpret_cast<float*>(stage_base);            // [4][256] pipeline smem is idle now
-        int* am_s_idx = reinterpret_cast<int*>(stage_base + 4 * 256 * 4);
+        float* tile_s = reinterpret_cast<float*>(stage_base);
         for (int c0 = half * 16; c0 < N; c0 += 32) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);
-            if (direct) {
-                if (n < P.n_out) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] = epi_scalar(P, v[j], n);
-                        if (c0 + j < rows_here) {
-                            if (P.out) P.out[(size_t)(row0 + c0 + j) * P.ldo + n] = v[j];
-                            if (P.out_pa) pa_store(P.out_pa, mode, N, P.n_out >> 6, row0 + c0 + j, n, v[j]);
-                        }
-                    }
-                }
-                if (do_am) {
+            for (int j = 0; j < 16; ++j) tile_s[(c0 + j) * kTileN + nl] = v[j];
+        }
+        tc_fence_before();
+    }
+
+    // ---- epilogue part 2: split-K partials meet through distributed shared memory.  The `splits` CTAs of
+    // a tile form one thread-block cluster; after the cluster barrier CTA `split` sums rows
+    // [lo, hi) of all partial tiles in fixed rank order (bit-reproducible), applies the fused epilogue and
+    // writes coalesced rows.  splits == 1 is the same code reading only its own tile.
+    if (P.splits > 1) {
+        __syncwarp();
+        cluster_sync_all();
+    } else {
+        __syncthreads();
+    }
+    if (threadIdx.x == 64) trace_stamp(L.dbg, 8);
+    if (warp >= 2) {
+        const int pt = threadIdx.x - 64;
+        const int lane2 = pt & 31;
+        const int rows_here = min(N, P.rows - row0);
+        const float* tile_s = reinterpret_cast<const float*>(stage_base);
+        const uint32_t tile_addr = smem_u32(tile_s);
+        uint32_t peer[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float bv = n < P.n_out ? v[j] : -INFINITY;
-                        int bi = n;
+        for (int r = 0; r < 8; ++r) peer[r] = (P.splits > 1 && r < P.splits) ? dsmem_map(tile_addr, (uint32_t)r) : tile_addr;
+        const int cnt = rows_here * 32;          // float4 groups (row b, outputs 4u..4u+3); one warp = one row
+        const int lo = (int)(((long long)rows_here * split) / P.splits) * 32;
+        const int hi = (int)(((long long)rows_here * (split + 1)) / P.splits) * 32;
+        (void)cnt;
+        const bool do_am = P.am_val != nullptr && P.splits == 1;
+        for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
+            const int b = idx >> 5, u = idx & 31;
+            const uint32_t off = (uint32_t)(b * kTileN + 4 * u) * 4u;
+            float4 g;
+            if (P.splits == 1) {
+                g = *reinterpret_cast<const float4*>(tile_s + b * kTileN + 4 * u);
+            } else {
+                float4 part[8];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                        }
-                        if (lane == 0) { am_s_val[q * 256 + c0 + j] = bv; am_s_idx[q * 256 + c0 + j] = bi; }
-                    }
+                for (int r = 0; r < 8; ++r)
+                    if (r < P.splits) part[r] = ld_dsmem_f4(peer[r] + off);
+                g = part[0];
+#pragma unroll
+                for (int r = 1; r < 8; ++r)
+                    if (r < P.splits) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
+            }
+            if (P.epi == kEpiLstm) {
+                const int unit = n_tile * 32 + u;
+                if (unit < P.H) {
+                    const float4 bb = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
+                    g.x += bb.x; g.y += bb.y; g.z += bb.z; g.w += bb.w;
+                    lstm_gates(P, g, row0 + b, unit, mode);
                 }
             } else {
+                const int ng = n_tile * kTileN + 4 * u;
+                float y[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < rows_here) wsp[(size_t)(c0 + j) * npad] = v[j];
+                for (int j = 0; j < 4; ++j)
+                    if (ng + j < P.n_out) y[j] = epi_scalar(P, y[j], ng + j);
+                if (P.out) {
+                    float* o = P.out + (size_t)(row0 + b) * P.ldo + ng;
+                    if (ng + 3 < P.n_out && (P.ldo & 3) == 0) {
+                        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (ng + j < P.n_out) o[j] = y[j];
+                    }
+                }
+                if (P.out_pa) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (ng + j < P.n_out) pa_store(P.out_pa, mode, N, P.n_out >> 6, row0 + b, ng + j, y[j]);
+                }
+                if (do_am) {
+                    // this warp holds the 128 outputs of row b of this tile: first maximum wins (tf.argmax)
+                    float bv = -INFINITY;
+                    int bi = 0x7fffffff;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (ng + j < P.n_out && y[j] > bv) { bv = y[j]; bi = ng + j; }
+#pragma unroll
+                    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o2);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o2);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (lane2 == 0) {
+                        const int tile_id = rt * P.n_tiles + n_tile;
+                        P.am_val[(size_t)tile_id * N + b] = bv;
+                        P.am_idx[(size_t)tile_id * N + b] = bi;
+                    }
+                }
             }
         }
         if (do_am) {
-            // tile candidates -> global; the last CTA of the problem reduces them per row (first maximum wins,
-            // like tf.argmax) and emits the prediction / the word fed to the next step
-            named_bar_sync(1, kLinProducers);
-            const int tile_id = rt * P.n_tiles + n_tile;
-            if (pt < N) {
-                float bv = am_s_val[pt];
-                int bi = am_s_idx[pt];
-#pragma unroll
-                for (int qq = 1; qq < 4; ++qq) {
-                    const float ov = am_s_val[qq * 256 + pt];
-                    const int oi = am_s_idx[qq * 256 + pt];
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                }
-                P.am_val[(size_t)tile_id * N + pt] = bv;
-                P.am_idx[(size_t)tile_id * N + pt] = bi;
-            }
+            // tile candidates are in global memory; the last CTA of the problem picks every row's word
             __threadfence();
             named_bar_sync(1, kLinProducers);
-            unsigned* flag = reinterpret_cast<unsigned*>(stage_base + 8192);
+            unsigned* flag = reinterpret_cast<unsigned*>(smem_raw + 512);
             if (pt == 0) *flag = atomicAdd(P.am_ctr, 1u) == (unsigned)(P.cta_count - 1) ? 1u : 0u;
             named_bar_sync(1, kLinProducers);
             if (*flag) {
                 __threadfence();
-                // 4 lanes per row, each scanning every 4th tile with the loads batched (the candidates sit in
-                // L2: a dependent-load loop would cost one L2 round trip per tile)
-                const int part = pt & 3;
+                const int part = pt & 3;   // 4 lanes per row, every 4th tile each, loads batched
                 for (int b0 = 0; b0 < P.rows; b0 += kLinProducers / 4) {
                     const int b = b0 + (pt >> 2);
                     const bool live = b < P.rows;
@@ -430,116 +472,14 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             P.am_next_word[b] = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi;
                     }
                 }
-                if (P.am_emb_pa) {
-                    // the word fed to the next step is known now: hand its embedding row to the next LSTM /
-                    // decode layers already packed (model.py:272-274 lookup + operand conversion)
-                    named_bar_sync(1, kLinProducers);   // next_word[] written by this CTA is visible to it
-                    const int groups = P.am_E >> 3;
-                    const int total = P.rows * groups;
-                    const size_t half = (size_t)N * kBK * 2;
-                    for (int u0 = pt; u0 < total; u0 += kLinProducers * 4) {
-                        float4 a[4], c4[4];
-                        int bb[4], gg[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int u = u0 + j * kLinProducers;
-                            bb[j] = -1;
-                            if (u < total) {
-                                bb[j] = u / groups;
-                                gg[j] = u - bb[j] * groups;
-                                const int w = P.am_next_word[bb[j]];
-                                const float4* src = reinterpret_cast<const float4*>(P.am_emb + (size_t)w * P.am_E + gg[j] * 8);
-                                a[j] = src[0];
-                                c4[j] = src[1];
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (bb[j] >= 0) {
-                                uint4 hi, lo;
-                                split_bf16x8(a[j], c4[j], hi, lo);
-                                const int rt2 = bb[j] / N, r = bb[j] - rt2 * N;
-                                uint8_t* dst = P.am_emb_pa + ((size_t)rt2 * (P.am_E >> 6) + (gg[j] >> 3)) * 2 * half +
-                                               umma_tile_off(mode, r, gg[j] & 7);
-                                *reinterpret_cast<uint4*>(dst) = hi;
-                                *reinterpret_cast<uint4*>(dst + half) = lo;
-                            }
-                        }
-                    }
-                }
                 if (pt == 0) *P.am_ctr = 0u;
             }
         }
-        tc_fence_before();
-
-        if (!direct) {
-            // ---- split-K rendezvous.  Every CTA of the tile publishes its partial, waits until all
-            // `splits` partials are visible (all CTAs are co-resident: cooperative launch), then reduces
-            // ITS 1/splits share of the tile in fixed split order (bit-reproducible) and applies the
-            // fused epilogue.  ctr[0] counts arrivals, ctr[1] departures; the last one out resets both.
-            unsigned* ctr = P.counters + 2 * (rt * P.n_tiles + n_tile);
-            __threadfence();
-            named_bar_sync(1, kLinProducers);
-            if (pt == 0) {
-                trace_stamp(L.dbg, 8);
-                atomicAdd(ctr, 1u);
-                const long long t0 = clock64();
-                while (ld_acquire_gpu(ctr) < (unsigned)P.splits) {
-                    if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
-                        printf("sat_b200: split-K rendezvous timed out (block %d)\n", (int)blockIdx.x);
-                        __trap();
-                    }
-                }
-            }
-            named_bar_sync(1, kLinProducers);
-            if (pt == 0) trace_stamp(L.dbg, 9);
-            const float* ws0 = P.ws + (size_t)row0 * npad + (size_t)n_tile * kTileN;
-            const size_t sstride = (size_t)rpad * npad;
-            const int cnt = rows_here * 32;  // float4 groups (row b, 4 consecutive outputs) in the tile
-            const int lo = (int)(((long long)cnt * split) / P.splits);
-            const int hi = (int)(((long long)cnt * (split + 1)) / P.splits);
-            for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
-                const int b = idx >> 5, u = idx & 31;
-                const float* p = ws0 + (size_t)b * npad + 4 * u;
-                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int s2 = 0; s2 < P.splits; s2 += 4) {
-                    float4 part[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (s2 + j < P.splits) part[j] = __ldcg(reinterpret_cast<const float4*>(p + (s2 + j) * sstride));
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (s2 + j < P.splits) { g.x += part[j].x; g.y += part[j].y; g.z += part[j].z; g.w += part[j].w; }
-                }
-                if (P.epi == kEpiLstm) {
-                    const int unit = n_tile * 32 + u;
-                    if (unit < P.H) {
-                        const float4 bb = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
-                        g.x += bb.x; g.y += bb.y; g.z += bb.z; g.w += bb.w;
-                        lstm_gates(P, g, row0 + b, unit, mode);
-                    }
-                } else {
-                    const int ng = n_tile * kTileN + 4 * u;
-                    const float gv[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (ng + j < P.n_out) {
-                            const float y = epi_scalar(P, gv[j], ng + j);
-                            if (P.out) P.out[(size_t)(row0 + b) * P.ldo + ng + j] = y;
-                            if (P.out_pa) pa_store(P.out_pa, mode, N, P.n_out >> 6, row0 + b, ng + j, y);
-                        }
-                    }
-                }
-            }
-            named_bar_sync(1, kLinProducers);
-            if (pt == 0) {
-                const unsigned old = atomicAdd(ctr + 1, 1u);
-                if (old == (unsigned)(P.splits - 1)) {  // everyone has passed the wait and finished reading
-                    ctr[0] = 0u;
-                    ctr[1] = 0u;
-                }
-            }
-        }
+    }
+    if (threadIdx.x == 64) trace_stamp(L.dbg, 9);
+    if (P.splits > 1) {
+        __syncwarp();
+        cluster_sync_all();   // peers may still be reading this CTA's tile
     }
 
     __syncthreads();
@@ -750,19 +690,31 @@ cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt) {
         if (L.p[i].row_tile > max_rt) max_rt = L.p[i].row_tile;
     }
     const size_t smem = lin_smem_bytes(max_rt, L.stages);
-    bool coop = false;
-    for (int i = 0; i < L.nprob; ++i) coop = coop || L.p[i].splits > 1;
-    coop = coop || L.x_mode == 1;
+    // every problem of a launch uses the same split factor: the `splits` CTAs of a tile are one cluster
+    const int splits = L.p[0].splits;
+    for (int i = 1; i < L.nprob; ++i)
+        if (L.p[i].splits != splits) return cudaErrorInvalidValue;
+    if (splits > 1 && L.x_mode == 1) return cudaErrorInvalidValue;   // grid barrier + clusters are not combined
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(total);
     cfg.blockDim = dim3(kLinThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
+    int na = 0;
+    if (splits > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)splits;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+    } else if (L.x_mode == 1) {   // the activation pre-pass ends in a grid barrier: CTAs must be co-resident
+        at[na].id = cudaLaunchAttributeCooperative;
+        at[na].val.cooperative = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = coop ? 1 : 0;   // split-K CTAs wait for each other: they must be co-resident
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, lin_umma_kernel, L);
 }
 
