@@ -82,8 +82,7 @@ __device__ __forceinline__ float epi_scalar(const LinProblem& P, float acc, int 
 // TF LSTMCell (un-vendored TF 1.7 dependency; gate order i, j, f, o and forget_bias 1.0
 // confirmed on the reference's recorded GraphDef, tests/golden/graph_fixture.json):
 //   c = sigmoid(f + 1) * c_prev + sigmoid(i) * tanh(j);  h = sigmoid(o) * tanh(c)
-__device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, int b, int unit, int mode) {
-    const float cp = P.c_in[(size_t)b * P.H + unit];
+__device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, float cp, int b, int unit, int mode) {
     const float c = sigmoidf_acc(g.z + 1.0f) * cp + sigmoidf_acc(g.x) * tanhf(g.y);
     const float h = sigmoidf_acc(g.w) * tanhf(c);
     P.c_out[(size_t)b * P.H + unit] = c;
@@ -363,9 +362,16 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         const int hi = (int)(((long long)rows_here * (split + 1)) / P.splits) * 32;
         (void)cnt;
         const bool do_am = P.am_val != nullptr && P.splits == 1;
+        // lo and the stride are multiples of 32: a thread keeps the same 4 outputs (u) for every row it
+        // visits, so its bias is loaded once, outside the row loop
+        const int u = pt & 31;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.epi != kEpiNone && P.bias) bias4 = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
         for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
-            const int b = idx >> 5, u = idx & 31;
+            const int b = idx >> 5;
             const uint32_t off = (uint32_t)(b * kTileN + 4 * u) * 4u;
+            float cprev = 0.f;
+            if (P.epi == kEpiLstm && n_tile * 32 + u < P.H) cprev = P.c_in[(size_t)(row0 + b) * P.H + n_tile * 32 + u];
             float4 g;
             if (P.splits == 1) {
                 g = *reinterpret_cast<const float4*>(tile_s + b * kTileN + 4 * u);
@@ -379,19 +385,17 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 for (int r = 1; r < 8; ++r)
                     if (r < P.splits) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
             }
+            g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w;
             if (P.epi == kEpiLstm) {
                 const int unit = n_tile * 32 + u;
-                if (unit < P.H) {
-                    const float4 bb = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
-                    g.x += bb.x; g.y += bb.y; g.z += bb.z; g.w += bb.w;
-                    lstm_gates(P, g, row0 + b, unit, mode);
-                }
+                if (unit < P.H) lstm_gates(P, g, cprev, row0 + b, unit, mode);
             } else {
                 const int ng = n_tile * kTileN + 4 * u;
                 float y[4] = {g.x, g.y, g.z, g.w};
+                if (P.epi == kEpiBiasTanh) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (ng + j < P.n_out) y[j] = epi_scalar(P, y[j], ng + j);
+                    for (int j = 0; j < 4; ++j) y[j] = tanhf(y[j]);
+                }
                 if (P.out) {
                     float* o = P.out + (size_t)(row0 + b) * P.ldo + ng;
                     if (ng + 3 < P.n_out && (P.ldo & 3) == 0) {
@@ -548,7 +552,8 @@ __global__ void __launch_bounds__(128) lin_simt_kernel(const __grid_constant__ L
             g.z = __shfl_sync(0xffffffffu, v, base + 2);
             g.w = __shfl_sync(0xffffffffu, v, base + 3);
             const int unit = n >> 2;
-            if ((lane & 3) == 0 && row0 + j < P.rows && unit < P.H) lstm_gates(P, g, row0 + j, unit, mode);
+            if ((lane & 3) == 0 && row0 + j < P.rows && unit < P.H)
+                lstm_gates(P, g, P.c_in[(size_t)(row0 + j) * P.H + unit], row0 + j, unit, mode);
         }
     } else if (n < P.n_out) {
         for (int j = 0; j < 16; ++j)

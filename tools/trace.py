@@ -38,6 +38,7 @@ def read_trace(n):
 
 
 def show(name, tr, labels):
+    tr = tr[tr[:, 0] > 0]
     t0 = tr[:, 0].min()
     print("== %s  (us after the first CTA started; mean / max over %d CTAs)" % (name, len(tr)))
     for i, lab in enumerate(labels):
