@@ -340,47 +340,59 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         int c_hi = (int)((((long long)(img + 1) * L - 1) * P) / NR);
         while (c_hi + 1 < P && att_rbegin(NR, P, c_hi + 1) <= (img + 1) * L - 1) ++c_hi;
         while (c_hi > 0 && att_rbegin(NR, P, c_hi) > (img + 1) * L - 1) --c_hi;
-        __threadfence();
-        named_bar_sync(1, NT);
+        named_bar_sync(1, NT);                                // every thread's partial stores are ordered before ...
         unsigned* flag = reinterpret_cast<unsigned*>(misc + 2 * G);
-        if (ct == 0) *flag = atomicAdd(p.rowcnt + img, 1u) == (unsigned)(c_hi - c_lo) ? 1u : 0u;
+        if (ct == 0) {
+            __threadfence();                                  // ... this (cumulative) release
+            *flag = atomicAdd(p.rowcnt + img, 1u) == (unsigned)(c_hi - c_lo) ? 1u : 0u;
+        }
         named_bar_sync(1, NT);
         if (ct == 0 && seg0 == r_begin) trace_stamp(p.dbg, 6);
         if (*flag) {
             __threadfence();
             if (ct == 0) p.rowcnt[img] = 0u;                  // ready for the next launch
-            // statistics of every contributor -> smem (one L2 round trip), then scales
+            // every thread redundantly reads the (max, sum) pair of each contributor (a few L2 loads, all in
+            // flight together with its own slice of the partial contexts and of the logits): one round trip
             const int nc = c_hi - c_lo + 1;
-            float* st_m = q_s;                                // q_s / vec_s are free to reuse only in the RV path;
-            float* st_sc = w_s;                               // w_s of this segment is consumed: reuse it for scales
-            (void)st_m;
-            for (int i = ct; i < nc * G; i += NT) {
-                const int cc = c_lo + i / G, g = i - (i / G) * G;
-                const int sid = img - att_rbegin(NR, P, cc) / L;
-                const float* pp = p.part + (((size_t)cc * p.segmax + sid) * G + g) * (D + 2);
-                st_sc[2 * i] = __ldcg(pp + D);
-                st_sc[2 * i + 1] = __ldcg(pp + D + 1);
-            }
-            named_bar_sync(1, NT);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
+                const float* er = p.e + ((size_t)img * G + g) * L;
+                float ev[2];
+                ev[0] = ct < L ? __ldcg(er + ct) : 0.f;
+                ev[1] = ct + NT < L ? __ldcg(er + ct + NT) : 0.f;
                 float M = -INFINITY;
-                for (int j = 0; j < nc; ++j) M = fmaxf(M, st_sc[2 * (j * G + g)]);
+                for (int j0 = 0; j0 < nc; j0 += 8) {
+                    float mm[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int j = j0 + jj;
+                        mm[jj] = -INFINITY;
+                        if (j < nc) {
+                            const int cc = c_lo + j;
+                            const int sid = img - att_rbegin(NR, P, cc) / L;
+                            mm[jj] = __ldcg(p.part + (((size_t)cc * p.segmax + sid) * G + g) * (D + 2) + D);
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) M = fmaxf(M, mm[jj]);
+                }
                 float S = 0.f;
-                for (int j = 0; j < nc; ++j) S = fmaf(st_sc[2 * (j * G + g) + 1], expf(st_sc[2 * (j * G + g)] - M), S);
-                const float inv = 1.0f / S;
                 float zz[kAttMaxDPerThread];
 #pragma unroll
                 for (int k = 0; k < kAttMaxDPerThread; ++k) zz[k] = 0.f;
                 for (int j0 = 0; j0 < nc; j0 += 4) {           // partials of up to 4 contributors in flight
-                    float v[4][kAttMaxDPerThread];
+                    float v[4][kAttMaxDPerThread], ms[4], ss[4];
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = j0 + jj;
+                        ms[jj] = -INFINITY;
+                        ss[jj] = 0.f;
                         if (j < nc) {
                             const int cc = c_lo + j;
                             const int sid = img - att_rbegin(NR, P, cc) / L;
                             const float* pp = p.part + (((size_t)cc * p.segmax + sid) * G + g) * (D + 2);
+                            ms[jj] = __ldcg(pp + D);
+                            ss[jj] = __ldcg(pp + D + 1);
 #pragma unroll
                             for (int k = 0; k < kAttMaxDPerThread; ++k) {
                                 const int d = feat(k);
@@ -390,14 +402,15 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
                     }
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j0 + jj;
-                        if (j < nc) {
-                            const float sc = expf(st_sc[2 * (j * G + g)] - M);
+                        if (j0 + jj < nc) {
+                            const float sc = expf(ms[jj] - M);
+                            S = fmaf(ss[jj], sc, S);
 #pragma unroll
                             for (int k = 0; k < kAttMaxDPerThread; ++k) zz[k] = fmaf(v[jj][k], sc, zz[k]);
                         }
                     }
                 }
+                const float inv = 1.0f / S;
 #pragma unroll
                 for (int k = 0; k < kAttMaxDPerThread; ++k) {
                     const int d = feat(k);
@@ -407,8 +420,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
                         if (p.pa_z) pa_store(p.pa_z, p.pa_mode, p.pa_row_tile, D >> 6, img * G + g, d, zv);
                     }
                 }
-                const float* er = p.e + ((size_t)img * G + g) * L;
-                for (int l = ct; l < L; l += NT) p.alpha[((size_t)img * G + g) * L + l] = expf(__ldcg(er + l) - M) * inv;
+                if (ct < L) p.alpha[((size_t)img * G + g) * L + ct] = expf(ev[0] - M) * inv;
+                if (ct + NT < L) p.alpha[((size_t)img * G + g) * L + ct + NT] = expf(ev[1] - M) * inv;
+                for (int l = ct + 2 * NT; l < L; l += NT) p.alpha[((size_t)img * G + g) * L + l] = expf(__ldcg(er + l) - M) * inv;
             }
             named_bar_sync(1, NT);                            // st_sc (= w_s) is rewritten by the next segment
         }
@@ -446,6 +460,13 @@ bool att_plan(AttParams& p, int smem_optin, int num_sms) {
     p.nslots = n;
     const long long NR = (long long)p.NI * p.L;
     p.grid = (int)(NR < num_sms ? NR : num_sms);
+    if (p.NI <= num_sms) {
+        // k CTAs per image: every CTA owns one segment of exactly one image (one softmax-statistics pass,
+        // one publish) and every image has exactly k contributors; costs at most (1 - NI*k/#SMs) of the SMs
+        int k = num_sms / p.NI;
+        if (k > p.L) k = p.L;
+        if (k >= 1 && (double)(p.NI * k) >= 0.8 * p.grid) p.grid = p.NI * k;
+    }
     const int share = (int)((NR + p.grid - 1) / p.grid);
     p.segmax = share / p.L + 2;
     return n >= 2;
