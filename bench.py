@@ -34,6 +34,9 @@ WORKLOADS = {
             B=64, L=196, D=512, H=1024, V=10000, T=20),
     3: dict(name="config3: B=256 L=196 D=2048 H=1536 E=512 A=512 Dd=1024 V=10000 T=20",
             B=256, L=196, D=2048, H=1536, V=10000, T=20),
+    # BASELINE.json configs[4]: beam search, 128 images x beam 3, T=30 (tokens = images x T)
+    5: dict(name="config5: beam search beam=3, 128 images, L=196 D=512 H=1024 V=10000 T=30 (device-side TopN)",
+            B=128, L=196, D=512, H=1024, V=10000, T=30, beam=3),
 }
 
 
@@ -188,7 +191,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     B, L, D, H, V, T = (wl[k] for k in "BLDHVT")
 
-    cfg = sat_b200.Config(batch_size=B, beam_size=1, num_ctx=L, dim_ctx=D, num_lstm_units=H, vocabulary_size=V,
+    beam = wl.get("beam", 1)
+    cfg = sat_b200.Config(batch_size=B, beam_size=beam, num_ctx=L, dim_ctx=D, num_lstm_units=H, vocabulary_size=V,
                           max_caption_length=T)
     model = sat_b200.CaptionGenerator(cfg)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
@@ -213,6 +217,8 @@ def main():
 
     # ---------------------------------------------------------------- device-resident loop
     def loop(i):
+        if beam > 1:
+            return model.beam_device(ctx_dev[i % pool], beam, T, 2)[0]
         return model.loop_device(ctx_dev[i % pool], T)[0]
 
     for i in range(max(args.warmup, 3) + 2 * pool):       # warm-up also builds one CUDA graph per pool entry
@@ -241,8 +247,19 @@ def main():
     import ctypes as C
     hp = lambda t: C.c_void_p(t.data_ptr())
 
+    if beam > 1:
+        b_sent = torch.empty(B, beam, T, dtype=torch.int32).pin_memory()
+        b_len = torch.empty(B, beam, dtype=torch.int32).pin_memory()
+        b_sc = torch.empty(B, beam, dtype=torch.float64).pin_memory()
+        b_n = torch.empty(B, dtype=torch.int32).pin_memory()
+        b_c = torch.empty(B, dtype=torch.int32).pin_memory()
+
     def e2e_step(i):
-        rc = model.lib.sat_decode_loop_host(model._h, hp(ctx_host[i % pool]), B, T, None, hp(tok_host), model._st())
+        if beam > 1:
+            rc = model.lib.sat_beam_search_host(model._h, hp(ctx_host[i % pool]), B, beam, T, 2, hp(b_sent), hp(b_len),
+                                                hp(b_sc), hp(b_n), hp(b_c), model._st())
+        else:
+            rc = model.lib.sat_decode_loop_host(model._h, hp(ctx_host[i % pool]), B, T, None, hp(tok_host), model._st())
         assert rc == 0, model.lib.sat_last_error()
 
     for i in range(3):
@@ -259,7 +276,7 @@ def main():
     # ---------------------------------------------------------------- attention kernel roofline
     roof = None
     extra = {}
-    if rank == 0:
+    if rank == 0 and beam == 1:
         pk = peaks()
         A = cfg.dim_attend_layer
         flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
@@ -312,7 +329,7 @@ def main():
                      / pk["hbm"])
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu and beam == 1:
         cpu = time_cpu_oracle(wl, 3, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
@@ -326,7 +343,9 @@ def main():
                            "precision": "fp32 in/out; GEMMs as split bf16x3 on tcgen05 with fp32 TMEM accumulation",
                            "l2": "inputs rotate over %d context batches (%.0f MB + 137 MB weights/activations) > 126 MB L2"
                                  % (pool, pool_mb),
-                           "step": "project contexts + initialize + %d decode steps (greedy) for %d images" % (T, B)},
+                           "step": ("project contexts + initialize + %d decode steps (greedy) for %d images" % (T, B))
+                           if beam == 1 else ("beam search: %d images x beam %d, %d steps, device-side TopN; tokens = "
+                                              "images x steps" % (B, beam, T))},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "detail": extra}
         print(json.dumps(line), flush=True)
