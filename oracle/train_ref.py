@@ -1,0 +1,176 @@
+"""Training-step oracle: forward + backward + clip + Adam of the unrolled training graph
+(model.py:250-334 losses, :461-511 optimizer) as a torch-CPU float64 restatement with autograd.
+
+TEST INFRASTRUCTURE ONLY (same rules as oracle/ref_step.py; PARITY UNPINNED for the same reason:
+TensorFlow cannot run here).  torch is used for autograd only; the arithmetic mirrors
+oracle/ref_step.train_forward line by line, and tests/test_oracle_train.py checks the two against
+each other.
+
+Dropout masks are INJECTED: both this oracle and the CUDA path derive them from the counter-based
+generator `dropout_mask` below (the reference uses unseeded TF random ops), so a
+training step is reproducible bit for bit on both sides.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import ref_step as R
+
+# ------------------------------------------------------------------ counter-based dropout RNG
+# u = 24 high bits of splitmix64(seed ^ stream*GOLDEN + idx*C1), mask = floor(keep + u) in float32
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+_C1 = np.uint64(0xBF58476D1CE4E5B9)
+_C2 = np.uint64(0x94D049BB133111EB)
+
+# mask streams of time step t: t * 16 + k
+ATT_CTX, ATT_OUT, ATT_MID, LSTM_IN, LSTM_STATE, LSTM_OUT, DEC_IN, DEC_MID = range(8)
+INIT_BASE = 0xFFFF0   # + 0 init_mean, + 1 init_a, + 2 init_b
+
+
+def uniform24(seed: int, stream: int, n: int) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64)
+        x = (np.uint64(seed) ^ (np.uint64(stream) * _GOLD)) + idx * _C1
+        x ^= x >> np.uint64(30)
+        x *= _C1
+        x ^= x >> np.uint64(27)
+        x *= _C2
+        x ^= x >> np.uint64(31)
+    return ((x >> np.uint64(40)).astype(np.float32)) * np.float32(2.0 ** -24)
+
+
+def dropout_mask(seed: int, stream: int, shape, keep: float) -> np.ndarray:
+    """0/1 mask = floor(keep + U[0,1)) (graph fixture */dropout/{Floor}), float32 arithmetic."""
+    n = int(np.prod(shape))
+    u = uniform24(seed, stream, n)
+    return np.floor(np.float32(keep) + u).astype(np.float32).reshape(shape)
+
+
+def step_masks(cfg: R.OracleConfig, seed: int, t: int, B: int):
+    """The eight injected masks of time step t (names as in ref_step.train_forward)."""
+    L, D, E, H = cfg.num_ctx, cfg.dim_ctx, cfg.dim_embedding, cfg.num_lstm_units
+    A, Dd = cfg.dim_attend_layer, cfg.dim_decode_layer
+    kf, kl = 1.0 - cfg.fc_drop_rate, 1.0 - cfg.lstm_drop_rate
+    s = t * 16
+    return dict(att_ctx=dropout_mask(seed, s + ATT_CTX, (B * L, D), kf),
+                att_out=dropout_mask(seed, s + ATT_OUT, (B, H), kf),
+                att_mid=dropout_mask(seed, s + ATT_MID, (B * L, A), kf),
+                lstm_in=dropout_mask(seed, s + LSTM_IN, (B, D + E), kl),
+                lstm_state=dropout_mask(seed, s + LSTM_STATE, (B, H), kl),
+                lstm_out=dropout_mask(seed, s + LSTM_OUT, (B, H), kl),
+                dec_in=dropout_mask(seed, s + DEC_IN, (B, H + D + E), kf),
+                dec_mid=dropout_mask(seed, s + DEC_MID, (B, Dd), kf))
+
+
+def init_masks(cfg: R.OracleConfig, seed: int, B: int):
+    kf = 1.0 - cfg.fc_drop_rate
+    return dict(init_mean=dropout_mask(seed, INIT_BASE + 0, (B, cfg.dim_ctx), kf),
+                init_a=dropout_mask(seed, INIT_BASE + 1, (B, cfg.dim_initalize_layer), kf),
+                init_b=dropout_mask(seed, INIT_BASE + 2, (B, cfg.dim_initalize_layer), kf))
+
+
+# ------------------------------------------------------------------ forward with autograd (2-layer modes)
+def forward_torch(cfg: R.OracleConfig, w, contexts, sentences, masks, seed=None,
+                  global_mask_sum=None, global_batch=None):
+    """Mirror of ref_step.train_forward on torch float64 tensors (2-layer attend/decode/initialize).
+
+    w: dict name -> torch tensor (requires_grad).  seed=None switches all dropout off.
+    global_mask_sum / global_batch: normalisers of the GLOBAL batch when this is one data-parallel shard
+    (model.py:316-318 divides by reduce_sum(masks) of the whole batch, :324-326 by batch_size*num_ctx).
+    """
+    import torch
+    assert cfg.num_attend_layers == 2 and cfg.num_decode_layers == 2 and cfg.num_initalize_layers == 2
+    f64 = torch.float64
+    B, T = sentences.shape
+    L = cfg.num_ctx
+    kf, kl = 1.0 - cfg.fc_drop_rate, 1.0 - cfg.lstm_drop_rate
+    ctx = torch.as_tensor(contexts, dtype=f64)
+    mk = torch.as_tensor(masks, dtype=f64)
+    sent = torch.as_tensor(np.asarray(sentences), dtype=torch.long)
+
+    def drop(x, m, keep):
+        if m is None:
+            return x
+        return x / keep * torch.as_tensor(m, dtype=f64)
+
+    def dense(x, name, act=None):
+        y = x @ w[name + "/kernel"] + w[name + "/bias"]
+        return act(y) if act else y
+
+    im = init_masks(cfg, seed, B) if seed is not None else {}
+    m = drop(ctx.mean(dim=1), im.get("init_mean"), kf)
+    c = dense(drop(dense(m, "initialize/fc_a1", torch.tanh), im.get("init_a"), kf), "initialize/fc_a2")
+    h_state = dense(drop(dense(m, "initialize/fc_b1", torch.tanh), im.get("init_b"), kf), "initialize/fc_b2")
+    h_out = h_state
+    word = torch.zeros(B, dtype=torch.long)
+    ces, alphas, correct = [], [], []
+    ctx2d = ctx.reshape(B * L, -1)
+    for t in range(T):
+        dm = step_masks(cfg, seed, t, B) if seed is not None else {}
+        t1 = dense(drop(ctx2d, dm.get("att_ctx"), kf), "attend/fc_1a", torch.tanh)
+        t2 = dense(drop(h_out, dm.get("att_out"), kf), "attend/fc_1b", torch.tanh)
+        temp = t1 + t2.repeat_interleave(L, dim=0)
+        temp = drop(temp, dm.get("att_mid"), kf)
+        e = (temp @ w["attend/fc_2/kernel"]).reshape(B, L)
+        alpha = torch.softmax(e, dim=1)
+        context = (ctx * alpha[:, :, None]).sum(dim=1)
+        alphas.append(alpha * mk[:, t:t + 1])
+        emb = w["word_embedding/weights"][word]
+        x = drop(torch.cat([context, emb], dim=1), dm.get("lstm_in"), kl)
+        g = torch.cat([x, h_state], dim=1) @ w["lstm/lstm_cell/kernel"] + w["lstm/lstm_cell/bias"]
+        i, j, f, o = torch.chunk(g, 4, dim=1)
+        c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+        h_raw = torch.sigmoid(o) * torch.tanh(c)
+        h_out = drop(h_raw, dm.get("lstm_out"), kl)
+        h_state = drop(h_raw, dm.get("lstm_state"), kl)
+        expanded = drop(torch.cat([h_out, context, emb], dim=1), dm.get("dec_in"), kf)
+        td = drop(dense(expanded, "decode/fc_1", torch.tanh), dm.get("dec_mid"), kf)
+        logits = dense(td, "decode/fc_2")
+        ce = torch.logsumexp(logits, dim=1) - logits[torch.arange(B), sent[:, t]]
+        ces.append(ce * mk[:, t])
+        pred = logits.argmax(dim=1)
+        correct.append(torch.where(pred == sent[:, t], mk[:, t], torch.zeros_like(mk[:, t])))
+        word = sent[:, t]
+    msum = mk.sum() if global_mask_sum is None else torch.tensor(float(global_mask_sum), dtype=f64)
+    gb = B if global_batch is None else int(global_batch)
+    ce_loss = torch.stack(ces, 1).sum() / msum
+    att = torch.stack(alphas, 2).sum(dim=2)
+    att_loss = cfg.attention_loss_factor * ((1.0 - att) ** 2).sum() / 2.0 / (gb * L)
+    reg = sum(cfg.fc_kernel_regularizer_scale * (w[n] ** 2).sum() / 2.0 for n in R.regularized_names(w))
+    acc = torch.stack(correct, 1).sum() / msum
+    return dict(cross_entropy_loss=ce_loss, attention_loss=att_loss, reg_loss=reg, accuracy=acc,
+                total_loss=ce_loss + att_loss + reg)
+
+
+def loss_and_grads(cfg, weights_np, contexts, sentences, masks, seed=None, global_mask_sum=None,
+                   global_batch=None, reg_in_grad=True):
+    """Losses (floats) and d total_loss / d w for every trainable tensor (numpy float64).
+
+    reg_in_grad=False leaves the regulariser's gradient out (a data-parallel shard adds it once, after the
+    all-reduce)."""
+    import torch
+    w = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=True) for k, v in weights_np.items()}
+    out = forward_torch(cfg, w, contexts, sentences, masks, seed, global_mask_sum, global_batch)
+    loss = out["total_loss"] if reg_in_grad else out["cross_entropy_loss"] + out["attention_loss"]
+    grads = torch.autograd.grad(loss, [w[k] for k in w], allow_unused=True)
+    g = {k: (np.zeros_like(weights_np[k], dtype=np.float64) if gi is None else gi.numpy()) for k, gi in zip(w, grads)}
+    return {k: float(v) for k, v in out.items()}, g
+
+
+def clip_and_adam(weights, grads, m, v, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-6, clip=5.0):
+    """tf.contrib.layers.optimize_loss(clip_gradients=5.0) + tf.train.AdamOptimizer (model.py:479-511).
+
+    clip_by_global_norm: g *= clip / max(norm, clip).  TF Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+    m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; w -= lr_t * m / (sqrt(v) + eps).  `step` counts from 1.
+    Returns (new_w, new_m, new_v, global_norm)."""
+    norm = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
+    scale = clip / max(norm, clip)
+    lr_t = lr * np.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+    nw, nm, nv = {}, {}, {}
+    for k in weights:
+        g = grads[k].astype(np.float64) * scale
+        nm[k] = beta1 * m[k] + (1 - beta1) * g
+        nv[k] = beta2 * v[k] + (1 - beta2) * g * g
+        nw[k] = weights[k].astype(np.float64) - lr_t * nm[k] / (np.sqrt(nv[k]) + eps)
+    return nw, nm, nv, norm
