@@ -142,6 +142,32 @@ int sat_vocab_gemm(sat_handle* h, const float* output, const float* context, con
 int sat_dense_fwd(sat_handle* h, const float* x, const float* w_tf, const float* b, float* y, int32_t rows,
                   int32_t K, int32_t n_out, int32_t act, int32_t splits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step (model.py:250-334 losses, :461-511 optimizer; driver base_model.py:39-68).  2-layer graph.
+ * The trainable variables live in ONE flat fp32 device buffer owned by the caller (parameters), with
+ * parallel buffers for the gradient and the two Adam slots; sat_train_var describes the layout
+ * (TF variable name, offset in floats, TF shape).  A data-parallel step is
+ *     sat_train_forward_backward  ->  all-reduce(sum) of `grads` across ranks (NCCL)  ->  sat_train_apply
+ * Dropout masks come from a counter-based generator keyed by `seed` (0 = dropout off), so a step is
+ * reproducible; ranks must use different seeds. */
+int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop_rate, float lstm_drop_rate,
+                   float attention_loss_factor, float fc_kernel_regularizer_scale);
+int sat_train_num_vars(sat_handle* h);
+/* i in [0, num_vars): name / offset / rows / cols / regularised of variable i; total = floats in the flat buffer */
+int sat_train_var(sat_handle* h, int32_t i, const char** name, int64_t* offset, int64_t* rows, int64_t* cols,
+                  int32_t* regularised, int64_t* total);
+/* replaces the forward+backward half of sess.run(opt_op) (base_model.py:57-60).  contexts [B,L,D], sentences
+ * int32 [B,T], masks [B,T]; global_mask_sum / global_batch are the normalisers of the WHOLE (all ranks) batch
+ * (model.py:316-318, 324-326).  losses (device, 4 floats): cross_entropy, accuracy, attention, reg.
+ * grads is overwritten with this shard's gradient WITHOUT the regulariser term. */
+int sat_train_forward_backward(sat_handle* h, const float* params, float* grads, const float* contexts,
+                               const int32_t* sentences, const float* masks, int32_t B, int32_t T, uint64_t seed,
+                               double global_mask_sum, int32_t global_batch, float* losses, void* stream);
+/* adds the L2-regulariser gradient, clips by the global norm (clip_gradients, config.py:36) and applies TF Adam
+ * (config.py:32-43).  step counts from 1.  grad_norm (device, 1 float, may be NULL) receives the squared norm. */
+int sat_train_apply(sat_handle* h, float* params, float* grads, float* adam_m, float* adam_v, int64_t step, float lr,
+                    float beta1, float beta2, float epsilon, float clip, float* grad_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@
 #include "sat_attention.cuh"
 #include "sat_linear.cuh"
 #include "sat_rows.cuh"
+#include "sat_internal.h"
 
 using namespace sat;
 
@@ -118,6 +119,8 @@ struct sat_handle {
     // valid for the duration of one step_impl call
     bool pa_on = false;
     uint8_t *pa_cur_h_in = nullptr, *pa_cur_h_out = nullptr;
+    void* train = nullptr;                 // training state (sat_train.cu)
+    void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
     int opt_trace = 0;
     int trace_at = 0;      // with trace == 1: index of the dense launch (counted from the option call) to stamp
@@ -184,12 +187,24 @@ static void layer_free(Layer& ly) {
     ly = Layer();
 }
 
+int sat_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+const sat_dims* sat_handle_dims(sat_handle* h) { return &h->d; }
+void** sat_handle_train_slot(sat_handle* h) { return &h->train; }
+void sat_handle_set_train_free(sat_handle* h, void (*fn)(void*)) { h->train_free = fn; }
+
 extern "C" int sat_version(void) { return 100; }
 extern "C" const char* sat_last_error(void) { return g_err; }
 
 extern "C" void sat_destroy(sat_handle* h) {
     if (!h) return;
     cudaDeviceSynchronize();
+    if (h->train && h->train_free) h->train_free(h->train);
     for (auto& g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     for (Layer* ly : h->layers) layer_free(*ly);

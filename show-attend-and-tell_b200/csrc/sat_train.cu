@@ -1,0 +1,740 @@
+// sat_train.cu — the training step of the unrolled decoder (model.py:250-334 losses, :461-511 optimizer):
+// forward with dropout and teacher forcing, backward through time, global-norm clip and Adam.
+//
+// First complete version: every op is a plain fp32 CUDA-core kernel (tiled SGEMM + element-wise kernels)
+// working on explicit, stashed intermediates, written to mirror the reference graph node by node so that
+// losses and every gradient can be checked against the autograd oracle (oracle/train_ref.py).  The
+// tensor-core versions of the large GEMMs (attend/fc_1a forward and weight gradient: ~70 % of the FLOPs)
+// are the next step; correctness comes first.
+//
+// Dropout masks come from a counter-based generator (splitmix64 of seed/stream/index, see
+// oracle/train_ref.py) — the reference's TF ops are unseeded, so injected masks are the only way to
+// compare a training step.
+//
+// Data parallelism: gradients are written into ONE flat fp32 buffer laid out like the parameters; the host
+// all-reduces it (NCCL) between sat_train_forward_backward and sat_train_apply.  Losses use the global
+// normalisers passed in (sum of masks, global batch), so the summed shard gradients equal the
+// single-process gradient; the L2-regulariser gradient is added once, in sat_train_apply.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sat_b200.h"
+#include "sat_internal.h"
+
+namespace {
+
+#define TCK(x)                                                                                          \
+    do {                                                                                                \
+        cudaError_t e_ = (x);                                                                           \
+        if (e_ != cudaSuccess) return sat_fail(SAT_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRET(x)                      \
+    do {                             \
+        int r_ = (x);                \
+        if (r_ != SAT_OK) return r_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ RNG
+__host__ __device__ inline float rng_u24(unsigned long long seed, unsigned long long stream, unsigned long long idx) {
+    unsigned long long x = (seed ^ (stream * 0x9E3779B97F4A7C15ull)) + idx * 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (float)(x >> 40) * 5.9604644775390625e-08f;  // 2^-24
+}
+__device__ inline float drop_scale(unsigned long long seed, unsigned long long stream, unsigned long long idx, float keep) {
+    // x / keep * floor(keep + U)
+    return floorf(keep + rng_u24(seed, stream, idx)) / keep;
+}
+
+// ------------------------------------------------------------------------------------------ SGEMM
+// C[M,N] = op(A)[M,K] * op(B)[K,N] (+ C if accumulate).  Row-major.  TA: A is stored [K,M]; TB: B is stored [N,K].
+// gridDim.z > 1 splits K and accumulates with atomics (only with accumulate semantics on a pre-set C).
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                    const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                    int accumulate, int kchunk) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int k_begin = blockIdx.z * kchunk, k_end = min(K, k_begin + kchunk);
+    float acc[4][4] = {};
+    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            int kk, mm;
+            if (TA) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            float v = 0.f;
+            if (gm < M && gk < k_end) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[kk][mm] = v;
+        }
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            int kk, nn;
+            if (TB) { kk = i & 15; nn = i >> 4; } else { nn = i & 63; kk = i >> 6; }
+            const int gn = n0 + nn, gk = k0 + kk;
+            float v = 0.f;
+            if (gn < N && gk < k_end) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float* c = C + (size_t)gm * ldc + gn;
+            if (gridDim.z > 1) atomicAdd(c, acc[i][j]);
+            else *c = accumulate ? *c + acc[i][j] : acc[i][j];
+        }
+    }
+}
+
+cudaError_t sgemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                  float* C, int ldc, bool accumulate) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
+    int kchunk = K;
+    const int tiles = grid.x * grid.y;
+    if (accumulate && tiles < 148 && K >= 2048) {   // weight gradients: huge K, small output -> split K over the SMs
+        int z = (296 + tiles - 1) / tiles;
+        if (z > K / 256) z = K / 256;
+        if (z < 1) z = 1;
+        kchunk = ((K + z - 1) / z + 15) / 16 * 16;
+        grid.z = (K + kchunk - 1) / kchunk;
+    }
+    const int acc = accumulate ? 1 : 0;
+    if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
+    else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
+    else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
+    else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ element-wise
+#define GRID1D(n) dim3((unsigned)(((n) + 255) / 256 < 65535 * 16 ? ((n) + 255) / 256 : 65535 * 16))
+
+// y[r, c] = x[r, c] * drop(seed, stream, r * cols + c) ; x / y may have different leading dimensions
+__global__ void dropout2d_kernel(float* y, int ldy, const float* x, int ldx, int rows, int cols, unsigned long long seed,
+                                 unsigned long long stream, float keep, int accumulate) {
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+        const float s = seed ? drop_scale(seed, stream, i, keep) : 1.0f;
+        const float v = x[(size_t)r * ldx + c] * s;
+        float* o = y + (size_t)r * ldy + c;
+        *o = accumulate ? *o + v : v;
+    }
+}
+// y = act(x + b[c]) in place ; act 0 none, 1 tanh
+__global__ void bias_act_kernel(float* x, const float* b, int rows, int cols, int act) {
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = x[i] + b[i % cols];
+        x[i] = act ? tanhf(v) : v;
+    }
+}
+// dx = dy * (1 - y^2) in place on dy
+__global__ void tanh_bwd_kernel(float* dy, const float* y, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dy[i] *= 1.0f - y[i] * y[i];
+}
+// db[c] += sum_r dx[r, c]
+__global__ void colsum_kernel(float* db, const float* dx, int rows, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const int r0 = blockIdx.y * 256, r1 = min(rows, r0 + 256);
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += dx[(size_t)r * cols + c];
+    atomicAdd(db + c, s);
+}
+__global__ void copy2d_kernel(float* y, int ldy, const float* x, int ldx, int rows, int cols, int accumulate) {
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+        float* o = y + (size_t)r * ldy + c;
+        const float v = x[(size_t)r * ldx + c];
+        *o = accumulate ? *o + v : v;
+    }
+}
+__global__ void gather_rows_kernel(float* y, int ldy, const float* table, int E, const int32_t* idx, int idx_ld, int rows) {
+    const size_t n = (size_t)rows * E;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / E), c = (int)(i - (size_t)r * E);
+        const int w = idx ? idx[(size_t)r * idx_ld] : 0;
+        y[(size_t)r * ldy + c] = table[(size_t)w * E + c];
+    }
+}
+__global__ void scatter_add_rows_kernel(float* dtable, int E, const int32_t* idx, int idx_ld, const float* dx, int ldx, int rows) {
+    const size_t n = (size_t)rows * E;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / E), c = (int)(i - (size_t)r * E);
+        const int w = idx ? idx[(size_t)r * idx_ld] : 0;
+        atomicAdd(dtable + (size_t)w * E + c, dx[(size_t)r * ldx + c]);
+    }
+}
+// temp[b*L + l, a] = (T1[b*L + l, a] + q[b, a]) * drop(att_mid)
+__global__ void att_temp_kernel(float* temp, const float* T1, const float* q, int B, int L, int A, unsigned long long seed,
+                                unsigned long long stream, float keep) {
+    const size_t n = (size_t)B * L * A;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int a = (int)(i % A);
+        const int b = (int)(i / ((size_t)L * A));
+        const float s = seed ? drop_scale(seed, stream, i, keep) : 1.0f;
+        temp[i] = (T1[i] + q[(size_t)b * A + a]) * s;
+    }
+}
+// e[r] = sum_a temp[r, a] * w2[a]       (one warp per row)
+__global__ void rowdot_kernel(float* e, const float* temp, const float* w2, int rows, int A) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    float s = 0.f;
+    for (int a = lane; a < A; a += 32) s = fmaf(temp[(size_t)warp * A + a], w2[a], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) e[warp] = s;
+}
+// softmax over L per row (one warp per row)
+__global__ void softmax_rows_kernel(float* alpha, const float* e, int rows, int L) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* x = e + (size_t)warp * L;
+    float m = -INFINITY;
+    for (int l = lane; l < L; l += 32) m = fmaxf(m, x[l]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) s += expf(x[l] - m);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int l = lane; l < L; l += 32) alpha[(size_t)warp * L + l] = expf(x[l] - m) / s;
+}
+// de = alpha * (dalpha - sum_l alpha*dalpha)   (one warp per row), written over dalpha
+__global__ void softmax_bwd_kernel(float* dalpha, const float* alpha, int rows, int L) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) s = fmaf(alpha[(size_t)warp * L + l], dalpha[(size_t)warp * L + l], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int l = lane; l < L; l += 32) {
+        const size_t i = (size_t)warp * L + l;
+        dalpha[i] = alpha[i] * (dalpha[i] - s);
+    }
+}
+// z[b, d] = sum_l alpha[b, l] * ctx[b, l, d]
+__global__ void context_fwd_kernel(float* z, const float* alpha, const float* ctx, int B, int L, int D) {
+    const int b = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const float* c = ctx + (size_t)b * L * D + d;
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s = fmaf(alpha[(size_t)b * L + l], c[(size_t)l * D], s);
+    z[(size_t)b * D + d] = s;
+}
+// dalpha[b, l] = sum_d dz[b, d] * ctx[b, l, d]  (+ extra[b, l] if given)   (one warp per (b, l))
+__global__ void context_bwd_kernel(float* dalpha, const float* dz, const float* ctx, const float* extra, int B, int L, int D) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B * L) return;
+    const int b = warp / L;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s = fmaf(dz[(size_t)b * D + d], ctx[(size_t)warp * D + d], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dalpha[warp] = s + (extra ? extra[warp] : 0.f);
+}
+// dtemp[r, a] = de[r] * w2[a] * drop(att_mid)   and  (1 - T1^2) applied later
+__global__ void att_dtemp_kernel(float* dtemp, const float* de, const float* w2, int rows, int A, unsigned long long seed,
+                                 unsigned long long stream, float keep) {
+    const size_t n = (size_t)rows * A;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int a = (int)(i % A);
+        const float s = seed ? drop_scale(seed, stream, i, keep) : 1.0f;
+        dtemp[i] = de[i / A] * w2[a] * s;
+    }
+}
+// dq[b, a] = sum_l dtemp[b*L + l, a]
+__global__ void segsum_kernel(float* dq, const float* dtemp, int B, int L, int A) {
+    const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += dtemp[((size_t)b * L + l) * A + a];
+    dq[(size_t)b * A + a] = s;
+}
+__device__ inline float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+// gates G [B, 4H] (blocks i, j, f, o) -> activated gates (in place), c, h_raw
+__global__ void lstm_fwd_kernel(float* G, const float* bias, const float* c_prev, float* c, float* h_raw, int B, int H) {
+    const size_t n = (size_t)B * H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / H), u = (int)(i - (size_t)b * H);
+        float* g = G + (size_t)b * 4 * H;
+        const float gi = sigm(g[u] + bias[u]);
+        const float gj = tanhf(g[H + u] + bias[H + u]);
+        const float gf = sigm(g[2 * H + u] + bias[2 * H + u] + 1.0f);
+        const float go = sigm(g[3 * H + u] + bias[3 * H + u]);
+        const float cc = gf * c_prev[i] + gi * gj;
+        g[u] = gi; g[H + u] = gj; g[2 * H + u] = gf; g[3 * H + u] = go;
+        c[i] = cc;
+        h_raw[i] = go * tanhf(cc);
+    }
+}
+// dh_raw, dc (in/out: on entry dc = gradient flowing into c_t from step t+1) -> dG (pre-activation), dc_prev
+__global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_raw, const float* acts, const float* c,
+                                const float* c_prev, int B, int H) {
+    const size_t n = (size_t)B * H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / H), u = (int)(i - (size_t)b * H);
+        const float* a = acts + (size_t)b * 4 * H;
+        const float gi = a[u], gj = a[H + u], gf = a[2 * H + u], go = a[3 * H + u];
+        const float tc = tanhf(c[i]);
+        const float dh = dh_raw[i];
+        const float dcc = dh * go * (1.0f - tc * tc) + dc[i];
+        float* d = dG + (size_t)b * 4 * H;
+        d[u] = dcc * gj * gi * (1.0f - gi);
+        d[H + u] = dcc * gi * (1.0f - gj * gj);
+        d[2 * H + u] = dcc * c_prev[i] * gf * (1.0f - gf);
+        d[3 * H + u] = dh * tc * go * (1.0f - go);
+        dc[i] = dcc * gf;
+    }
+}
+// masked cross entropy of one time step + its gradient; one block per row
+__global__ void __launch_bounds__(256) ce_kernel(const float* logits, float* dlogits, const int32_t* sent, int sent_ld, int t,
+                                                 const float* masks, int V, float inv_msum, float* loss_acc) {
+    __shared__ float red[8];
+    __shared__ int redi[8];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* x = logits + (size_t)b * V;
+    float m = -INFINITY;
+    int mi = 0x7fffffff;
+    for (int i = threadIdx.x; i < V; i += 256) {
+        const float v = x[i];
+        if (v > m || (v == m && i < mi)) { m = v; mi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ov > m || (ov == m && oi < mi)) { m = ov; mi = oi; }
+    }
+    if (lane == 0) { red[warp] = m; redi[warp] = mi; }
+    __syncthreads();
+    m = red[0]; mi = redi[0];
+    for (int w = 1; w < 8; ++w)
+        if (red[w] > m || (red[w] == m && redi[w] < mi)) { m = red[w]; mi = redi[w]; }
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < V; i += 256) s += expf(x[i] - m);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    const int y = sent[(size_t)b * sent_ld + t];
+    const float mk = masks[(size_t)b * sent_ld + t];
+    const float scale = mk * inv_msum;
+    for (int i = threadIdx.x; i < V; i += 256) {
+        const float p = expf(x[i] - m) / s;
+        dlogits[(size_t)b * V + i] = (p - (i == y ? 1.0f : 0.0f)) * scale;
+    }
+    if (threadIdx.x == 0) {
+        const float ce = logf(s) + m - x[y];
+        atomicAdd(loss_acc + 0, ce * scale);                       // cross entropy (already / sum of masks)
+        atomicAdd(loss_acc + 1, (mi == y ? mk : 0.0f) * inv_msum);  // accuracy
+    }
+}
+// att[b, l] += alpha[b, l] * mask[b, t]
+__global__ void coverage_acc_kernel(float* att, const float* alpha, const float* masks, int mld, int t, int B, int L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * L) return;
+    att[i] += alpha[i] * masks[(size_t)(i / L) * mld + t];
+}
+// loss = factor * sum (1 - att)^2 / 2 / (GB * L);  datt = -factor * (1 - att) / (GB * L)
+__global__ void coverage_loss_kernel(float* datt, const float* att, int n, float factor, float inv_gbl, float* loss_acc) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float d = 1.0f - att[i];
+        s += d * d;
+        datt[i] = -factor * d * inv_gbl;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) t += red[w];
+        atomicAdd(loss_acc + 2, t * 0.5f * factor * inv_gbl);
+    }
+}
+// extra[b, l] = datt[b, l] * mask[b, t]
+__global__ void coverage_grad_kernel(float* extra, const float* datt, const float* masks, int mld, int t, int B, int L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * L) return;
+    extra[i] = datt[i] * masks[(size_t)(i / L) * mld + t];
+}
+__global__ void mean_L_kernel(float* out, const float* ctx, int L, int D) {
+    const int b = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += ctx[((size_t)b * L + l) * D + d];
+    out[(size_t)b * D + d] = s / (float)L;
+}
+// out[0] += scale * sum x^2
+__global__ void sumsq_kernel(const float* x, size_t n, float scale, float* out) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s = fmaf(x[i], x[i], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) t += red[w];
+        atomicAdd(out, t * scale);
+    }
+}
+__global__ void axpy_kernel(float* y, const float* x, float a, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = fmaf(a, x[i], y[i]);
+}
+// clip_by_global_norm + TF Adam.  norm2 = sum of squares of the (already reduced, regularised) gradient
+__global__ void adam_kernel(float* w, const float* g, float* m, float* v, size_t n, const float* norm2, float clip, float lr_t,
+                            float b1, float b2, float eps) {
+    const float norm = sqrtf(*norm2);
+    const float scale = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * scale;
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ state
+enum Var { vEmb = 0, vIa1W, vIa1B, vIa2W, vIa2B, vIb1W, vIb1B, vIb2W, vIb2B, vA1aW, vA1aB, vA1bW, vA1bB, vA2W, vLW, vLB,
+           vD1W, vD1B, vD2W, vD2B, kNumVars };
+const char* kVarNames[kNumVars] = {
+    "word_embedding/weights", "initialize/fc_a1/kernel", "initialize/fc_a1/bias", "initialize/fc_a2/kernel",
+    "initialize/fc_a2/bias", "initialize/fc_b1/kernel", "initialize/fc_b1/bias", "initialize/fc_b2/kernel",
+    "initialize/fc_b2/bias", "attend/fc_1a/kernel", "attend/fc_1a/bias", "attend/fc_1b/kernel", "attend/fc_1b/bias",
+    "attend/fc_2/kernel", "lstm/lstm_cell/kernel", "lstm/lstm_cell/bias", "decode/fc_1/kernel", "decode/fc_1/bias",
+    "decode/fc_2/kernel", "decode/fc_2/bias"};
+
+struct TrainState {
+    sat_dims d;
+    int B = 0, T = 0;
+    float keep_fc = 0.5f, keep_lstm = 0.7f, att_factor = 0.01f, reg_scale = 1e-4f;
+    size_t off[kNumVars + 1];
+    int rows[kNumVars], cols[kNumVars];
+    bool regularised[kNumVars];
+    // stashes (index [t])
+    std::vector<float*> T1, q, hd, alpha, z, lstm_in, acts, c, h_out, h_state, expd, t1, td, dlogits, emb;
+    float *ctxd = nullptr, *temp = nullptr, *e = nullptr, *G = nullptr, *h_raw = nullptr, *logits = nullptr;
+    float *mean = nullptr, *meand = nullptr, *ia1 = nullptr, *ia1d = nullptr, *ib1 = nullptr, *ib1d = nullptr, *c0 = nullptr,
+          *h0 = nullptr;
+    float *att = nullptr, *datt = nullptr, *extra = nullptr;
+    // backward scratch
+    float *dtd = nullptr, *dexp = nullptr, *dh_out = nullptr, *dh_state = nullptr, *dh_raw = nullptr, *dc = nullptr, *dG = nullptr,
+          *dlin = nullptr, *dz = nullptr, *demb = nullptr, *dalpha = nullptr, *dtemp = nullptr, *dq = nullptr, *dhd = nullptr,
+          *dbuf = nullptr;
+    float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2
+    std::vector<void*> all;
+};
+
+int talloc(TrainState* s, float** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(float));
+    if (e != cudaSuccess) return sat_fail(SAT_ERR_NOMEM, "training buffer of %zu floats: %s", n, cudaGetErrorString(e));
+    s->all.push_back(*p);
+    return SAT_OK;
+}
+
+void train_free(void* p) {
+    TrainState* s = (TrainState*)p;
+    if (!s) return;
+    for (void* b : s->all) cudaFree(b);
+    delete s;
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+extern "C" int sat_train_num_vars(sat_handle* h) {
+    (void)h;
+    return kNumVars;
+}
+
+static void fill_layout(TrainState* s) {
+    const sat_dims& d = s->d;
+    const int D = d.dim_ctx, E = d.dim_embedding, H = d.num_lstm_units, A = d.dim_attend_layer, Dd = d.dim_decode_layer,
+              I = d.dim_initalize_layer, V = d.vocabulary_size;
+    const int shp[kNumVars][2] = {{V, E}, {D, I}, {1, I}, {I, H}, {1, H}, {D, I}, {1, I}, {I, H}, {1, H}, {D, A}, {1, A}, {H, A},
+                                  {1, A}, {A, 1}, {D + E + H, 4 * H}, {1, 4 * H}, {H + D + E, Dd}, {1, Dd}, {Dd, V}, {1, V}};
+    size_t o = 0;
+    for (int i = 0; i < kNumVars; ++i) {
+        s->off[i] = o;
+        s->rows[i] = shp[i][0];
+        s->cols[i] = shp[i][1];
+        o += ((size_t)shp[i][0] * shp[i][1] + 31) / 32 * 32;
+        // L2-regularised: embedding + every dense kernel, not the LSTM kernel, not biases (nn.py:33-37)
+        s->regularised[i] = (i == vEmb) || (shp[i][0] > 1 && i != vLW) || i == vA2W;
+    }
+    s->off[kNumVars] = o;
+}
+
+extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop_rate, float lstm_drop_rate,
+                              float attention_loss_factor, float fc_kernel_regularizer_scale) {
+    if (!h) return sat_fail(SAT_ERR_INVALID, "null handle");
+    const sat_dims* dp = sat_handle_dims(h);
+    if (dp->num_attend_layers != 2 || dp->num_decode_layers != 2 || dp->num_initalize_layers != 2)
+        return sat_fail(SAT_ERR_UNSUPPORTED, "the training step supports the 2-layer attend/decode/initialize graph only");
+    if (B < 1 || T < 1) return sat_fail(SAT_ERR_INVALID, "bad B/T");
+    void** slot = sat_handle_train_slot(h);
+    if (*slot) { train_free(*slot); *slot = nullptr; }
+    TrainState* s = new TrainState();
+    s->d = *dp;
+    s->B = B;
+    s->T = T;
+    s->keep_fc = (float)(1.0 - (double)fc_drop_rate);      // same value as numpy's float32(1 - rate)
+    s->keep_lstm = (float)(1.0 - (double)lstm_drop_rate);
+    s->att_factor = attention_loss_factor;
+    s->reg_scale = fc_kernel_regularizer_scale;
+    fill_layout(s);
+    const sat_dims& d = s->d;
+    const size_t BL = (size_t)B * d.num_ctx, D = d.dim_ctx, E = d.dim_embedding, H = d.num_lstm_units, A = d.dim_attend_layer,
+                 Dd = d.dim_decode_layer, I = d.dim_initalize_layer, V = d.vocabulary_size, L = d.num_ctx;
+    int rc = SAT_OK;
+    auto A1 = [&](float** p, size_t n) { if (rc == SAT_OK) rc = talloc(s, p, n); };
+    auto AT = [&](std::vector<float*>& v, size_t n) {
+        v.assign(T, nullptr);
+        for (int t = 0; t < T; ++t) A1(&v[t], n);
+    };
+    AT(s->T1, BL * A); AT(s->q, B * A); AT(s->hd, B * H); AT(s->alpha, B * L); AT(s->z, B * D); AT(s->lstm_in, B * (D + E + H));
+    AT(s->acts, B * 4 * H); AT(s->c, B * H); AT(s->h_out, B * H); AT(s->h_state, B * H); AT(s->expd, B * (H + D + E));
+    AT(s->t1, B * Dd); AT(s->td, B * Dd); AT(s->dlogits, B * V); AT(s->emb, B * E);
+    A1(&s->ctxd, BL * D); A1(&s->temp, BL * A); A1(&s->e, BL); A1(&s->G, B * 4 * H); A1(&s->h_raw, B * H); A1(&s->logits, B * V);
+    A1(&s->mean, B * D); A1(&s->meand, B * D); A1(&s->ia1, B * I); A1(&s->ia1d, B * I); A1(&s->ib1, B * I); A1(&s->ib1d, B * I);
+    A1(&s->c0, B * H); A1(&s->h0, B * H); A1(&s->att, BL); A1(&s->datt, BL); A1(&s->extra, BL);
+    A1(&s->dtd, B * Dd); A1(&s->dexp, B * (H + D + E)); A1(&s->dh_out, B * H); A1(&s->dh_state, B * H); A1(&s->dh_raw, B * H);
+    A1(&s->dc, B * H); A1(&s->dG, B * 4 * H); A1(&s->dlin, B * (D + E + H)); A1(&s->dz, B * D); A1(&s->demb, B * E);
+    A1(&s->dalpha, BL); A1(&s->dtemp, BL * A); A1(&s->dq, B * A); A1(&s->dhd, B * H); A1(&s->dbuf, B * (D + E + I + H));
+    A1(&s->loss_acc, 8);
+    if (rc != SAT_OK) { train_free(s); return rc; }
+    *slot = s;
+    sat_handle_set_train_free(h, train_free);
+    return SAT_OK;
+}
+
+extern "C" int sat_train_var(sat_handle* h, int32_t i, const char** name, int64_t* offset, int64_t* rows, int64_t* cols,
+                             int32_t* regularised, int64_t* total) {
+    if (!h) return sat_fail(SAT_ERR_INVALID, "null handle");
+    TrainState tmp;
+    TrainState* s = (TrainState*)*sat_handle_train_slot(h);
+    if (!s) { tmp.d = *sat_handle_dims(h); fill_layout(&tmp); s = &tmp; }
+    if (total) *total = (int64_t)s->off[kNumVars];
+    if (i < 0 || i >= kNumVars) return i == -1 ? SAT_OK : sat_fail(SAT_ERR_INVALID, "variable index %d", i);
+    if (name) *name = kVarNames[i];
+    if (offset) *offset = (int64_t)s->off[i];
+    if (rows) *rows = s->rows[i];
+    if (cols) *cols = s->cols[i];
+    if (regularised) *regularised = s->regularised[i] ? 1 : 0;
+    return SAT_OK;
+}
+
+// y = act(dropout?(x) W + b)
+static int dense_fwd(cudaStream_t st, const float* x, int rows, int K, const float* W, const float* b, int N, float* y, int act) {
+    TCK(sgemm(st, false, false, rows, N, K, x, K, W, N, y, N, false));
+    bias_act_kernel<<<GRID1D((size_t)rows * N), 256, 0, st>>>(y, b, rows, N, act);
+    return SAT_OK;
+}
+// given dy (w.r.t. pre-activation): dW += x^T dy, db += colsum(dy), dx = dy W^T (if dx)
+static int dense_bwd(cudaStream_t st, const float* x, int rows, int K, const float* W, int N, const float* dy, float* dW,
+                     float* db, float* dx) {
+    TCK(sgemm(st, true, false, K, N, rows, x, K, dy, N, dW, N, true));
+    if (db) colsum_kernel<<<dim3((N + 127) / 128, (rows + 255) / 256), 128, 0, st>>>(db, dy, rows, N);
+    if (dx) TCK(sgemm(st, false, true, rows, K, N, dy, N, W, N, dx, K, false));
+    return SAT_OK;
+}
+
+extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, float* grads, const float* contexts,
+                                          const int32_t* sentences, const float* masks, int32_t B, int32_t T,
+                                          uint64_t seed, double global_mask_sum, int32_t global_batch, float* losses,
+                                          void* stream) {
+    if (!h || !params || !grads || !contexts || !sentences || !masks || !losses)
+        return sat_fail(SAT_ERR_INVALID, "sat_train_forward_backward: null argument");
+    TrainState* s = (TrainState*)*sat_handle_train_slot(h);
+    if (!s || s->B != B || s->T != T) return sat_fail(SAT_ERR_STATE, "call sat_train_init(B=%d, T=%d) first", B, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    const sat_dims& d = s->d;
+    const int L = d.num_ctx, D = d.dim_ctx, E = d.dim_embedding, H = d.num_lstm_units, A = d.dim_attend_layer,
+              Dd = d.dim_decode_layer, I = d.dim_initalize_layer, V = d.vocabulary_size;
+    const int BL = B * L, XL = D + E + H, XD = H + D + E;
+    const float kf = s->keep_fc, kl = s->keep_lstm;   // 1 - fc_drop_rate, 1 - lstm_drop_rate (config.py:25-26)
+    auto P = [&](int v) { return params + s->off[v]; };
+    auto Gd = [&](int v) { return grads + s->off[v]; };
+    auto ST = [&](int t, int k) { return (unsigned long long)(t * 16 + k); };
+    const unsigned long long INIT = 0xFFFF0ull;
+    const float inv_msum = (float)(1.0 / global_mask_sum);
+    const float inv_gbl = 1.0f / ((float)global_batch * (float)L);
+
+    TCK(cudaMemsetAsync(grads, 0, s->off[kNumVars] * sizeof(float), st));
+    TCK(cudaMemsetAsync(s->loss_acc, 0, 8 * sizeof(float), st));
+    TCK(cudaMemsetAsync(s->att, 0, (size_t)BL * sizeof(float), st));
+
+    // ------------------------------------------------------------ initialize (model.py:239-242, 358-393)
+    mean_L_kernel<<<dim3((D + 127) / 128, B), 128, 0, st>>>(s->mean, contexts, L, D);
+    dropout2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->meand, D, s->mean, D, B, D, seed, INIT + 0, kf, 0);
+    TRET(dense_fwd(st, s->meand, B, D, P(vIa1W), P(vIa1B), I, s->ia1, 1));
+    dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(s->ia1d, I, s->ia1, I, B, I, seed, INIT + 1, kf, 0);
+    TRET(dense_fwd(st, s->ia1d, B, I, P(vIa2W), P(vIa2B), H, s->c0, 0));
+    TRET(dense_fwd(st, s->meand, B, D, P(vIb1W), P(vIb1B), I, s->ib1, 1));
+    dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(s->ib1d, I, s->ib1, I, B, I, seed, INIT + 2, kf, 0);
+    TRET(dense_fwd(st, s->ib1d, B, I, P(vIb2W), P(vIb2B), H, s->h0, 0));
+
+    // ------------------------------------------------------------ forward through time (model.py:258-312)
+    for (int t = 0; t < T; ++t) {
+        const float* h_out_prev = t ? s->h_out[t - 1] : s->h0;
+        const float* h_state_prev = t ? s->h_state[t - 1] : s->h0;
+        const float* c_prev = t ? s->c[t - 1] : s->c0;
+        // attend (model.py:395-436)
+        dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
+        TRET(dense_fwd(st, s->ctxd, BL, D, P(vA1aW), P(vA1aB), A, s->T1[t], 1));
+        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
+        TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
+        att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
+        rowdot_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->e, s->temp, P(vA2W), BL, A);
+        softmax_rows_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(s->alpha[t], s->e, B, L);
+        context_fwd_kernel<<<dim3((D + 127) / 128, B), 128, 0, st>>>(s->z[t], s->alpha[t], contexts, B, L, D);   // un-dropped ctx
+        coverage_acc_kernel<<<(BL + 255) / 256, 256, 0, st>>>(s->att, s->alpha[t], masks, T, t, B, L);
+        // embedding of the previous word: 0 at t = 0, then teacher forcing (model.py:254, 310)
+        gather_rows_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->emb[t], E, P(vEmb), E, t ? sentences + (t - 1) : nullptr, T, B);
+        // LSTM with DropoutWrapper (model.py:228-236, 276-279)
+        copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dlin, D + E, s->z[t], D, B, D, 0);
+        copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->dlin + D, D + E, s->emb[t], E, B, E, 0);
+        dropout2d_kernel<<<GRID1D((size_t)B * (D + E)), 256, 0, st>>>(s->lstm_in[t], XL, s->dlin, D + E, B, D + E, seed, ST(t, 3), kl, 0);
+        copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->lstm_in[t] + D + E, XL, h_state_prev, H, B, H, 0);
+        TCK(sgemm(st, false, false, B, 4 * H, XL, s->lstm_in[t], XL, P(vLW), 4 * H, s->acts[t], 4 * H, false));
+        lstm_fwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->acts[t], P(vLB), c_prev, s->c[t], s->h_raw, B, H);
+        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->h_out[t], H, s->h_raw, H, B, H, seed, ST(t, 5), kl, 0);
+        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->h_state[t], H, s->h_raw, H, B, H, seed, ST(t, 4), kl, 0);
+        // decode (model.py:282-287, 438-459)
+        copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dexp, XD, s->h_out[t], H, B, H, 0);
+        copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dexp + H, XD, s->z[t], D, B, D, 0);
+        copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->dexp + H + D, XD, s->emb[t], E, B, E, 0);
+        dropout2d_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->expd[t], XD, s->dexp, XD, B, XD, seed, ST(t, 6), kf, 0);
+        TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), Dd, s->t1[t], 1));
+        dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->td[t], Dd, s->t1[t], Dd, B, Dd, seed, ST(t, 7), kf, 0);
+        TRET(dense_fwd(st, s->td[t], B, Dd, P(vD2W), P(vD2B), V, s->logits, 0));
+        // masked cross entropy + accuracy, and d loss / d logits (model.py:292-305, 316-318, 332-334)
+        ce_kernel<<<B, 256, 0, st>>>(s->logits, s->dlogits[t], sentences, T, t, masks, V, inv_msum, s->loss_acc);
+    }
+    // attention coverage loss (model.py:320-326) and L2 regulariser (model.py:328)
+    coverage_loss_kernel<<<64, 256, 0, st>>>(s->datt, s->att, BL, s->att_factor, inv_gbl, s->loss_acc);
+    for (int v = 0; v < kNumVars; ++v)
+        if (s->regularised[v])
+            sumsq_kernel<<<128, 256, 0, st>>>(P(v), (size_t)s->rows[v] * s->cols[v], 0.5f * s->reg_scale, s->loss_acc + 3);
+
+    // ------------------------------------------------------------ backward through time
+    TCK(cudaMemsetAsync(s->dh_out, 0, (size_t)B * H * sizeof(float), st));    // d loss / d h_out[t] from step t+1's attend
+    TCK(cudaMemsetAsync(s->dh_state, 0, (size_t)B * H * sizeof(float), st));  // d loss / d h_state[t] from step t+1's LSTM
+    TCK(cudaMemsetAsync(s->dc, 0, (size_t)B * H * sizeof(float), st));
+    for (int t = T - 1; t >= 0; --t) {
+        const float* h_state_prev = t ? s->h_state[t - 1] : s->h0;
+        const float* c_prev = t ? s->c[t - 1] : s->c0;
+        (void)h_state_prev;
+        // decode fc_2, fc_1
+        TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), s->dtd));
+        dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->dtd, Dd, s->dtd, Dd, B, Dd, seed, ST(t, 7), kf, 0);
+        tanh_bwd_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->dtd, s->t1[t], (size_t)B * Dd);
+        TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, s->dtd, Gd(vD1W), Gd(vD1B), s->dexp));
+        dropout2d_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->dexp, XD, s->dexp, XD, B, XD, seed, ST(t, 6), kf, 0);
+        // dexp = [dh_out | dz | demb]
+        copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dexp, XD, B, H, 1);
+        copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dz, D, s->dexp + H, XD, B, D, 0);
+        copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->demb, E, s->dexp + H + D, XD, B, E, 0);
+        // h_out = drop_out(h_raw), h_state = drop_state(h_raw)
+        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_out, H, B, H, seed, ST(t, 5), kl, 0);
+        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_state, H, B, H, seed, ST(t, 4), kl, 1);
+        lstm_bwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dG, s->dc, s->dh_raw, s->acts[t], s->c[t], c_prev, B, H);
+        TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, s->dG, Gd(vLW), Gd(vLB), s->dlin));
+        // dlin = [d xd (D+E) | dh_state_prev]
+        copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_state, H, s->dlin + D + E, XL, B, H, 0);
+        dropout2d_kernel<<<GRID1D((size_t)B * (D + E)), 256, 0, st>>>(s->dbuf, D + E, s->dlin, XL, B, D + E, seed, ST(t, 3), kl, 0);
+        copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dz, D, s->dbuf, D + E, B, D, 1);
+        copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->demb, E, s->dbuf + D, D + E, B, E, 1);
+        scatter_add_rows_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(Gd(vEmb), E, t ? sentences + (t - 1) : nullptr, T, s->demb, E, B);
+        // attention: context vector, softmax, scorer
+        coverage_grad_kernel<<<(BL + 255) / 256, 256, 0, st>>>(s->extra, s->datt, masks, T, t, B, L);
+        context_bwd_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->dalpha, s->dz, contexts, s->extra, B, L, D);
+        softmax_bwd_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
+        att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
+        TCK(sgemm(st, true, false, A, 1, BL, s->temp, A, s->dalpha, 1, Gd(vA2W), 1, true));                  // dw2 += temp^T de
+        att_dtemp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
+        segsum_kernel<<<dim3((A + 127) / 128, B), 128, 0, st>>>(s->dq, s->dtemp, B, L, A);
+        tanh_bwd_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->T1[t], (size_t)BL * A);
+        dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
+        TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));           // contexts are inputs
+        tanh_bwd_kernel<<<GRID1D((size_t)B * A), 256, 0, st>>>(s->dq, s->q[t], (size_t)B * A);
+        TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, s->dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
+        // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
+        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
+    }
+    // ------------------------------------------------------------ initialize backward
+    // h0 is both h_out[-1] (attend of step 0) and h_state[-1] (LSTM of step 0); c0 receives dc
+    copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dh_state, H, B, H, 1);
+    float* dmean = s->dbuf;                 // [B, D]
+    float* dmid = s->dbuf + (size_t)B * D;  // [B, I]
+    TRET(dense_bwd(st, s->ib1d, B, I, P(vIb2W), H, s->dh_out, Gd(vIb2W), Gd(vIb2B), dmid));
+    dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, I, dmid, I, B, I, seed, INIT + 2, kf, 0);
+    tanh_bwd_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, s->ib1, (size_t)B * I);
+    TRET(dense_bwd(st, s->meand, B, D, P(vIb1W), I, dmid, Gd(vIb1W), Gd(vIb1B), nullptr));
+    TRET(dense_bwd(st, s->ia1d, B, I, P(vIa2W), H, s->dc, Gd(vIa2W), Gd(vIa2B), dmid));
+    dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, I, dmid, I, B, I, seed, INIT + 1, kf, 0);
+    tanh_bwd_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, s->ia1, (size_t)B * I);
+    TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), I, dmid, Gd(vIa1W), Gd(vIa1B), nullptr));
+    (void)dmean;
+    TCK(cudaGetLastError());
+    TCK(cudaMemcpyAsync(losses, s->loss_acc, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SAT_OK;
+}
+
+// grads: the (all-reduced) sum over data-parallel shards.  Adds the L2-regulariser gradient once, clips by the
+// global norm (clip_gradients = 5.0, model.py:505-510) and applies TF Adam (model.py:480-485).  step counts from 1.
+extern "C" int sat_train_apply(sat_handle* h, float* params, float* grads, float* adam_m, float* adam_v, int64_t step, float lr,
+                               float beta1, float beta2, float epsilon, float clip, float* grad_norm, void* stream) {
+    if (!h || !params || !grads || !adam_m || !adam_v) return sat_fail(SAT_ERR_INVALID, "sat_train_apply: null argument");
+    TrainState* s = (TrainState*)*sat_handle_train_slot(h);
+    if (!s) return sat_fail(SAT_ERR_STATE, "call sat_train_init first");
+    if (step < 1) return sat_fail(SAT_ERR_INVALID, "step counts from 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int v = 0; v < kNumVars; ++v)
+        if (s->regularised[v]) {
+            const size_t n = (size_t)s->rows[v] * s->cols[v];
+            axpy_kernel<<<GRID1D(n), 256, 0, st>>>(grads + s->off[v], params + s->off[v], s->reg_scale, n);
+        }
+    TCK(cudaMemsetAsync(s->loss_acc + 4, 0, sizeof(float), st));
+    sumsq_kernel<<<296, 256, 0, st>>>(grads, s->off[kNumVars], 1.0f, s->loss_acc + 4);   // padding entries are zero
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+    adam_kernel<<<GRID1D(s->off[kNumVars]), 256, 0, st>>>(params, grads, adam_m, adam_v, s->off[kNumVars], s->loss_acc + 4, clip,
+                                                          (float)lr_t, beta1, beta2, epsilon);
+    TCK(cudaGetLastError());
+    if (grad_norm) TCK(cudaMemcpyAsync(grad_norm, s->loss_acc + 4, sizeof(float), cudaMemcpyDeviceToDevice, st));  // norm^2
+    return SAT_OK;
+}

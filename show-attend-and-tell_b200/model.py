@@ -177,6 +177,118 @@ class CaptionGenerator(object):
         missing = self.set_weights(data)
         return len(self._shapes) - missing
 
+    # ------------------------------------------------------------------ training step (base_model.py:39-68)
+    def train_setup(self, batch_size, num_steps=None, weights=None):
+        """Allocate the flat parameter / gradient / Adam buffers for training with `batch_size` images per
+        process and `num_steps` unrolled time steps (config.max_caption_length).  `weights`: initial values
+        (dict of TF variable names); default U(-s, s) kernels and zero biases like the reference
+        (utils/nn.py:29-31).  The reference's trainable set (model.py:225: embedding, dense layers, LSTM)."""
+        torch = self.torch
+        cfg = self.config
+        T = int(num_steps or cfg.max_caption_length)
+        self._check(self.lib.sat_train_init(self._h, int(batch_size), T, float(cfg.fc_drop_rate),
+                                            float(cfg.lstm_drop_rate), float(cfg.attention_loss_factor),
+                                            float(cfg.fc_kernel_regularizer_scale)))
+        self._train_BT = (int(batch_size), T)
+        n = self.lib.sat_train_num_vars(self._h)
+        self._train_vars = []
+        total = C.c_int64()
+        for i in range(n):
+            name, off, rows, cols, reg = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+            self._check(self.lib.sat_train_var(self._h, i, C.byref(name), C.byref(off), C.byref(rows), C.byref(cols),
+                                               C.byref(reg), C.byref(total)))
+            self._train_vars.append((name.value.decode(), off.value, rows.value, cols.value, bool(reg.value)))
+        self.params = torch.zeros(total.value, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.adam_m = torch.zeros_like(self.params)
+        self.adam_v = torch.zeros_like(self.params)
+        self._train_losses = torch.zeros(4, device=self.device)
+        self._train_norm = torch.zeros(1, device=self.device)
+        self.global_step = 0
+        if weights is None:
+            g = torch.Generator(device="cpu").manual_seed(0)
+            sc = cfg.fc_kernel_initializer_scale
+            weights = {nm: (torch.zeros(r * c) if nm.endswith("/bias") else torch.rand(r * c, generator=g) * 2 * sc - sc)
+                       for nm, _, r, c, _ in self._train_vars}
+        self.train_load(weights)
+        return self
+
+    def _var_view(self, buf, name):
+        for nm, off, r, c, _ in self._train_vars:
+            if nm == name:
+                shp = self._shapes[nm]
+                return buf[off:off + r * c].view(*shp)
+        raise KeyError(name)
+
+    def train_load(self, weights):
+        given = {(k[:-2] if k.endswith(":0") else k): v for k, v in weights.items()}
+        for nm, off, r, c, _ in self._train_vars:
+            if nm in given:
+                self.params[off:off + r * c].copy_(self._dev(given[nm], self.torch.float32).reshape(-1))
+
+    def train_state_dict(self, which="params"):
+        """{tf variable name: tensor view} of the parameters ('params'), gradients ('grads') or Adam slots."""
+        buf = dict(params=self.params, grads=self.grads, m=self.adam_m, v=self.adam_v)[which]
+        return {nm: self._var_view(buf, nm) for nm, *_ in self._train_vars}
+
+    def sync_inference_weights(self):
+        """Repack the trained parameters for the decode kernels (so beam_search / decode_step use them)."""
+        return self.set_weights(self.train_state_dict("params"))
+
+    def train_forward_backward(self, contexts, sentences, masks, seed=0, global_mask_sum=None, global_batch=None):
+        """Forward + backward of one batch shard; fills self.grads (no regulariser term) and returns the losses
+        {cross_entropy_loss, accuracy, attention_loss, reg_loss, total_loss} as floats."""
+        torch = self.torch
+        B, T = self._train_BT
+        ctx = self._dev(contexts, torch.float32)
+        sent = self._dev(sentences, torch.int32)
+        mk = self._dev(masks, torch.float32)
+        assert tuple(sent.shape) == (B, T) and tuple(mk.shape) == (B, T) and ctx.shape[0] == B
+        gms = float(mk.sum().item()) if global_mask_sum is None else float(global_mask_sum)
+        gb = B if global_batch is None else int(global_batch)
+        self._sync_in()
+        self._check(self.lib.sat_train_forward_backward(self._h, self._p(self.params), self._p(self.grads), self._p(ctx),
+                                                        self._p(sent), self._p(mk), B, T, int(seed), gms, gb,
+                                                        self._p(self._train_losses), self._st()))
+        self._sync_out()
+        self._keep["train_in"] = (ctx, sent, mk)
+        return self._train_losses
+
+    def train_apply(self):
+        """Regulariser gradient + global-norm clip + Adam on self.grads (already summed over ranks)."""
+        cfg = self.config
+        self.global_step += 1
+        self._sync_in()
+        self._check(self.lib.sat_train_apply(self._h, self._p(self.params), self._p(self.grads), self._p(self.adam_m),
+                                             self._p(self.adam_v), self.global_step, float(cfg.initial_learning_rate),
+                                             float(cfg.beta1), float(cfg.beta2), float(cfg.epsilon),
+                                             float(cfg.clip_gradients), self._p(self._train_norm), self._st()))
+        self._sync_out()
+        return self._train_norm
+
+    def train_step(self, contexts, sentences, masks, seed=0):
+        """One optimisation step (the sess.run(opt_op) of base_model.py:57-60) on this process's shard; with
+        torch.distributed initialised the gradients are summed over the ranks by ONE all-reduce of the flat
+        buffer (NCCL) and the losses are normalised by the global batch."""
+        import torch.distributed as dist
+        torch = self.torch
+        B, T = self._train_BT
+        mk = self._dev(masks, torch.float32)
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        msum = mk.sum().reshape(1).double()
+        if world > 1:
+            dist.all_reduce(msum)
+            seed = int(seed) + 0x1000003 * dist.get_rank() if seed else 0
+        losses = self.train_forward_backward(contexts, sentences, mk, seed, float(msum.item()), B * world)
+        if world > 1:
+            dist.all_reduce(self.grads)                    # the single gradient all-reduce of the step
+            losses = losses.clone()
+            dist.all_reduce(losses[:3])                    # CE / accuracy / attention are sums of shard parts
+        norm2 = self.train_apply()
+        ce, acc, att, reg = [float(x) for x in losses.tolist()]
+        return dict(cross_entropy_loss=ce, accuracy=acc, attention_loss=att, reg_loss=reg, total_loss=ce + att + reg,
+                    gradient_norm=float(norm2.item()) ** 0.5)
+
     # ------------------------------------------------------------------ device API
     def prepare(self, contexts, want_state=True):
         """Project the contexts once per image batch and run `initialize`.  contexts: CUDA tensor

@@ -1,0 +1,108 @@
+"""Training step on the GPU (sat_train.cu) against the autograd oracle (oracle/train_ref.py): losses, every
+gradient, clip + Adam, and the data-parallel shard identity — with dropout off and with injected masks."""
+import numpy as np
+import pytest
+
+from _util import make_pair
+from oracle import ref_step as R
+from oracle import train_ref as TR
+
+pytestmark = pytest.mark.gpu
+
+TDIMS = dict(num_ctx=9, dim_ctx=64, dim_embedding=32, num_lstm_units=32, dim_initalize_layer=16,
+             dim_attend_layer=24, dim_decode_layer=40, vocabulary_size=50, max_caption_length=5)
+
+
+def setup(B=4, seed=3, dims=TDIMS):
+    ocfg, w, m = make_pair(B, seed=seed, **dims)
+    T = ocfg.max_caption_length
+    rng = np.random.RandomState(seed)
+    ctx = R.synth_contexts(ocfg, B, seed)
+    sent = rng.randint(1, ocfg.vocabulary_size, (B, T)).astype(np.int32)
+    lens = rng.randint(2, T + 1, B)
+    masks = (np.arange(T)[None, :] < lens[:, None]).astype(np.float32)
+    m.train_setup(B, T, weights=w)
+    return ocfg, w, m, ctx, sent, masks
+
+
+def grad_check(m, ref_g, tol):
+    got = {k: v.detach().cpu().numpy() for k, v in m.train_state_dict("grads").items()}
+    worst = 0.0
+    for k, g in ref_g.items():
+        scale = max(np.abs(g).max(), 1e-12)
+        err = np.abs(got[k].reshape(g.shape) - g).max() / scale
+        worst = max(worst, err)
+        assert err < tol, "%s: gradient max-norm relative error %.3e" % (k, err)
+    return worst
+
+
+@pytest.mark.parametrize("seed", [0, 77])
+def test_losses_and_gradients_match_autograd(seed):
+    ocfg, w, m, ctx, sent, masks = setup()
+    ref_l, ref_g = TR.loss_and_grads(ocfg, w, ctx, sent, masks, seed if seed else None, reg_in_grad=False)
+    losses = m.train_forward_backward(ctx, sent, masks, seed=seed).cpu().numpy()
+    ce, acc, att, reg = [float(x) for x in losses]
+    assert abs(ce - ref_l["cross_entropy_loss"]) < 1e-4 * ref_l["cross_entropy_loss"]
+    assert abs(att - ref_l["attention_loss"]) < 1e-4 * ref_l["attention_loss"] + 1e-9
+    assert abs(reg - ref_l["reg_loss"]) < 1e-4 * ref_l["reg_loss"]
+    assert abs(acc - ref_l["accuracy"]) < 1e-6
+    grad_check(m, ref_g, 2e-4)
+
+
+def test_adam_update_matches_tf_semantics():
+    ocfg, w, m, ctx, sent, masks = setup(seed=5)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    mm = {k: np.zeros_like(v) for k, v in w64.items()}
+    vv = {k: np.zeros_like(v) for k, v in w64.items()}
+    for step in (1, 2, 3):
+        _, g = TR.loss_and_grads(ocfg, w64, ctx, sent, masks, 100 + step, reg_in_grad=True)
+        # exaggerate the gradient so that the global-norm clip is active on step 2
+        w64, mm, vv, norm = TR.clip_and_adam(w64, g, mm, vv, step, lr=1e-4, clip=5.0 if step != 2 else 1e-3)
+        m.config.clip_gradients = 5.0 if step != 2 else 1e-3
+        out = m.train_step(ctx, sent, masks, seed=100 + step)
+        assert abs(out["gradient_norm"] - norm) < 2e-4 * norm
+        got = {k: v.detach().cpu().numpy() for k, v in m.train_state_dict("params").items()}
+        for k in w64:
+            # parameters move by ~lr per step: compare the UPDATE, not the value
+            np.testing.assert_allclose(got[k].reshape(w64[k].shape), w64[k], rtol=0, atol=3e-6)
+    m.config.clip_gradients = 5.0
+
+
+def test_data_parallel_shards_sum_to_global_gradient():
+    ocfg, w, m, ctx, sent, masks = setup(B=4, seed=9)
+    _, ref_g = TR.loss_and_grads(ocfg, w, ctx, sent, masks, None, reg_in_grad=False)
+    msum = float(masks.sum())
+    m.train_setup(2, ocfg.max_caption_length, weights=w)          # a "rank" holds half of the batch
+    tot = None
+    for lo in (0, 2):
+        m.train_forward_backward(ctx[lo:lo + 2], sent[lo:lo + 2], masks[lo:lo + 2], 0, msum, 4)
+        g = m.grads.clone()
+        tot = g if tot is None else tot + g                        # what the NCCL all-reduce computes
+    m.grads.copy_(tot)
+    grad_check(m, ref_g, 2e-4)
+
+
+def test_training_reduces_the_loss_and_feeds_the_decoder():
+    ocfg, w, m, ctx, sent, masks = setup(seed=11)
+    m.config.initial_learning_rate = 3e-3
+    first = m.train_step(ctx, sent, masks, seed=1)["total_loss"]
+    for it in range(2, 30):
+        last = m.train_step(ctx, sent, masks, seed=it)["total_loss"]
+    assert last < 0.7 * first
+    assert m.sync_inference_weights() == 0                          # trained weights drive the decode kernels
+    toks = m.decode_loop(ctx, ocfg.max_caption_length)
+    assert toks.shape == (4, ocfg.max_caption_length)
+
+
+def test_reference_shapes_one_step():
+    """default reference graph (L=196, D=512, H=512, V=5000), B=8, T=4: losses against the oracle forward."""
+    dims = dict(max_caption_length=4)
+    ocfg, w, m, ctx, sent, masks = setup(B=8, seed=2, dims=dims)
+    dm = [TR.step_masks(ocfg, 5, t, 8) for t in range(4)]
+    ref = R.train_forward(ocfg, w, ctx, sent, masks, np.float32, dm, TR.init_masks(ocfg, 5, 8))
+    ce, acc, att, reg = [float(x) for x in m.train_forward_backward(ctx, sent, masks, seed=5).cpu().numpy()]
+    assert abs(ce - ref["cross_entropy_loss"]) < 1e-3 * ref["cross_entropy_loss"]
+    assert abs(att - ref["attention_loss"]) < 1e-3 * ref["attention_loss"]
+    assert abs(reg - ref["reg_loss"]) < 1e-3 * ref["reg_loss"]
+    g = m.grads
+    assert bool(g.isfinite().all()) and float(g.abs().max()) > 0
