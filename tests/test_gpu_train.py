@@ -28,8 +28,11 @@ def setup(B=4, seed=3, dims=TDIMS):
 def grad_check(m, ref_g, tol):
     got = {k: v.detach().cpu().numpy() for k, v in m.train_state_dict("grads").items()}
     worst = 0.0
+    # some gradients are mathematically zero (dropout off: the 2-layer scorer does not depend on the state
+    # branch): compare those against the size of a typical gradient, not against round-off
+    floor = 1e-4 * max(np.abs(g).max() for g in ref_g.values())
     for k, g in ref_g.items():
-        scale = max(np.abs(g).max(), 1e-12)
+        scale = max(np.abs(g).max(), floor)
         err = np.abs(got[k].reshape(g.shape) - g).max() / scale
         worst = max(worst, err)
         assert err < tol, "%s: gradient max-norm relative error %.3e" % (k, err)
