@@ -34,6 +34,10 @@ WORKLOADS = {
             B=64, L=196, D=512, H=1024, V=10000, T=20),
     3: dict(name="config3: B=256 L=196 D=2048 H=1536 E=512 A=512 Dd=1024 V=10000 T=20",
             B=256, L=196, D=2048, H=1536, V=10000, T=20),
+    # BASELINE.json configs[3]: training step, 64 images per GPU (512 on 8 GPUs), forward + backward + gradient
+    # all-reduce + clip + Adam; tokens = teacher-forced words per step
+    4: dict(name="config4: training step B=64/GPU L=196 D=512 H=1024 V=10000 T=20, fwd+bwd+all-reduce+Adam (fp32 "
+                 "CUDA-core kernels, dropout on)", B=64, L=196, D=512, H=1024, V=10000, T=20, train=True),
     # BASELINE.json configs[4]: beam search, 128 images x beam 3, T=30 (tokens = images x T)
     5: dict(name="config5: beam search beam=3, 128 images, L=196 D=512 H=1024 V=10000 T=30 (device-side TopN)",
             B=128, L=196, D=512, H=1024, V=10000, T=30, beam=3),
@@ -159,6 +163,76 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_training(args, wl, model, cfg, rank, local_rank, world, dev):
+    """config 4: one optimisation step per bench step (forward + backward + ONE NCCL all-reduce of the flat
+    gradient + clip + Adam); weak scaling, 64 images per GPU."""
+    import torch
+    import torch.distributed as dist
+    from sat_b200 import parallel
+    B, L, D, T, V = wl["B"], wl["L"], wl["D"], wl["T"], wl["V"]
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    model.train_setup(B, T)
+    pool = 3
+    ctx_host = [torch.relu(torch.randn(B, L, D, generator=g)).pin_memory() for _ in range(pool)]
+    ctx_dev = [c.to(dev) for c in ctx_host]
+    sent = torch.randint(1, V, (B, T), generator=g, dtype=torch.int32).to(dev)
+    lens = torch.randint(8, T + 1, (B,), generator=g)
+    masks = (torch.arange(T)[None, :] < lens[:, None]).float().to(dev)
+    st = model.stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        out = model.train_step(ctx_dev[i % pool], sent, masks, seed=1 + i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(st):
+        ev0.record(st)
+        for i in range(args.steps):
+            out = model.train_step(ctx_dev[i % pool], sent, masks, seed=100 + i)
+        ev1.record(st)
+    barrier()
+    ms = parallel.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * T * args.steps / (ms / 1e3)
+    # end to end: contexts come from pinned host memory every step, the losses go back to the host
+    for i in range(2):
+        model.train_step(ctx_host[i % pool].to(dev, non_blocking=True), sent, masks, seed=7)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = model.train_step(ctx_host[i % pool].to(dev, non_blocking=True), sent, masks, seed=200 + i)
+    torch.cuda.synchronize()
+    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    if rank == 0:
+        nparams = int(model.params.numel())
+        line = {"metric": "training tokens/sec (teacher-forced words per second, fwd+bwd+all-reduce+Adam)",
+                "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world,
+                           "parallelism": "dp%d: batch sharded, replicated weights, one NCCL all-reduce of the flat "
+                                          "fp32 gradient (%d floats) per step" % (world, nparams),
+                           "l2": "activations of a step (>1.5 GB stashed) exceed L2"},
+                "e2e": {"value": world * B * T * args.steps / e2e_s, "unit": "tokens/s",
+                        "h2d_bytes_per_step": B * L * D * 4, "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": None, "clocks": clocks, "roofline": None, "cpu_baseline": None,
+                "detail": {"last_losses": out}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +275,9 @@ def main():
     weights = {n: (torch.rand(*s, generator=wg) * 0.16 - 0.08) for n, s in shapes.items()}
     assert model.set_weights(weights) == 0
     del weights
+
+    if wl.get("train"):
+        return run_training(args, wl, model, cfg, rank, local_rank, world, dev)
 
     pool = max(1, args.pool)
     ctx_host = [torch.relu(torch.randn(B, L, D, generator=g)).pin_memory() for _ in range(pool)]
