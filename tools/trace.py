@@ -54,6 +54,7 @@ def run(kind, fn, grid, labels, trace_mode, cold):
         if cold:
             flush.zero_()
         m.set_option("trace", trace_mode)
+        m.set_option("trace_at", 0)
         torch.cuda.synchronize()
         fn()
         torch.cuda.synchronize()
