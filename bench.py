@@ -390,8 +390,13 @@ def main():
         model.set_option("profile", 0)
         att_bytes = 4 * (B * L * (D + A) + B * A + A + B * L + B * D)
         achieved = att_bytes / att_ns                                       # bytes/ns == GB/s
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "att_traffic.json")   # dram__bytes_read+write of one ncu --set full capture
+        if os.path.exists(tp) and args.workload == 2:
+            tj = json.load(open(tp))
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         roof = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
-                    traffic=None, kernel="att_fused_kernel<1>", us_per_launch=att_ns / 1e3,
+                    traffic=traffic, kernel="att_fused_kernel<1>", us_per_launch=att_ns / 1e3,
                     algorithmic_bytes=att_bytes, peak_source=pk["src"] + " HBM copy, burst",
                     timing="CUDA events around the kernel on its launch stream, 256 MB L2 flush between launches")
         E = cfg.dim_embedding
