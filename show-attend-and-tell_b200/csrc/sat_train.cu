@@ -57,56 +57,108 @@ __device__ inline float drop_scale(unsigned long long seed, unsigned long long s
 
 // ------------------------------------------------------------------------------------------ SGEMM
 // C[M,N] = op(A)[M,K] * op(B)[K,N] (+ C if accumulate).  Row-major.  TA: A is stored [K,M]; TB: B is stored [N,K].
-// gridDim.z > 1 splits K and accumulates with atomics (only with accumulate semantics on a pre-set C).
+// 128x128x8 tiles, 256 threads x (8x8) outputs, double-buffered shared memory, float4 global loads where the
+// operand is aligned.  gridDim.z > 1 splits K and accumulates with atomics (accumulate semantics on a pre-set C).
+constexpr int GM = 128, GN = 128, GK = 8;
+
+template <bool TRANS>   // TRANS: the tile's fast axis in memory is the M/N axis (A stored [K,M] / B stored [K,N])
+__device__ __forceinline__ void gemm_load_tile(float (&reg)[4], const float* __restrict__ P, int ld, int mn0, int k0, int MN,
+                                               int k_end, int tid) {
+    // tile = 128 (mn) x 8 (k) = 256 float4; thread `tid` owns one float4
+    if (TRANS) {
+        const int k = tid >> 5, mn = (tid & 31) * 4;           // float4 along mn
+        const int gk = k0 + k, gmn = mn0 + mn;
+        const float* p = P + (size_t)gk * ld + gmn;
+        if (gk < k_end && gmn + 3 < MN && ((((size_t)p) & 15) == 0)) {
+            const float4 v = *reinterpret_cast<const float4*>(p);
+            reg[0] = v.x; reg[1] = v.y; reg[2] = v.z; reg[3] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reg[i] = (gk < k_end && gmn + i < MN) ? p[i] : 0.f;
+        }
+    } else {
+        const int mn = tid >> 1, k = (tid & 1) * 4;            // float4 along k
+        const int gmn = mn0 + mn, gk = k0 + k;
+        const float* p = P + (size_t)gmn * ld + gk;
+        if (gmn < MN && gk + 3 < k_end && ((((size_t)p) & 15) == 0)) {
+            const float4 v = *reinterpret_cast<const float4*>(p);
+            reg[0] = v.x; reg[1] = v.y; reg[2] = v.z; reg[3] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reg[i] = (gmn < MN && gk + i < k_end) ? p[i] : 0.f;
+        }
+    }
+}
+template <bool TRANS>
+__device__ __forceinline__ void gemm_store_tile(float (*sm)[GM + 4], const float (&reg)[4], int tid) {
+    if (TRANS) {
+        const int k = tid >> 5, mn = (tid & 31) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sm[k][mn + i] = reg[i];
+    } else {
+        const int mn = tid >> 1, k = (tid & 1) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sm[k + i][mn] = reg[i];
+    }
+}
+
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                     const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                     int accumulate, int kchunk) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64 + 4];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    __shared__ float As[2][GK][GM + 4];
+    __shared__ float Bs[2][GK][GN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads; thread owns rows ty*4+{0..3}, 64+ty*4+{0..3}; cols likewise
+    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
     const int k_begin = blockIdx.z * kchunk, k_end = min(K, k_begin + kchunk);
-    float acc[4][4] = {};
-    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-            int kk, mm;
-            if (TA) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
-            const int gm = m0 + mm, gk = k0 + kk;
-            float v = 0.f;
-            if (gm < M && gk < k_end) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-            As[kk][mm] = v;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float ra[4], rb[4];
+    // A tile: TA means memory is [K, M] (fast axis m) -> TRANS = TA.  B tile: memory [K, N] (fast axis n) unless TB.
+    gemm_load_tile<TA>(ra, A, lda, m0, k_begin, M, k_end, tid);
+    gemm_load_tile<!TB>(rb, B, ldb, n0, k_begin, N, k_end, tid);
+    gemm_store_tile<TA>(As[0], ra, tid);
+    gemm_store_tile<!TB>(Bs[0], rb, tid);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += GK) {
+        const bool more = k0 + GK < k_end;
+        if (more) {
+            gemm_load_tile<TA>(ra, A, lda, m0, k0 + GK, M, k_end, tid);
+            gemm_load_tile<!TB>(rb, B, ldb, n0, k0 + GK, N, k_end, tid);
         }
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-            int kk, nn;
-            if (TB) { kk = i & 15; nn = i >> 4; } else { nn = i & 63; kk = i >> 6; }
-            const int gn = n0 + nn, gk = k0 + kk;
-            float v = 0.f;
-            if (gn < N && gk < k_end) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
-            Bs[kk][nn] = v;
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            float a[8], b[8];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        if (more) {
+            gemm_store_tile<TA>(As[buf ^ 1], ra, tid);
+            gemm_store_tile<!TB>(Bs[buf ^ 1], rb, tid);
+            __syncthreads();
+            buf ^= 1;
         }
-        __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
         if (gm >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
+        for (int j = 0; j < 8; ++j) {
+            const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
             if (gn >= N) continue;
             float* c = C + (size_t)gm * ldc + gn;
             if (gridDim.z > 1) atomicAdd(c, acc[i][j]);
@@ -117,14 +169,14 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
 
 cudaError_t sgemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                   float* C, int ldc, bool accumulate) {
-    dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
+    dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, 1);
     int kchunk = K;
     const int tiles = grid.x * grid.y;
-    if (accumulate && tiles < 148 && K >= 2048) {   // weight gradients: huge K, small output -> split K over the SMs
+    if (accumulate && tiles < 148 && K >= 1024) {   // weight gradients: huge K, small output -> split K over the SMs
         int z = (296 + tiles - 1) / tiles;
         if (z > K / 256) z = K / 256;
         if (z < 1) z = 1;
-        kchunk = ((K + z - 1) / z + 15) / 16 * 16;
+        kchunk = ((K + z - 1) / z + GK - 1) / GK * GK;
         grid.z = (K + kchunk - 1) / kchunk;
     }
     const int acc = accumulate ? 1 : 0;
