@@ -172,12 +172,21 @@ cudaError_t sgemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const 
     dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, 1);
     int kchunk = K;
     const int tiles = grid.x * grid.y;
-    if (accumulate && tiles < 148 && K >= 1024) {   // weight gradients: huge K, small output -> split K over the SMs
+    if (tiles < 148 && K >= 512) {
+        // few output tiles (batch-sized M, or weight gradients with a huge K): split K over the SMs and sum
+        // with atomics.  A non-accumulating product starts from a zeroed C (ldc == N: contiguous).
         int z = (296 + tiles - 1) / tiles;
-        if (z > K / 256) z = K / 256;
+        if (z > K / 128) z = K / 128;
         if (z < 1) z = 1;
         kchunk = ((K + z - 1) / z + GK - 1) / GK * GK;
         grid.z = (K + kchunk - 1) / kchunk;
+        if (grid.z > 1 && !accumulate) {
+            if (ldc != N) { grid.z = 1; kchunk = K; }
+            else {
+                cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
+                if (e != cudaSuccess) return e;
+            }
+        }
     }
     const int acc = accumulate ? 1 : 0;
     if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
