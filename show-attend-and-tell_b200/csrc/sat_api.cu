@@ -119,6 +119,9 @@ struct sat_handle {
     // valid for the duration of one step_impl call
     bool pa_on = false;
     uint8_t *pa_cur_h_in = nullptr, *pa_cur_h_out = nullptr;
+    cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int opt_overlap = 1;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -205,6 +208,9 @@ extern "C" void sat_destroy(sat_handle* h) {
     if (!h) return;
     cudaDeviceSynchronize();
     if (h->train && h->train_free) h->train_free(h->train);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (auto& g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     for (Layer* ly : h->layers) layer_free(*ly);
@@ -346,6 +352,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "coop") h->opt_coop = (int)value;
     else if (k == "xpack") h->opt_xpack = (int)value;
     else if (k == "pa") h->opt_pa = (int)value;
+    else if (k == "overlap") h->opt_overlap = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -798,7 +805,7 @@ static int attach_argmax(sat_handle* h, Layer& ly, LinProblem& P, const RowsPara
 // returns 1 in *argmax_done if the prediction / next word were produced by the vocabulary layer itself
 static int decode_impl(sat_handle* h, const float* h_out, const float* z, const int32_t* last_word, float* logits,
                        int rows, cudaStream_t st, bool make_next_q = false, const RowsParams* am = nullptr,
-                       int* argmax_done = nullptr) {
+                       int* argmax_done = nullptr, int phase = 0, bool pack_next_emb = false) {
     const sat_dims& d = h->d;
     LinProblem P[2];
     int used = 0;
@@ -808,6 +815,7 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
     if (d.num_decode_layers == 2) {
         const int group = make_next_q ? 2 : 1;
         const bool pa = h->pa_on;
+        if (phase != 2) {
         RET(plan(h, h->dec_1, P[0],
                  {seg(h_out, d.num_lstm_units, d.num_lstm_units, nullptr, pa ? h->pa_cur_h_out : nullptr),
                   seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? h->pa_z : nullptr),
@@ -820,13 +828,20 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
             np = 2;
         }
         RET(launch(h, P, np, st));
+        }
+        if (phase == 1) return SAT_OK;
         h->cur_tag = kTagDec2;
         RET(plan(h, h->dec_2, P[0], {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer, nullptr, pa ? h->pa_t : nullptr)},
                  rows, kEpiBias, logits, d.vocabulary_size, st));
         used = attach_argmax(h, h->dec_2, P[0], am, st);
         if (used < 0) return used;
-        // (the embedding row of the chosen word is packed by the next step's attention kernel, off the
-        //  critical path; the in-epilogue variant P.am_emb_pa serialised 4096 gathers on one CTA)
+        // the embedding row of the chosen word is normally packed by the next step's attention kernel; when
+        // that kernel runs CONCURRENTLY with this layer (decode loop), the last CTA of this layer does it
+        if (used && pa && pack_next_emb) {
+            P[0].am_emb = h->embedding;
+            P[0].am_E = d.dim_embedding;
+            P[0].am_emb_pa = h->pa_emb;
+        }
         RET(launch(h, P, 1, st));
         if (argmax_done) *argmax_done = used;
         return SAT_OK;
@@ -956,9 +971,60 @@ static int run_graphed(sat_handle* h, const std::vector<long long>& key, cudaStr
 }
 
 // ------------------------------------------------------------------- loop
+// Decode loop with the attention of step t+1 (needs only q(t+1) = f(h_t)) running CONCURRENTLY with the
+// vocabulary layer of step t (needs only t_dec(t)); they join before the LSTM of step t+1, which consumes the
+// context vector of the one and the chosen word of the other.
+static int loop_enqueue_overlap(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
+                                float* logits_all, cudaStream_t st) {
+    if (!h->side) {
+        CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    const sat_dims& d = h->d;
+    RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st, h->pa_h[0]));
+    CK(cudaMemsetAsync(h->word, 0, (size_t)B * sizeof(int32_t), st));  // <start> = 0 (model.py:254)
+    for (int t = 0; t < T; ++t) {
+        const float *c_in = h->st_c[t & 1], *h_in = h->st_h[t & 1];
+        float *c_out = h->st_c[(t + 1) & 1], *h_out = h->st_h[(t + 1) & 1];
+        h->pa_on = true;
+        h->pa_cur_h_in = h->pa_h[t & 1];
+        h->pa_cur_h_out = h->pa_h[(t + 1) & 1];
+        if (t == 0)   // q(0), attention(0) and the embedding of <start>
+            RET(attention_impl(h, ctx, B, 1, h_in, nullptr, h->z, st, false, h->word));
+        RET(lstm_impl(h, h->z, h->word, c_in, h_in, c_out, h_out, B, st));
+        float* logits = logits_all ? logits_all + (size_t)t * B * d.vocabulary_size : h->logits;
+        RET(decode_impl(h, h_out, h->z, h->word, logits, B, st, t + 1 < T, nullptr, nullptr, 1));   // fc_1 (+ q(t+1))
+        if (t + 1 < T) {
+            // fork: attention(t+1) on the side stream; its inputs (q, T1, contexts) are complete
+            CK(cudaEventRecord(h->ev_fork, st));
+            CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+            h->pa_cur_h_in = h->pa_h[(t + 1) & 1];
+            RET(attention_impl(h, ctx, B, 1, h_out, nullptr, h->z, h->side, true, nullptr));
+            CK(cudaEventRecord(h->ev_join, h->side));
+            h->pa_cur_h_in = h->pa_h[t & 1];
+        }
+        RowsParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.tokens = tokens; rp.tokens_ld = T; rp.step = t;
+        rp.next_word = h->word; rp.forced = forced; rp.forced_ld = T;
+        int fused = 0;
+        RET(decode_impl(h, h_out, h->z, h->word, logits, B, st, false, &rp, &fused, 2, t + 1 < T));  // fc_2 + argmax
+        if (!fused) {
+            h->pa_on = false;
+            return fail(SAT_ERR_STATE, "overlapped loop needs the fused argmax of the vocabulary layer");
+        }
+        if (t + 1 < T) CK(cudaStreamWaitEvent(st, h->ev_join, 0));   // join before the LSTM of step t+1
+    }
+    h->pa_on = false;
+    return SAT_OK;
+}
+
 static int loop_enqueue(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
                         float* logits_all, cudaStream_t st) {
     const bool pa = h->pa_ok && h->opt_pa && h->opt_gemm != 0;
+    if (pa && h->opt_overlap && h->d.num_decode_layers == 2 && st != nullptr && st != cudaStreamLegacy)
+        return loop_enqueue_overlap(h, ctx, B, T, forced, tokens, logits_all, st);
     RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st, pa ? h->pa_h[0] : nullptr));
     CK(cudaMemsetAsync(h->word, 0, (size_t)B * sizeof(int32_t), st));  // <start> = 0 (model.py:254)
     bool emb_valid = false;

@@ -476,6 +476,45 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             P.am_next_word[b] = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi;
                     }
                 }
+                if (P.am_emb_pa) {
+                    // decode loop: the attention kernel of the next step is already running, so this CTA hands the
+                    // embedding row of every chosen word (model.py:272-274) to the next LSTM / decode layers,
+                    // packed; 8 gathers per thread in flight
+                    named_bar_sync(1, kLinProducers);   // next_word[] written above is visible to the CTA
+                    const int groups = P.am_E >> 3;
+                    const int total = P.rows * groups;
+                    const size_t halfb = (size_t)N * kBK * 2;
+                    for (int u0 = pt; u0 < total; u0 += kLinProducers * 8) {
+                        float4 a[8], c4[8];
+                        int bb[8], gg[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int uu = u0 + j * kLinProducers;
+                            bb[j] = -1;
+                            gg[j] = 0;
+                            if (uu < total) {
+                                bb[j] = uu / groups;
+                                gg[j] = uu - bb[j] * groups;
+                                const int w = P.am_next_word[bb[j]];
+                                const float4* src = reinterpret_cast<const float4*>(P.am_emb + (size_t)w * P.am_E + gg[j] * 8);
+                                a[j] = __ldg(src);
+                                c4[j] = __ldg(src + 1);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (bb[j] >= 0) {
+                                uint4 hi, lo;
+                                split_bf16x8(a[j], c4[j], hi, lo);
+                                const int rt2 = bb[j] / N, r = bb[j] - rt2 * N;
+                                uint8_t* dst = P.am_emb_pa + ((size_t)rt2 * (P.am_E >> 6) + (gg[j] >> 3)) * 2 * halfb +
+                                               umma_tile_off(mode, r, gg[j] & 7);
+                                *reinterpret_cast<uint4*>(dst) = hi;
+                                *reinterpret_cast<uint4*>(dst + halfb) = lo;
+                            }
+                        }
+                    }
+                }
                 if (pt == 0) *P.am_ctr = 0u;
             }
         }
