@@ -121,7 +121,7 @@ struct sat_handle {
     uint8_t *pa_cur_h_in = nullptr, *pa_cur_h_out = nullptr;
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 1;
+    int opt_overlap = 1, opt_att_sms = 0;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -353,6 +353,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "xpack") h->opt_xpack = (int)value;
     else if (k == "pa") h->opt_pa = (int)value;
     else if (k == "overlap") h->opt_overlap = (int)value;
+    else if (k == "att_sms") h->opt_att_sms = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -685,7 +686,7 @@ static int plan_att_state(sat_handle* h, LinProblem& P, const float* h_in, int r
 }
 
 static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, const float* h_in, float* alpha, float* z,
-                          cudaStream_t st, bool q_ready = false, const int32_t* last_word = nullptr) {
+                          cudaStream_t st, bool q_ready = false, const int32_t* last_word = nullptr, int sm_budget = 0) {
     const sat_dims& d = h->d;
     const int rows = n_img * G;
     AttParams ap;
@@ -726,7 +727,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     ap.D = d.dim_ctx;
     ap.l2_t = h->opt_l2_t;
     ap.l2_ctx = h->opt_l2_ctx;
-    if (!att_plan(ap, h->smem_optin, h->num_sms))
+    if (!att_plan(ap, h->smem_optin, sm_budget > 0 ? sm_budget : h->num_sms))
         return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
     const size_t pneed = att_part_floats(ap);
     if (pneed > h->att_part_floats) {
@@ -1000,7 +1001,10 @@ static int loop_enqueue_overlap(sat_handle* h, const float* ctx, int B, int T, c
             CK(cudaEventRecord(h->ev_fork, st));
             CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
             h->pa_cur_h_in = h->pa_h[(t + 1) & 1];
-            RET(attention_impl(h, ctx, B, 1, h_out, nullptr, h->z, h->side, true, nullptr));
+            // it shares the GPU with the vocabulary layer (n_tiles CTAs, one per SM): size it for the SMs left over
+            int budget = h->opt_att_sms > 0 ? h->opt_att_sms : h->num_sms - h->dec_2.n_tiles;
+            if (budget < h->num_sms / 4) budget = h->num_sms;
+            RET(attention_impl(h, ctx, B, 1, h_out, nullptr, h->z, h->side, true, nullptr, budget));
             CK(cudaEventRecord(h->ev_join, h->side));
             h->pa_cur_h_in = h->pa_h[t & 1];
         }

@@ -33,9 +33,9 @@ def timeit(n=30):
     return a.elapsed_time(b) / n
 
 
-base = dict(l2_w=2, l2_t=1, l2_ctx=0, xpack=1, graphs=1)
-variants = [dict(), dict(l2_w=0, l2_t=0), dict(l2_w=2, l2_t=0), dict(l2_w=2, l2_t=1, l2_ctx=2),
-            dict(l2_w=2, l2_t=2, l2_ctx=2), dict(l2_w=0, l2_t=1), dict(xpack=0), dict(graphs=0)]
+base = dict(overlap=1, att_sms=0, pa=1, graphs=1)
+variants = [dict(), dict(overlap=0), dict(att_sms=148), dict(att_sms=128), dict(att_sms=96), dict(att_sms=64),
+            dict(pa=0, overlap=0), dict(graphs=0)]
 for v in variants:
     o = dict(base)
     o.update(v)
