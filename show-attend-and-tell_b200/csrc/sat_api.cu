@@ -727,6 +727,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     ap.D = d.dim_ctx;
     ap.l2_t = h->opt_l2_t;
     ap.l2_ctx = h->opt_l2_ctx;
+    if (sm_budget <= 0 && h->opt_att_sms > 0) sm_budget = h->opt_att_sms;   // experiment knob
     if (!att_plan(ap, h->smem_optin, sm_budget > 0 ? sm_budget : h->num_sms))
         return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
     const size_t pneed = att_part_floats(ap);
@@ -833,7 +834,7 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
         if (phase == 1) return SAT_OK;
         h->cur_tag = kTagDec2;
         RET(plan(h, h->dec_2, P[0], {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer, nullptr, pa ? h->pa_t : nullptr)},
-                 rows, kEpiBias, logits, d.vocabulary_size, st));
+                 rows, kEpiBias, logits, d.vocabulary_size, st, am ? 1 : 0));   // the fused argmax needs whole rows per CTA
         used = attach_argmax(h, h->dec_2, P[0], am, st);
         if (used < 0) return used;
         // the embedding row of the chosen word is normally packed by the next step's attention kernel; when
