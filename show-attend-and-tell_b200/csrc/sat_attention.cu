@@ -169,46 +169,69 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
             mbar_wait(&full[s], (uint32_t)(idx / p.nslots) & 1u);
             if (ct == 0 && r == r_begin) trace_stamp(p.dbg, 2);
             const float* buf = reinterpret_cast<const float*>(slots + (size_t)s * p.slot_bytes);
-            for (int row = warp; row < n; row += kAttConsumerWarps) {
-                float acc[G];
+            // two rows per warp at a time (rows `row` and `row + 8`), two independent partial sums per row and
+            // per g: four FMA chains in flight instead of one 16-deep dependent chain, and the two warp
+            // reductions interleave
+            for (int row = warp; row < n; row += 2 * kAttConsumerWarps) {
+                const int rowB = row + kAttConsumerWarps;
+                const bool hasB = rowB < n;
+                float accA[G][2], accB[G][2];
 #pragma unroll
-                for (int g = 0; g < G; ++g) acc[g] = 0.f;
-                const float4* trow = reinterpret_cast<const float4*>(buf + (size_t)row * RL);
+                for (int g = 0; g < G; ++g) { accA[g][0] = accA[g][1] = accB[g][0] = accB[g][1] = 0.f; }
+                const float4* trA = reinterpret_cast<const float4*>(buf + (size_t)row * RL);
+                const float4* trB = reinterpret_cast<const float4*>(buf + (size_t)(hasB ? rowB : row) * RL);
                 if (RV > 0) {
+                    float4 tA[RV > 0 ? RV : 1], tB[RV > 0 ? RV : 1];
+#pragma unroll
+                    for (int k = 0; k < (RV > 0 ? RV : 1); ++k) { tA[k] = trA[lane + 32 * k]; tB[k] = trB[lane + 32 * k]; }
 #pragma unroll
                     for (int k = 0; k < (RV > 0 ? RV : 1); ++k) {
-                        const float4 t = trow[lane + 32 * k];
                         const float4 w = wreg[k];
 #pragma unroll
                         for (int g = 0; g < G; ++g) {
                             const float4 qq = qreg[g][k];
-                            acc[g] = fmaf(w.x, t.x + qq.x, acc[g]);
-                            acc[g] = fmaf(w.y, t.y + qq.y, acc[g]);
-                            acc[g] = fmaf(w.z, t.z + qq.z, acc[g]);
-                            acc[g] = fmaf(w.w, t.w + qq.w, acc[g]);
+                            accA[g][0] = fmaf(w.x, tA[k].x + qq.x, accA[g][0]);
+                            accA[g][1] = fmaf(w.y, tA[k].y + qq.y, accA[g][1]);
+                            accA[g][0] = fmaf(w.z, tA[k].z + qq.z, accA[g][0]);
+                            accA[g][1] = fmaf(w.w, tA[k].w + qq.w, accA[g][1]);
+                            accB[g][0] = fmaf(w.x, tB[k].x + qq.x, accB[g][0]);
+                            accB[g][1] = fmaf(w.y, tB[k].y + qq.y, accB[g][1]);
+                            accB[g][0] = fmaf(w.z, tB[k].z + qq.z, accB[g][0]);
+                            accB[g][1] = fmaf(w.w, tB[k].w + qq.w, accB[g][1]);
                         }
                     }
                 } else {
                     for (int j = lane; j < RL / 4; j += 32) {
-                        const float4 t = trow[j];
+                        const float4 ta = trA[j], tb = trB[j];
                         const float4 w = reinterpret_cast<const float4*>(vec_s)[j];
 #pragma unroll
                         for (int g = 0; g < G; ++g) {
                             float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (p.q) qq = reinterpret_cast<const float4*>(q_s + (size_t)g * RL)[j];
-                            acc[g] = fmaf(w.x, t.x + qq.x, acc[g]);
-                            acc[g] = fmaf(w.y, t.y + qq.y, acc[g]);
-                            acc[g] = fmaf(w.z, t.z + qq.z, acc[g]);
-                            acc[g] = fmaf(w.w, t.w + qq.w, acc[g]);
+                            accA[g][0] = fmaf(w.x, ta.x + qq.x, accA[g][0]);
+                            accA[g][1] = fmaf(w.y, ta.y + qq.y, accA[g][1]);
+                            accA[g][0] = fmaf(w.z, ta.z + qq.z, accA[g][0]);
+                            accA[g][1] = fmaf(w.w, ta.w + qq.w, accA[g][1]);
+                            accB[g][0] = fmaf(w.x, tb.x + qq.x, accB[g][0]);
+                            accB[g][1] = fmaf(w.y, tb.y + qq.y, accB[g][1]);
+                            accB[g][0] = fmaf(w.z, tb.z + qq.z, accB[g][0]);
+                            accB[g][1] = fmaf(w.w, tb.w + qq.w, accB[g][1]);
                         }
                     }
                 }
-                const int ll = r + row - seg0;            // location index within the segment
-                const int l = r + row - img * L;          // location index within the image
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    float sum = warp_sum(acc[g]);
-                    if (lane == 0) {
+                    float sa = accA[g][0] + accA[g][1], sb = accB[g][0] + accB[g][1];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                    }
+                    if (lane < 2 && (lane == 0 || hasB)) {
+                        const int rr = lane == 0 ? row : rowB;
+                        float sum = lane == 0 ? sa : sb;
+                        const int ll = r + rr - seg0;            // location index within the segment
+                        const int l = r + rr - img * L;          // location index within the image
                         const size_t o = ((size_t)img * G + g) * L + l;
                         if (p.eadd) sum += p.eadd[o];
                         p.e[o] = sum;
@@ -257,26 +280,40 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
                 const float2* b2 = reinterpret_cast<const float2*>(buf) + ct;
                 const int rowstride = D / 2;   // float2 per row
                 int row = 0;
-                for (; row + 4 <= n; row += 4) {
-                    const int ll = r + row - seg0;
-                    float wv[G][4];
+                for (; row + 8 <= n; row += 8) {
+                    const int ll = r + row - seg0;      // chunks start at multiples of cch (a multiple of 4): aligned
+                    float wv[G][8];
 #pragma unroll
-                    for (int g = 0; g < G; ++g)
+                    for (int g = 0; g < G; ++g) {
+                        if (((g * Lp + ll) & 3) == 0) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(w_s + g * Lp + ll);
+                            const float4 w1 = *reinterpret_cast<const float4*>(w_s + g * Lp + ll + 4);
+                            wv[g][0] = w0.x; wv[g][1] = w0.y; wv[g][2] = w0.z; wv[g][3] = w0.w;
+                            wv[g][4] = w1.x; wv[g][5] = w1.y; wv[g][6] = w1.z; wv[g][7] = w1.w;
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) wv[g][j] = w_s[g * Lp + ll + j];
+                            for (int j = 0; j < 8; ++j) wv[g][j] = w_s[g * Lp + ll + j];
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < kAttMaxDPerThread / 2; ++k) {
                         if (k < nk2) {
-                            float2 x[4];
+                            float2 x[8];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) x[j] = b2[(size_t)(row + j) * rowstride + 256 * k];
+                            for (int j = 0; j < 8; ++j) x[j] = b2[(size_t)(row + j) * rowstride + 256 * k];
 #pragma unroll
-                            for (int g = 0; g < G; ++g)
+                            for (int g = 0; g < G; ++g) {
+                                float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;   // two chains per feature
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    zacc[g][2 * k] = fmaf(wv[g][j], x[j].x, zacc[g][2 * k]);
-                                    zacc[g][2 * k + 1] = fmaf(wv[g][j], x[j].y, zacc[g][2 * k + 1]);
+                                for (int j = 0; j < 8; j += 2) {
+                                    s0 = fmaf(wv[g][j], x[j].x, s0);
+                                    s1 = fmaf(wv[g][j], x[j].y, s1);
+                                    t0 = fmaf(wv[g][j + 1], x[j + 1].x, t0);
+                                    t1 = fmaf(wv[g][j + 1], x[j + 1].y, t1);
                                 }
+                                zacc[g][2 * k] += s0 + t0;
+                                zacc[g][2 * k + 1] += s1 + t1;
+                            }
                         }
                     }
                 }
@@ -441,7 +478,7 @@ size_t att_smem_bytes(const AttParams& p) {
 bool att_plan(AttParams& p, int smem_optin, int num_sms) {
     if (p.G < 1 || p.G > 4 || p.L < 1 || (p.D % 4) || (p.RL % 4) || p.D > kAttMaxDPerThread * kAttConsumerWarps * 32)
         return false;
-    const int target = 24 * 1024;                       // bytes per ring slot
+    const int target = 32 * 1024;                       // bytes per ring slot (16 rows of 512 floats: 2 rows per warp)
     int rch = target / (p.RL * 4), cch = target / (p.D * 4);
     if (rch < 1) rch = 1;
     if (cch < 1) cch = 1;
