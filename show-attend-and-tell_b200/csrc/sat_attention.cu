@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
     const int nper = (D + NT - 1) / NT;   // context features per thread (d = ct + NT*k)
     int idx = 0;
     bool first_seg = true;
+    long long wait1 = 0, wait2 = 0;   // cycles thread 0 spent blocked on "chunk landed" in pass 1 / pass 2 (trace)
     if (p.emb_pa) {
         // embedding rows of the words fed to this step -> packed operand tiles (a few 16-byte groups per CTA)
         const int groups = p.emb_E >> 3;
@@ -166,7 +167,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         for (int r = seg0; r < seg1; r += p.rch, ++idx) {
             const int n = min(p.rch, seg1 - r);
             const int s = idx % p.nslots;
+            const long long tw = p.dbg ? clock64() : 0;
             mbar_wait(&full[s], (uint32_t)(idx / p.nslots) & 1u);
+            if (p.dbg) wait1 += clock64() - tw;
             if (ct == 0 && r == r_begin) trace_stamp(p.dbg, 2);
             const float* buf = reinterpret_cast<const float*>(slots + (size_t)s * p.slot_bytes);
             // two rows per warp at a time (rows `row` and `row + 8`), two independent partial sums per row and
@@ -273,7 +276,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         for (int r = seg0; r < seg1; r += p.cch, ++idx) {
             const int n = min(p.cch, seg1 - r);
             const int s = idx % p.nslots;
+            const long long tw = p.dbg ? clock64() : 0;
             mbar_wait(&full[s], (uint32_t)(idx / p.nslots) & 1u);
+            if (p.dbg) wait2 += clock64() - tw;
             if (ct == 0 && r == r_begin) trace_stamp(p.dbg, 4);
             const float* buf = reinterpret_cast<const float*>(slots + (size_t)s * p.slot_bytes);
             if (vec2) {
@@ -466,6 +471,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_
         seg0 = seg1;
     }
     if (ct == 0) trace_stamp(p.dbg, 7);
+    if (ct == 0 && p.dbg) {
+        p.dbg[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)wait1;
+        p.dbg[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)wait2;
+    }
 }
 
 size_t att_smem_bytes(const AttParams& p) {

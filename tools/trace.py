@@ -40,6 +40,10 @@ def read_trace(n):
 def show(name, tr, labels):
     tr = tr[tr[:, 0] > 0]
     t0 = tr[:, 0].min()
+    if name.startswith("attention"):
+        print("  [thread 0 blocked on data: pass 1 %.2f us, pass 2 %.2f us (mean, at 1.965 GHz)]"
+              % (tr[:, 8].mean() / 1965.0, tr[:, 9].mean() / 1965.0))
+        tr = tr.copy(); tr[:, 8:10] = 0
     print("== %s  (us after the first CTA started; mean / max over %d CTAs)" % (name, len(tr)))
     for i, lab in enumerate(labels):
         col = tr[:, i]
