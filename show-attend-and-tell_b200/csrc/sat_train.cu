@@ -200,8 +200,9 @@ cudaError_t sgemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const 
 #define GRID1D(n) dim3((unsigned)(((n) + 255) / 256 < 65535 * 16 ? ((n) + 255) / 256 : 65535 * 16))
 
 // y[r, c] = x[r, c] * drop(seed, stream, r * cols + c) ; x / y may have different leading dimensions
-__global__ void dropout2d_kernel(float* y, int ldy, const float* x, int ldx, int rows, int cols, unsigned long long seed,
-                                 unsigned long long stream, float keep, int accumulate) {
+__global__ void dropout2d_kernel(float* y, int ldy, const float* x, int ldx, int rows, int cols,
+                                 const unsigned long long* seedp, unsigned long long stream, float keep, int accumulate) {
+    const unsigned long long seed = *seedp;
     const size_t n = (size_t)rows * cols;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
@@ -259,8 +260,9 @@ __global__ void scatter_add_rows_kernel(float* dtable, int E, const int32_t* idx
     }
 }
 // temp[b*L + l, a] = (T1[b*L + l, a] + q[b, a]) * drop(att_mid)
-__global__ void att_temp_kernel(float* temp, const float* T1, const float* q, int B, int L, int A, unsigned long long seed,
-                                unsigned long long stream, float keep) {
+__global__ void att_temp_kernel(float* temp, const float* T1, const float* q, int B, int L, int A,
+                                const unsigned long long* seedp, unsigned long long stream, float keep) {
+    const unsigned long long seed = *seedp;
     const size_t n = (size_t)B * L * A;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int a = (int)(i % A);
@@ -323,8 +325,9 @@ __global__ void context_bwd_kernel(float* dalpha, const float* dz, const float* 
     if (lane == 0) dalpha[warp] = s + (extra ? extra[warp] : 0.f);
 }
 // dtemp[r, a] = de[r] * w2[a] * drop(att_mid)   and  (1 - T1^2) applied later
-__global__ void att_dtemp_kernel(float* dtemp, const float* de, const float* w2, int rows, int A, unsigned long long seed,
-                                 unsigned long long stream, float keep) {
+__global__ void att_dtemp_kernel(float* dtemp, const float* de, const float* w2, int rows, int A,
+                                 const unsigned long long* seedp, unsigned long long stream, float keep) {
+    const unsigned long long seed = *seedp;
     const size_t n = (size_t)rows * A;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int a = (int)(i % A);
@@ -378,7 +381,8 @@ __global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_raw, const
 }
 // masked cross entropy of one time step + its gradient; one block per row
 __global__ void __launch_bounds__(256) ce_kernel(const float* logits, float* dlogits, const int32_t* sent, int sent_ld, int t,
-                                                 const float* masks, int V, float inv_msum, float* loss_acc) {
+                                                 const float* masks, int V, const float* inv_msum_p, float* loss_acc) {
+    const float inv_msum = *inv_msum_p;
     __shared__ float red[8];
     __shared__ int redi[8];
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -517,6 +521,13 @@ struct TrainState {
           *dlin = nullptr, *dz = nullptr, *demb = nullptr, *dalpha = nullptr, *dtemp = nullptr, *dq = nullptr, *dhd = nullptr,
           *dbuf = nullptr;
     float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2
+    // per-call scalars live in device cells (fed from pinned host memory before each launch), so that the
+    // ~3500 launches of a step are captured once into a CUDA graph and replayed
+    unsigned long long* seed_d = nullptr;
+    float* inv_msum_d = nullptr;
+    unsigned long long* seed_h = nullptr;   // pinned: [0] seed, [1] bits of inv_msum
+    struct GEntry { std::vector<long long> key; int seen = 0; cudaGraphExec_t exec = nullptr; };
+    std::vector<GEntry> graphs;
     std::vector<void*> all;
 };
 
@@ -531,6 +542,9 @@ void train_free(void* p) {
     TrainState* s = (TrainState*)p;
     if (!s) return;
     for (void* b : s->all) cudaFree(b);
+    for (auto& g : s->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (s->seed_h) cudaFreeHost(s->seed_h);
     delete s;
 }
 
@@ -597,6 +611,13 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
     A1(&s->dc, B * H); A1(&s->dG, B * 4 * H); A1(&s->dlin, B * (D + E + H)); A1(&s->dz, B * D); A1(&s->demb, B * E);
     A1(&s->dalpha, BL); A1(&s->dtemp, BL * A); A1(&s->dq, B * A); A1(&s->dhd, B * H); A1(&s->dbuf, B * (D + E + I + H));
     A1(&s->loss_acc, 8);
+    float* cells = nullptr;
+    A1(&cells, 8);
+    if (rc == SAT_OK) {
+        s->seed_d = reinterpret_cast<unsigned long long*>(cells);
+        s->inv_msum_d = cells + 2;
+        if (cudaMallocHost((void**)&s->seed_h, 16) != cudaSuccess) rc = sat_fail(SAT_ERR_NOMEM, "pinned staging");
+    }
     if (rc != SAT_OK) { train_free(s); return rc; }
     *slot = s;
     sat_handle_set_train_free(h, train_free);
@@ -634,15 +655,9 @@ static int dense_bwd(cudaStream_t st, const float* x, int rows, int K, const flo
     return SAT_OK;
 }
 
-extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, float* grads, const float* contexts,
-                                          const int32_t* sentences, const float* masks, int32_t B, int32_t T,
-                                          uint64_t seed, double global_mask_sum, int32_t global_batch, float* losses,
-                                          void* stream) {
-    if (!h || !params || !grads || !contexts || !sentences || !masks || !losses)
-        return sat_fail(SAT_ERR_INVALID, "sat_train_forward_backward: null argument");
-    TrainState* s = (TrainState*)*sat_handle_train_slot(h);
-    if (!s || s->B != B || s->T != T) return sat_fail(SAT_ERR_STATE, "call sat_train_init(B=%d, T=%d) first", B, T);
-    cudaStream_t st = (cudaStream_t)stream;
+static int train_enqueue(TrainState* s, const float* params, float* grads, const float* contexts,
+                         const int32_t* sentences, const float* masks, int32_t B, int32_t T, int32_t global_batch,
+                         float* losses, cudaStream_t st) {
     const sat_dims& d = s->d;
     const int L = d.num_ctx, D = d.dim_ctx, E = d.dim_embedding, H = d.num_lstm_units, A = d.dim_attend_layer,
               Dd = d.dim_decode_layer, I = d.dim_initalize_layer, V = d.vocabulary_size;
@@ -652,7 +667,8 @@ extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, fl
     auto Gd = [&](int v) { return grads + s->off[v]; };
     auto ST = [&](int t, int k) { return (unsigned long long)(t * 16 + k); };
     const unsigned long long INIT = 0xFFFF0ull;
-    const float inv_msum = (float)(1.0 / global_mask_sum);
+    const unsigned long long* seed = s->seed_d;
+    const float* inv_msum = s->inv_msum_d;
     const float inv_gbl = 1.0f / ((float)global_batch * (float)L);
 
     TCK(cudaMemsetAsync(grads, 0, s->off[kNumVars] * sizeof(float), st));
@@ -773,6 +789,53 @@ extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, fl
     (void)dmean;
     TCK(cudaGetLastError());
     TCK(cudaMemcpyAsync(losses, s->loss_acc, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SAT_OK;
+}
+
+extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, float* grads, const float* contexts,
+                                          const int32_t* sentences, const float* masks, int32_t B, int32_t T,
+                                          uint64_t seed, double global_mask_sum, int32_t global_batch, float* losses,
+                                          void* stream) {
+    if (!h || !params || !grads || !contexts || !sentences || !masks || !losses)
+        return sat_fail(SAT_ERR_INVALID, "sat_train_forward_backward: null argument");
+    TrainState* s = (TrainState*)*sat_handle_train_slot(h);
+    if (!s || s->B != B || s->T != T) return sat_fail(SAT_ERR_STATE, "call sat_train_init(B=%d, T=%d) first", B, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    // per-call scalars -> device cells (the pinned staging must not be overwritten while a copy is in flight)
+    TCK(cudaStreamSynchronize(st));
+    s->seed_h[0] = seed;
+    const float inv = (float)(1.0 / global_mask_sum);
+    memcpy(&s->seed_h[1], &inv, sizeof(float));
+    TCK(cudaMemcpyAsync(s->seed_d, &s->seed_h[0], 8, cudaMemcpyHostToDevice, st));
+    TCK(cudaMemcpyAsync(s->inv_msum_d, &s->seed_h[1], 4, cudaMemcpyHostToDevice, st));
+    auto enqueue = [&]() { return train_enqueue(s, params, grads, contexts, sentences, masks, B, T, global_batch, losses, st); };
+    if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return enqueue();
+    std::vector<long long> key = {(long long)params, (long long)grads, (long long)contexts, (long long)sentences,
+                                  (long long)masks, (long long)losses, B, T, global_batch};
+    TrainState::GEntry* ent = nullptr;
+    for (auto& g : s->graphs)
+        if (g.key == key) ent = &g;
+    if (!ent) {
+        if (s->graphs.size() >= 8) {
+            if (s->graphs.front().exec) cudaGraphExecDestroy(s->graphs.front().exec);
+            s->graphs.erase(s->graphs.begin());
+        }
+        s->graphs.emplace_back();
+        ent = &s->graphs.back();
+        ent->key = key;
+    }
+    if (ent->exec) { TCK(cudaGraphLaunch(ent->exec, st)); return SAT_OK; }
+    if (ent->seen++ == 0) return enqueue();           // first call eager
+    TCK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != SAT_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return sat_fail(SAT_ERR_CUDA, "training graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&ent->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { ent->exec = nullptr; return sat_fail(SAT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+    TCK(cudaGraphLaunch(ent->exec, st));
     return SAT_OK;
 }
 
