@@ -153,6 +153,8 @@ int sat_dense_fwd(sat_handle* h, const float* x, const float* w_tf, const float*
 int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop_rate, float lstm_drop_rate,
                    float attention_loss_factor, float fc_kernel_regularizer_scale);
 int sat_train_num_vars(sat_handle* h);
+/* the counter-based dropout generator, U[0,1) with 24 bits: mask = floor(keep + u) (host function, no GPU) */
+float sat_train_rng_uniform(uint64_t seed, uint64_t stream, uint64_t index);
 /* i in [0, num_vars): name / offset / rows / cols / regularised of variable i; total = floats in the flat buffer */
 int sat_train_var(sat_handle* h, int32_t i, const char** name, int64_t* offset, int64_t* rows, int64_t* cols,
                   int32_t* regularised, int64_t* total);

@@ -551,6 +551,9 @@ void train_free(void* p) {
 }  // namespace
 
 // =========================================================================================== C ABI
+// the dropout generator on the host: lets a CPU test pin it against the numpy copy in oracle/train_ref.py
+extern "C" float sat_train_rng_uniform(uint64_t seed, uint64_t stream, uint64_t index) { return rng_u24(seed, stream, index); }
+
 extern "C" int sat_train_num_vars(sat_handle* h) {
     (void)h;
     return kNumVars;

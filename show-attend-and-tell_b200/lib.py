@@ -48,6 +48,7 @@ SIGNATURES = {
     "sat_dense_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "sat_train_init": (C.c_int, [_P, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float]),
     "sat_train_num_vars": (C.c_int, [_P]),
+    "sat_train_rng_uniform": (C.c_float, [C.c_uint64, C.c_uint64, C.c_uint64]),
     "sat_train_var": (C.c_int, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L),
                                 C.POINTER(_I), C.POINTER(_L)]),
     "sat_train_forward_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, C.c_uint64, C.c_double, _I, _P, _P]),

@@ -44,6 +44,18 @@ def test_shard_range_partitions_exactly():
         parallel.shard_range(4, 2, 2)
 
 
+def test_dropout_generator_matches_the_numpy_copy(built_lib):
+    """the C generator used by the training kernels == oracle/train_ref.uniform24 (runs on the host)"""
+    from oracle import train_ref as TR
+    lib = sat_b200.load_library()
+    for seed, stream in ((1234, 5), (77, 16 * 19 + 7), (2 ** 40 + 3, 0xFFFF2)):
+        ref = TR.uniform24(seed, stream, 64)
+        got = np.array([lib.sat_train_rng_uniform(seed, stream, i) for i in range(64)], np.float32)
+        assert np.array_equal(ref, got)
+    big = TR.uniform24(9, 1, 1 << 20)
+    assert lib.sat_train_rng_uniform(9, 1, (1 << 20) - 1) == big[-1]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
