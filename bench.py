@@ -185,7 +185,7 @@ def run_training(args, wl, model, cfg, rank, local_rank, world, dev):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3 * pool)):   # eager pass + graph capture + first replay per context buffer
         out = model.train_step(ctx_dev[i % pool], sent, masks, seed=1 + i)
     barrier()
     sampler = ClockSampler(local_rank)
