@@ -35,8 +35,8 @@ constexpr int kAttMaxDPerThread = 8;   // D <= 2048
 
 __device__ __forceinline__ int att_rbegin(long long NR, int P, int c) { return (int)(NR * c / P); }
 
-template <int G, int RV>
-__global__ void __launch_bounds__(kAttThreads, 1) att_fused_kernel(const __grid_constant__ AttParams p) {
+template <int G, int RV, int OCC>
+__global__ void __launch_bounds__(kAttThreads, OCC) att_fused_kernel(const __grid_constant__ AttParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // layout: [slots][barriers 2*nslots*8][vec RL][q G*RL][w G*Lp][misc 64]
     uint8_t* slots = smem;
@@ -485,6 +485,12 @@ size_t att_smem_bytes(const AttParams& p) {
 
 // Fill in chunking / ring parameters from the device limits.  Returns false if the shape is unsupported.
 bool att_plan(AttParams& p, int smem_optin, int num_sms) {
+    // occ CTAs per SM: each CTA gets 1/occ of the shared memory (a shorter ring) and the SM holds occ x 8
+    // consumer warps, which hides the shared-memory / shuffle latencies of the two passes
+    const int occ = (p.occ == 2 && p.G == 1) ? 2 : 1;
+    p.occ = occ;
+    smem_optin = occ == 2 ? (smem_optin - 2048) / 2 : smem_optin;
+    num_sms *= occ;
     if (p.G < 1 || p.G > 4 || p.L < 1 || (p.D % 4) || (p.RL % 4) || p.D > kAttMaxDPerThread * kAttConsumerWarps * 32)
         return false;
     const int target = 32 * 1024;                       // bytes per ring slot (16 rows of 512 floats: 2 rows per warp)
@@ -520,13 +526,18 @@ bool att_plan(AttParams& p, int smem_optin, int num_sms) {
 
 size_t att_part_floats(const AttParams& p) { return (size_t)p.grid * p.segmax * p.G * (p.D + 2); }
 
+template <int G, int RV, int OCC>
+static cudaError_t att_launch_gro(const AttParams& p, cudaStream_t st) {
+    const size_t smem = att_smem_bytes(p);
+    cudaError_t e = cudaFuncSetAttribute(att_fused_kernel<G, RV, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    att_fused_kernel<G, RV, OCC><<<p.grid, kAttThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
 template <int G, int RV>
 static cudaError_t att_launch_gr(const AttParams& p, cudaStream_t st) {
-    const size_t smem = att_smem_bytes(p);
-    cudaError_t e = cudaFuncSetAttribute(att_fused_kernel<G, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    att_fused_kernel<G, RV><<<p.grid, kAttThreads, smem, st>>>(p);
-    return cudaGetLastError();
+    if (G == 1 && p.occ == 2) return att_launch_gro<G, RV, (G == 1 ? 2 : 1)>(p, st);
+    return att_launch_gro<G, RV, 1>(p, st);
 }
 
 template <int G>
