@@ -544,8 +544,6 @@ static int plan(sat_handle* h, Layer& ly, LinProblem& P, std::initializer_list<L
         }
     }
     P.splits = best;
-    P.ws = nullptr;
-    P.counters = nullptr;
     P.cta_count = tiles * best;
     // packed-activation scratch for the cooperative pre-pass (used when the launch fits one wave)
     const size_t xneed = (size_t)P.n_row_tiles * P.k_blocks * 2 * P.row_tile * kBK * 2;

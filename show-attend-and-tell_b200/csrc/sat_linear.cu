@@ -15,15 +15,20 @@
 // W is repacked once at sat_set_weight() into the exact shared-memory image of
 // the UMMA K-major operand (hi and lo halves adjacent: 4 bytes per weight, the
 // same HBM traffic as the fp32 original), so a pipeline stage is filled by ONE
-// 32 KB cp.async.bulk (TMA) per CTA.  X (tiny) is converted fp32 -> bf16 hi/lo
-// by four producer warps straight from its fp32 sources (context vector, word
-// embedding row gather, hidden state: the concat of model.py:277,283-286 is
-// never materialised).  Split-K partials meet in an L2-resident workspace; the
-// last-arriving CTA of a tile reduces them in fixed order (deterministic) and
-// applies the fused epilogue (bias / tanh / LSTM gates).
+// 32 KB cp.async.bulk (TMA) per CTA.  X (tiny) arrives the same way when its
+// producer kernel wrote it as a "packed activation" (x_mode 2, the steady state
+// of the decode loop); otherwise all CTAs convert it once in a cooperative
+// pre-pass (x_mode 1) or producer warps convert it per stage (x_mode 0).  The
+// concats of model.py:277,283-286 are never materialised: the K range of a
+// problem is a list of segments.
+// Split-K: the S CTAs of a tile are one thread-block cluster; partial tiles meet
+// in distributed shared memory and are summed in fixed rank order
+// (bit-reproducible), then the fused epilogue runs (bias / tanh / LSTM gates /
+// greedy argmax of the vocabulary layer / packed copy for the next layer).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM
-// allocator + MMA issuer (one lane), warps 2..5 = X producers, then epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM
+// allocator + MMA issuer (one lane), warps 2..9 = X producers (modes 0/1), then
+// epilogue.
 #include "sat_common.cuh"
 #include "sat_linear.cuh"
 

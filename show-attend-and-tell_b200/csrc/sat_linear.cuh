@@ -50,11 +50,9 @@ struct LinProblem {
     int n_row_tiles;
     int n_out;      // valid outputs
     int n_tiles;    // ceil(n_out / 128)
-    int splits;     // split-K factor
+    int splits;     // split-K factor = thread-block cluster size (1, 2, 4 or 8)
     const uint8_t* wpack;  // [n_tiles][k_blocks][hi|lo][128 x 64 bf16, canonical UMMA K-major layout]
     const float* bias;     // packed output order, n_tiles*128 entries (zero padded); may be null for kEpiNone
-    float* ws;             // split-K partials [splits][n_row_tiles*row_tile][n_tiles*128]
-    unsigned* counters;    // [2 * n_row_tiles * n_tiles] (arrivals, departures), zero between launches
     uint8_t* xpack;        // x_mode 1: packed activations [n_row_tiles][k_blocks][hi|lo][row_tile x 64 bf16]
     unsigned* xbar;        // x_mode 1: grid barrier {count, generation}
     int epi;
