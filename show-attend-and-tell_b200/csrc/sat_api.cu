@@ -121,7 +121,7 @@ struct sat_handle {
     uint8_t *pa_cur_h_in = nullptr, *pa_cur_h_out = nullptr;
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 1, opt_att_sms = 0, opt_att_occ = 1;
+    int opt_overlap = 1, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -355,6 +355,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "overlap") h->opt_overlap = (int)value;
     else if (k == "att_sms") h->opt_att_sms = (int)value;
     else if (k == "att_occ") h->opt_att_occ = (int)value;
+    else if (k == "att_warps") h->opt_att_warps = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -727,6 +728,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     ap.l2_t = h->opt_l2_t;
     ap.l2_ctx = h->opt_l2_ctx;
     ap.occ = h->opt_att_occ;
+    ap.warps = h->opt_att_warps;
     if (sm_budget <= 0 && h->opt_att_sms > 0) sm_budget = h->opt_att_sms;   // experiment knob
     if (!att_plan(ap, h->smem_optin, sm_budget > 0 ? sm_budget : h->num_sms))
         return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);

@@ -29,14 +29,15 @@
 
 namespace sat {
 
-constexpr int kAttConsumerWarps = 8;
-constexpr int kAttThreads = (kAttConsumerWarps + 1) * 32;
+// consumer warps per CTA: 8 (all G) or 16 (G == 1: twice the warps hide the shared-memory / shuffle latency
+// of the two passes; needs <= 112 registers per thread)
 constexpr int kAttMaxDPerThread = 8;   // D <= 2048
 
 __device__ __forceinline__ int att_rbegin(long long NR, int P, int c) { return (int)(NR * c / P); }
 
-template <int G, int RV, int OCC>
-__global__ void __launch_bounds__(kAttThreads, OCC) att_fused_kernel(const __grid_constant__ AttParams p) {
+template <int G, int RV, int OCC, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, OCC) att_fused_kernel(const __grid_constant__ AttParams p) {
+    constexpr int kAttConsumerWarps = NW;
     extern __shared__ __align__(1024) uint8_t smem[];
     // layout: [slots][barriers 2*nslots*8][vec RL][q G*RL][w G*Lp][misc 64]
     uint8_t* slots = smem;
@@ -271,8 +272,10 @@ __global__ void __launch_bounds__(kAttThreads, OCC) att_fused_kernel(const __gri
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int k = 0; k < kAttMaxDPerThread; ++k) zacc[g][k] = 0.f;
-        const bool vec2 = (D % 512) == 0;
-        const int nk2 = D / 512;
+        const bool vec2 = (D % (2 * NT)) == 0;
+        const int nk2 = D / (2 * NT);
+        const bool vec1 = !vec2 && (D % NT) == 0;      // one float per NT features (16 warps, D = 512)
+        const int nk1 = D / NT;
         for (int r = seg0; r < seg1; r += p.cch, ++idx) {
             const int n = min(p.cch, seg1 - r);
             const int s = idx % p.nslots;
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(kAttThreads, OCC) att_fused_kernel(const __gri
                         if (k < nk2) {
                             float2 x[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = b2[(size_t)(row + j) * rowstride + 256 * k];
+                            for (int j = 0; j < 8; ++j) x[j] = b2[(size_t)(row + j) * rowstride + NT * k];
 #pragma unroll
                             for (int g = 0; g < G; ++g) {
                                 float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;   // two chains per feature
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kAttThreads, OCC) att_fused_kernel(const __gri
 #pragma unroll
                     for (int k = 0; k < kAttMaxDPerThread / 2; ++k) {
                         if (k < nk2) {
-                            const float2 x = b2[(size_t)row * rowstride + 256 * k];
+                            const float2 x = b2[(size_t)row * rowstride + NT * k];
 #pragma unroll
                             for (int g = 0; g < G; ++g) {
                                 const float wv = w_s[g * Lp + ll];
@@ -336,6 +339,45 @@ __global__ void __launch_bounds__(kAttThreads, OCC) att_fused_kernel(const __gri
                             }
                         }
                     }
+                }
+            } else if (vec1) {
+                const float* b1 = buf + ct;
+                int row = 0;
+                for (; row + 8 <= n; row += 8) {
+                    const int ll = r + row - seg0;
+                    float wv[G][8];
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) wv[g][j] = w_s[g * Lp + ll + j];
+#pragma unroll
+                    for (int k = 0; k < kAttMaxDPerThread; ++k) {
+                        if (k < nk1) {
+                            float x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = b1[(size_t)(row + j) * D + NT * k];
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 8; j += 2) {
+                                    s0 = fmaf(wv[g][j], x[j], s0);
+                                    s1 = fmaf(wv[g][j + 1], x[j + 1], s1);
+                                }
+                                zacc[g][k] += s0 + s1;
+                            }
+                        }
+                    }
+                }
+                for (; row < n; ++row) {
+                    const int ll = r + row - seg0;
+#pragma unroll
+                    for (int k = 0; k < kAttMaxDPerThread; ++k)
+                        if (k < nk1) {
+                            const float x = b1[(size_t)row * D + NT * k];
+#pragma unroll
+                            for (int g = 0; g < G; ++g) zacc[g][k] = fmaf(w_s[g * Lp + ll], x, zacc[g][k]);
+                        }
                 }
             } else {
                 for (int row = 0; row < n; ++row) {
@@ -359,7 +401,7 @@ __global__ void __launch_bounds__(kAttThreads, OCC) att_fused_kernel(const __gri
             if (lane == 0) mbar_arrive(&empty[s]);
         }
         // feature index of accumulator k of this thread
-        auto feat = [&](int k) { return vec2 ? 2 * ct + 512 * (k >> 1) + (k & 1) : ct + NT * k; };
+        auto feat = [&](int k) { return vec2 ? 2 * ct + 2 * NT * (k >> 1) + (k & 1) : ct + NT * k; };
         const int nacc = vec2 ? 2 * nk2 : nper;
 
         if (ct == 0 && seg0 == r_begin) trace_stamp(p.dbg, 5);
@@ -491,8 +533,8 @@ bool att_plan(AttParams& p, int smem_optin, int num_sms) {
     p.occ = occ;
     smem_optin = occ == 2 ? (smem_optin - 2048) / 2 : smem_optin;
     num_sms *= occ;
-    if (p.G < 1 || p.G > 4 || p.L < 1 || (p.D % 4) || (p.RL % 4) || p.D > kAttMaxDPerThread * kAttConsumerWarps * 32)
-        return false;
+    if (p.G < 1 || p.G > 4 || p.L < 1 || (p.D % 4) || (p.RL % 4) || p.D > kAttMaxDPerThread * 8 * 32) return false;
+    if (p.warps != 16 || p.G != 1 || p.occ == 2) p.warps = 8;
     const int target = 32 * 1024;                       // bytes per ring slot (16 rows of 512 floats: 2 rows per warp)
     int rch = target / (p.RL * 4), cch = target / (p.D * 4);
     if (rch < 1) rch = 1;
@@ -526,18 +568,19 @@ bool att_plan(AttParams& p, int smem_optin, int num_sms) {
 
 size_t att_part_floats(const AttParams& p) { return (size_t)p.grid * p.segmax * p.G * (p.D + 2); }
 
-template <int G, int RV, int OCC>
+template <int G, int RV, int OCC, int NW>
 static cudaError_t att_launch_gro(const AttParams& p, cudaStream_t st) {
     const size_t smem = att_smem_bytes(p);
-    cudaError_t e = cudaFuncSetAttribute(att_fused_kernel<G, RV, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(att_fused_kernel<G, RV, OCC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    att_fused_kernel<G, RV, OCC><<<p.grid, kAttThreads, smem, st>>>(p);
+    att_fused_kernel<G, RV, OCC, NW><<<p.grid, (NW + 1) * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 template <int G, int RV>
 static cudaError_t att_launch_gr(const AttParams& p, cudaStream_t st) {
-    if (G == 1 && p.occ == 2) return att_launch_gro<G, RV, (G == 1 ? 2 : 1)>(p, st);
-    return att_launch_gro<G, RV, 1>(p, st);
+    if (G == 1 && p.occ == 2) return att_launch_gro<G, RV, (G == 1 ? 2 : 1), 8>(p, st);
+    if (G == 1 && p.warps == 16) return att_launch_gro<G, RV, 1, (G == 1 ? 16 : 8)>(p, st);
+    return att_launch_gro<G, RV, 1, 8>(p, st);
 }
 
 template <int G>

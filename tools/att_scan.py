@@ -14,9 +14,9 @@ alpha = torch.empty(B, L, device="cuda"); z = torch.empty(B, D, device="cuda")
 flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
 m.prepare(ctx, want_state=False)
 p = lambda t: C.c_void_p(t.data_ptr())
-for occ, sms in ((1, 148), (2, 148), (2, 128), (2, 74), (1, 64), (2, 64), (2, 37)):
+for occ, sms in ((8, 148), (16, 148), (8, 64), (16, 64)):
     for cold in (True, False):
-        m.set_option("att_occ", occ)
+        m.set_option("att_warps", occ)
         m.set_option("att_sms", sms)
         m.set_option("profile", 0)
         with torch.cuda.stream(m.stream):
@@ -28,4 +28,4 @@ for occ, sms in ((1, 148), (2, 148), (2, 128), (2, 74), (1, 64), (2, 64), (2, 37
                 m.lib.sat_attention_fwd(m._h, p(ctx), p(hs), p(alpha), p(z), B, 1, m._st())
         torch.cuda.synchronize()
         us = m.info("prof_ns_att") / max(1, m.info("prof_n_att")) / 1e3
-        print("occ %d att_sms %3d  %s  %.2f us/launch (events)  -> %.0f GB/s" % (occ, sms, "cold" if cold else "warm", us, 51.69e6 / us / 1e3), flush=True)
+        print("warps %d att_sms %3d  %s  %.2f us/launch (events)  -> %.0f GB/s" % (occ, sms, "cold" if cold else "warm", us, 51.69e6 / us / 1e3), flush=True)
