@@ -118,7 +118,9 @@ struct sat_handle {
     uint8_t *pa_z = nullptr, *pa_emb = nullptr, *pa_t = nullptr;
     // valid for the duration of one step_impl call
     bool pa_on = false;
-    uint8_t *pa_cur_h_in = nullptr, *pa_cur_h_out = nullptr;
+    uint8_t *pa_cur_h_in = nullptr, *pa_cur_h_out = nullptr, *pa_cur_z = nullptr;
+    float* z2[2] = {nullptr, nullptr};       // context vectors, double buffered for the overlapped loop
+    uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_overlap = 1, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8;
@@ -217,7 +219,7 @@ extern "C" void sat_destroy(sat_handle* h) {
     void* bufs[] = {h->att_vec.dev, h->embedding, h->T1, h->q, h->e, h->alpha, h->z, h->mean, h->tmp_a, h->tmp_b,
                     h->t_dec, h->logits, h->st_c[0], h->st_c[1], h->st_h[0], h->st_h[1], h->word, h->zero_word,
                     h->rowcnt, h->topk_idx, h->part_n, h->comp_n, h->comp_sent, h->sent[0], h->sent[1], h->topk_p,
-                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part, h->trace, h->pa_h[0], h->pa_h[1], h->pa_z, h->pa_emb, h->pa_t};
+                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part, h->trace, h->pa_h[0], h->pa_h[1], h->pa_z, h->pa_emb, h->pa_t, h->pa_z2[1], h->z2[1]};
     for (void* b : bufs) cudaFree(b);
     delete h;
 }
@@ -311,6 +313,10 @@ extern "C" int sat_create(const sat_dims* dims, sat_handle** out) {
             RET(dmalloc(&h->pa_h[0], RP * H * 4));
             RET(dmalloc(&h->pa_h[1], RP * H * 4));
             RET(dmalloc(&h->pa_z, RP * D * 4));
+            RET(dmalloc(&h->pa_z2[1], RP * D * 4));
+            h->pa_z2[0] = h->pa_z;
+            RET(dmalloc(&h->z2[1], R * D));
+            h->z2[0] = h->z;
             RET(dmalloc(&h->pa_emb, RP * E * 4));
             RET(dmalloc(&h->pa_t, RP * Dd * 4));
         }
@@ -744,7 +750,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     }
     ap.part = h->att_part;
     if (h->pa_on) {
-        ap.pa_z = h->pa_z;
+        ap.pa_z = h->pa_cur_z ? h->pa_cur_z : h->pa_z;
         ap.pa_row_tile = row_tile_for(rows);
         ap.pa_mode = h->opt_layout;
         if (last_word) {   // the embedding rows of this step's words are packed on the side
@@ -771,7 +777,7 @@ static int lstm_impl(sat_handle* h, const float* z, const int32_t* last_word, co
     // current_input = concat([context, word_embed]) (model.py:277); LSTMCell concat([x, h]) (TF)
     const bool pa = h->pa_on;
     RET(plan(h, h->lstm, P,
-             {seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? h->pa_z : nullptr),
+             {seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? (h->pa_cur_z ? h->pa_cur_z : h->pa_z) : nullptr),
               seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word, pa ? h->pa_emb : nullptr),
               seg(h_in, d.num_lstm_units, d.num_lstm_units, nullptr, pa ? h->pa_cur_h_in : nullptr)},
              rows, kEpiLstm, nullptr, 0, st));
@@ -822,7 +828,7 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
         if (phase != 2) {
         RET(plan(h, h->dec_1, P[0],
                  {seg(h_out, d.num_lstm_units, d.num_lstm_units, nullptr, pa ? h->pa_cur_h_out : nullptr),
-                  seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? h->pa_z : nullptr),
+                  seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? (h->pa_cur_z ? h->pa_cur_z : h->pa_z) : nullptr),
                   seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word, pa ? h->pa_emb : nullptr)},
                  rows, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st, 0, group));
         P[0].out_pa = pa ? h->pa_t : nullptr;
@@ -855,7 +861,7 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
     const bool pa = h->pa_on;
     RET(plan(h, h->dec_2, P[0],
              {seg(h_out, d.num_lstm_units, d.num_lstm_units, nullptr, pa ? h->pa_cur_h_out : nullptr),
-              seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? h->pa_z : nullptr),
+              seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? (h->pa_cur_z ? h->pa_cur_z : h->pa_z) : nullptr),
               seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word, pa ? h->pa_emb : nullptr)},
              rows, kEpiBias, logits, d.vocabulary_size, st, 0, group));
     int np = 1;
@@ -876,6 +882,7 @@ static int step_impl(sat_handle* h, StepIO& io, cudaStream_t st) {
     if (h->pa_on) {
         h->pa_cur_h_in = h->pa_h[io.pa_slot & 1];
         h->pa_cur_h_out = h->pa_h[(io.pa_slot & 1) ^ 1];
+        h->pa_cur_z = h->pa_z;
         PackJob jobs[2];
         int nj = 0;
         const int rtile = row_tile_for(rows);
@@ -994,29 +1001,39 @@ static int loop_enqueue_overlap(sat_handle* h, const float* ctx, int B, int T, c
         h->pa_on = true;
         h->pa_cur_h_in = h->pa_h[t & 1];
         h->pa_cur_h_out = h->pa_h[(t + 1) & 1];
+        float* zcur = h->z2[t & 1];          // context vector of this step (fp32 + packed), written by attention(t)
+        h->pa_cur_z = h->pa_z2[t & 1];
         if (t == 0)   // q(0), attention(0) and the embedding of <start>
-            RET(attention_impl(h, ctx, B, 1, h_in, nullptr, h->z, st, false, h->word));
-        RET(lstm_impl(h, h->z, h->word, c_in, h_in, c_out, h_out, B, st));
+            RET(attention_impl(h, ctx, B, 1, h_in, nullptr, zcur, st, false, h->word));
+        RET(lstm_impl(h, zcur, h->word, c_in, h_in, c_out, h_out, B, st));
         float* logits = logits_all ? logits_all + (size_t)t * B * d.vocabulary_size : h->logits;
-        RET(decode_impl(h, h_out, h->z, h->word, logits, B, st, t + 1 < T, nullptr, nullptr, 1));   // fc_1 (+ q(t+1))
         if (t + 1 < T) {
-            // fork: attention(t+1) on the side stream; its inputs (q, T1, contexts) are complete
+            // fork right after the LSTM: the side stream computes q(t+1) = f(h_t) and then attention(t+1) while
+            // this stream runs decode fc_1 and the vocabulary layer of step t
             CK(cudaEventRecord(h->ev_fork, st));
             CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+            LinProblem Pq;
+            h->cur_tag = kTagAttState;
+            RET(plan_att_state(h, Pq, h_out, B, h->side, 1, h->pa_cur_h_out));
+            RET(launch(h, &Pq, 1, h->side));
             h->pa_cur_h_in = h->pa_h[(t + 1) & 1];
-            // it shares the GPU with the vocabulary layer (n_tiles CTAs, one per SM): size it for the SMs left over
+            h->pa_cur_z = h->pa_z2[(t + 1) & 1];
+            // it shares the GPU with decode fc_1 / the vocabulary layer (n_tiles CTAs, one per SM): size it for
+            // the SMs left over
             int budget = h->opt_att_sms > 0 ? h->opt_att_sms : h->num_sms - h->dec_2.n_tiles;
             if (budget < h->num_sms / 4) budget = h->num_sms;
-            RET(attention_impl(h, ctx, B, 1, h_out, nullptr, h->z, h->side, true, nullptr, budget));
+            RET(attention_impl(h, ctx, B, 1, h_out, nullptr, h->z2[(t + 1) & 1], h->side, true, nullptr, budget));
             CK(cudaEventRecord(h->ev_join, h->side));
             h->pa_cur_h_in = h->pa_h[t & 1];
+            h->pa_cur_z = h->pa_z2[t & 1];
         }
+        RET(decode_impl(h, h_out, zcur, h->word, logits, B, st, false, nullptr, nullptr, 1));   // fc_1
         RowsParams rp;
         memset(&rp, 0, sizeof(rp));
         rp.tokens = tokens; rp.tokens_ld = T; rp.step = t;
         rp.next_word = h->word; rp.forced = forced; rp.forced_ld = T;
         int fused = 0;
-        RET(decode_impl(h, h_out, h->z, h->word, logits, B, st, false, &rp, &fused, 2, t + 1 < T));  // fc_2 + argmax
+        RET(decode_impl(h, h_out, zcur, h->word, logits, B, st, false, &rp, &fused, 2, t + 1 < T));  // fc_2 + argmax
         if (!fused) {
             h->pa_on = false;
             return fail(SAT_ERR_STATE, "overlapped loop needs the fused argmax of the vocabulary layer");
@@ -1024,6 +1041,7 @@ static int loop_enqueue_overlap(sat_handle* h, const float* ctx, int B, int T, c
         if (t + 1 < T) CK(cudaStreamWaitEvent(st, h->ev_join, 0));   // join before the LSTM of step t+1
     }
     h->pa_on = false;
+    h->pa_cur_z = nullptr;
     return SAT_OK;
 }
 
