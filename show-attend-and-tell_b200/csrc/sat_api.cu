@@ -129,6 +129,8 @@ struct sat_handle {
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
     int opt_trace = 0;
     int trace_at = 0;      // with trace == 1: index of the dense launch (counted from the option call) to stamp
+    int tl_count = 0;      // with trace == 3: launches recorded so far ({min start, max end} per launch)
+    std::vector<std::string> tl_names;
 
     std::vector<GraphEntry> graphs;
 
@@ -365,7 +367,14 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
-        if (h->trace) CK(cudaMemset(h->trace, 0, 1024 * 16 * sizeof(unsigned long long)));
+        if (h->trace) CK(cudaMemset(h->trace, value == 3 ? 0xFF : 0, 1024 * 16 * sizeof(unsigned long long)));
+        if (value == 3 && h->trace) {   // max cells start at 0, min cells at ~0
+            std::vector<unsigned long long> init(1024 * 16);
+            for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+            CK(cudaMemcpy(h->trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+        }
+        h->tl_count = 0;
+        h->tl_names.clear();
         return SAT_OK;
     } else if (k == "trace_at") { h->trace_at = (int)value; return SAT_OK; }
     else if (k == "l2_w") h->opt_l2_w = (int)value;
@@ -405,6 +414,13 @@ extern "C" int sat_get_info(sat_handle* h, const char* key, int64_t* value) {
         *value = want_n ? n : (int64_t)ns;
     }
     else if (k == "trace_ptr") *value = (int64_t)(uintptr_t)h->trace;
+    else if (k == "tl_count") *value = h->tl_count;
+    else if (k.rfind("tl_tag_", 0) == 0) {   // family code of timeline entry i: index into the tag list, grid in the high bits
+        const int i = atoi(k.c_str() + 7);
+        if (i < 0 || i >= (int)h->tl_names.size()) return fail(SAT_ERR_INVALID, "timeline index");
+        snprintf(g_err, sizeof(g_err), "%s", h->tl_names[i].c_str());   // name returned through sat_last_error()
+        *value = i;
+    }
     else if (k == "weight_bytes") {
         size_t b = 0;
         for (Layer* ly : h->layers) b += (size_t)ly->n_tiles * ly->k_blocks * kWStageBytes;
@@ -593,7 +609,12 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.stages = lin_pick_stages(max_rt);
     L.l2_w = h->opt_l2_w;
     L.dbg = nullptr;
+    L.tl = nullptr;
     if (h->opt_trace == 1 && begin <= 1024 && h->trace_at-- == 0) L.dbg = h->trace;
+    if (h->opt_trace == 3 && h->tl_count < 8000) {
+        L.tl = h->trace + 2 * h->tl_count++;
+        h->tl_names.push_back(std::string(kTagNames[h->cur_tag]) + "/" + std::to_string(begin));
+    }
     bool all_pa = true;
     for (int i = 0; i < n; ++i)
         for (int sgi = 0; sgi < probs[i].nseg; ++sgi) all_pa = all_pa && probs[i].seg[sgi].pa != nullptr;
@@ -761,6 +782,11 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         }
     }
     ap.dbg = h->opt_trace == 2 ? h->trace : nullptr;
+    ap.tl = nullptr;
+    if (h->opt_trace == 3 && h->tl_count < 8000) {
+        ap.tl = h->trace + 2 * h->tl_count++;
+        h->tl_names.push_back("attention/" + std::to_string(ap.grid));
+    }
     {
         ProfScope ps(h, kTagAtt, st);
         CK(att_launch(ap, st));

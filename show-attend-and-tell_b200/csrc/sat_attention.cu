@@ -57,6 +57,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) att_fused_kernel(const __g
 
     if (threadIdx.x == 0) {
         trace_stamp(p.dbg, 0);
+        tl_begin(p.tl);
         for (int s = 0; s < p.nslots; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kAttConsumerWarps);
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) att_fused_kernel(const __g
         }
         seg0 = seg1;
     }
-    if (ct == 0) trace_stamp(p.dbg, 7);
+    if (ct == 0) { trace_stamp(p.dbg, 7); tl_end(p.tl); }
     if (ct == 0 && p.dbg) {
         p.dbg[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)wait1;
         p.dbg[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)wait2;

@@ -33,6 +33,7 @@ struct AttParams {
     uint8_t* emb_pa;
     int emb_E;
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
+    unsigned long long* tl;   // optional {min start, max end} of this launch
 };
 
 bool att_plan(AttParams& p, int smem_optin, int num_sms);

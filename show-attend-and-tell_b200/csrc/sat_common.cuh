@@ -215,6 +215,14 @@ __device__ __forceinline__ void trace_stamp(unsigned long long* dbg, int slot) {
     if (dbg) dbg[(size_t)blockIdx.x * 16 + slot] = globaltimer_ns();
 }
 
+// loop timeline (debug option "trace" = 3): per launch two cells, min CTA start and max CTA end
+__device__ __forceinline__ void tl_begin(unsigned long long* tl) {
+    if (tl) atomicMin(tl, globaltimer_ns());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl) {
+    if (tl) atomicMax(tl + 1, globaltimer_ns());
+}
+
 // --------------------------------------------------------------- misc math
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     // ---- one-time setup
     if (threadIdx.x == 0) {
         trace_stamp(L.dbg, 0);
+        tl_begin(L.tl);
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_w[s], 1);
             mbar_init(&full_x[s], xtma ? 1 : kLinProducers);
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     }
 
     __syncthreads();
-    if (threadIdx.x == 0) trace_stamp(L.dbg, 10);
+    if (threadIdx.x == 0) { trace_stamp(L.dbg, 10); tl_end(L.tl); }
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();

@@ -89,6 +89,7 @@ struct LinLaunch {
     int stages;
     int l2_w;         // L2 eviction policy of the weight stream (see l2_policy)
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
+    unsigned long long* tl;   // optional {min start, max end} of this launch
     int x_mode;       // 0 = producer warps convert X per stage; 1 = cooperative pre-pack + TMA (grid <= #SMs);
                       // 2 = every operand segment arrives packed from its producer (TMA from t = 0)
 };

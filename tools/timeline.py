@@ -1,0 +1,39 @@
+"""GPU timeline of one decode loop (config 2): per kernel launch, first CTA start and last CTA end.
+    python tools/timeline.py [overlap]"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sat_b200
+B, L, D, H, V, T = 64, 196, 512, 1024, 10000, 20
+cfg = sat_b200.Config(batch_size=B, beam_size=1, num_ctx=L, dim_ctx=D, num_lstm_units=H, vocabulary_size=V, max_caption_length=T)
+m = sat_b200.CaptionGenerator(cfg)
+g = torch.Generator().manual_seed(1)
+m.set_weights({n: torch.rand(*s, generator=g) * 0.16 - 0.08 for n, s in sat_b200.weight_shapes(cfg).items()})
+ctx = torch.relu(torch.randn(B, L, D, generator=g)).cuda()
+for overlap in (1, 0):
+    m.set_option("overlap", overlap)
+    m.set_option("graphs", 0)
+    for i in range(3):
+        m.loop_device(ctx, T)
+    torch.cuda.synchronize()
+    m.set_option("trace", 3)
+    m.loop_device(ctx, T)
+    torch.cuda.synchronize()
+    import cuda.bindings.runtime as cr
+    n = m.info("tl_count")
+    host = np.zeros(1024 * 16, np.uint64)
+    cr.cudaMemcpy(host.ctypes.data, m.info("trace_ptr"), host.nbytes, cr.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    names = []
+    for i in range(n):
+        m.info("tl_tag_%d" % i)
+        names.append(m.lib.sat_last_error().decode())
+    m.set_option("trace", 0)
+    t0 = int(host[0])
+    print("=== overlap=%d: %d launches; steps 5..7 (us since loop start; eager launches)" % (overlap, n))
+    per = 4 if overlap else 4
+    rows = [(names[i], (int(host[2 * i]) - t0) / 1e3, (int(host[2 * i + 1]) - t0) / 1e3) for i in range(n)]
+    lstm_idx = [i for i, r in enumerate(rows) if r[0].startswith("lstm")]
+    lo, hi = lstm_idx[5], lstm_idx[8]
+    for nm, a, b in rows[lo:hi]:
+        print("  %-18s start %9.2f  end %9.2f  dur %7.2f" % (nm, a, b, b - a))
+    print("  step period: %.2f us" % ((rows[lstm_idx[15]][1] - rows[lstm_idx[5]][1]) / 10))
