@@ -51,8 +51,7 @@ struct Layer {
     uint8_t* xpack = nullptr;  // packed activations (x_mode 1)
     size_t xpack_bytes = 0;
     unsigned* xbar = nullptr;  // {count, generation}
-    float* am_val = nullptr;   // fused-argmax tile candidates
-    int32_t* am_idx = nullptr;
+    unsigned long long* am_key = nullptr;   // fused-argmax tile candidates
     unsigned* am_ctr = nullptr;
     size_t am_n = 0;
 };
@@ -123,7 +122,7 @@ struct sat_handle {
     uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 1, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8;
+    int opt_overlap = 1, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 0, opt_warm = 1;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -188,8 +187,7 @@ static void layer_free(Layer& ly) {
     cudaFree(ly.bias);
     cudaFree(ly.xpack);
     cudaFree(ly.xbar);
-    cudaFree(ly.am_val);
-    cudaFree(ly.am_idx);
+    cudaFree(ly.am_key);
     cudaFree(ly.am_ctr);
     ly = Layer();
 }
@@ -364,13 +362,15 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "att_sms") h->opt_att_sms = (int)value;
     else if (k == "att_occ") h->opt_att_occ = (int)value;
     else if (k == "att_warps") h->opt_att_warps = (int)value;
+    else if (k == "pdl") h->opt_pdl = (int)value;
+    else if (k == "warm") h->opt_warm = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
         if (h->trace) CK(cudaMemset(h->trace, value == 3 ? 0xFF : 0, 1024 * 16 * sizeof(unsigned long long)));
         if (value == 3 && h->trace) {   // max cells start at 0, min cells at ~0
             std::vector<unsigned long long> init(1024 * 16);
-            for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+            for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;   // cells 0,2 are minima, 1,3 maxima
             CK(cudaMemcpy(h->trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
         }
         h->tl_count = 0;
@@ -610,9 +610,11 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.l2_w = h->opt_l2_w;
     L.dbg = nullptr;
     L.tl = nullptr;
+    L.warm_epilogue = h->opt_warm;
+    L.pdl = (h->opt_pdl && L.x_mode != 1) ? 1 : 0;   // (the cooperative pre-pass launch keeps full serialization)
     if (h->opt_trace == 1 && begin <= 1024 && h->trace_at-- == 0) L.dbg = h->trace;
-    if (h->opt_trace == 3 && h->tl_count < 8000) {
-        L.tl = h->trace + 2 * h->tl_count++;
+    if (h->opt_trace == 3 && h->tl_count < 4000) {
+        L.tl = h->trace + 4 * h->tl_count++;
         h->tl_names.push_back(std::string(kTagNames[h->cur_tag]) + "/" + std::to_string(begin));
     }
     bool all_pa = true;
@@ -781,10 +783,11 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
             ap.emb_E = h->d.dim_embedding;
         }
     }
+    ap.pdl = h->opt_pdl ? 1 : 0;
     ap.dbg = h->opt_trace == 2 ? h->trace : nullptr;
     ap.tl = nullptr;
-    if (h->opt_trace == 3 && h->tl_count < 8000) {
-        ap.tl = h->trace + 2 * h->tl_count++;
+    if (h->opt_trace == 3 && h->tl_count < 4000) {
+        ap.tl = h->trace + 4 * h->tl_count++;
         h->tl_names.push_back("attention/" + std::to_string(ap.grid));
     }
     {
@@ -822,17 +825,16 @@ static int attach_argmax(sat_handle* h, Layer& ly, LinProblem& P, const RowsPara
     if (need > ly.am_n) {
         if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: scratch growth during graph capture", ly.name.c_str());
         CK(cudaDeviceSynchronize());
-        cudaFree(ly.am_val); cudaFree(ly.am_idx);
-        ly.am_val = nullptr; ly.am_idx = nullptr; ly.am_n = 0;
-        RET(dmalloc(&ly.am_val, need));
-        RET(dmalloc(&ly.am_idx, need));
+        cudaFree(ly.am_key);
+        ly.am_key = nullptr; ly.am_n = 0;
+        RET(dmalloc(&ly.am_key, need));
         ly.am_n = need;
         if (!ly.am_ctr) {
             RET(dmalloc(&ly.am_ctr, (size_t)1));
             CK(cudaMemset(ly.am_ctr, 0, sizeof(unsigned)));
         }
     }
-    P.am_val = ly.am_val; P.am_idx = ly.am_idx; P.am_ctr = ly.am_ctr;
+    P.am_key = ly.am_key; P.am_ctr = ly.am_ctr;
     P.am_tokens = am->tokens; P.am_tokens_ld = am->tokens_ld; P.am_step = am->step;
     P.am_next_word = am->next_word; P.am_forced = am->forced; P.am_forced_ld = am->forced_ld;
     return 1;
@@ -871,6 +873,7 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
                  rows, kEpiBias, logits, d.vocabulary_size, st, am ? 1 : 0));   // the fused argmax needs whole rows per CTA
         used = attach_argmax(h, h->dec_2, P[0], am, st);
         if (used < 0) return used;
+        if (used && logits == h->logits) P[0].out = nullptr;   // nobody asked for the logits: only the word is kept
         // the embedding row of the chosen word is normally packed by the next step's attention kernel; when
         // that kernel runs CONCURRENTLY with this layer (decode loop), the last CTA of this layer does it
         if (used && pa && pack_next_emb) {

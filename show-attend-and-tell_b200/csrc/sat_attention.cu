@@ -55,6 +55,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) att_fused_kernel(const __g
     const long long NR = (long long)p.NI * L;
     const int r_begin = att_rbegin(NR, P, c), r_end = att_rbegin(NR, P, c + 1);
 
+    if (p.pdl) pdl_launch_dependents();
     if (threadIdx.x == 0) {
         trace_stamp(p.dbg, 0);
         tl_begin(p.tl);
@@ -65,6 +66,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) att_fused_kernel(const __g
         fence_mbar_init();
     }
     __syncthreads();
+    if (p.pdl) pdl_wait();   // q / word of this step come from the predecessor; outputs must not race with its reads
+    if (threadIdx.x == 0) tl_go(p.tl);
 
     if (warp == kAttConsumerWarps) {
         // ============================ producer ============================
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) att_fused_kernel(const __g
         }
         named_bar_sync(1, NT);
         if (ct == 0 && seg0 == r_begin) trace_stamp(p.dbg, 6);
+        if (ct == 0 && seg1 == r_end) tl_main_done(p.tl);
         if (*flag) {
             __threadfence();
             if (ct == 0) p.rowcnt[img] = 0u;                  // ready for the next launch
@@ -574,8 +578,17 @@ static cudaError_t att_launch_gro(const AttParams& p, cudaStream_t st) {
     const size_t smem = att_smem_bytes(p);
     cudaError_t e = cudaFuncSetAttribute(att_fused_kernel<G, RV, OCC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    att_fused_kernel<G, RV, OCC, NW><<<p.grid, (NW + 1) * 32, smem, st>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3((NW + 1) * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, att_fused_kernel<G, RV, OCC, NW>, p);
 }
 template <int G, int RV>
 static cudaError_t att_launch_gr(const AttParams& p, cudaStream_t st) {

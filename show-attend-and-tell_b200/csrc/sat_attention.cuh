@@ -34,6 +34,7 @@ struct AttParams {
     int emb_E;
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
     unsigned long long* tl;   // optional {min start, max end} of this launch
+    int pdl;             // launched with programmatic stream serialization
 };
 
 bool att_plan(AttParams& p, int smem_optin, int num_sms);

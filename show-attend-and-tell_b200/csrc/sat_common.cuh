@@ -187,10 +187,20 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream is still draining; it must not touch memory the predecessor (or anything before it) writes, nor
+// write anything they read, before pdl_wait() returns (= all prerequisite grids complete and flushed).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------ thread-block clusters / distributed shared memory
 __device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split form for a barrier that only orders "I am done reading your shared memory" (no data is published)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t dsmem_map(uint32_t local_smem_addr, uint32_t cta_rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
@@ -215,16 +225,31 @@ __device__ __forceinline__ void trace_stamp(unsigned long long* dbg, int slot) {
     if (dbg) dbg[(size_t)blockIdx.x * 16 + slot] = globaltimer_ns();
 }
 
-// loop timeline (debug option "trace" = 3): per launch two cells, min CTA start and max CTA end
+// loop timeline (debug option "trace" = 3): per launch four cells: min CTA start, max CTA end, min "go" (first
+// CTA past its dependency wait), max "main loop done" (accumulator complete / streaming complete)
 __device__ __forceinline__ void tl_begin(unsigned long long* tl) {
     if (tl) atomicMin(tl, globaltimer_ns());
 }
 __device__ __forceinline__ void tl_end(unsigned long long* tl) {
     if (tl) atomicMax(tl + 1, globaltimer_ns());
 }
+__device__ __forceinline__ void tl_go(unsigned long long* tl) {
+    if (tl) atomicMin(tl + 2, globaltimer_ns());
+}
+__device__ __forceinline__ void tl_main_done(unsigned long long* tl) {
+    if (tl) atomicMax(tl + 3, globaltimer_ns());
+}
 
 // --------------------------------------------------------------- misc math
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Activations of the fused dense epilogues.  Those epilogues run once per launch from a cold instruction cache,
+// so they are built from the short ex2/rcp forms: a handful of instructions each, absolute error ~2e-7 (the
+// parity budget of the decode path is 1e-3 relative).
+__device__ __forceinline__ float act_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float act_tanh(float x) {
+    const float e = __expf(-2.0f * fabsf(x));                 // in (0, 1]: no overflow, no cancellation blow-up
+    return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

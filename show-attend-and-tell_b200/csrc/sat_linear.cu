@@ -81,15 +81,16 @@ struct EpiCtx {
 __device__ __forceinline__ float epi_scalar(const LinProblem& P, float acc, int n) {
     if (P.epi == kEpiNone) return acc;
     acc += P.bias[n];
-    return P.epi == kEpiBiasTanh ? tanhf(acc) : acc;
+    return P.epi == kEpiBiasTanh ? act_tanh(acc) : acc;
 }
 
 // TF LSTMCell (un-vendored TF 1.7 dependency; gate order i, j, f, o and forget_bias 1.0
 // confirmed on the reference's recorded GraphDef, tests/golden/graph_fixture.json):
 //   c = sigmoid(f + 1) * c_prev + sigmoid(i) * tanh(j);  h = sigmoid(o) * tanh(c)
-__device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, float cp, int b, int unit, int mode) {
-    const float c = sigmoidf_acc(g.z + 1.0f) * cp + sigmoidf_acc(g.x) * tanhf(g.y);
-    const float h = sigmoidf_acc(g.w) * tanhf(c);
+__device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, float cp, int b, int unit, int mode, bool dry) {
+    const float c = act_sigmoid(g.z + 1.0f) * cp + act_sigmoid(g.x) * act_tanh(g.y);
+    const float h = act_sigmoid(g.w) * act_tanh(c);
+    if (dry) return;   // instruction-cache warm-up pass: no side effects
     P.c_out[(size_t)b * P.H + unit] = c;
     P.h_out[(size_t)b * P.H + unit] = h;
     if (P.out_pa) pa_store(P.out_pa, mode, P.row_tile, P.H >> 6, b, unit, h);   // h feeds the next dense layers
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     while ((int)tmem_cols < N) tmem_cols <<= 1;
 
     // ---- one-time setup
+    if (L.pdl) pdl_launch_dependents();   // the next kernel of the stream may begin its own prologue
     if (threadIdx.x == 0) {
         trace_stamp(L.dbg, 0);
         tl_begin(L.tl);
@@ -162,6 +164,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
     const uint32_t x_stage_bytes = 2 * x_half_bytes;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);   // epilogue warps: bias of this thread's 4 outputs
+    // Programmatic dependent launch: everything above touched no global memory.  The weights are immutable
+    // while a step runs, so the TMA lane may fetch them before the predecessor has finished; every other
+    // global access (activations, outputs) waits for the predecessor.
+    const bool tma_lane = warp == 0 && lane == 0;
+    if (L.pdl && !tma_lane) pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer: one 32 KB bulk copy per stage =====================
@@ -187,12 +195,19 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 tma_bulk_g2s(stage_base + (size_t)s * stage_bytes + kWStageBytes, xs, x_stage_bytes, &full_x[s]);
             };
             const int pre = nkb < S ? nkb : S;
+            if (!L.pdl) tl_go(L.tl);
+            if (L.pdl) {
+                for (int it = 0; it < pre; ++it) load_w(it);
+                pdl_wait();
+                tl_go(L.tl);
+                if (xpa) for (int it = 0; it < pre; ++it) load_x(it);
+            }
             if (xpa) {
-                for (int it = 0; it < pre; ++it) { load_w(it); load_x(it); }
+                if (!L.pdl) for (int it = 0; it < pre; ++it) { load_w(it); load_x(it); }
             } else if (xpre) {
                 // weights do not depend on the activation pre-pass: fill the pipeline with W first, then
                 // wait for the grid-wide pack to complete and fetch the X halves of the same stages
-                for (int it = 0; it < pre; ++it) load_w(it);
+                if (!L.pdl) for (int it = 0; it < pre; ++it) load_w(it);
                 const long long t0 = clock64();
                 while (ld_acquire_gpu(P.xbar + 1) == gen0) {
                     if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
@@ -204,7 +219,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 trace_stamp(L.dbg, 3);
                 for (int it = 0; it < pre; ++it) load_x(it);
             }
-            for (int it = xtma ? pre : 0; it < nkb; ++it) {
+            for (int it = (xtma || L.pdl) ? pre : 0; it < nkb; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
@@ -243,6 +258,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             }
             umma_commit(tmem_full);
             trace_stamp(L.dbg, 6);
+            if (L.tl) { mbar_wait(tmem_full, 0); tl_main_done(L.tl); }
         }
     } else {
         // ===================== X producers (warps 2..9), then epilogue =====================
@@ -323,213 +339,251 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             cur = nxt;
         }
 
-        // ---- epilogue part 1: accumulator tile TMEM -> shared memory (two warps per TMEM lane quadrant).
-        // tile_s[col][n] (fp32, n fastest) lives in the idle pipeline stages: every TMA write has landed and
-        // every MMA has read its operands once tmem_full fires.
-        const int q = warp & 3;               // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;     // 0 or 1
-        const int nl = q * 32 + lane;          // output feature within the tile (TMEM lane)
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        if (pt == 0) trace_stamp(L.dbg, 7);
-        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-        float* tile_s = reinterpret_cast<float*>(stage_base);
-        for (int c0 = half * 16; c0 < N; c0 += 32) {
-            float v[16];
-            tmem_ld16(taddr + (uint32_t)c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) tile_s[(c0 + j) * kTileN + nl] = v[j];
-        }
-        tc_fence_before();
-    }
-
-    // ---- epilogue part 2: split-K partials meet through distributed shared memory.  The `splits` CTAs of
-    // a tile form one thread-block cluster; after the cluster barrier CTA `split` sums rows
-    // [lo, hi) of all partial tiles in fixed rank order (bit-reproducible), applies the fused epilogue and
-    // writes coalesced rows.  splits == 1 is the same code reading only its own tile.
-    if (P.splits > 1) {
-        __syncwarp();
-        cluster_sync_all();
-    } else {
-        __syncthreads();
-    }
-    if (threadIdx.x == 64) trace_stamp(L.dbg, 8);
-    if (warp >= 2) {
-        const int pt = threadIdx.x - 64;
-        const int lane2 = pt & 31;
-        const int rows_here = min(N, P.rows - row0);
-        const float* tile_s = reinterpret_cast<const float*>(stage_base);
-        const uint32_t tile_addr = smem_u32(tile_s);
-        uint32_t peer[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) peer[r] = (P.splits > 1 && r < P.splits) ? dsmem_map(tile_addr, (uint32_t)r) : tile_addr;
-        const int cnt = rows_here * 32;          // float4 groups (row b, outputs 4u..4u+3); one warp = one row
-        const int lo = (int)(((long long)rows_here * split) / P.splits) * 32;
-        const int hi = (int)(((long long)rows_here * (split + 1)) / P.splits) * 32;
-        (void)cnt;
-        const bool do_am = P.am_val != nullptr && P.splits == 1;
-        // lo and the stride are multiples of 32: a thread keeps the same 4 outputs (u) for every row it
-        // visits, so its bias is loaded once, outside the row loop
+        // ---- epilogue.  Code that runs once per launch is fetched cold (the instruction caches do not survive
+        // the other kernels of a step), and a cold straight-line epilogue costs several microseconds on the
+        // critical path.  In the TMA-fed modes these warps are idle while the main loop streams, so they first
+        // run the epilogue once "dry" (same instructions, loads from harmless addresses, no stores, no
+        // synchronisation with other CTAs) purely to pull its code into the instruction caches.
+        // (the bias does not depend on the accumulator: fetch it while the main loop runs)
+        if (P.epi != kEpiNone && P.bias) bias4 = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * (pt & 31));
         const int u = pt & 31;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (P.epi != kEpiNone && P.bias) bias4 = *reinterpret_cast<const float4*>(P.bias + n_tile * kTileN + 4 * u);
-        for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
-            const int b = idx >> 5;
-            const uint32_t off = (uint32_t)(b * kTileN + 4 * u) * 4u;
-            float cprev = 0.f;
-            if (P.epi == kEpiLstm && n_tile * 32 + u < P.H) cprev = P.c_in[(size_t)(row0 + b) * P.H + n_tile * 32 + u];
-            float4 g;
-            if (P.splits == 1) {
-                g = *reinterpret_cast<const float4*>(tile_s + b * kTileN + 4 * u);
-            } else {
-                float4 part[8];
+        // problem fields used in the loops, hoisted out of (indexed) constant memory
+        const int splits = P.splits, epi = P.epi, n_out = P.n_out, ldo = P.ldo, Hh = P.H;
+        float* const out = P.out;
+        uint8_t* const out_pa = P.out_pa;
+        const float* const c_in = P.c_in;
+        const int rows_here = min(N, P.rows - row0);
+        float* tile_s = reinterpret_cast<float*>(stage_base);
+        const uint32_t tile_addr = smem_u32(tile_s);
+        const int lo = (int)(((long long)rows_here * split) / splits) * 32;
+        const int hi = (int)(((long long)rows_here * (split + 1)) / splits) * 32;
+        const bool do_am = P.am_key != nullptr && splits == 1;
+        const int ng = n_tile * kTileN + 4 * u;          // first of this thread's 4 outputs (all rows)
+        const int unit = n_tile * 32 + u;                // LSTM: the unit whose 4 gates this thread holds
+        const bool vec_out = ng + 3 < n_out && (ldo & 3) == 0;
+        // the row loop is skipped when the arg-max is all that is wanted from this layer
+        const bool row_loop = epi == kEpiLstm || out != nullptr || out_pa != nullptr;
+        unsigned long long* const am_key = do_am ? P.am_key + (size_t)(rt * P.n_tiles + n_tile) * N : nullptr;
+#pragma unroll 1
+        for (int pass = (xtma && L.warm_epilogue) ? 0 : 1; pass < 2; ++pass) {
+            const bool dry = pass == 0;
+            if (!dry) {
+                // ---- part 1: accumulator tile TMEM -> shared memory (two warps per TMEM lane quadrant).
+                // tile_s[col][n] (fp32, n fastest) lives in the idle pipeline stages: every TMA write has landed
+                // and every MMA has read its operands once tmem_full fires.
+                const int q = warp & 3;               // TMEM lane quadrant this warp may access
+                const int half = (warp - 2) >> 2;     // 0 or 1
+                const int nl = q * 32 + lane;         // output feature within the tile (TMEM lane)
+                mbar_wait(tmem_full, 0);
+                tc_fence_after();
+                if (pt == 0) trace_stamp(L.dbg, 7);
+                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                for (int c0 = half * 16; c0 < N; c0 += 32) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (r < P.splits) part[r] = ld_dsmem_f4(peer[r] + off);
-                g = part[0];
-#pragma unroll
-                for (int r = 1; r < 8; ++r)
-                    if (r < P.splits) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
-            }
-            g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w;
-            if (P.epi == kEpiLstm) {
-                const int unit = n_tile * 32 + u;
-                if (unit < P.H) lstm_gates(P, g, cprev, row0 + b, unit, mode);
-            } else {
-                const int ng = n_tile * kTileN + 4 * u;
-                float y[4] = {g.x, g.y, g.z, g.w};
-                if (P.epi == kEpiBiasTanh) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) y[j] = tanhf(y[j]);
+                    for (int j = 0; j < 16; ++j) tile_s[(c0 + j) * kTileN + nl] = v[j];
                 }
-                if (P.out) {
-                    float* o = P.out + (size_t)(row0 + b) * P.ldo + ng;
-                    if (ng + 3 < P.n_out && (P.ldo & 3) == 0) {
-                        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                tc_fence_before();
+                // ---- split-K partials meet through distributed shared memory.  The `splits` CTAs of a tile form
+                // one thread-block cluster; after the cluster barrier CTA `split` sums rows [lo, hi) of all
+                // partial tiles in fixed rank order (bit-reproducible), applies the fused epilogue and writes
+                // coalesced rows.  splits == 1 is the same code reading only its own tile.
+                if (splits > 1) {
+                    __syncwarp();
+                    cluster_sync_all();
+                } else {
+                    __syncthreads();
+                }
+                if (pt == 0) trace_stamp(L.dbg, 8);
+            }
+            // ---- part 2: one warp = one activation row per iteration (lane u owns outputs 4u..4u+3).  Kept
+            // ROLLED and small on purpose: this code runs a handful of times per launch, so its cost is the
+            // number of distinct instructions fetched, not arithmetic.
+            uint32_t peer[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)   // (dry: the own tile stands in for every peer)
+                peer[r] = (splits > 1 && r < splits) ? dsmem_map(tile_addr, (uint32_t)(dry ? split : r)) : tile_addr;
+            if (row_loop) {
+#pragma unroll 1
+                for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
+                    const int bb = idx >> 5;
+                    float cprev = 0.f;
+                    if (epi == kEpiLstm && unit < Hh) cprev = c_in[(size_t)(row0 + bb) * Hh + unit];
+                    float4 g;
+                    if (splits == 1) {
+                        g = *reinterpret_cast<const float4*>(tile_s + bb * kTileN + 4 * u);
                     } else {
+                        const uint32_t off = (uint32_t)(bb * kTileN + 4 * u) * 4u;
+                        float4 part[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (ng + j < P.n_out) o[j] = y[j];
+                        for (int r = 0; r < 8; ++r)
+                            if (r < splits) part[r] = ld_dsmem_f4(peer[r] + off);
+                        g = part[0];
+#pragma unroll
+                        for (int r = 1; r < 8; ++r)
+                            if (r < splits) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
                     }
-                }
-                if (P.out_pa) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (ng + j < P.n_out) pa_store(P.out_pa, mode, N, P.n_out >> 6, row0 + b, ng + j, y[j]);
-                }
-                if (do_am) {
-                    // this warp holds the 128 outputs of row b of this tile: first maximum wins (tf.argmax)
-                    float bv = -INFINITY;
-                    int bi = 0x7fffffff;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (ng + j < P.n_out && y[j] > bv) { bv = y[j]; bi = ng + j; }
-#pragma unroll
-                    for (int o2 = 16; o2 > 0; o2 >>= 1) {
-                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o2);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o2);
-                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w;
+                    if (epi == kEpiLstm) {
+                        if (unit < Hh) lstm_gates(P, g, cprev, row0 + bb, unit, mode, dry);
+                        continue;
                     }
-                    if (lane2 == 0) {
-                        const int tile_id = rt * P.n_tiles + n_tile;
-                        P.am_val[(size_t)tile_id * N + b] = bv;
-                        P.am_idx[(size_t)tile_id * N + b] = bi;
+                    if (epi == kEpiBiasTanh) { g.x = act_tanh(g.x); g.y = act_tanh(g.y); g.z = act_tanh(g.z); g.w = act_tanh(g.w); }
+                    if (dry) continue;
+                    if (out) {
+                        float* o = out + (size_t)(row0 + bb) * ldo + ng;
+                        if (vec_out) {
+                            *reinterpret_cast<float4*>(o) = g;
+                        } else {
+                            if (ng + 0 < n_out) o[0] = g.x;
+                            if (ng + 1 < n_out) o[1] = g.y;
+                            if (ng + 2 < n_out) o[2] = g.z;
+                            if (ng + 3 < n_out) o[3] = g.w;
+                        }
+                    }
+                    if (out_pa) {
+                        const float y[4] = {g.x, g.y, g.z, g.w};
+                        if (ng + 3 < n_out) {
+                            pa_store4(out_pa, mode, N, n_out >> 6, row0 + bb, ng, y);
+                        } else {
+#pragma unroll 1
+                            for (int e = 0; e < 4; ++e)
+                                if (ng + e < n_out) pa_store(out_pa, mode, N, n_out >> 6, row0 + bb, ng + e, y[e]);
+                        }
                     }
                 }
             }
-        }
-        if (do_am) {
-            // tile candidates are in global memory; the last CTA of the problem picks every row's word
-            __threadfence();
-            named_bar_sync(1, kLinProducers);
-            unsigned* flag = reinterpret_cast<unsigned*>(smem_raw + 512);
-            if (pt == 0) *flag = atomicAdd(P.am_ctr, 1u) == (unsigned)(P.cta_count - 1) ? 1u : 0u;
-            named_bar_sync(1, kLinProducers);
-            if (*flag) {
-                __threadfence();
-                const int part = pt & 3;   // 4 lanes per row, every 4th tile each, loads batched
-                for (int b0 = 0; b0 < P.rows; b0 += kLinProducers / 4) {
-                    const int b = b0 + (pt >> 2);
-                    const bool live = b < P.rows;
-                    const int rt2 = live ? b / N : 0, c = live ? b - rt2 * N : 0;
-                    const float* pv = P.am_val + (size_t)rt2 * P.n_tiles * N + c;
-                    const int32_t* pi2 = P.am_idx + (size_t)rt2 * P.n_tiles * N + c;
+            if (do_am) {
+                // greedy prediction (model.py:289): 4 threads per row, each scans 32 of the tile's 128 outputs
+                // (accumulator + bias, the value the row loop stores) in a skewed, bank-conflict-free order;
+                // first maximum wins (tf.argmax), so ties go to the smaller index
+                const int part = pt & 3;
+                const float4* bias_t = reinterpret_cast<const float4*>(P.bias + n_tile * kTileN) + part * 8;
+#pragma unroll 1
+                for (int r0 = 0; r0 < rows_here; r0 += kLinProducers / 4) {
+                    const int r = r0 + (pt >> 2);
+                    const bool live = r < rows_here;
+                    const float4* row_t = reinterpret_cast<const float4*>(tile_s + (live ? r : 0) * kTileN) + part * 8;
                     float bv = -INFINITY;
                     int bi = 0x7fffffff;
-                    for (int tl = part; tl < P.n_tiles; tl += 32) {
-                        float ov[8];
-                        int oi[8];
+#pragma unroll 1
+                    for (int j = 0; j < 8; ++j) {
+                        const int jj = (j + pt) & 7;
+                        const float4 a4 = row_t[jj];
+                        const float4 b4 = __ldg(bias_t + jj);
+                        const int i0 = n_tile * kTileN + part * 32 + jj * 4;
+                        const float y0 = a4.x + b4.x, y1 = a4.y + b4.y, y2 = a4.z + b4.z, y3 = a4.w + b4.w;
+                        if (i0 + 0 < n_out && (y0 > bv || (y0 == bv && i0 + 0 < bi))) { bv = y0; bi = i0 + 0; }
+                        if (i0 + 1 < n_out && (y1 > bv || (y1 == bv && i0 + 1 < bi))) { bv = y1; bi = i0 + 1; }
+                        if (i0 + 2 < n_out && (y2 > bv || (y2 == bv && i0 + 2 < bi))) { bv = y2; bi = i0 + 2; }
+                        if (i0 + 3 < n_out && (y3 > bv || (y3 == bv && i0 + 3 < bi))) { bv = y3; bi = i0 + 3; }
+                    }
+                    unsigned long long key = argmax_key(bv, bi);
+                    key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+                    key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
+                    if (live && part == 0 && !dry) am_key[r] = key;
+                }
+            }
+            if (splits > 1 && !dry) cluster_arrive_relaxed();   // this CTA no longer reads its peers' tiles
+            if (do_am) {
+                // tile candidates are in global memory; the last CTA of the problem picks every row's word
+                unsigned* flag = reinterpret_cast<unsigned*>(smem_raw + 512);
+                if (!dry) {
+                    if (pt == 0) trace_stamp(L.dbg, 11);
+                    __threadfence();
+                    named_bar_sync(1, kLinProducers);
+                    if (pt == 0) *flag = atomicAdd(P.am_ctr, 1u) == (unsigned)(P.cta_count - 1) ? 1u : 0u;
+                    named_bar_sync(1, kLinProducers);
+                }
+                if (dry || *flag) {
+                    if (pt == 0 && !dry) trace_stamp(L.dbg, 12);
+                    __threadfence();
+                    // 4 lanes per row; every lane's candidates are fetched in ONE batch of independent loads, so the
+                    // merge costs one L2 round trip (a dependent chain here is what a concurrent kernel stretches)
+                    constexpr int kBatch = 24;
+                    int32_t* s_word = reinterpret_cast<int32_t*>(stage_base);    // tile_s is dead by now
+                    const int part = pt & 3;
+                    const int n_tiles = P.n_tiles;
+                    for (int b0 = 0; b0 < P.rows; b0 += kLinProducers / 4) {
+                        const int b = b0 + (pt >> 2);
+                        const bool live = b < P.rows;
+                        const int rt2 = live ? b / N : 0, c = live ? b - rt2 * N : 0;
+                        const unsigned long long* pk = P.am_key + (size_t)rt2 * n_tiles * N + c;
+                        unsigned long long best = 0ull;
+                        for (int tl = part; tl < n_tiles; tl += 4 * kBatch) {
+                            unsigned long long k[kBatch];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int tt = tl + 4 * u;
-                            const bool ok = live && tt < P.n_tiles;
-                            ov[u] = ok ? __ldcg(pv + (size_t)tt * N) : -INFINITY;
-                            oi[u] = ok ? __ldcg(pi2 + (size_t)tt * N) : 0x7fffffff;
+                            for (int q2 = 0; q2 < kBatch; ++q2) {
+                                const int tt = tl + 4 * q2;
+                                k[q2] = (live && tt < n_tiles) ? __ldcg(pk + (size_t)tt * N) : 0ull;
+                            }
+#pragma unroll
+                            for (int q2 = 0; q2 < kBatch; ++q2) best = k[q2] > best ? k[q2] : best;
                         }
 #pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (ov[u] > bv || (ov[u] == bv && oi[u] < bi)) { bv = ov[u]; bi = oi[u]; }
+                        for (int o = 1; o <= 2; o <<= 1) {
+                            const unsigned long long ok2 = __shfl_xor_sync(0xffffffffu, best, o);
+                            best = ok2 > best ? ok2 : best;
+                        }
+                        if (live && part == 0 && !dry) {
+                            const int bi2 = argmax_key_index(best);
+                            const int nw = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi2;
+                            if (P.am_tokens) P.am_tokens[(size_t)b * P.am_tokens_ld + P.am_step] = bi2;
+                            if (P.am_next_word) P.am_next_word[b] = nw;
+                            if (b < kAmSmemWords) s_word[b] = nw;
+                        }
                     }
-#pragma unroll
-                    for (int o = 1; o <= 2; o <<= 1) {
-                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                    }
-                    if (live && part == 0) {
-                        if (P.am_tokens) P.am_tokens[(size_t)b * P.am_tokens_ld + P.am_step] = bi;
-                        if (P.am_next_word)
-                            P.am_next_word[b] = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi;
-                    }
-                }
-                if (P.am_emb_pa) {
-                    // decode loop: the attention kernel of the next step is already running, so this CTA hands the
-                    // embedding row of every chosen word (model.py:272-274) to the next LSTM / decode layers,
-                    // packed; 8 gathers per thread in flight
-                    named_bar_sync(1, kLinProducers);   // next_word[] written above is visible to the CTA
-                    const int groups = P.am_E >> 3;
-                    const int total = P.rows * groups;
-                    const size_t halfb = (size_t)N * kBK * 2;
-                    for (int u0 = pt; u0 < total; u0 += kLinProducers * 8) {
-                        float4 a[8], c4[8];
-                        int bb[8], gg[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int uu = u0 + j * kLinProducers;
-                            bb[j] = -1;
-                            gg[j] = 0;
-                            if (uu < total) {
-                                bb[j] = uu / groups;
-                                gg[j] = uu - bb[j] * groups;
-                                const int w = P.am_next_word[bb[j]];
-                                const float4* src = reinterpret_cast<const float4*>(P.am_emb + (size_t)w * P.am_E + gg[j] * 8);
-                                a[j] = __ldg(src);
-                                c4[j] = __ldg(src + 1);
+                    if (pt == 0 && !dry) trace_stamp(L.dbg, 13);
+                    if (P.am_emb_pa && !dry) {
+                        // decode loop: the attention kernel of the next step is already running, so this CTA hands
+                        // the embedding row of every chosen word (model.py:272-274) to the next LSTM / decode
+                        // layers, packed.  The rows are gathered by bulk copies (all in flight at once: one HBM
+                        // round trip) into the idle pipeline stages, then converted from shared memory.
+                        const int E = P.am_E;
+                        const int groups = E >> 3;
+                        const size_t halfb = (size_t)N * kBK * 2;
+                        float* emb_s = reinterpret_cast<float*>(stage_base + 4096);     // after s_word
+                        const int cap = (int)(((size_t)S * stage_bytes - 4096) / ((size_t)E * 4));
+                        const int rows_am = min(P.rows, kAmSmemWords);
+                        uint32_t ph = 1;   // tmem_full completed phase 0 in the main loop; re-used as the copy barrier
+                        for (int r0 = 0; r0 < rows_am; r0 += cap) {
+                            const int nr = min(cap, rows_am - r0);
+                            fence_proxy_async_smem();           // generic accesses of this memory before the bulk writes
+                            named_bar_sync(1, kLinProducers);   // s_word visible; previous batch fully converted
+                            if (pt == 0) mbar_arrive_expect_tx(tmem_full, (uint32_t)nr * (uint32_t)E * 4u);
+                            named_bar_sync(1, kLinProducers);
+                            for (int r = pt; r < nr; r += kLinProducers)
+                                tma_bulk_g2s(emb_s + (size_t)r * E, P.am_emb + (size_t)s_word[r0 + r] * E, (uint32_t)E * 4u, tmem_full);
+                            mbar_wait(tmem_full, ph);
+                            ph ^= 1u;
+                            for (int uu = pt; uu < nr * groups; uu += kLinProducers) {
+                                const int r = uu / groups, gi = uu - r * groups;
+                                const float4* src = reinterpret_cast<const float4*>(emb_s + (size_t)r * E + gi * 8);
+                                uint4 hi4, lo4;
+                                split_bf16x8(src[0], src[1], hi4, lo4);
+                                const int bb = r0 + r;
+                                const int rt2 = bb / N, rr = bb - rt2 * N;
+                                uint8_t* dst = P.am_emb_pa + ((size_t)rt2 * (E >> 6) + (gi >> 3)) * 2 * halfb +
+                                               umma_tile_off(mode, rr, gi & 7);
+                                *reinterpret_cast<uint4*>(dst) = hi4;
+                                *reinterpret_cast<uint4*>(dst + halfb) = lo4;
                             }
                         }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (bb[j] >= 0) {
-                                uint4 hi, lo;
-                                split_bf16x8(a[j], c4[j], hi, lo);
-                                const int rt2 = bb[j] / N, r = bb[j] - rt2 * N;
-                                uint8_t* dst = P.am_emb_pa + ((size_t)rt2 * (P.am_E >> 6) + (gg[j] >> 3)) * 2 * halfb +
-                                               umma_tile_off(mode, r, gg[j] & 7);
-                                *reinterpret_cast<uint4*>(dst) = hi;
-                                *reinterpret_cast<uint4*>(dst + halfb) = lo;
-                            }
-                        }
                     }
+                    if (pt == 0 && !dry) { trace_stamp(L.dbg, 14); *P.am_ctr = 0u; }
                 }
-                if (pt == 0) *P.am_ctr = 0u;
             }
         }
+    }
+    if (warp < 2) {   // the TMA / MMA warps join the epilogue's rendezvous
+        __syncwarp();
+        if (P.splits > 1) cluster_sync_all(); else __syncthreads();
+        if (P.splits > 1) cluster_arrive_relaxed();
     }
     if (threadIdx.x == 64) trace_stamp(L.dbg, 9);
-    if (P.splits > 1) {
-        __syncwarp();
-        cluster_sync_all();   // peers may still be reading this CTA's tile
-    }
+    if (P.splits > 1) cluster_wait();   // peers may still be reading this CTA's tile
 
     __syncthreads();
     if (threadIdx.x == 0) { trace_stamp(L.dbg, 10); tl_end(L.tl); }
@@ -598,7 +652,7 @@ __global__ void __launch_bounds__(128) lin_simt_kernel(const __grid_constant__ L
             g.w = __shfl_sync(0xffffffffu, v, base + 3);
             const int unit = n >> 2;
             if ((lane & 3) == 0 && row0 + j < P.rows && unit < P.H)
-                lstm_gates(P, g, P.c_in[(size_t)(row0 + j) * P.H + unit], row0 + j, unit, mode);
+                lstm_gates(P, g, P.c_in[(size_t)(row0 + j) * P.H + unit], row0 + j, unit, mode, false);
         }
     } else if (n < P.n_out) {
         for (int j = 0; j < 16; ++j)
@@ -750,7 +804,7 @@ cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt) {
     cfg.blockDim = dim3(kLinThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[3];
     int na = 0;
     if (splits > 1) {
         at[na].id = cudaLaunchAttributeClusterDimension;
@@ -761,6 +815,11 @@ cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt) {
     } else if (L.x_mode == 1) {   // the activation pre-pass ends in a grid barrier: CTAs must be co-resident
         at[na].id = cudaLaunchAttributeCooperative;
         at[na].val.cooperative = 1;
+        ++na;
+    }
+    if (L.pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
     }
     cfg.attrs = at;

@@ -64,8 +64,7 @@ struct LinProblem {
     int H;
     // optional fused greedy argmax over the outputs (decode fc_2 -> prediction, model.py:289):
     // per-tile candidates, then the last CTA of the problem picks the word of every row
-    float* am_val;         // [n_row_tiles * n_tiles * row_tile]
-    int32_t* am_idx;
+    unsigned long long* am_key;   // [n_row_tiles * n_tiles * row_tile] candidates, see argmax_key
     unsigned* am_ctr;      // zero between launches
     int32_t* am_tokens;    // [rows, am_tokens_ld] or null
     int am_tokens_ld;
@@ -90,6 +89,8 @@ struct LinLaunch {
     int l2_w;         // L2 eviction policy of the weight stream (see l2_policy)
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
     unsigned long long* tl;   // optional {min start, max end} of this launch
+    int pdl;          // launched with programmatic stream serialization (see pdl_wait)
+    int warm_epilogue;  // idle epilogue warps pre-run the epilogue code (no side effects) to warm the instruction caches
     int x_mode;       // 0 = producer warps convert X per stage; 1 = cooperative pre-pack + TMA (grid <= #SMs);
                       // 2 = every operand segment arrives packed from its producer (TMA from t = 0)
 };
@@ -113,7 +114,35 @@ __device__ __forceinline__ void pa_store(uint8_t* pa, int mode, int row_tile, in
     *reinterpret_cast<__nv_bfloat16*>(dst) = h;
     *reinterpret_cast<__nv_bfloat16*>(dst + half) = l;
 }
+// four consecutive outputs (col % 4 == 0): one 8-byte store per half
+__device__ __forceinline__ void pa_store4(uint8_t* pa, int mode, int row_tile, int kblocks, int b, int col, const float* v) {
+    const int rt = b / row_tile, r = b - rt * row_tile;
+    const int kb = col >> 6, kg = (col & 63) >> 3, e = col & 7;
+    const size_t half = (size_t)row_tile * kBK * 2;
+    uint8_t* dst = pa + ((size_t)rt * kblocks + kb) * 2 * half + umma_tile_off(mode, r, kg) + e * 2;
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint2*>(dst) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(dst + half) = make_uint2(l[0], l[1]);
+}
+// arg-max candidate as one ordered 64-bit key: larger value wins, then the smaller index (tf.argmax keeps the
+// first maximum).  0 is below every real candidate.
+__device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+    const unsigned bits = __float_as_uint(v + 0.0f);                      // -0 -> +0
+    const unsigned ord = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+    return ((unsigned long long)ord << 32) | (unsigned long long)(0xffffffffu - (unsigned)idx);
+}
+__device__ __forceinline__ int argmax_key_index(unsigned long long key) { return (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)); }
 #endif
+
+constexpr int kAmSmemWords = 1024;   // rows whose chosen word the last CTA keeps in shared memory
 
 struct PackJob {           // fp32 rows (optionally gathered) -> packed activation
     const float* src;

@@ -33,13 +33,21 @@ def timeit(n=30):
     return a.elapsed_time(b) / n
 
 
-base = dict(overlap=1, att_sms=0, pa=1, graphs=1)
-variants = [dict(), dict(overlap=0), dict(att_sms=148), dict(att_sms=128), dict(att_sms=96), dict(att_sms=64),
-            dict(pa=0, overlap=0), dict(graphs=0)]
+base = dict(overlap=1, att_sms=0, pa=1, graphs=1, pdl=0)
+variants = [dict(), dict(pdl=1), dict(overlap=0), dict(overlap=0, pdl=1), dict(graphs=0), dict(graphs=0, pdl=1),
+            dict(graphs=0, overlap=0), dict(graphs=0, overlap=0, pdl=1)]
+ref = {}
 for v in variants:
     o = dict(base)
     o.update(v)
     for k, val in o.items():
         m.set_option(k, val)
     ms = timeit()
-    print("options %-60s  %.3f ms/loop  %.1f us/step  %.0f tok/s" % (o, ms, ms * 1e3 / T, B * T / ms * 1e3), flush=True)
+    tok, lg = m.loop_device(pool[0], T, want_logits=True)
+    torch.cuda.synchronize()
+    key = o["overlap"]
+    if key not in ref:
+        ref[key] = (tok.clone(), lg.clone())
+    same = bool((tok == ref[key][0]).all()) and bool((lg == ref[key][1]).all())
+    print("options %-64s  %.3f ms/loop  %.1f us/step  %.0f tok/s  bit-identical to first overlap=%d run: %s"
+          % (o, ms, ms * 1e3 / T, B * T / ms * 1e3, key, same), flush=True)

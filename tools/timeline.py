@@ -10,8 +10,10 @@ m = sat_b200.CaptionGenerator(cfg)
 g = torch.Generator().manual_seed(1)
 m.set_weights({n: torch.rand(*s, generator=g) * 0.16 - 0.08 for n, s in sat_b200.weight_shapes(cfg).items()})
 ctx = torch.relu(torch.randn(B, L, D, generator=g)).cuda()
-for overlap in (1, 0):
+import cuda.bindings.runtime as cr
+for overlap, pdl in ((1, 0), (1, 1), (0, 0), (0, 1)):
     m.set_option("overlap", overlap)
+    m.set_option("pdl", pdl)
     m.set_option("graphs", 0)
     for i in range(3):
         m.loop_device(ctx, T)
@@ -19,7 +21,6 @@ for overlap in (1, 0):
     m.set_option("trace", 3)
     m.loop_device(ctx, T)
     torch.cuda.synchronize()
-    import cuda.bindings.runtime as cr
     n = m.info("tl_count")
     host = np.zeros(1024 * 16, np.uint64)
     cr.cudaMemcpy(host.ctypes.data, m.info("trace_ptr"), host.nbytes, cr.cudaMemcpyKind.cudaMemcpyDeviceToHost)
@@ -29,11 +30,12 @@ for overlap in (1, 0):
         names.append(m.lib.sat_last_error().decode())
     m.set_option("trace", 0)
     t0 = int(host[0])
-    print("=== overlap=%d: %d launches; steps 5..7 (us since loop start; eager launches)" % (overlap, n))
-    per = 4 if overlap else 4
-    rows = [(names[i], (int(host[2 * i]) - t0) / 1e3, (int(host[2 * i + 1]) - t0) / 1e3) for i in range(n)]
+    print("=== overlap=%d pdl=%d: %d launches; 3 steps (us since loop start; eager launches)" % (overlap, pdl, n))
+    f = lambda i, k: (int(host[4 * i + k]) - t0) / 1e3
+    rows = [(names[i], f(i, 0), f(i, 2), f(i, 3), f(i, 1)) for i in range(n)]
     lstm_idx = [i for i, r in enumerate(rows) if r[0].startswith("lstm")]
     lo, hi = lstm_idx[5], lstm_idx[8]
-    for nm, a, b in rows[lo:hi]:
-        print("  %-18s start %9.2f  end %9.2f  dur %7.2f" % (nm, a, b, b - a))
+    for nm, a, go, md, b in rows[lo:hi]:
+        print("  %-18s start %9.2f  go %9.2f  main-done %9.2f  end %9.2f   | prologue %5.2f main %6.2f tail %5.2f"
+              % (nm, a, go, md, b, go - a, md - go, b - md))
     print("  step period: %.2f us" % ((rows[lstm_idx[15]][1] - rows[lstm_idx[5]][1]) / 10))
