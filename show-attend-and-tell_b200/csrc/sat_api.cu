@@ -122,7 +122,7 @@ struct sat_handle {
     uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 1, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 0, opt_warm = 1;
+    int opt_overlap = 1, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 0, opt_warm = 1, opt_att_wpc = 1;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -364,6 +364,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "att_warps") h->opt_att_warps = (int)value;
     else if (k == "pdl") h->opt_pdl = (int)value;
     else if (k == "warm") h->opt_warm = (int)value;
+    else if (k == "att_wpc") h->opt_att_wpc = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -758,6 +759,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     ap.l2_ctx = h->opt_l2_ctx;
     ap.occ = h->opt_att_occ;
     ap.warps = h->opt_att_warps;
+    ap.wpc = h->opt_att_wpc;
     if (sm_budget <= 0 && h->opt_att_sms > 0) sm_budget = h->opt_att_sms;   // experiment knob
     if (!att_plan(ap, h->smem_optin, sm_budget > 0 ? sm_budget : h->num_sms))
         return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);

@@ -23,6 +23,7 @@ struct AttParams {
     int grid, segmax;
     int occ;             // requested CTAs per SM (1 or 2; 2 only for G == 1)
     int warps;           // consumer warps per CTA: 8, or 16 (G == 1 only)
+    int wpc;             // in: warp-per-chunk kernel wanted; out of att_plan: used (needs RL == D == 512)
     int l2_t, l2_ctx;    // L2 eviction policies of the two streams (see l2_policy)
     uint8_t* pa_z;       // optional packed copy of z for the dense layers that consume it
     int pa_row_tile, pa_mode;

@@ -191,6 +191,8 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
 // the stream is still draining; it must not touch memory the predecessor (or anything before it) writes, nor
 // write anything they read, before pdl_wait() returns (= all prerequisite grids complete and flushed).
+// Every kernel here calls pdl_launch_dependents() only after its own pdl_wait(): a kernel therefore never starts
+// before the predecessor of its predecessor has completed, and may read that older data without waiting.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

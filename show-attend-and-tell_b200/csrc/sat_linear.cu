@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     while ((int)tmem_cols < N) tmem_cols <<= 1;
 
     // ---- one-time setup
-    if (L.pdl) pdl_launch_dependents();   // the next kernel of the stream may begin its own prologue
     if (threadIdx.x == 0) {
         trace_stamp(L.dbg, 0);
         tl_begin(L.tl);
@@ -169,7 +168,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     // while a step runs, so the TMA lane may fetch them before the predecessor has finished; every other
     // global access (activations, outputs) waits for the predecessor.
     const bool tma_lane = warp == 0 && lane == 0;
-    if (L.pdl && !tma_lane) pdl_wait();
+    // launch_dependents is issued only AFTER the wait, which gives every kernel of the chain the invariant
+    // "when I start, everything before my immediate predecessor is complete and visible".
+    if (L.pdl && !tma_lane) { pdl_wait(); pdl_launch_dependents(); }
 
     if (warp == 0) {
         // ===================== TMA producer: one 32 KB bulk copy per stage =====================
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             if (L.pdl) {
                 for (int it = 0; it < pre; ++it) load_w(it);
                 pdl_wait();
+                pdl_launch_dependents();
                 tl_go(L.tl);
                 if (xpa) for (int it = 0; it < pre; ++it) load_x(it);
             }
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
 #pragma unroll
             for (int r = 0; r < 8; ++r)   // (dry: the own tile stands in for every peer)
                 peer[r] = (splits > 1 && r < splits) ? dsmem_map(tile_addr, (uint32_t)(dry ? split : r)) : tile_addr;
+            if (pt == 0 && !dry) trace_stamp(L.dbg, 15);
             if (row_loop) {
 #pragma unroll 1
                 for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
@@ -426,12 +429,15 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             if (r < splits) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
                     }
                     g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w;
+                    if (pt == 0 && !dry && L.dbg && g.x != 12345.678f) trace_stamp(L.dbg, 2);   // partial sums arrived
                     if (epi == kEpiLstm) {
                         if (unit < Hh) lstm_gates(P, g, cprev, row0 + bb, unit, mode, dry);
+                        if (pt == 0 && !dry) trace_stamp(L.dbg, 3);
                         continue;
                     }
                     if (epi == kEpiBiasTanh) { g.x = act_tanh(g.x); g.y = act_tanh(g.y); g.z = act_tanh(g.z); g.w = act_tanh(g.w); }
                     if (dry) continue;
+                    if (pt == 0 && L.dbg && g.x != 12345.678f) trace_stamp(L.dbg, 3);   // activation done
                     if (out) {
                         float* o = out + (size_t)(row0 + bb) * ldo + ng;
                         if (vec_out) {

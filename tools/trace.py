@@ -43,7 +43,9 @@ def show(name, tr, labels):
     if name.startswith("attention"):
         print("  [thread 0 blocked on data: pass 1 %.2f us, pass 2 %.2f us (mean, at 1.965 GHz)]"
               % (tr[:, 8].mean() / 1965.0, tr[:, 9].mean() / 1965.0))
-        tr = tr.copy(); tr[:, 8:10] = 0
+        print("  [thread 0 cycles->us: pass-1 loads+FMA %.2f, reduce %.2f, store+arrive %.2f; pass-2 compute+arrive %.2f]"
+              % tuple(tr[:, k].mean() / 1965.0 for k in (10, 11, 12, 13)))
+        tr = tr.copy(); tr[:, 8:14] = 0
     print("== %s  (us after the first CTA started; mean / max over %d CTAs)" % (name, len(tr)))
     for i, lab in enumerate(labels):
         col = tr[:, i]
@@ -83,15 +85,13 @@ def step_traced(k):
 with torch.cuda.stream(m.stream):
     m.step_device(ctx, lw, cstate, hstate, want=())     # allocate everything once
     torch.cuda.synchronize()
-    # dense launches of one step: 0 = state branch q, 1 = LSTM, 2 = decode fc_1, 3 = decode fc_2
-    for k, (name, grid) in enumerate([("step: att state (q)", 64), ("step: LSTM [packed operands]", 128),
-                                      ("step: decode fc_1 [packed operands]", 128), ("step: decode fc_2 [packed]", 79)]):
-        run(name, step_traced(k), grid, lin_labels, 1, False)
-    for cold in (True, False):
-        run("attention", lambda: m.lib.sat_attention_fwd(m._h, p(ctx), p(hstate), p(alpha), p(z), B, 1, m._st()), 148,
-            att_labels, 2, cold)
-        # note: sat_attention_fwd also launches the state-branch dense layer first (traced only in mode 1)
-        run("lstm", lambda: m.lib.sat_lstm_fwd(m._h, p(z), p(lw), p(cstate), p(hstate), p(c2), p(h2), B, m._st()), 128,
-            lin_labels, 1, cold)
-        run("decode (fc_1 then fc_2; last launch = fc_2, 79 CTAs)",
-            lambda: m.lib.sat_vocab_gemm(m._h, p(h2), p(z), p(lw), p(logits), B, m._st()), 79, lin_labels, 1, cold)
+    if "--dense" in sys.argv:
+        # dense launches of one step: 0 = state branch q, 1 = LSTM, 2 = decode fc_1, 3 = decode fc_2
+        for k, (name, grid) in enumerate([("step: att state (q)", 64), ("step: LSTM [packed operands]", 128),
+                                          ("step: decode fc_1 [packed operands]", 128), ("step: decode fc_2 [packed]", 79)]):
+            run(name, step_traced(k), grid, lin_labels, 1, False)
+    for sms in (0, 64):
+        m.set_option("att_sms", sms)
+        for cold in (True, False):
+            run("attention att_sms=%d" % sms, lambda: m.lib.sat_attention_fwd(m._h, p(ctx), p(hstate), p(alpha), p(z), B, 1, m._st()), 148,
+                att_labels, 2, cold)
