@@ -122,7 +122,7 @@ struct sat_handle {
     uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 1, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 0, opt_warm = 1, opt_att_wpc = 1;
+    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -612,7 +612,6 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.dbg = nullptr;
     L.tl = nullptr;
     L.warm_epilogue = h->opt_warm;
-    L.pdl = (h->opt_pdl && L.x_mode != 1) ? 1 : 0;   // (the cooperative pre-pass launch keeps full serialization)
     if (h->opt_trace == 1 && begin <= 1024 && h->trace_at-- == 0) L.dbg = h->trace;
     if (h->opt_trace == 3 && h->tl_count < 4000) {
         L.tl = h->trace + 4 * h->tl_count++;
@@ -623,6 +622,7 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
         for (int sgi = 0; sgi < probs[i].nseg; ++sgi) all_pa = all_pa && probs[i].seg[sgi].pa != nullptr;
     if (all_pa) L.x_mode = 2;   // operands were packed by their producers: nothing to convert, nothing to wait for
     else L.x_mode = (h->opt_xpack && smin == 1 && begin <= h->num_sms) ? 1 : 0;  // pre-pass: grid barrier, no clusters
+    L.pdl = (h->opt_pdl && L.x_mode != 1) ? 1 : 0;   // (the cooperative pre-pass launch keeps full serialization)
     if (L.stages < 1) return fail(SAT_ERR_UNSUPPORTED, "row tile %d does not fit in shared memory", max_rt);
     {
         ProfScope ps(h, h->cur_tag, st);
@@ -640,6 +640,14 @@ static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStre
     LinProblem P;
     RET(plan(h, h->att_1a, P, {seg(ctx, h->d.dim_ctx, h->d.dim_ctx)}, n_img * h->d.num_ctx, kEpiBiasTanh, h->T1,
              h->d.dim_attend_layer, st));
+    if (h->opt_gemm != 0 && h->opt_pa && (h->d.dim_ctx % 64) == 0) {
+        // thousands of rows: converting them inside the GEMM's producer warps is latency bound, so the
+        // contexts are packed once by a streaming kernel and the GEMM fetches them by TMA
+        PackJob job{ctx, nullptr, h->d.dim_ctx, h->d.dim_ctx, P.rows, P.row_tile, P.xpack};
+        CK(pack_rows_launch(&job, 1, h->opt_layout, st));
+        h->launches += 1;
+        P.seg[0].pa = P.xpack;
+    }
     return launch(h, &P, 1, st);
 }
 
@@ -716,7 +724,8 @@ static int plan_att_state(sat_handle* h, LinProblem& P, const float* h_in, int r
 }
 
 static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, const float* h_in, float* alpha, float* z,
-                          cudaStream_t st, bool q_ready = false, const int32_t* last_word = nullptr, int sm_budget = 0) {
+                          cudaStream_t st, bool q_ready = false, const int32_t* last_word = nullptr, int sm_budget = 0,
+                          bool nowait = false) {
     const sat_dims& d = h->d;
     const int rows = n_img * G;
     AttParams ap;
@@ -786,6 +795,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
         }
     }
     ap.pdl = h->opt_pdl ? 1 : 0;
+    ap.nowait = (nowait && ap.pdl) ? 1 : 0;
     ap.dbg = h->opt_trace == 2 ? h->trace : nullptr;
     ap.tl = nullptr;
     if (h->opt_trace == 3 && h->tl_count < 4000) {
@@ -832,8 +842,8 @@ static int attach_argmax(sat_handle* h, Layer& ly, LinProblem& P, const RowsPara
         RET(dmalloc(&ly.am_key, need));
         ly.am_n = need;
         if (!ly.am_ctr) {
-            RET(dmalloc(&ly.am_ctr, (size_t)1));
-            CK(cudaMemset(ly.am_ctr, 0, sizeof(unsigned)));
+            RET(dmalloc(&ly.am_ctr, (size_t)2));   // {arrival counter, generation of "words picked"}
+            CK(cudaMemset(ly.am_ctr, 0, 2 * sizeof(unsigned)));
         }
     }
     P.am_key = ly.am_key; P.am_ctr = ly.am_ctr;
@@ -1076,9 +1086,56 @@ static int loop_enqueue_overlap(sat_handle* h, const float* ctx, int B, int T, c
     return SAT_OK;
 }
 
+// Single-stream loop built on programmatic dependent launch (option overlap = 2).  Launch order per step:
+//   LSTM(t) -> [decode fc_1(t) || q(t+1)] -> vocabulary layer(t) -> attention(t+1)
+// The attention kernel of step t+1 needs q(t+1) (two launches back: complete by the time it may start, see
+// pdl_wait) and nothing from the vocabulary layer, so it starts on the SMs the vocabulary layer's one-wave
+// grid leaves idle and the two run side by side without a second stream; it only waits for its predecessor
+// right before it exits, which keeps "kernel k complete => kernel k-1 complete" for the LSTM that follows.
+static int loop_enqueue_chain(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
+                              float* logits_all, cudaStream_t st) {
+    const sat_dims& d = h->d;
+    RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st, h->pa_h[0]));
+    CK(cudaMemsetAsync(h->word, 0, (size_t)B * sizeof(int32_t), st));  // <start> = 0 (model.py:254)
+    int budget = h->opt_att_sms > 0 ? h->opt_att_sms : h->num_sms - h->dec_2.n_tiles;
+    if (budget < h->num_sms / 4) budget = h->num_sms;
+    for (int t = 0; t < T; ++t) {
+        const float *c_in = h->st_c[t & 1], *h_in = h->st_h[t & 1];
+        float *c_out = h->st_c[(t + 1) & 1], *h_out = h->st_h[(t + 1) & 1];
+        h->pa_on = true;
+        h->pa_cur_h_in = h->pa_h[t & 1];
+        h->pa_cur_h_out = h->pa_h[(t + 1) & 1];
+        h->pa_cur_z = h->pa_z;
+        if (t == 0)   // q(0), attention(0) and the embedding of <start>
+            RET(attention_impl(h, ctx, B, 1, h_in, nullptr, h->z, st, false, h->word));
+        RET(lstm_impl(h, h->z, h->word, c_in, h_in, c_out, h_out, B, st));
+        float* logits = logits_all ? logits_all + (size_t)t * B * d.vocabulary_size : h->logits;
+        RET(decode_impl(h, h_out, h->z, h->word, logits, B, st, t + 1 < T, nullptr, nullptr, 1));   // fc_1 || q(t+1)
+        RowsParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.tokens = tokens; rp.tokens_ld = T; rp.step = t;
+        rp.next_word = h->word; rp.forced = forced; rp.forced_ld = T;
+        int fused = 0;
+        RET(decode_impl(h, h_out, h->z, h->word, logits, B, st, false, &rp, &fused, 2, t + 1 < T));  // fc_2 + argmax
+        if (!fused) {
+            h->pa_on = false;
+            return fail(SAT_ERR_STATE, "chained loop needs the fused argmax of the vocabulary layer");
+        }
+        if (t + 1 < T) {
+            h->pa_cur_h_in = h->pa_h[(t + 1) & 1];
+            RET(attention_impl(h, ctx, B, 1, h_out, nullptr, h->z, st, true, nullptr, budget, true));
+        }
+    }
+    h->pa_on = false;
+    h->pa_cur_z = nullptr;
+    return SAT_OK;
+}
+
 static int loop_enqueue(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
                         float* logits_all, cudaStream_t st) {
     const bool pa = h->pa_ok && h->opt_pa && h->opt_gemm != 0;
+    if (pa && h->opt_overlap == 2 && h->opt_pdl && h->d.num_decode_layers == 2)
+        return loop_enqueue_chain(h, ctx, B, T, forced, tokens, logits_all, st);
     if (pa && h->opt_overlap && h->d.num_decode_layers == 2 && st != nullptr && st != cudaStreamLegacy)
         return loop_enqueue_overlap(h, ctx, B, T, forced, tokens, logits_all, st);
     RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st, pa ? h->pa_h[0] : nullptr));

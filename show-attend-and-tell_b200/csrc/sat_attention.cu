@@ -635,8 +635,9 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
                 }
                 seg0 = seg1;
             }
+            // (only this lane: a blocking wait issued by the idle lanes would stall the whole warp, loop included)
+            if (p.pdl) { pdl_wait(); pdl_launch_dependents(); }
         }
-        if (p.pdl) { pdl_wait(); pdl_launch_dependents(); }
         return;
     }
 
@@ -645,7 +646,9 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
     float4 wreg[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) wreg[k] = __ldg(reinterpret_cast<const float4*>(p.vec) + lane + 32 * k);
-    if (p.pdl) { pdl_wait(); pdl_launch_dependents(); }   // q / the fed words come from earlier kernels of the step
+    // q / the fed words come from earlier kernels of the step; with `nowait` the immediate predecessor produced
+    // none of them (and everything older is complete, see pdl_wait), so this kernel runs beside it
+    if (p.pdl) { if (!p.nowait) pdl_wait(); pdl_launch_dependents(); }
     if (threadIdx.x == 0) tl_go(p.tl);
     if (p.emb_pa) att_pack_embedding(p, c * NT + ct, P * NT, G);
     if (ct == 0) trace_stamp(p.dbg, 1);
@@ -890,6 +893,7 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
         seg0 = seg1;
     }
     if (ct == 0) { trace_stamp(p.dbg, 7); tl_end(p.tl); }
+    if (p.pdl && p.nowait) pdl_wait();   // do not complete before the predecessor: later kernels rely on the chain
 }
 
 size_t att_smem_bytes(const AttParams& p) {

@@ -36,6 +36,8 @@ struct AttParams {
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
     unsigned long long* tl;   // optional {min start, max end} of this launch
     int pdl;             // launched with programmatic stream serialization
+    int nowait;          // (with pdl, warp-per-chunk kernel) nothing of the immediate predecessor is read: run beside it
+                         // and wait for it only before exiting
 };
 
 bool att_plan(AttParams& p, int smem_optin, int num_sms);

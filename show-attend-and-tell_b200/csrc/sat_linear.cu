@@ -167,10 +167,11 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     // Programmatic dependent launch: everything above touched no global memory.  The weights are immutable
     // while a step runs, so the TMA lane may fetch them before the predecessor has finished; every other
     // global access (activations, outputs) waits for the predecessor.
-    const bool tma_lane = warp == 0 && lane == 0;
     // launch_dependents is issued only AFTER the wait, which gives every kernel of the chain the invariant
     // "when I start, everything before my immediate predecessor is complete and visible".
-    if (L.pdl && !tma_lane) { pdl_wait(); pdl_launch_dependents(); }
+    // Only the epilogue warps (and, later, the TMA lane) wait: the MMA lane touches no global memory, and a
+    // blocking wait issued by the idle lanes of warp 0 would stall the TMA lane's weight prefetch with them.
+    if (L.pdl && warp >= 2) { pdl_wait(); pdl_launch_dependents(); }
 
     if (warp == 0) {
         // ===================== TMA producer: one 32 KB bulk copy per stage =====================
@@ -366,6 +367,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         // the row loop is skipped when the arg-max is all that is wanted from this layer
         const bool row_loop = epi == kEpiLstm || out != nullptr || out_pa != nullptr;
         unsigned long long* const am_key = do_am ? P.am_key + (size_t)(rt * P.n_tiles + n_tile) * N : nullptr;
+        // generation of the "words picked" signal, sampled before any CTA of this launch can have raised it
+        const unsigned am_gen0 = (do_am && P.am_emb_pa && pt == 0) ? ld_acquire_gpu(P.am_ctr + 1) : 0u;
 #pragma unroll 1
         for (int pass = (xtma && L.warm_epilogue) ? 0 : 1; pass < 2; ++pass) {
             const bool dry = pass == 0;
@@ -542,43 +545,52 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                         }
                     }
                     if (pt == 0 && !dry) trace_stamp(L.dbg, 13);
-                    if (P.am_emb_pa && !dry) {
-                        // decode loop: the attention kernel of the next step is already running, so this CTA hands
-                        // the embedding row of every chosen word (model.py:272-274) to the next LSTM / decode
-                        // layers, packed.  The rows are gathered by bulk copies (all in flight at once: one HBM
-                        // round trip) into the idle pipeline stages, then converted from shared memory.
-                        const int E = P.am_E;
-                        const int groups = E >> 3;
-                        const size_t halfb = (size_t)N * kBK * 2;
-                        float* emb_s = reinterpret_cast<float*>(stage_base + 4096);     // after s_word
-                        const int cap = (int)(((size_t)S * stage_bytes - 4096) / ((size_t)E * 4));
-                        const int rows_am = min(P.rows, kAmSmemWords);
-                        uint32_t ph = 1;   // tmem_full completed phase 0 in the main loop; re-used as the copy barrier
-                        for (int r0 = 0; r0 < rows_am; r0 += cap) {
-                            const int nr = min(cap, rows_am - r0);
-                            fence_proxy_async_smem();           // generic accesses of this memory before the bulk writes
-                            named_bar_sync(1, kLinProducers);   // s_word visible; previous batch fully converted
-                            if (pt == 0) mbar_arrive_expect_tx(tmem_full, (uint32_t)nr * (uint32_t)E * 4u);
-                            named_bar_sync(1, kLinProducers);
-                            for (int r = pt; r < nr; r += kLinProducers)
-                                tma_bulk_g2s(emb_s + (size_t)r * E, P.am_emb + (size_t)s_word[r0 + r] * E, (uint32_t)E * 4u, tmem_full);
-                            mbar_wait(tmem_full, ph);
-                            ph ^= 1u;
-                            for (int uu = pt; uu < nr * groups; uu += kLinProducers) {
-                                const int r = uu / groups, gi = uu - r * groups;
-                                const float4* src = reinterpret_cast<const float4*>(emb_s + (size_t)r * E + gi * 8);
-                                uint4 hi4, lo4;
-                                split_bf16x8(src[0], src[1], hi4, lo4);
-                                const int bb = r0 + r;
-                                const int rt2 = bb / N, rr = bb - rt2 * N;
-                                uint8_t* dst = P.am_emb_pa + ((size_t)rt2 * (E >> 6) + (gi >> 3)) * 2 * halfb +
-                                               umma_tile_off(mode, rr, gi & 7);
+                    if (!dry) {
+                        // publish: the words are picked (every other CTA of this layer may be waiting for them)
+                        __threadfence();
+                        named_bar_sync(1, kLinProducers);
+                        if (pt == 0) { *P.am_ctr = 0u; atomicAdd(P.am_ctr + 1, 1u); }
+                    }
+                }
+                if (P.am_emb_pa) {
+                    // decode loop: the embedding row of every chosen word (model.py:272-274) is handed, packed, to
+                    // the next LSTM / decode layers.  Every CTA of the layer waits for the words and then converts
+                    // its share of the rows (one gather round trip in parallel instead of a serial pass of the
+                    // last CTA).  All CTAs of this one-wave launch are co-resident, so the wait cannot deadlock.
+                    if (!dry && !*flag) {
+                        if (pt == 0) {
+                            const long long t0 = clock64();
+                            while (ld_acquire_gpu(P.am_ctr + 1) == am_gen0) {
+                                if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
+                                    printf("sat_b200: arg-max rendezvous timed out (block %d)\n", (int)blockIdx.x);
+                                    __trap();
+                                }
+                            }
+                        }
+                        named_bar_sync(1, kLinProducers);
+                    }
+                    const int E = P.am_E;
+                    const int groups = E >> 3;
+                    const size_t halfb = (size_t)N * kBK * 2;
+#pragma unroll 1
+                    for (int r = local; r < P.rows; r += P.cta_count) {
+                        const int w = dry ? 0 : __ldcg(P.am_next_word + r);
+                        const int rt2 = r / N, rr = r - rt2 * N;
+#pragma unroll 1
+                        for (int gi = pt; gi < groups; gi += kLinProducers) {
+                            const float4* src = reinterpret_cast<const float4*>(P.am_emb + (size_t)w * E + gi * 8);
+                            const float4 a4 = __ldg(src), c4 = __ldg(src + 1);
+                            uint4 hi4, lo4;
+                            split_bf16x8(a4, c4, hi4, lo4);
+                            uint8_t* dst = P.am_emb_pa + ((size_t)rt2 * (E >> 6) + (gi >> 3)) * 2 * halfb +
+                                           umma_tile_off(mode, rr, gi & 7);
+                            if (!dry) {
                                 *reinterpret_cast<uint4*>(dst) = hi4;
                                 *reinterpret_cast<uint4*>(dst + halfb) = lo4;
                             }
                         }
                     }
-                    if (pt == 0 && !dry) { trace_stamp(L.dbg, 14); *P.am_ctr = 0u; }
+                    if (pt == 0 && !dry && *flag) trace_stamp(L.dbg, 14);
                 }
             }
         }
@@ -752,7 +764,7 @@ cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cu
         total = max(total, nrt * jobs[i].row_tile * (jobs[i].width >> 3));
     }
     int grid = (total + 255) / 256;
-    if (grid > 148) grid = 148;
+    if (grid > 148 * 8) grid = 148 * 8;   // every thread converts a few 32-byte groups: short dependent chains
     if (grid < 1) grid = 1;
     pack_rows_kernel<<<grid, 256, 0, st>>>(J);
     return cudaGetLastError();

@@ -5,5 +5,5 @@ echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -n 3 gpurun_out/pytest_gpu.log
 timeout 600 python tools/sweep.py > gpurun_out/sweep.log 2>&1
 grep -v "timed out" gpurun_out/sweep.log | head -30
-timeout 600 python tools/sweep.py > gpurun_out/sweep2.log 2>&1
-grep -v "timed out" gpurun_out/sweep2.log | head -30
+timeout 600 python tools/timeline.py > gpurun_out/timeline.log 2>&1
+grep -A7 "===\|period\|whole" gpurun_out/timeline.log | head -60

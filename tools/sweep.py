@@ -33,9 +33,8 @@ def timeit(n=30):
     return a.elapsed_time(b) / n
 
 
-base = dict(overlap=1, att_sms=0, pa=1, graphs=1, pdl=0)
-variants = [dict(), dict(pdl=1), dict(overlap=0), dict(overlap=0, pdl=1), dict(graphs=0), dict(graphs=0, pdl=1),
-            dict(graphs=0, overlap=0), dict(graphs=0, overlap=0, pdl=1)]
+base = dict(overlap=1, att_sms=0, pa=1, graphs=1, pdl=1)
+variants = [dict(), dict(overlap=2), dict(overlap=0), dict(overlap=2, att_sms=148), dict(graphs=0), dict(graphs=0, overlap=2), dict(graphs=0, overlap=0), dict(pdl=0)]
 ref = {}
 for v in variants:
     o = dict(base)
@@ -45,9 +44,10 @@ for v in variants:
     ms = timeit()
     tok, lg = m.loop_device(pool[0], T, want_logits=True)
     torch.cuda.synchronize()
-    key = o["overlap"]
+    key = (o["overlap"], o["att_sms"])
     if key not in ref:
         ref[key] = (tok.clone(), lg.clone())
     same = bool((tok == ref[key][0]).all()) and bool((lg == ref[key][1]).all())
-    print("options %-64s  %.3f ms/loop  %.1f us/step  %.0f tok/s  bit-identical to first overlap=%d run: %s"
-          % (o, ms, ms * 1e3 / T, B * T / ms * 1e3, key, same), flush=True)
+    tsame = bool((tok == ref[(1, 0)][0]).all())
+    print("options %-64s  %.3f ms/loop  %.1f us/step  %.0f tok/s  bit-identical to first run of this layout: %s; tokens == base: %s"
+          % (o, ms, ms * 1e3 / T, B * T / ms * 1e3, same, tsame), flush=True)
