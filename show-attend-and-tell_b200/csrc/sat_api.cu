@@ -832,7 +832,8 @@ static int lstm_impl(sat_handle* h, const float* z, const int32_t* last_word, co
 
 // fused greedy argmax on the vocabulary layer: only when it runs un-split in one wave
 static int attach_argmax(sat_handle* h, Layer& ly, LinProblem& P, const RowsParams* am, cudaStream_t st) {
-    if (!am || P.splits != 1 || h->opt_gemm == 0) return 0;
+    // (its tail is a grid barrier: every CTA of the layer must be resident at once)
+    if (!am || P.splits != 1 || h->opt_gemm == 0 || P.n_tiles * P.n_row_tiles > h->num_sms) return 0;
     const size_t need = (size_t)P.n_row_tiles * P.n_tiles * P.row_tile;
     if (need > ly.am_n) {
         if (stream_capturing(st)) return fail(SAT_ERR_STATE, "%s: scratch growth during graph capture", ly.name.c_str());

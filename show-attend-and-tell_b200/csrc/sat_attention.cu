@@ -574,14 +574,16 @@ __device__ __forceinline__ float warp_reduce8(const float (&a)[8], int lane) {
 // here, and an mbarrier wait only distinguishes the current phase from the one before it: a warp that ran ahead
 // (bulk copies may complete out of order) could otherwise mistake "the previous occupant has not even landed"
 // for "my chunk is here".  Waiting first for the previous occupant's release (which the producer needs as well
-// before it issues this chunk) pins the phase the second wait refers to.
+// before it issues this chunk) pins the phase the second wait refers to.  That first wait cannot be fooled in
+// turn: this warp has consumed chunk id-8, whose producer lane had issued chunk id-nslots before it (same lane,
+// in order, because nslots is even and > 8), which required the release of chunk id-2*nslots.
 __device__ __forceinline__ void att_wpc_wait(uint64_t* full, uint64_t* empty, int s, int round) {
     if (round > 0) mbar_wait(&empty[s], (uint32_t)(round - 1) & 1u);
     mbar_wait(&full[s], (uint32_t)round & 1u);
 }
 
 template <int G>
-__global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constant__ AttParams p) {
+__global__ void __launch_bounds__(10 * 32, 1) att_wpc_kernel(const __grid_constant__ AttParams p) {
     constexpr int NW = 8, NT = NW * 32, RW = 512, CR = 8, RW4 = RW / 4;
     extern __shared__ __align__(1024) uint8_t smem[];
     // layout: [slots][full, empty barriers][w_s G*Lp][misc 64][zred NW*G*512]
@@ -610,13 +612,18 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
     }
     __syncthreads();
 
-    if (warp == NW) {
-        // ============================ producer ============================
-        // T1 and ctx do not change while a caption is decoded: the ring is filled before the predecessor kernel
-        // has finished (programmatic dependent launch); only the consumers wait for it.
+    if (warp >= NW) {
+        // ============================ producers ============================
+        // Two producer warps (one lane each) take the even / odd chunks, so that issuing a chunk (wait for the
+        // slot, arm the barrier, bulk copy) is not a single serial chain.  T1 and ctx do not change while a
+        // caption is decoded: the ring is filled before the predecessor kernel has finished (programmatic
+        // dependent launch); only the consumers wait for it.
         if (lane == 0) {
+            const int pw = warp - NW;                           // 0 or 1
             const uint64_t pol_t = l2_policy(p.l2_t), pol_c = l2_policy(p.l2_ctx);
-            int idx = 0;
+            int idx = 0;                                        // chunk counter (all chunks)
+            int s = 0;                                          // its ring slot and the use count of that slot
+            uint32_t round = 0;
             for (int seg0 = r_begin; seg0 < r_end;) {
                 const int img = seg0 / L;
                 const int seg1 = min(r_end, (img + 1) * L);
@@ -625,12 +632,14 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
                     const int pol_k = pass == 0 ? p.l2_t : p.l2_ctx;
                     const uint64_t pol = pass == 0 ? pol_t : pol_c;
                     for (int r = seg0; r < seg1; r += CR, ++idx) {
-                        const int n = min(CR, seg1 - r);
-                        const int s = idx % p.nslots;
-                        mbar_wait(&empty[s], ((uint32_t)(idx / p.nslots) & 1u) ^ 1u);
-                        const uint32_t bytes = (uint32_t)n * RW * 4u;
-                        mbar_arrive_expect_tx(&full[s], bytes);
-                        tma_bulk_g2s_hint(slots + (size_t)s * p.slot_bytes, src + (size_t)r * RW, bytes, &full[s], pol_k, pol);
+                        if ((idx & 1) == pw) {
+                            const int n = min(CR, seg1 - r);
+                            mbar_wait(&empty[s], (round & 1u) ^ 1u);
+                            const uint32_t bytes = (uint32_t)n * RW * 4u;
+                            mbar_arrive_expect_tx(&full[s], bytes);
+                            tma_bulk_g2s_hint(slots + (size_t)s * p.slot_bytes, src + (size_t)r * RW, bytes, &full[s], pol_k, pol);
+                        }
+                        if (++s == p.nslots) { s = 0; ++round; }
                     }
                 }
                 seg0 = seg1;
@@ -653,7 +662,11 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
     if (p.emb_pa) att_pack_embedding(p, c * NT + ct, P * NT, G);
     if (ct == 0) trace_stamp(p.dbg, 1);
 
+    // this warp's next chunk is number `mine` (chunks idx, idx+1, ... go to warps idx % 8, ...); its ring slot and
+    // the use count of that slot advance by 8 chunks at a time without divisions
     int idx = 0;
+    int ms = warp % p.nslots;
+    uint32_t mround = (uint32_t)(warp / p.nslots);
     bool first_seg = true;
     for (int seg0 = r_begin; seg0 < r_end;) {
         const int img = seg0 / L;
@@ -671,9 +684,10 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
 
         // ---- pass 1: logits of this warp's chunks
         for (int ci = ((warp - idx) % NW + NW) % NW; ci < nch; ci += NW) {
-            const int id = idx + ci;
-            const int s = id % p.nslots;
-            att_wpc_wait(full, empty, s, id / p.nslots);
+            const int s = ms;
+            att_wpc_wait(full, empty, s, (int)mround);
+            ms += NW;
+            while (ms >= p.nslots) { ms -= p.nslots; ++mround; }
             if (ct == 0 && first_seg && ci < NW) trace_stamp(p.dbg, 2);
             const float4* buf = reinterpret_cast<const float4*>(slots + (size_t)s * p.slot_bytes);
             const int n = min(CR, nseg - ci * CR);
@@ -740,8 +754,7 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
             for (int k = 0; k < 16; ++k) zacc[g][k] = 0.f;
         }
         for (int ci = ((warp - idx) % NW + NW) % NW; ci < nch; ci += NW) {
-            const int id = idx + ci;
-            const int s = id % p.nslots;
+            const int s = ms;
             const int n = min(CR, nseg - ci * CR);
             float wl[G];
 #pragma unroll
@@ -749,7 +762,9 @@ __global__ void __launch_bounds__(9 * 32, 1) att_wpc_kernel(const __grid_constan
                 wl[g] = lane < n ? expf(w_s[g * Lp + ci * CR + lane] - m[g]) : 0.f;
                 wsum[g] += wl[g];
             }
-            att_wpc_wait(full, empty, s, id / p.nslots);
+            att_wpc_wait(full, empty, s, (int)mround);
+            ms += NW;
+            while (ms >= p.nslots) { ms -= p.nslots; ++mround; }
             if (ct == 0 && first_seg && ci < NW) trace_stamp(p.dbg, 4);
             const float4* buf = reinterpret_cast<const float4*>(slots + (size_t)s * p.slot_bytes);
 #pragma unroll
@@ -932,6 +947,9 @@ bool att_plan(AttParams& p, int smem_optin, int num_sms) {
     if ((size_t)smem_optin < fixed + 2 * (size_t)slot) return false;
     int n = (int)(((size_t)smem_optin - fixed) / ((size_t)slot + 16));
     if (n > (p.wpc ? 24 : 16)) n = p.wpc ? 24 : 16;
+    // warp-per-chunk kernel: an even ring, so that the successive occupants of a slot come from the same one of
+    // its two producer lanes (each issues its chunks in order), which is what att_wpc_wait's argument needs
+    if (p.wpc) n &= ~1;
     p.nslots = n;
     const long long NR = (long long)p.NI * p.L;
     p.grid = (int)(NR < num_sms ? NR : num_sms);
@@ -987,7 +1005,7 @@ static cudaError_t att_launch_wpc(const AttParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.grid);
-    cfg.blockDim = dim3(9 * 32);
+    cfg.blockDim = dim3(10 * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];

@@ -367,8 +367,20 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         // the row loop is skipped when the arg-max is all that is wanted from this layer
         const bool row_loop = epi == kEpiLstm || out != nullptr || out_pa != nullptr;
         unsigned long long* const am_key = do_am ? P.am_key + (size_t)(rt * P.n_tiles + n_tile) * N : nullptr;
+        // arg-max layers fold the bias into the tile as it leaves TMEM (this thread's TMEM lane = one output): the
+        // arg-max scan then reads finished values; the row loop must not add it again
+        const float bias_fold = (do_am && P.bias) ? P.bias[n_tile * kTileN + (warp & 3) * 32 + lane] : 0.f;
+        // LSTM: c_prev of the (at most two) rows this thread finishes, fetched while the main loop runs
+        float cpre[2] = {0.f, 0.f};
+        if (epi == kEpiLstm && unit < Hh) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int idx = lo + pt + j * kLinProducers;
+                if (idx < hi) cpre[j] = c_in[(size_t)(row0 + (idx >> 5)) * Hh + unit];
+            }
+        }
         // generation of the "words picked" signal, sampled before any CTA of this launch can have raised it
-        const unsigned am_gen0 = (do_am && P.am_emb_pa && pt == 0) ? ld_acquire_gpu(P.am_ctr + 1) : 0u;
+        const unsigned am_gen0 = (do_am && pt == 0) ? ld_acquire_gpu(P.am_ctr + 1) : 0u;
 #pragma unroll 1
         for (int pass = (xtma && L.warm_epilogue) ? 0 : 1; pass < 2; ++pass) {
             const bool dry = pass == 0;
@@ -388,7 +400,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                     float v[16];
                     tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) tile_s[(c0 + j) * kTileN + nl] = v[j];
+                    for (int j = 0; j < 16; ++j) tile_s[(c0 + j) * kTileN + nl] = v[j] + bias_fold;
                 }
                 tc_fence_before();
                 // ---- split-K partials meet through distributed shared memory.  The `splits` CTAs of a tile form
@@ -415,8 +427,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
 #pragma unroll 1
                 for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
                     const int bb = idx >> 5;
-                    float cprev = 0.f;
-                    if (epi == kEpiLstm && unit < Hh) cprev = c_in[(size_t)(row0 + bb) * Hh + unit];
+                    float cprev = idx == lo + pt ? cpre[0] : cpre[1];
+                    if (epi == kEpiLstm && unit < Hh && idx >= lo + pt + 2 * kLinProducers)
+                        cprev = c_in[(size_t)(row0 + bb) * Hh + unit];
                     float4 g;
                     if (splits == 1) {
                         g = *reinterpret_cast<const float4*>(tile_s + bb * kTileN + 4 * u);
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                         for (int r = 1; r < 8; ++r)
                             if (r < splits) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
                     }
-                    g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w;
+                    if (!do_am) { g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w; }
                     if (pt == 0 && !dry && L.dbg && g.x != 12345.678f) trace_stamp(L.dbg, 2);   // partial sums arrived
                     if (epi == kEpiLstm) {
                         if (unit < Hh) lstm_gates(P, g, cprev, row0 + bb, unit, mode, dry);
@@ -466,10 +479,10 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             }
             if (do_am) {
                 // greedy prediction (model.py:289): 4 threads per row, each scans 32 of the tile's 128 outputs
-                // (accumulator + bias, the value the row loop stores) in a skewed, bank-conflict-free order;
+                // (accumulator + bias, folded in part 1: the value the row loop stores) in a skewed,
+                // bank-conflict-free order;
                 // first maximum wins (tf.argmax), so ties go to the smaller index
                 const int part = pt & 3;
-                const float4* bias_t = reinterpret_cast<const float4*>(P.bias + n_tile * kTileN) + part * 8;
 #pragma unroll 1
                 for (int r0 = 0; r0 < rows_here; r0 += kLinProducers / 4) {
                     const int r = r0 + (pt >> 2);
@@ -481,9 +494,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                     for (int j = 0; j < 8; ++j) {
                         const int jj = (j + pt) & 7;
                         const float4 a4 = row_t[jj];
-                        const float4 b4 = __ldg(bias_t + jj);
                         const int i0 = n_tile * kTileN + part * 32 + jj * 4;
-                        const float y0 = a4.x + b4.x, y1 = a4.y + b4.y, y2 = a4.z + b4.z, y3 = a4.w + b4.w;
+                        const float y0 = a4.x, y1 = a4.y, y2 = a4.z, y3 = a4.w;
                         if (i0 + 0 < n_out && (y0 > bv || (y0 == bv && i0 + 0 < bi))) { bv = y0; bi = i0 + 0; }
                         if (i0 + 1 < n_out && (y1 > bv || (y1 == bv && i0 + 1 < bi))) { bv = y1; bi = i0 + 1; }
                         if (i0 + 2 < n_out && (y2 > bv || (y2 == bv && i0 + 2 < bi))) { bv = y2; bi = i0 + 2; }
@@ -497,68 +509,23 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             }
             if (splits > 1 && !dry) cluster_arrive_relaxed();   // this CTA no longer reads its peers' tiles
             if (do_am) {
-                // tile candidates are in global memory; the last CTA of the problem picks every row's word
-                unsigned* flag = reinterpret_cast<unsigned*>(smem_raw + 512);
+                // Tile candidates are in global memory.  All CTAs of the layer (one wave: co-resident, so waiting
+                // cannot deadlock) meet at a grid barrier; then CTA i finishes row i, i + #CTAs, ...: it merges the
+                // row's per-tile candidates (one L2 round trip), records the word and - in the decode loop - hands
+                // the embedding row of the chosen word (model.py:272-274), packed, to the next LSTM / decode layers.
+                // Every step of this tail is a round trip on the critical path of the decode step, which is why it
+                // is spread over the CTAs instead of being a serial pass of the last one.
+                unsigned long long* red_s = reinterpret_cast<unsigned long long*>(smem_raw + 520);   // [8] + word
                 if (!dry) {
                     if (pt == 0) trace_stamp(L.dbg, 11);
                     __threadfence();
                     named_bar_sync(1, kLinProducers);
-                    if (pt == 0) *flag = atomicAdd(P.am_ctr, 1u) == (unsigned)(P.cta_count - 1) ? 1u : 0u;
-                    named_bar_sync(1, kLinProducers);
-                }
-                if (dry || *flag) {
-                    if (pt == 0 && !dry) trace_stamp(L.dbg, 12);
-                    __threadfence();
-                    // 4 lanes per row; every lane's candidates are fetched in ONE batch of independent loads, so the
-                    // merge costs one L2 round trip (a dependent chain here is what a concurrent kernel stretches)
-                    constexpr int kBatch = 24;
-                    int32_t* s_word = reinterpret_cast<int32_t*>(stage_base);    // tile_s is dead by now
-                    const int part = pt & 3;
-                    const int n_tiles = P.n_tiles;
-                    for (int b0 = 0; b0 < P.rows; b0 += kLinProducers / 4) {
-                        const int b = b0 + (pt >> 2);
-                        const bool live = b < P.rows;
-                        const int rt2 = live ? b / N : 0, c = live ? b - rt2 * N : 0;
-                        const unsigned long long* pk = P.am_key + (size_t)rt2 * n_tiles * N + c;
-                        unsigned long long best = 0ull;
-                        for (int tl = part; tl < n_tiles; tl += 4 * kBatch) {
-                            unsigned long long k[kBatch];
-#pragma unroll
-                            for (int q2 = 0; q2 < kBatch; ++q2) {
-                                const int tt = tl + 4 * q2;
-                                k[q2] = (live && tt < n_tiles) ? __ldcg(pk + (size_t)tt * N) : 0ull;
-                            }
-#pragma unroll
-                            for (int q2 = 0; q2 < kBatch; ++q2) best = k[q2] > best ? k[q2] : best;
-                        }
-#pragma unroll
-                        for (int o = 1; o <= 2; o <<= 1) {
-                            const unsigned long long ok2 = __shfl_xor_sync(0xffffffffu, best, o);
-                            best = ok2 > best ? ok2 : best;
-                        }
-                        if (live && part == 0 && !dry) {
-                            const int bi2 = argmax_key_index(best);
-                            const int nw = P.am_forced ? P.am_forced[(size_t)b * P.am_forced_ld + P.am_step] : bi2;
-                            if (P.am_tokens) P.am_tokens[(size_t)b * P.am_tokens_ld + P.am_step] = bi2;
-                            if (P.am_next_word) P.am_next_word[b] = nw;
-                            if (b < kAmSmemWords) s_word[b] = nw;
-                        }
-                    }
-                    if (pt == 0 && !dry) trace_stamp(L.dbg, 13);
-                    if (!dry) {
-                        // publish: the words are picked (every other CTA of this layer may be waiting for them)
-                        __threadfence();
-                        named_bar_sync(1, kLinProducers);
-                        if (pt == 0) { *P.am_ctr = 0u; atomicAdd(P.am_ctr + 1, 1u); }
-                    }
-                }
-                if (P.am_emb_pa) {
-                    // decode loop: the embedding row of every chosen word (model.py:272-274) is handed, packed, to
-                    // the next LSTM / decode layers.  Every CTA of the layer waits for the words and then converts
-                    // its share of the rows (one gather round trip in parallel instead of a serial pass of the
-                    // last CTA).  All CTAs of this one-wave launch are co-resident, so the wait cannot deadlock.
-                    if (!dry && !*flag) {
-                        if (pt == 0) {
+                    if (pt == 0) {
+                        if (atomicAdd(P.am_ctr, 1u) == (unsigned)(P.cta_count - 1)) {
+                            *P.am_ctr = 0u;
+                            __threadfence();
+                            atomicAdd(P.am_ctr + 1, 1u);          // opens the generation: every candidate is visible
+                        } else {
                             const long long t0 = clock64();
                             while (ld_acquire_gpu(P.am_ctr + 1) == am_gen0) {
                                 if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
@@ -567,17 +534,40 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                                 }
                             }
                         }
-                        named_bar_sync(1, kLinProducers);
+                        trace_stamp(L.dbg, 12);
                     }
-                    const int E = P.am_E;
-                    const int groups = E >> 3;
-                    const size_t halfb = (size_t)N * kBK * 2;
+                    named_bar_sync(1, kLinProducers);
+                }
+                const int n_tiles = P.n_tiles;
+                const int E = P.am_E;
+                const size_t halfb = (size_t)N * kBK * 2;
 #pragma unroll 1
-                    for (int r = local; r < P.rows; r += P.cta_count) {
-                        const int w = dry ? 0 : __ldcg(P.am_next_word + r);
-                        const int rt2 = r / N, rr = r - rt2 * N;
+                for (int r = local; r < P.rows; r += P.cta_count) {
+                    const int rt2 = r / N, cc = r - rt2 * N;
+                    const unsigned long long* pk = P.am_key + (size_t)rt2 * n_tiles * N + cc;
+                    unsigned long long best = 0ull;
+                    for (int tl = pt; tl < n_tiles; tl += kLinProducers) best = max(best, __ldcg(pk + (size_t)tl * N));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    if ((pt & 31) == 0) red_s[pt >> 5] = best;
+                    named_bar_sync(1, kLinProducers);
+                    if (pt == 0) {
+#pragma unroll
+                        for (int w = 1; w < kLinProducers / 32; ++w) best = max(best, red_s[w]);
+                        const int bi2 = argmax_key_index(best);
+                        const int nw = P.am_forced ? P.am_forced[(size_t)r * P.am_forced_ld + P.am_step] : bi2;
+                        if (!dry) {
+                            if (P.am_tokens) P.am_tokens[(size_t)r * P.am_tokens_ld + P.am_step] = bi2;
+                            if (P.am_next_word) P.am_next_word[r] = nw;
+                        }
+                        *reinterpret_cast<int*>(red_s + 8) = dry ? 0 : nw;
+                    }
+                    named_bar_sync(1, kLinProducers);
+                    if (P.am_emb_pa) {
+                        const int w = *reinterpret_cast<const int*>(red_s + 8);
+                        const int rr = cc;
 #pragma unroll 1
-                        for (int gi = pt; gi < groups; gi += kLinProducers) {
+                        for (int gi = pt; gi < (E >> 3); gi += kLinProducers) {
                             const float4* src = reinterpret_cast<const float4*>(P.am_emb + (size_t)w * E + gi * 8);
                             const float4 a4 = __ldg(src), c4 = __ldg(src + 1);
                             uint4 hi4, lo4;
@@ -590,8 +580,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             }
                         }
                     }
-                    if (pt == 0 && !dry && *flag) trace_stamp(L.dbg, 14);
                 }
+                if (pt == 0 && !dry) trace_stamp(L.dbg, 13);
             }
         }
     }
