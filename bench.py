@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -301,10 +301,21 @@ def main():
     for i in range(max(args.warmup, 3) + 2 * pool):       # warm-up also builds one CUDA graph per pool entry
         loop(i)
     barrier()
+    # The timed region (K loops, a few tens of ms) is shorter than nvidia-smi's sampling period, so it is embedded
+    # in a continuous run of the SAME loop: identical untimed loops keep the GPU in the same state while the
+    # sampler collects clocks / throttle reasons before, during and after the K timed ones.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+    def roll(seconds, need_rows):
+        t_end = time.time() + seconds
+        i = 0
+        while time.time() < t_end or (rank == 0 and len(sampler.rows) < need_rows and time.time() < t_end + 3.0):
+            loop(i); i += 1
+            if i % 16 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    roll(0.4, 2)
     model.set_option("reset_counters", 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -316,7 +327,11 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = model.info("launches")
+    roll(0.3, len(sampler.rows) + 2 if rank == 0 else 0)
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["note"] = ("nvidia-smi sampled every 50 ms while the same decode loop ran back to back for ~0.4 s before, "
+                          "during and ~0.3 s after the timed steps")
     ms = parallel.max_over_ranks(ms, dev)
     value = world * B * T * args.steps / (ms / 1e3)
 
@@ -339,16 +354,41 @@ def main():
             rc = model.lib.sat_decode_loop_host(model._h, hp(ctx_host[i % pool]), B, T, None, hp(tok_host), model._st())
         assert rc == 0, model.lib.sat_last_error()
 
-    for i in range(3):
-        e2e_step(i)
+    tok_pipe = [torch.empty(B, T, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def e2e_run(n):
+        """n batches through the public host-buffer API; every batch's contexts are uploaded from pinned host
+        memory and its tokens read back inside the region."""
+        if beam > 1:
+            for i in range(n):
+                e2e_step(i)                              # synchronous: returns with the captions in host memory
+            return
+        # greedy loop: the pipelined form (submit batch i+1, then wait for batch i) overlaps uploads with decoding
+        checksum = 0
+        for i in range(n):
+            model.loop_host_submit(ctx_host[i % pool], T, tok_pipe[i & 1], i & 1)
+            if i >= 1:
+                checksum += int(model.loop_host_wait((i - 1) & 1)[0, 0])      # tokens of batch i-1 are on the host
+        checksum += int(model.loop_host_wait((n - 1) & 1)[0, 0])
+        return checksum
+
+    e2e_run(4)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)                                      # synchronous: returns with tokens in host memory
+    e2e_run(args.steps)
     torch.cuda.synchronize()
     e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    # the plain synchronous call (upload, decode, download, one after the other), for reference
+    t1 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_sync_s = time.perf_counter() - t1
     e2e = dict(value=world * B * T * args.steps / e2e_s, unit="tokens/s", h2d_bytes_per_step=B * L * D * 4,
-               d2h_bytes_per_step=B * T * 4, ms_per_step=1e3 * e2e_s / args.steps)
+               d2h_bytes_per_step=B * T * 4, ms_per_step=1e3 * e2e_s / args.steps,
+               api=("sat_decode_loop_host_submit/_wait (two staging slots: upload of batch i+1 overlaps decode of batch i)"
+                    if beam == 1 else "sat_beam_search_host (synchronous)"),
+               synchronous_call_tokens_per_s=B * T * args.steps / e2e_sync_s)
 
     # ---------------------------------------------------------------- attention kernel roofline
     roof = None
@@ -362,20 +402,38 @@ def main():
         z = torch.empty(B, D, device=dev)
         model.prepare(ctx_dev[0], want_state=False)
         torch.cuda.synchronize()
-        model.set_option("profile", 1)
-        reps = 20
-        for i in range(reps + 3):
-            if i == 3:
-                torch.cuda.synchronize(); model.set_option("profile", 1)   # drop warm-up records
-            with torch.cuda.stream(st):
-                # the L2 flush runs on the SAME stream just before: it evicts L2 and keeps the GPU busy
-                # while the host enqueues event / kernel / event, so no host latency is inside the interval
-                flush.zero_()
-                rc = model.lib.sat_attention_fwd(model._h, hp(ctx_dev[0]), hp(hstate), hp(alpha), hp(z), B, 1,
-                                                 model._st())
-                assert rc == 0, model.lib.sat_last_error()
-        torch.cuda.synchronize()
-        att_ns = model.info("prof_ns_att") / max(1, model.info("prof_n_att"))
+        def time_attention(sms, reps=20):
+            """Duration of one attention launch with a cold L2, from CUDA events on the launch stream.  Events around
+            a single ~12 us kernel mostly measure launch latency (~6 us here), so the interval covers `reps`
+            back-to-back (256 MB L2 flush, attention kernel) pairs and the same number of flushes alone is
+            subtracted: (T[reps x (flush + kernel)] - T[reps x flush]) / reps."""
+            model.set_option("att_sms", sms)
+            rc = model.lib.sat_attention_fwd(model._h, hp(ctx_dev[0]), hp(hstate), hp(alpha), hp(z), B, 1, model._st())
+            assert rc == 0, model.lib.sat_last_error()
+            model.set_option("att_reuse_q", 1)        # q of the call above: the following calls launch the kernel alone
+            def series(with_kernel):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(st):
+                    flush.zero_()
+                    e0.record(st)
+                    for i in range(reps):
+                        flush.zero_()
+                        if with_kernel:
+                            rc = model.lib.sat_attention_fwd(model._h, hp(ctx_dev[0]), hp(hstate), hp(alpha), hp(z), B, 1,
+                                                             model._st())
+                            assert rc == 0, model.lib.sat_last_error()
+                    e1.record(st)
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) * 1e6
+            series(True); series(False)
+            both = min(series(True) for _ in range(3))
+            base = min(series(False) for _ in range(3))
+            model.set_option("att_reuse_q", 0)
+            model.set_option("att_sms", 0)
+            return (both - base) / reps
+        loop_grid = model.info("att_loop_grid")       # CTAs of the attention launches inside the timed decode loop
+        att_ns_full = time_attention(0)                # whole GPU
+        att_ns = time_attention(loop_grid) if 0 < loop_grid < 148 else att_ns_full
         # per-family times of one eager step (cold L2), for the breakdown
         model.set_option("profile", 1)
         lw = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -396,9 +454,13 @@ def main():
             tj = json.load(open(tp))
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         roof = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
-                    traffic=traffic, kernel="att_fused_kernel<1>", us_per_launch=att_ns / 1e3,
+                    traffic=traffic, kernel=("att_wpc_kernel<1>" if (D == 512 and A == 512) else "att_fused_kernel<1>"),
+                    grid=loop_grid, us_per_launch=att_ns / 1e3, us_per_launch_whole_gpu=att_ns_full / 1e3,
+                    achieved_whole_gpu=att_bytes / att_ns_full,
                     algorithmic_bytes=att_bytes, peak_source=pk["src"] + " HBM copy, burst",
-                    timing="CUDA events around the kernel on its launch stream, 256 MB L2 flush between launches")
+                    timing=("CUDA events on the launch stream around 20 x (256 MB L2 flush, kernel) minus 20 x flush, / 20; "
+                            "grid = the one the decode loop launches (there it shares the GPU with the vocabulary layer), "
+                            "timed alone"))
         E = cfg.dim_embedding
         Dd = cfg.dim_decode_layer
         lstm_bytes = 4 * ((D + E + H) * 4 * H + 4 * H)

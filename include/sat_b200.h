@@ -122,6 +122,14 @@ int sat_decode_step_host(sat_handle* h, const float* contexts_host, int32_t cont
                          float* probs_host, int32_t B, void* stream);
 int sat_decode_loop_host(sat_handle* h, const float* contexts_host, int32_t B, int32_t T,
                          const int32_t* forced_words_host, int32_t* tokens_host, void* stream);
+/* Pipelined form of sat_decode_loop_host for a stream of batches (what a caption server / the eval loop of
+ * base_model.py:94-140 does batch after batch).  submit() enqueues upload (own copy stream) -> loop -> download for
+ * staging slot 0 or 1 and returns; wait() blocks until that slot's tokens are in tokens_host.  Submit batch i+1 on
+ * the other slot before waiting for batch i and its upload overlaps batch i's decode.  The host buffers must stay
+ * valid (and, for true overlap, be pinned) until wait(). */
+int sat_decode_loop_host_submit(sat_handle* h, const float* contexts_host, int32_t B, int32_t T,
+                                const int32_t* forced_words_host, int32_t* tokens_host, int32_t slot, void* stream);
+int sat_decode_loop_host_wait(sat_handle* h, int32_t slot);
 int sat_beam_search_host(sat_handle* h, const float* contexts_host, int32_t n_img, int32_t beam_size, int32_t T,
                          int32_t eos_id, int32_t* sentences_host, int32_t* lengths_host, double* scores_host,
                          int32_t* n_results_host, int32_t* is_complete_host, void* stream);

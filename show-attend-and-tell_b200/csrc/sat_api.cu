@@ -104,6 +104,13 @@ struct sat_handle {
     float* stage_ctx = nullptr;
     void* stage_misc = nullptr;
     size_t stage_misc_bytes = 0;
+    // pipelined host-buffer loop (sat_decode_loop_host_submit / _wait): two staging slots and a copy stream
+    float* pipe_ctx[2] = {nullptr, nullptr};
+    int32_t* pipe_tok[2] = {nullptr, nullptr};   // [tokens | forced words]
+    size_t pipe_tok_elems[2] = {0, 0};
+    cudaStream_t pipe_copy = nullptr;
+    cudaEvent_t pipe_up[2] = {nullptr, nullptr}, pipe_done[2] = {nullptr, nullptr};
+    bool pipe_busy[2] = {false, false};
 
     // contexts state
     const float* prep_ctx = nullptr;
@@ -122,12 +129,13 @@ struct sat_handle {
     uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1;
+    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
     int opt_trace = 0;
     int trace_at = 0;      // with trace == 1: index of the dense launch (counted from the option call) to stamp
+    int att_loop_grid = 0; // CTAs of the last attention launch that ran beside the vocabulary layer (decode loop)
     int tl_count = 0;      // with trace == 3: launches recorded so far ({min start, max end} per launch)
     std::vector<std::string> tl_names;
 
@@ -213,6 +221,13 @@ extern "C" void sat_destroy(sat_handle* h) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->pipe_copy) cudaStreamDestroy(h->pipe_copy);
+    for (int i = 0; i < 2; ++i) {
+        if (h->pipe_up[i]) cudaEventDestroy(h->pipe_up[i]);
+        if (h->pipe_done[i]) cudaEventDestroy(h->pipe_done[i]);
+        cudaFree(h->pipe_ctx[i]);
+        cudaFree(h->pipe_tok[i]);
+    }
     for (auto& g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     for (Layer* ly : h->layers) layer_free(*ly);
@@ -365,6 +380,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "pdl") h->opt_pdl = (int)value;
     else if (k == "warm") h->opt_warm = (int)value;
     else if (k == "att_wpc") h->opt_att_wpc = (int)value;
+    else if (k == "att_reuse_q") h->opt_att_reuse_q = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -416,6 +432,7 @@ extern "C" int sat_get_info(sat_handle* h, const char* key, int64_t* value) {
     }
     else if (k == "trace_ptr") *value = (int64_t)(uintptr_t)h->trace;
     else if (k == "tl_count") *value = h->tl_count;
+    else if (k == "att_loop_grid") *value = h->att_loop_grid;
     else if (k.rfind("tl_tag_", 0) == 0) {   // family code of timeline entry i: index into the tag list, grid in the high bits
         const int i = atoi(k.c_str() + 7);
         if (i < 0 || i >= (int)h->tl_names.size()) return fail(SAT_ERR_INVALID, "timeline index");
@@ -772,6 +789,16 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     if (sm_budget <= 0 && h->opt_att_sms > 0) sm_budget = h->opt_att_sms;   // experiment knob
     if (!att_plan(ap, h->smem_optin, sm_budget > 0 ? sm_budget : h->num_sms))
         return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
+    if (nowait && (!ap.wpc || n_img > ap.grid)) {
+        // running beside the vocabulary layer on the SMs it leaves idle only pays when the kernel can skip the
+        // wait (warp-per-chunk kernel) and one CTA per image fits that budget; otherwise: whole GPU, in order
+        nowait = false;
+        ap.occ = h->opt_att_occ;
+        ap.warps = h->opt_att_warps;
+        ap.wpc = h->opt_att_wpc;
+        if (!att_plan(ap, h->smem_optin, h->opt_att_sms > 0 ? h->opt_att_sms : h->num_sms))
+            return fail(SAT_ERR_UNSUPPORTED, "attention shape unsupported (G=%d L=%d D=%d)", G, ap.L, ap.D);
+    }
     const size_t pneed = att_part_floats(ap);
     if (pneed > h->att_part_floats) {
         if (stream_capturing(st)) return fail(SAT_ERR_STATE, "attention scratch growth during graph capture");
@@ -796,6 +823,7 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     }
     ap.pdl = h->opt_pdl ? 1 : 0;
     ap.nowait = (nowait && ap.pdl) ? 1 : 0;
+    if (q_ready && !h->opt_att_reuse_q) h->att_loop_grid = ap.grid;
     ap.dbg = h->opt_trace == 2 ? h->trace : nullptr;
     ap.tl = nullptr;
     if (h->opt_trace == 3 && h->tl_count < 4000) {
@@ -1312,6 +1340,61 @@ extern "C" int sat_decode_loop_host(sat_handle* h, const float* contexts_host, i
     return SAT_OK;
 }
 
+// Pipelined host-buffer loop.  submit(slot) enqueues, without blocking the host: the upload of the batch on a copy
+// stream into staging slot `slot`, the decode loop behind it on `stream`, and the download of the tokens; wait(slot)
+// returns once that batch's tokens are in tokens_host.  Submitting batch i+1 (other slot) before waiting for batch
+// i overlaps its upload with batch i's decode: the caller's pageable/pinned buffers must stay valid until wait().
+extern "C" int sat_decode_loop_host_submit(sat_handle* h, const float* contexts_host, int32_t B, int32_t T,
+                                           const int32_t* forced_words_host, int32_t* tokens_host, int32_t slot,
+                                           void* stream) {
+    RET(require_ready(h));
+    if (!contexts_host || !tokens_host) return fail(SAT_ERR_INVALID, "sat_decode_loop_host_submit: null buffer");
+    if (B < 1 || B > h->max_rows || T < 1) return fail(SAT_ERR_INVALID, "bad B/T");
+    if (slot < 0 || slot > 1) return fail(SAT_ERR_INVALID, "slot must be 0 or 1");
+    if (h->pipe_busy[slot]) return fail(SAT_ERR_STATE, "slot %d was submitted and not waited for", slot);
+    const sat_dims& d = h->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->pipe_copy) {
+        CK(cudaStreamCreateWithFlags(&h->pipe_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&h->pipe_up[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->pipe_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (!h->pipe_ctx[slot]) RET(dmalloc(&h->pipe_ctx[slot], (size_t)h->max_rows * d.num_ctx * d.dim_ctx));
+    const size_t TB = (size_t)B * T;
+    if (2 * TB > h->pipe_tok_elems[slot]) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(h->pipe_tok[slot]);
+        h->pipe_tok[slot] = nullptr;
+        h->pipe_tok_elems[slot] = 0;
+        RET(dmalloc(&h->pipe_tok[slot], 2 * TB));
+        h->pipe_tok_elems[slot] = 2 * TB;
+    }
+    int32_t* tok = h->pipe_tok[slot];
+    int32_t* forced = forced_words_host ? tok + TB : nullptr;
+    // (the previous batch of this slot was waited for, so its staging buffers are free)
+    CK(cudaMemcpyAsync(h->pipe_ctx[slot], contexts_host, (size_t)B * d.num_ctx * d.dim_ctx * sizeof(float),
+                       cudaMemcpyHostToDevice, h->pipe_copy));
+    if (forced) CK(cudaMemcpyAsync(forced, forced_words_host, TB * sizeof(int32_t), cudaMemcpyHostToDevice, h->pipe_copy));
+    CK(cudaEventRecord(h->pipe_up[slot], h->pipe_copy));
+    CK(cudaStreamWaitEvent(st, h->pipe_up[slot], 0));
+    RET(sat_decode_loop(h, h->pipe_ctx[slot], B, T, forced, tok, nullptr, stream));
+    CK(cudaMemcpyAsync(tokens_host, tok, TB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->pipe_done[slot], st));
+    h->pipe_busy[slot] = true;
+    return SAT_OK;
+}
+
+extern "C" int sat_decode_loop_host_wait(sat_handle* h, int32_t slot) {
+    if (!h) return fail(SAT_ERR_INVALID, "null handle");
+    if (slot < 0 || slot > 1) return fail(SAT_ERR_INVALID, "slot must be 0 or 1");
+    if (!h->pipe_busy[slot]) return fail(SAT_ERR_STATE, "slot %d has no batch in flight", slot);
+    CK(cudaEventSynchronize(h->pipe_done[slot]));
+    h->pipe_busy[slot] = false;
+    return SAT_OK;
+}
+
 extern "C" int sat_beam_search_host(sat_handle* h, const float* contexts_host, int32_t n_img, int32_t beam_size,
                                     int32_t T, int32_t eos_id, int32_t* sentences_host, int32_t* lengths_host,
                                     double* scores_host, int32_t* n_results_host, int32_t* is_complete_host,
@@ -1348,7 +1431,8 @@ extern "C" int sat_attention_fwd(sat_handle* h, const float* contexts, const flo
     if (!contexts || !output || !context) return fail(SAT_ERR_INVALID, "sat_attention_fwd: null tensor");
     if (n_img < 1 || group < 1 || (long long)n_img * group > h->max_rows)
         return fail(SAT_ERR_INVALID, "n_img*group outside [1, %d]", h->max_rows);
-    return attention_impl(h, contexts, n_img, group, output, alpha, context, (cudaStream_t)stream);
+    // (debug option "att_reuse_q": keep the state branch of the previous call, launch the attention kernel alone)
+    return attention_impl(h, contexts, n_img, group, output, alpha, context, (cudaStream_t)stream, h->opt_att_reuse_q != 0);
 }
 
 extern "C" int sat_lstm_fwd(sat_handle* h, const float* context, const int32_t* last_word, const float* last_memory,

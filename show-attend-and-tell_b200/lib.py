@@ -42,6 +42,8 @@ SIGNATURES = {
     "sat_decode_step_host": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
     "sat_decode_loop_host": (C.c_int, [_P, _P, _I, _I, _P, _P, _P]),
     "sat_beam_search_host": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "sat_decode_loop_host_submit": (C.c_int, [_P, _P, _I, _I, _P, _P, _I, _P]),
+    "sat_decode_loop_host_wait": (C.c_int, [_P, _I]),
     "sat_attention_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "sat_lstm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "sat_vocab_gemm": (C.c_int, [_P, _P, _P, _P, _P, _I, _P]),

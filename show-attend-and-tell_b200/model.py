@@ -332,6 +332,19 @@ class CaptionGenerator(object):
         self._keep["loop"] = (contexts, forced_words, tokens, logits)
         return tokens, logits
 
+    def loop_host_submit(self, contexts_host, num_steps, tokens_host, slot, forced_words_host=None):
+        """Pipelined host-buffer greedy loop (sat_decode_loop_host_submit): upload on a copy stream, decode,
+        download; returns at once.  Pair with loop_host_wait(slot).  Host tensors should be pinned."""
+        B = contexts_host.shape[0]
+        self._check(self.lib.sat_decode_loop_host_submit(self._h, self._p(contexts_host), B, num_steps,
+                                                         self._p(forced_words_host), self._p(tokens_host), slot,
+                                                         self._st()))
+        self._keep["pipe%d" % slot] = (contexts_host, tokens_host, forced_words_host)
+
+    def loop_host_wait(self, slot):
+        self._check(self.lib.sat_decode_loop_host_wait(self._h, slot))
+        return self._keep.pop("pipe%d" % slot)[1]
+
     def beam_device(self, contexts, beam_size, num_steps, eos_id):
         torch = self.torch
         n = contexts.shape[0]

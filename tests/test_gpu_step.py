@@ -119,10 +119,39 @@ def test_packed_activation_and_prepass_paths_agree():
         for k, v in opts.items():
             m.set_option(k, v)
         toks[name] = m.decode_loop(ctx, 6, None, want_logits=True)
-    m.set_option("pa", 1); m.set_option("xpack", 1); m.set_option("overlap", 1)
+    m.set_option("pa", 1); m.set_option("xpack", 1); m.set_option("overlap", 2)
     for name in ("prepass", "warps"):
         assert np.array_equal(toks["pa"][0], toks[name][0])
         assert np.array_equal(toks["pa"][1], toks[name][1]), name
+
+
+def test_loop_layouts_agree_and_pipelined_host_api():
+    """The launch layouts of the greedy loop (in-order, two streams, chained on programmatic dependent launch)
+    choose the same words; the pipelined host API returns what the synchronous call returns, batch by batch."""
+    import torch
+    ocfg, w, m = make_pair(64, num_lstm_units=1024, vocabulary_size=10000)
+    rng = np.random.RandomState(5)
+    batches = [R.synth_contexts(ocfg, 64) * np.float32(0.5 + 0.25 * i) for i in range(4)]
+    ref = [m.decode_loop(b, 20) for b in batches]                      # default layout, synchronous host call
+    for overlap, pdl, graphs in ((0, 0, 1), (0, 1, 1), (1, 1, 1), (2, 1, 0), (1, 0, 0)):
+        m.set_option("overlap", overlap); m.set_option("pdl", pdl); m.set_option("graphs", graphs)
+        for rep in range(2):
+            got = m.decode_loop(batches[1], 20)
+            assert np.array_equal(got, ref[1]), (overlap, pdl, graphs, rep)
+    m.set_option("overlap", 2); m.set_option("pdl", 1); m.set_option("graphs", 1)
+    host = [torch.from_numpy(b).pin_memory() for b in batches]
+    toks = [torch.empty(64, 20, dtype=torch.int32).pin_memory() for _ in range(2)]
+    out = []
+    for rep in range(2):                                               # second round replays the captured graphs
+        for i, hb in enumerate(host):
+            m.loop_host_submit(hb, 20, toks[i & 1], i & 1)
+            if i >= 1:
+                out.append(m.loop_host_wait((i - 1) & 1).numpy().copy())
+        out.append(m.loop_host_wait((len(host) - 1) & 1).numpy().copy())
+    for i, o in enumerate(out):
+        assert np.array_equal(o, ref[i % 4]), i
+    with pytest.raises(Exception):
+        m.loop_host_wait(0)                                            # nothing in flight
 
 
 def test_error_behaviour():

@@ -1,9 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -n 3 gpurun_out/pytest_gpu.log
-timeout 600 python tools/sweep.py > gpurun_out/sweep.log 2>&1
-grep -v "timed out" gpurun_out/sweep.log | head -30
-timeout 600 python tools/timeline.py > gpurun_out/timeline.log 2>&1
-grep -A7 "===\|period\|whole" gpurun_out/timeline.log | head -60
+timeout 600 python tools/att_time.py > gpurun_out/att_time.log 2>&1
+cat gpurun_out/att_time.log
