@@ -74,7 +74,7 @@ struct sat_handle {
     sat_dims d;
     int dev = 0, num_sms = 0, smem_optin = 0;
     int opt_gemm = 1, opt_layout = 0, opt_graphs = 1, opt_hoist = 1, opt_coop = 1, opt_xpack = 1;
-    int opt_l2_w = 2, opt_l2_t = 1, opt_l2_ctx = 0;  // weights evict_last, projected contexts evict_first
+    int opt_l2_w = 2, opt_l2_t = 1, opt_l2_ctx = 1;  // weights evict_last; both attention streams evict_first
     bool weights_locked = false;
 
     Layer init_a1, init_a2, init_b1, init_b2;  // 1-layer mode uses init_a1 / init_b1 as fc_a / fc_b
@@ -129,7 +129,7 @@ struct sat_handle {
     uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0;
+    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0, opt_l2_vocab = -1, opt_l2_prefetch = 0;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -395,6 +395,8 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
         return SAT_OK;
     } else if (k == "trace_at") { h->trace_at = (int)value; return SAT_OK; }
     else if (k == "l2_w") h->opt_l2_w = (int)value;
+    else if (k == "l2_vocab") h->opt_l2_vocab = (int)value;
+    else if (k == "l2_prefetch") h->opt_l2_prefetch = (int)value;
     else if (k == "l2_t") h->opt_l2_t = (int)value;
     else if (k == "l2_ctx") h->opt_l2_ctx = (int)value;
     else if (k == "profile") {
@@ -625,10 +627,11 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.nprob = n;
     L.layout_mode = h->opt_layout;
     L.stages = lin_pick_stages(max_rt);
-    L.l2_w = h->opt_l2_w;
+    L.l2_w = (h->cur_tag == kTagDec2 && h->opt_l2_vocab >= 0) ? h->opt_l2_vocab : h->opt_l2_w;   // vocabulary layer: own policy
     L.dbg = nullptr;
     L.tl = nullptr;
     L.warm_epilogue = h->opt_warm;
+    L.l2_prefetch = h->opt_l2_prefetch;
     if (h->opt_trace == 1 && begin <= 1024 && h->trace_at-- == 0) L.dbg = h->trace;
     if (h->opt_trace == 3 && h->tl_count < 4000) {
         L.tl = h->trace + 4 * h->tl_count++;

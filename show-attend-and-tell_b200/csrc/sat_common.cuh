@@ -64,6 +64,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Bring a span of global memory into L2 without a destination (no shared memory, no barrier): used by kernels that
+// were launched early (programmatic dependent launch) to pull their weight stream towards the SMs while the
+// predecessor is still in its tail and the HBM channels are idle.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // L2 eviction-priority policies for TMA loads: 0 = none, 1 = evict_first (streamed once per step),
 // 2 = evict_last (weights: keep resident in the 126 MB L2 across decode steps), 3 = evict_normal.
 __device__ __forceinline__ uint64_t l2_policy(int kind) {

@@ -200,6 +200,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             if (!L.pdl) tl_go(L.tl);
             if (L.pdl) {
                 for (int it = 0; it < pre; ++it) load_w(it);
+                // the rest of this CTA's weight stream: into L2 while the predecessor drains
+                if (L.l2_prefetch)
+                    for (int it = pre; it < nkb; ++it) prefetch_l2_bulk(src + (size_t)it * kWStageBytes, kWStageBytes);
                 pdl_wait();
                 pdl_launch_dependents();
                 tl_go(L.tl);

@@ -1,0 +1,28 @@
+"""L2 eviction-policy sweep of the chained decode loop (config 2)."""
+import itertools, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sat_b200
+B, L, D, H, V, T = 64, 196, 512, 1024, 10000, 20
+cfg = sat_b200.Config(batch_size=B, beam_size=1, num_ctx=L, dim_ctx=D, num_lstm_units=H, vocabulary_size=V, max_caption_length=T)
+m = sat_b200.CaptionGenerator(cfg)
+g = torch.Generator().manual_seed(1)
+m.set_weights({n: torch.rand(*s, generator=g) * 0.16 - 0.08 for n, s in sat_b200.weight_shapes(cfg).items()})
+pool = [torch.relu(torch.randn(B, L, D, generator=g)).cuda() for _ in range(6)]
+def timeit(n=30):
+    for i in range(14):
+        m.loop_device(pool[i % 6], T)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(m.stream):
+        a.record(m.stream)
+        for i in range(n):
+            m.loop_device(pool[i % 6], T)
+        b.record(m.stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+m.set_option("graphs", 0)   # options are baked into captured graphs: measure eagerly
+for pf, lw, lv in [(0, 2, -1), (1, 2, -1), (1, 2, 1), (1, 0, -1), (1, 1, -1), (0, 2, -1), (1, 2, -1)]:
+    m.set_option("l2_prefetch", pf); m.set_option("l2_w", lw); m.set_option("l2_vocab", lv)
+    ms = min(timeit() for _ in range(2))
+    print("l2_prefetch=%d l2_w=%d l2_vocab=%2d : %.3f ms/loop  %.1f us/step" % (pf, lw, lv, ms, ms * 1e3 / T), flush=True)

@@ -13,12 +13,11 @@ m.set_weights({n: torch.rand(*s, generator=g) * 0.16 - 0.08 for n, s in sat_b200
 ctx = torch.relu(torch.randn(B, L, D, generator=g)).cuda()
 labels = ["start", "producers start", "row loop: sums + bias ready (last row)", "row loop: activation done (last row)", "MMA: first W stage",
           "MMA: first X stage", "MMA: all issued", "epilogue: accumulator ready", "partials written",
-          "rendezvous passed", "end", "am: candidates stored", "am: last CTA elected", "am: words picked", "am: emb packed", "row loop begins"]
+          "rendezvous passed", "end", "am: candidates stored", "am: grid barrier passed", "am: rows of this CTA finished", "-", "row loop begins"]
 want = set(int(a) for a in sys.argv[1:]) or {79}
-for overlap, warm in ((0, 1), (0, 0)):
+for overlap, warm in ((2, 1),):
     m.set_option("overlap", overlap)
     m.set_option("warm", warm)
-    print("##### warm =", warm)
     m.set_option("graphs", 0)
     for i in range(3):
         m.loop_device(ctx, T)
