@@ -427,26 +427,35 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 peer[r] = (splits > 1 && r < splits) ? dsmem_map(tile_addr, (uint32_t)(dry ? split : r)) : tile_addr;
             if (pt == 0 && !dry) trace_stamp(L.dbg, 15);
             if (row_loop) {
+                // the partial tiles of the NEXT row are requested before the current row is finished: the DSMEM /
+                // shared-memory round trips of a thread's (typically two) rows overlap
+                float4 cur[8], nxt[8];
+                auto fetch = [&](float4 (&dst)[8], int idx) {
+                    const int bb = idx >> 5;
+                    if (splits == 1) {
+                        dst[0] = *reinterpret_cast<const float4*>(tile_s + bb * kTileN + 4 * u);
+                    } else {
+                        const uint32_t off = (uint32_t)(bb * kTileN + 4 * u) * 4u;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (r < splits) dst[r] = ld_dsmem_f4(peer[r] + off);
+                    }
+                };
+                if (lo + pt < hi) fetch(cur, lo + pt);
+                if (lo + pt + kLinProducers < hi) fetch(nxt, lo + pt + kLinProducers);
 #pragma unroll 1
                 for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
                     const int bb = idx >> 5;
                     float cprev = idx == lo + pt ? cpre[0] : cpre[1];
                     if (epi == kEpiLstm && unit < Hh && idx >= lo + pt + 2 * kLinProducers)
                         cprev = c_in[(size_t)(row0 + bb) * Hh + unit];
-                    float4 g;
-                    if (splits == 1) {
-                        g = *reinterpret_cast<const float4*>(tile_s + bb * kTileN + 4 * u);
-                    } else {
-                        const uint32_t off = (uint32_t)(bb * kTileN + 4 * u) * 4u;
-                        float4 part[8];
+                    float4 g = cur[0];
 #pragma unroll
-                        for (int r = 0; r < 8; ++r)
-                            if (r < splits) part[r] = ld_dsmem_f4(peer[r] + off);
-                        g = part[0];
+                    for (int r = 1; r < 8; ++r)
+                        if (r < splits) { g.x += cur[r].x; g.y += cur[r].y; g.z += cur[r].z; g.w += cur[r].w; }
 #pragma unroll
-                        for (int r = 1; r < 8; ++r)
-                            if (r < splits) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
-                    }
+                    for (int r = 0; r < 8; ++r) cur[r] = nxt[r];
+                    if (idx + 2 * kLinProducers < hi) fetch(nxt, idx + 2 * kLinProducers);
                     if (!do_am) { g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w; }
                     if (pt == 0 && !dry && L.dbg && g.x != 12345.678f) trace_stamp(L.dbg, 2);   // partial sums arrived
                     if (epi == kEpiLstm) {

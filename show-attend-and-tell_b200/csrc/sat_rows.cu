@@ -45,16 +45,44 @@ __device__ __forceinline__ float block_sum(float x, float* sm) {
     return r;
 }
 
+// One block per row.  The row (V <= 256*4*kRowCache floats, V % 4 == 0) is read from global memory ONCE into
+// registers (float4 per thread and 1024 elements) and the three passes — arg-max, sum of exponentials,
+// probabilities + top-k — run on the cached copy; wider or unaligned rows re-read global memory (CACHED = false).
+constexpr int kRowCache = 12;
+
+template <bool CACHED>
 __global__ void __launch_bounds__(kRowThreads) rows_softmax_kernel(const RowsParams p) {
     __shared__ ValIdx sm_vi[kRowThreads / 32];
     __shared__ float sm_f[kRowThreads / 32];
     const int row = blockIdx.x;
     const float* x = p.logits + (size_t)row * p.V;
+    const int V = p.V, n4 = V >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4 c[CACHED ? kRowCache : 1];
+    if (CACHED) {
+#pragma unroll
+        for (int k = 0; k < kRowCache; ++k) {
+            const int i4 = threadIdx.x + kRowThreads * k;
+            c[k] = i4 < n4 ? x4[i4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+    }
+    auto elem = [&](int k, int e) -> float { return e == 0 ? c[k].x : e == 1 ? c[k].y : e == 2 ? c[k].z : c[k].w; };
 
     ValIdx best = {-INFINITY, 0x7fffffff};
-    for (int i = threadIdx.x; i < p.V; i += kRowThreads) {
-        const float v = x[i];
-        if (better(v, i, best.v, best.i)) { best.v = v; best.i = i; }
+    if (CACHED) {
+#pragma unroll
+        for (int k = 0; k < kRowCache; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 4 * (threadIdx.x + kRowThreads * k) + e;
+                const float v = elem(k, e);
+                if (i < V && better(v, i, best.v, best.i)) { best.v = v; best.i = i; }
+            }
+    } else {
+        for (int i = threadIdx.x; i < V; i += kRowThreads) {
+            const float v = x[i];
+            if (better(v, i, best.v, best.i)) { best.v = v; best.i = i; }
+        }
     }
     best = block_best(best, sm_vi);
     const float m = best.v;
@@ -66,34 +94,69 @@ __global__ void __launch_bounds__(kRowThreads) rows_softmax_kernel(const RowsPar
     if (!p.probs && p.topk == 0) return;  // greedy / teacher-forced loops only need the argmax
 
     float s = 0.f;
-    for (int i = threadIdx.x; i < p.V; i += kRowThreads) s += expf(x[i] - m);
+    if (CACHED) {
+#pragma unroll
+        for (int k = 0; k < kRowCache; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s += expf(elem(k, e) - m);          // padding is -inf: contributes 0
+    } else {
+        for (int i = threadIdx.x; i < V; i += kRowThreads) s += expf(x[i] - m);
+    }
     s = block_sum(s, sm_f);
     const float inv = 1.0f / s;
 
-    // probabilities + thread-local top-K (K <= kMaxTopK), sorted by (prob desc, index asc)
+    // probabilities + thread-local top-kMaxTopK, kept sorted by (prob desc, index asc) with a compare-and-swap
+    // chain on registers (static indices only)
     float tv[kMaxTopK];
     int ti[kMaxTopK];
 #pragma unroll
     for (int k = 0; k < kMaxTopK; ++k) { tv[k] = -1.f; ti[k] = 0x7fffffff; }
-    float* pr = p.probs ? p.probs + (size_t)row * p.V : nullptr;
-    for (int i = threadIdx.x; i < p.V; i += kRowThreads) {
-        const float pv = expf(x[i] - m) * inv;
-        if (pr) pr[i] = pv;
-        if (p.topk > 0 && better(pv, i, tv[p.topk - 1], ti[p.topk - 1])) {
-            int k = p.topk - 1;
-            while (k > 0 && better(pv, i, tv[k - 1], ti[k - 1])) { tv[k] = tv[k - 1]; ti[k] = ti[k - 1]; --k; }
-            tv[k] = pv; ti[k] = i;
+    auto offer = [&](float pv, int i) {
+        if (!better(pv, i, tv[kMaxTopK - 1], ti[kMaxTopK - 1])) return;
+#pragma unroll
+        for (int k = 0; k < kMaxTopK; ++k) {
+            if (better(pv, i, tv[k], ti[k])) {
+                const float fv = tv[k]; const int fi = ti[k];
+                tv[k] = pv; ti[k] = i;
+                pv = fv; i = fi;
+            }
+        }
+    };
+    float* pr = p.probs ? p.probs + (size_t)row * V : nullptr;
+    if (CACHED) {
+#pragma unroll
+        for (int k = 0; k < kRowCache; ++k) {
+            const int i4 = threadIdx.x + kRowThreads * k;
+            float pv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pv[e] = expf(elem(k, e) - m) * inv;
+            if (i4 < n4) {
+                if (pr) *reinterpret_cast<float4*>(pr + 4 * i4) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                if (p.topk > 0) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) offer(pv[e], 4 * i4 + e);
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < V; i += kRowThreads) {
+            const float pv = expf(x[i] - m) * inv;
+            if (pr) pr[i] = pv;
+            if (p.topk > 0) offer(pv, i);
         }
     }
     if (p.topk > 0) {
-        int head = 0;
         for (int k = 0; k < p.topk; ++k) {
-            ValIdx c;
-            c.v = head < p.topk ? tv[head] : -1.f;
-            c.i = head < p.topk ? ti[head] : 0x7fffffff;
-            // local arrays are indexed dynamically only through `head`; keep it simple
-            const ValIdx w = block_best(c, sm_vi);
-            if (w.i == c.i && w.v == c.v && c.i != 0x7fffffff) ++head;
+            ValIdx cnd;
+            cnd.v = tv[0];
+            cnd.i = ti[0];
+            const ValIdx w = block_best(cnd, sm_vi);
+            if (w.i == cnd.i && w.v == cnd.v && cnd.i != 0x7fffffff) {   // this thread's head won: pop it
+#pragma unroll
+                for (int q = 0; q + 1 < kMaxTopK; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
+                tv[kMaxTopK - 1] = -1.f;
+                ti[kMaxTopK - 1] = 0x7fffffff;
+            }
             if (threadIdx.x == 0) {
                 p.topk_idx[(size_t)row * p.topk + k] = w.i;
                 p.topk_p[(size_t)row * p.topk + k] = w.v;
@@ -104,7 +167,10 @@ __global__ void __launch_bounds__(kRowThreads) rows_softmax_kernel(const RowsPar
 
 cudaError_t rows_softmax_launch(const RowsParams& p, int rows, cudaStream_t st) {
     if (p.topk > kMaxTopK) return cudaErrorInvalidValue;
-    rows_softmax_kernel<<<rows, kRowThreads, 0, st>>>(p);
+    const bool cached = (p.V % 4) == 0 && p.V <= kRowThreads * 4 * kRowCache &&
+                        (reinterpret_cast<uintptr_t>(p.logits) % 16) == 0 && (!p.probs || (reinterpret_cast<uintptr_t>(p.probs) % 16) == 0);
+    if (cached) rows_softmax_kernel<true><<<rows, kRowThreads, 0, st>>>(p);
+    else rows_softmax_kernel<false><<<rows, kRowThreads, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -140,24 +206,34 @@ __device__ void heap_siftup(T* h, int n, int pos) {
     heap_siftdown(h, startpos, pos);
 }
 
-__global__ void __launch_bounds__(128) beam_update_kernel(const BeamParams p) {
+__global__ void __launch_bounds__(256) beam_update_kernel(const BeamParams p) {
     __shared__ PItem newp[kMaxBeam];
     __shared__ int newn;
+    __shared__ int s_idx[kMaxBeam * (kMaxBeam + 1)];
+    __shared__ float s_p[kMaxBeam * (kMaxBeam + 1)];
+    __shared__ double s_ps[kMaxBeam];
     const int img = blockIdx.x;
     const int beam = p.beam, K = p.beam + 1, G = p.nlive, T = p.T, idx = p.step;
     const int* sent_cur = p.sent[idx & 1] + (size_t)img * beam * T;
     int* sent_next = p.sent[(idx + 1) & 1] + (size_t)img * beam * T;
+
+    // the candidates of this image (G live beams x K words) and the beams' scores: one parallel round trip
+    if ((int)threadIdx.x < G * K) {
+        s_idx[threadIdx.x] = p.topk_idx[(size_t)img * G * K + threadIdx.x];
+        s_p[threadIdx.x] = p.topk_p[(size_t)img * G * K + threadIdx.x];
+    }
+    if ((int)threadIdx.x < G) s_ps[threadIdx.x] = idx == 0 ? 1.0 : p.part_score[(size_t)img * beam + threadIdx.x];   // base_model.py:178
+    __syncthreads();
 
     if (threadIdx.x == 0) {
         int np = 0;
         CItem* ch = p.comp_heap + (size_t)img * beam;
         int cn = p.comp_n[img];
         for (int b = 0; b < G; ++b) {
-            const double ps = idx == 0 ? 1.0 : p.part_score[(size_t)img * beam + b];   // base_model.py:178
-            const size_t row = (size_t)img * G + b;
+            const double ps = s_ps[b];
             for (int j = 0; j < K; ++j) {
-                const int w = p.topk_idx[row * K + j];
-                const double sc = ps * (double)p.topk_p[row * K + j];                   // base_model.py:224
+                const int w = s_idx[b * K + j];
+                const double sc = ps * (double)s_p[b * K + j];                           // base_model.py:224
                 if (w == p.eos_id) {                                                   // base_model.py:229-230
                     int slot = -1;
                     if (cn < beam) {
@@ -193,20 +269,24 @@ __global__ void __launch_bounds__(128) beam_update_kernel(const BeamParams p) {
         for (int j = 0; j < np; ++j) p.part_score[(size_t)img * beam + j] = newp[j].score;
     }
     __syncthreads();
-    // materialise the surviving beams: sentences, last word, LSTM state rows
+    // materialise the surviving beams: sentences, last word, LSTM state rows (float4 rows, all beams in one sweep)
     const int np = newn;
-    for (int j = 0; j < np; ++j) {
-        const int b = newp[j].parent, w = newp[j].word;
-        for (int t = threadIdx.x; t < idx; t += blockDim.x) sent_next[(size_t)j * T + t] = sent_cur[(size_t)b * T + t];
-        if (threadIdx.x == 0) {
-            sent_next[(size_t)j * T + idx] = w;
-            p.next_word[(size_t)img * beam + j] = w;
-        }
-        const float* cs = p.c_out + ((size_t)img * G + b) * p.H;
-        const float* hs = p.h_out + ((size_t)img * G + b) * p.H;
-        float* cd = p.c_next + ((size_t)img * beam + j) * p.H;
-        float* hd = p.h_next + ((size_t)img * beam + j) * p.H;
-        for (int u = threadIdx.x; u < p.H; u += blockDim.x) { cd[u] = cs[u]; hd[u] = hs[u]; }
+    for (int u = threadIdx.x; u < np * idx; u += blockDim.x) {
+        const int j = u / idx, t = u - j * idx;
+        sent_next[(size_t)j * T + t] = sent_cur[(size_t)newp[j].parent * T + t];
+    }
+    if ((int)threadIdx.x < np) {
+        sent_next[(size_t)threadIdx.x * T + idx] = newp[threadIdx.x].word;
+        p.next_word[(size_t)img * beam + threadIdx.x] = newp[threadIdx.x].word;
+    }
+    const int H4 = p.H >> 2;   // H % 32 == 0 (sat_create)
+    for (int u = threadIdx.x; u < np * H4; u += blockDim.x) {
+        const int j = u / H4, q = u - j * H4;
+        const int b = newp[j].parent;
+        reinterpret_cast<float4*>(p.c_next + ((size_t)img * beam + j) * p.H)[q] =
+            reinterpret_cast<const float4*>(p.c_out + ((size_t)img * G + b) * p.H)[q];
+        reinterpret_cast<float4*>(p.h_next + ((size_t)img * beam + j) * p.H)[q] =
+            reinterpret_cast<const float4*>(p.h_out + ((size_t)img * G + b) * p.H)[q];
     }
 }
 
@@ -262,7 +342,7 @@ __global__ void beam_finalize_kernel(const BeamParams p) {
 
 cudaError_t beam_update_launch(const BeamParams& p, cudaStream_t st) {
     if (p.beam > kMaxBeam) return cudaErrorInvalidValue;
-    beam_update_kernel<<<p.NI, 128, 0, st>>>(p);
+    beam_update_kernel<<<p.NI, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t beam_finalize_launch(const BeamParams& p, cudaStream_t st) {

@@ -1,6 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python tools/l2_sweep.py > gpurun_out/l2_sweep.log 2>&1
-cat gpurun_out/l2_sweep.log
+timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -n 3 gpurun_out/pytest_gpu.log
 timeout 600 python tools/timeline.py > gpurun_out/timeline.log 2>&1
-grep -A8 "===\|period\|whole" gpurun_out/timeline.log | head -24
+grep -A8 "===\|period\|whole" gpurun_out/timeline.log | head -12
+timeout 600 python tools/sweep.py > gpurun_out/sweep.log 2>&1
+head -3 gpurun_out/sweep.log
