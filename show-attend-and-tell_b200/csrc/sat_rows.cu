@@ -45,46 +45,41 @@ __device__ __forceinline__ float block_sum(float x, float* sm) {
     return r;
 }
 
-// One block per row.  The row (V <= 256*4*kRowCache floats, V % 4 == 0) is read from global memory ONCE into
-// registers (float4 per thread and 1024 elements) and the three passes — arg-max, sum of exponentials,
-// probabilities + top-k — run on the cached copy; wider or unaligned rows re-read global memory (CACHED = false).
-constexpr int kRowCache = 12;
-
+// One block per row.  The row is read from global memory ONCE into shared memory (CACHED: V % 4 == 0 and 4*V bytes
+// of dynamic shared memory available) and the three passes — arg-max, sum of exponentials, probabilities + top-k
+// — run on that copy in small ROLLED loops (this kernel runs once per step from a cold instruction cache: a
+// fully unrolled register-cached version executed 6 k instructions per warp and was instruction-fetch bound).
 template <bool CACHED>
 __global__ void __launch_bounds__(kRowThreads) rows_softmax_kernel(const RowsParams p) {
+    extern __shared__ __align__(16) float row_s[];
     __shared__ ValIdx sm_vi[kRowThreads / 32];
     __shared__ float sm_f[kRowThreads / 32];
     const int row = blockIdx.x;
     const float* x = p.logits + (size_t)row * p.V;
     const int V = p.V, n4 = V >> 2;
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-    float4 c[CACHED ? kRowCache : 1];
-    if (CACHED) {
-#pragma unroll
-        for (int k = 0; k < kRowCache; ++k) {
-            const int i4 = threadIdx.x + kRowThreads * k;
-            c[k] = i4 < n4 ? x4[i4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
-    }
-    auto elem = [&](int k, int e) -> float { return e == 0 ? c[k].x : e == 1 ? c[k].y : e == 2 ? c[k].z : c[k].w; };
+    const float4* src4 = CACHED ? reinterpret_cast<const float4*>(row_s) : reinterpret_cast<const float4*>(x);
 
     ValIdx best = {-INFINITY, 0x7fffffff};
     if (CACHED) {
-#pragma unroll
-        for (int k = 0; k < kRowCache; ++k)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int i = 4 * (threadIdx.x + kRowThreads * k) + e;
-                const float v = elem(k, e);
-                if (i < V && better(v, i, best.v, best.i)) { best.v = v; best.i = i; }
-            }
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4* d4 = reinterpret_cast<float4*>(row_s);
+#pragma unroll 2
+        for (int i4 = threadIdx.x; i4 < n4; i4 += kRowThreads) {
+            const float4 v = x4[i4];
+            d4[i4] = v;
+            const int i = 4 * i4;
+            if (better(v.x, i, best.v, best.i)) { best.v = v.x; best.i = i; }
+            if (better(v.y, i + 1, best.v, best.i)) { best.v = v.y; best.i = i + 1; }
+            if (better(v.z, i + 2, best.v, best.i)) { best.v = v.z; best.i = i + 2; }
+            if (better(v.w, i + 3, best.v, best.i)) { best.v = v.w; best.i = i + 3; }
+        }
     } else {
         for (int i = threadIdx.x; i < V; i += kRowThreads) {
             const float v = x[i];
             if (better(v, i, best.v, best.i)) { best.v = v; best.i = i; }
         }
     }
-    best = block_best(best, sm_vi);
+    best = block_best(best, sm_vi);       // (its barriers also publish row_s)
     const float m = best.v;
     if (threadIdx.x == 0) {
         if (p.argmax) p.argmax[row] = best.i;
@@ -95,10 +90,11 @@ __global__ void __launch_bounds__(kRowThreads) rows_softmax_kernel(const RowsPar
 
     float s = 0.f;
     if (CACHED) {
-#pragma unroll
-        for (int k = 0; k < kRowCache; ++k)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) s += expf(elem(k, e) - m);          // padding is -inf: contributes 0
+#pragma unroll 1
+        for (int i4 = threadIdx.x; i4 < n4; i4 += kRowThreads) {
+            const float4 v = src4[i4];
+            s += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+        }
     } else {
         for (int i = threadIdx.x; i < V; i += kRowThreads) s += expf(x[i] - m);
     }
@@ -123,22 +119,15 @@ __global__ void __launch_bounds__(kRowThreads) rows_softmax_kernel(const RowsPar
         }
     };
     float* pr = p.probs ? p.probs + (size_t)row * V : nullptr;
-    if (CACHED) {
-#pragma unroll
-        for (int k = 0; k < kRowCache; ++k) {
-            const int i4 = threadIdx.x + kRowThreads * k;
-            float pv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pv[e] = expf(elem(k, e) - m) * inv;
-            if (i4 < n4) {
-                if (pr) *reinterpret_cast<float4*>(pr + 4 * i4) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                if (p.topk > 0) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) offer(pv[e], 4 * i4 + e);
-                }
-            }
-        }
-    } else {
+    const int n_el = CACHED ? V : 0;
+#pragma unroll 1
+    for (int i = threadIdx.x; i < n_el; i += kRowThreads) {      // element-wise: one copy of `offer` in the binary
+        const float pv = expf(row_s[i] - m) * inv;
+        if (pr) pr[i] = pv;
+        if (p.topk > 0) offer(pv, i);
+    }
+    if (!CACHED) {
+#pragma unroll 1
         for (int i = threadIdx.x; i < V; i += kRowThreads) {
             const float pv = expf(x[i] - m) * inv;
             if (pr) pr[i] = pv;
@@ -146,6 +135,7 @@ __global__ void __launch_bounds__(kRowThreads) rows_softmax_kernel(const RowsPar
         }
     }
     if (p.topk > 0) {
+#pragma unroll 1
         for (int k = 0; k < p.topk; ++k) {
             ValIdx cnd;
             cnd.v = tv[0];
@@ -167,10 +157,19 @@ __global__ void __launch_bounds__(kRowThreads) rows_softmax_kernel(const RowsPar
 
 cudaError_t rows_softmax_launch(const RowsParams& p, int rows, cudaStream_t st) {
     if (p.topk > kMaxTopK) return cudaErrorInvalidValue;
-    const bool cached = (p.V % 4) == 0 && p.V <= kRowThreads * 4 * kRowCache &&
-                        (reinterpret_cast<uintptr_t>(p.logits) % 16) == 0 && (!p.probs || (reinterpret_cast<uintptr_t>(p.probs) % 16) == 0);
-    if (cached) rows_softmax_kernel<true><<<rows, kRowThreads, 0, st>>>(p);
-    else rows_softmax_kernel<false><<<rows, kRowThreads, 0, st>>>(p);
+    const size_t bytes = (size_t)p.V * sizeof(float);
+    const bool cached = (p.V % 4) == 0 && bytes <= 96 * 1024 && (reinterpret_cast<uintptr_t>(p.logits) % 16) == 0;
+    if (cached) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(rows_softmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        rows_softmax_kernel<true><<<rows, kRowThreads, bytes, st>>>(p);
+    } else {
+        rows_softmax_kernel<false><<<rows, kRowThreads, 0, st>>>(p);
+    }
     return cudaGetLastError();
 }
 
