@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             *P.am_ctr = 0u;
                             __threadfence();
                             atomicAdd(P.am_ctr + 1, 1u);          // opens the generation: every candidate is visible
-                        } else {
+                        } else if (local < P.rows) {             // (CTAs with no row to finish leave at once)
                             const long long t0 = clock64();
                             while (ld_acquire_gpu(P.am_ctr + 1) == am_gen0) {
                                 if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
