@@ -1036,28 +1036,29 @@ cudaError_t att_launch(const AttParams& p, cudaStream_t st) {
 }
 
 // mean over the L locations (model.py:240): out[i, d] = (1/L) sum_l ctx[i, l, d]
-// One block per (image, 256-feature slab): 4 row groups x 64 float4 columns, rows summed in location order per
-// group and the 4 groups added in fixed order (bit-reproducible); loads of 4 rows are in flight per thread.
+// One block per (image, 128-feature slab): 8 row groups x 32 float4 columns, rows summed in location order per
+// group and the 8 groups added in fixed order (bit-reproducible); loads of 4 rows are in flight per thread.
 __global__ void __launch_bounds__(256) ctx_mean_kernel(const float* __restrict__ ctx, float* __restrict__ out, int L, int D) {
-    __shared__ float4 red[4][64];
+    constexpr int RG = 8, C4 = 32;
+    __shared__ float4 red[RG][C4];
     const int i = blockIdx.y;
-    const int c4 = threadIdx.x & 63, rg = threadIdx.x >> 6;
-    const int d = blockIdx.x * 256 + 4 * c4;
+    const int c4 = threadIdx.x % C4, rg = threadIdx.x / C4;
+    const int d = blockIdx.x * (4 * C4) + 4 * c4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (d < D) {
         const float* p = ctx + (size_t)i * L * D + d;
         int l = rg;
-        for (; l + 12 < L; l += 16) {
+        for (; l + 3 * RG < L; l += 4 * RG) {
             const float4 a = *reinterpret_cast<const float4*>(p + (size_t)l * D);
-            const float4 b = *reinterpret_cast<const float4*>(p + (size_t)(l + 4) * D);
-            const float4 c = *reinterpret_cast<const float4*>(p + (size_t)(l + 8) * D);
-            const float4 e = *reinterpret_cast<const float4*>(p + (size_t)(l + 12) * D);
+            const float4 b = *reinterpret_cast<const float4*>(p + (size_t)(l + RG) * D);
+            const float4 c = *reinterpret_cast<const float4*>(p + (size_t)(l + 2 * RG) * D);
+            const float4 e = *reinterpret_cast<const float4*>(p + (size_t)(l + 3 * RG) * D);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
             s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
             s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
             s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
         }
-        for (; l < L; l += 4) {
+        for (; l < L; l += RG) {
             const float4 a = *reinterpret_cast<const float4*>(p + (size_t)l * D);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
@@ -1067,14 +1068,14 @@ __global__ void __launch_bounds__(256) ctx_mean_kernel(const float* __restrict__
     if (rg == 0 && d < D) {
         float4 t = red[0][c4];
 #pragma unroll
-        for (int r = 1; r < 4; ++r) { t.x += red[r][c4].x; t.y += red[r][c4].y; t.z += red[r][c4].z; t.w += red[r][c4].w; }
+        for (int r = 1; r < RG; ++r) { t.x += red[r][c4].x; t.y += red[r][c4].y; t.z += red[r][c4].z; t.w += red[r][c4].w; }
         const float inv = 1.0f / (float)L;
         *reinterpret_cast<float4*>(out + (size_t)i * D + d) = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
     }
 }
 
 cudaError_t ctx_mean_launch(const float* ctx, float* out, int NI, int L, int D, cudaStream_t st) {
-    dim3 grid((D + 255) / 256, NI);
+    dim3 grid((D + 127) / 128, NI);
     ctx_mean_kernel<<<grid, 256, 0, st>>>(ctx, out, L, D);
     return cudaGetLastError();
 }

@@ -385,7 +385,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         // generation of the "words picked" signal, sampled before any CTA of this launch can have raised it
         const unsigned am_gen0 = (do_am && pt == 0) ? ld_acquire_gpu(P.am_ctr + 1) : 0u;
 #pragma unroll 1
-        for (int pass = (xtma && L.warm_epilogue) ? 0 : 1; pass < 2; ++pass) {
+        // (the warm-up pass only pays for short epilogues: a long row loop warms itself)
+        for (int pass = (xtma && L.warm_epilogue && hi - lo <= 4 * kLinProducers) ? 0 : 1; pass < 2; ++pass) {
             const bool dry = pass == 0;
             if (!dry) {
                 // ---- part 1: accumulator tile TMEM -> shared memory (two warps per TMEM lane quadrant).
@@ -441,21 +442,28 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             if (r < splits) dst[r] = ld_dsmem_f4(peer[r] + off);
                     }
                 };
-                if (lo + pt < hi) fetch(cur, lo + pt);
-                if (lo + pt + kLinProducers < hi) fetch(nxt, lo + pt + kLinProducers);
+                if (splits > 1) {
+                    if (lo + pt < hi) fetch(cur, lo + pt);
+                    if (lo + pt + kLinProducers < hi) fetch(nxt, lo + pt + kLinProducers);
+                }
 #pragma unroll 1
                 for (int idx = lo + pt; idx < hi; idx += kLinProducers) {
                     const int bb = idx >> 5;
                     float cprev = idx == lo + pt ? cpre[0] : cpre[1];
                     if (epi == kEpiLstm && unit < Hh && idx >= lo + pt + 2 * kLinProducers)
                         cprev = c_in[(size_t)(row0 + bb) * Hh + unit];
-                    float4 g = cur[0];
+                    float4 g;
+                    if (splits == 1) {
+                        g = *reinterpret_cast<const float4*>(tile_s + bb * kTileN + 4 * u);
+                    } else {
+                        g = cur[0];
 #pragma unroll
-                    for (int r = 1; r < 8; ++r)
-                        if (r < splits) { g.x += cur[r].x; g.y += cur[r].y; g.z += cur[r].z; g.w += cur[r].w; }
+                        for (int r = 1; r < 8; ++r)
+                            if (r < splits) { g.x += cur[r].x; g.y += cur[r].y; g.z += cur[r].z; g.w += cur[r].w; }
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) cur[r] = nxt[r];
-                    if (idx + 2 * kLinProducers < hi) fetch(nxt, idx + 2 * kLinProducers);
+                        for (int r = 0; r < 8; ++r) cur[r] = nxt[r];
+                        if (idx + 2 * kLinProducers < hi) fetch(nxt, idx + 2 * kLinProducers);
+                    }
                     if (!do_am) { g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w; }
                     if (pt == 0 && !dry && L.dbg && g.x != 12345.678f) trace_stamp(L.dbg, 2);   // partial sums arrived
                     if (epi == kEpiLstm) {
