@@ -673,11 +673,13 @@ static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStre
 
 // initialize (model.py:239-242, 358-393)
 static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st,
-                          uint8_t* h0_pa = nullptr) {
+                          uint8_t* h0_pa = nullptr, bool mean_ready = false) {
     const sat_dims& d = h->d;
     h->cur_tag = kTagInit;
-    CK(ctx_mean_launch(ctx, h->mean, n_img, d.num_ctx, d.dim_ctx, st));
-    h->launches += 1;
+    if (!mean_ready) {
+        CK(ctx_mean_launch(ctx, h->mean, n_img, d.num_ctx, d.dim_ctx, st));
+        h->launches += 1;
+    }
     LinProblem P[2];
     if (d.num_initalize_layers == 1) {
         RET(plan(h, h->init_a1, P[0], {seg(h->mean, d.dim_ctx, d.dim_ctx)}, n_img, kEpiBias, c0, d.num_lstm_units, st, 0, 2));
@@ -698,12 +700,19 @@ static int run_initialize(sat_handle* h, const float* ctx, int n_img, float* c0,
 static int prepare_impl(sat_handle* h, const float* ctx, int n_img, float* c0, float* h0, cudaStream_t st,
                         uint8_t* h0_pa = nullptr) {
     if (n_img < 1 || n_img > h->max_rows) return fail(SAT_ERR_INVALID, "n_img %d outside [1, %d]", n_img, h->max_rows);
+    // the mean of the contexts first: the projection and the initialize layers are then consecutive dense
+    // launches, chained by programmatic dependent launch instead of separated by a fully serialised small kernel
+    const bool want_init = c0 && h0;
+    if (want_init) {
+        CK(ctx_mean_launch(ctx, h->mean, n_img, h->d.num_ctx, h->d.dim_ctx, st));
+        h->launches += 1;
+    }
     if (h->opt_hoist) {
         RET(project_contexts(h, ctx, n_img, st));
         h->prep_ctx = ctx;
         h->prep_ni = n_img;
     }
-    if (c0 && h0) RET(run_initialize(h, ctx, n_img, c0, h0, st, h0_pa));
+    if (want_init) RET(run_initialize(h, ctx, n_img, c0, h0, st, h0_pa, true));
     return SAT_OK;
 }
 

@@ -427,7 +427,32 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             for (int r = 0; r < 8; ++r)   // (dry: the own tile stands in for every peer)
                 peer[r] = (splits > 1 && r < splits) ? dsmem_map(tile_addr, (uint32_t)(dry ? split : r)) : tile_addr;
             if (pt == 0 && !dry) trace_stamp(L.dbg, 15);
-            if (row_loop) {
+            const bool long_rows = row_loop && splits == 1 && epi != kEpiLstm && !out_pa && vec_out && !dry &&
+                                   hi - lo > 4 * kLinProducers;
+            if (long_rows) {
+                // many rows per warp and nothing but bias / tanh / a coalesced store to do (context projection,
+                // wide batches): four rows per iteration keep four shared-memory loads, activation chains and
+                // stores in flight instead of one
+#pragma unroll 1
+                for (int idx = lo + pt; idx < hi; idx += 4 * kLinProducers) {
+                    float4 g4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int id = idx + j * kLinProducers;
+                        if (id < hi) g4[j] = *reinterpret_cast<const float4*>(tile_s + (id >> 5) * kTileN + 4 * u);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int id = idx + j * kLinProducers;
+                        if (id < hi) {
+                            float4 g = g4[j];
+                            if (!do_am) { g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w; }
+                            if (epi == kEpiBiasTanh) { g.x = act_tanh(g.x); g.y = act_tanh(g.y); g.z = act_tanh(g.z); g.w = act_tanh(g.w); }
+                            if (out) *reinterpret_cast<float4*>(out + (size_t)(row0 + (id >> 5)) * ldo + ng) = g;
+                        }
+                    }
+                }
+            } else if (row_loop) {
                 // the partial tiles of the NEXT row are requested before the current row is finished: the DSMEM /
                 // shared-memory round trips of a thread's (typically two) rows overlap
                 float4 cur[8], nxt[8];
