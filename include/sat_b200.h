@@ -64,14 +64,27 @@ void sat_destroy(sat_handle* h);
 const char* sat_last_error(void);
 int sat_version(void);
 
-/* integer knobs: "gemm" (1 = tcgen05 [default], 0 = CUDA-core bring-up kernels),
- * "umma_layout" (0 = interleaved, 1 = 128B swizzle; must be set before sat_set_weight),
- * "graphs" (1 = replay CUDA graphs in loops [default]), "hoist" (1 = project the contexts
- * once per image batch [default]; 0 = recompute every step like model.py:259-262),
- * "coop" (1 = cooperative launch of the attention kernel [default]), "xpack" (1 = dense layers
- * convert their activations once in a cooperative pre-pass and fetch them by TMA [default];
- * 0 = per-stage conversion by producer warps), "profile" (1 = record CUDA events around every
- * eager kernel launch; read back with sat_get_info "prof_ns_<family>" / "prof_n_<family>"). */
+/* integer knobs (defaults in brackets; all of them are for experiments and tests, none changes results beyond
+ * the summation order noted):
+ *   "gemm"        1 = tcgen05 [1], 0 = CUDA-core bring-up kernels
+ *   "umma_layout" 0 = interleaved [0], 1 = 128B swizzle; must be set before sat_set_weight
+ *   "graphs"      1 = replay CUDA graphs in loops [1]
+ *   "hoist"       1 = project the contexts once per image batch [1]; 0 = recompute every step like model.py:259-262
+ *   "pa"          1 = activations travel between dense layers as packed UMMA operands [1]
+ *   "xpack"       1 = cooperative activation pre-pass when operands are not packed [1]; 0 = producer warps
+ *   "pdl"         1 = launches carry the programmatic-dependent-launch attribute [1]
+ *   "overlap"     launch layout of the greedy loop: 2 = one stream, the attention kernel of step t+1 runs beside the
+ *                 vocabulary layer of step t without waiting for it [2]; 1 = two streams, fork/join; 0 = in order.
+ *                 (the attention grid, hence the split-L merge order, differs between 0 and 1/2)
+ *   "warm"        1 = idle epilogue warps pre-run the epilogue code to warm the instruction caches [1]
+ *   "att_wpc"     1 = warp-per-chunk attention kernel for 512-float rows [1]
+ *   "att_sms", "att_occ", "att_warps", "l2_w", "l2_vocab", "l2_t", "l2_ctx", "l2_prefetch": grid / cache-policy knobs
+ *   "profile"     1 = record CUDA events around every eager kernel launch; read back with sat_get_info
+ *                 "prof_ns_<family>" / "prof_n_<family>"
+ *   "trace"       1 / 2 / 3 = in-kernel globaltimer stamps of a dense launch ("trace_at") / of the attention kernel /
+ *                 of every launch of a loop (tools/trace*.py, tools/timeline.py)
+ * A handle expects the GPU to itself while a loop runs: the fused arg-max of the vocabulary layer ends in a grid-wide
+ * rendezvous of its one-wave launch (a stuck rendezvous traps with a message after a few seconds). */
 int sat_set_option(sat_handle* h, const char* key, int64_t value);
 int sat_get_info(sat_handle* h, const char* key, int64_t* value);
 

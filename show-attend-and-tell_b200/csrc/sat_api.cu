@@ -104,6 +104,18 @@ struct sat_handle {
     float* stage_ctx = nullptr;
     void* stage_misc = nullptr;
     size_t stage_misc_bytes = 0;
+    // cross-batch overlap of the loop prologue (option "xbatch"): the projection / initialize of batch i+1 run on
+    // their own stream into the other of two buffer sets while batch i decodes
+    struct XbSlot {
+        float *T1 = nullptr, *c0 = nullptr, *h0 = nullptr;
+        uint8_t* pa_h0 = nullptr;
+        cudaEvent_t ev_prep = nullptr, ev_done = nullptr;
+        bool used = false;
+    } xb[2];
+    cudaStream_t xb_stream = nullptr;
+    int xb_next = 0;
+    int opt_xbatch = 0;
+    int ops_since_xb = 0;   // compute entry points called since the last overlapped loop (they share slot 0's buffers)
     // pipelined host-buffer loop (sat_decode_loop_host_submit / _wait): two staging slots and a copy stream
     float* pipe_ctx[2] = {nullptr, nullptr};
     int32_t* pipe_tok[2] = {nullptr, nullptr};   // [tokens | forced words]
@@ -221,6 +233,12 @@ extern "C" void sat_destroy(sat_handle* h) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->xb_stream) cudaStreamDestroy(h->xb_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (h->xb[i].ev_prep) cudaEventDestroy(h->xb[i].ev_prep);
+        if (h->xb[i].ev_done) cudaEventDestroy(h->xb[i].ev_done);
+        if (i == 1) { cudaFree(h->xb[i].T1); cudaFree(h->xb[i].c0); cudaFree(h->xb[i].h0); cudaFree(h->xb[i].pa_h0); }   // slot 0 aliases the handle's own buffers
+    }
     if (h->pipe_copy) cudaStreamDestroy(h->pipe_copy);
     for (int i = 0; i < 2; ++i) {
         if (h->pipe_up[i]) cudaEventDestroy(h->pipe_up[i]);
@@ -381,6 +399,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "warm") h->opt_warm = (int)value;
     else if (k == "att_wpc") h->opt_att_wpc = (int)value;
     else if (k == "att_reuse_q") h->opt_att_reuse_q = (int)value;
+    else if (k == "xbatch") h->opt_xbatch = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -406,6 +425,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
         return SAT_OK;
     } else if (k == "reset_counters") { h->launches = 0; return SAT_OK; }
     else return fail(SAT_ERR_INVALID, "unknown option '%s'", key);
+    if (h->xb_stream) cudaStreamSynchronize(h->xb_stream);
     for (auto& g : h->graphs) {  // options change the captured work
         if (g.exec) cudaGraphExecDestroy(g.exec);
     }
@@ -458,6 +478,7 @@ extern "C" int sat_set_weight(sat_handle* h, const char* tf_var_name, const floa
     if (name.size() > 2 && name.compare(name.size() - 2, 2, ":0") == 0) name.resize(name.size() - 2);
     h->weights_locked = true;
     h->prep_ctx = nullptr;
+    if (h->xb_stream) CK(cudaStreamSynchronize(h->xb_stream));   // a prologue may still be reading the old weights
     if (name == "word_embedding/weights") {
         if (rows != h->d.vocabulary_size || cols != h->d.dim_embedding)
             return fail(SAT_ERR_INVALID, "%s: expected [%d,%d], got [%lld,%lld]", name.c_str(), h->d.vocabulary_size,
@@ -511,6 +532,7 @@ extern "C" int sat_weights_missing(sat_handle* h) {
 
 static int require_ready(sat_handle* h) {
     if (!h) return fail(SAT_ERR_INVALID, "null handle");
+    ++h->ops_since_xb;
     for (Layer* ly : h->layers) {
         if (!ly->w_set) return fail(SAT_ERR_STATE, "variable %s/kernel was never set", ly->name.c_str());
         if (!ly->b_set) return fail(SAT_ERR_STATE, "variable %s/bias was never set", ly->name.c_str());
@@ -1022,7 +1044,7 @@ static int run_graphed(sat_handle* h, const std::vector<long long>& key, cudaStr
     for (auto& g : h->graphs)
         if (g.key == key) ent = &g;
     if (!ent) {
-        if (h->graphs.size() >= 16) {
+        if (h->graphs.size() >= 48) {
             if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec);
             h->graphs.erase(h->graphs.begin());
         }
@@ -1134,9 +1156,9 @@ static int loop_enqueue_overlap(sat_handle* h, const float* ctx, int B, int T, c
 // grid leaves idle and the two run side by side without a second stream; it only waits for its predecessor
 // right before it exits, which keeps "kernel k complete => kernel k-1 complete" for the LSTM that follows.
 static int loop_enqueue_chain(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
-                              float* logits_all, cudaStream_t st) {
+                              float* logits_all, cudaStream_t st, bool prepared = false) {
     const sat_dims& d = h->d;
-    RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st, h->pa_h[0]));
+    if (!prepared) RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st, h->pa_h[0]));
     CK(cudaMemsetAsync(h->word, 0, (size_t)B * sizeof(int32_t), st));  // <start> = 0 (model.py:254)
     int budget = h->opt_att_sms > 0 ? h->opt_att_sms : h->num_sms - h->dec_2.n_tiles;
     if (budget < h->num_sms / 4) budget = h->num_sms;
@@ -1203,6 +1225,69 @@ static int loop_enqueue(sat_handle* h, const float* ctx, int B, int T, const int
     return SAT_OK;
 }
 
+static bool chain_loop_available(sat_handle* h) {
+    return h->pa_ok && h->opt_pa && h->opt_gemm != 0 && h->opt_overlap == 2 && h->opt_pdl && h->d.num_decode_layers == 2 &&
+           h->opt_hoist && h->d.num_attend_layers == 2;
+}
+
+// Greedy / teacher-forced loop with its prologue on a second stream (option "xbatch", and always for the pipelined
+// host-buffer API): the context projection, mean and initialize layers of this call write one of two buffer sets
+// (T1, c0/h0, packed h0) on `xb_stream` and only wait for the previous user of that set, so they run while the
+// previous call's decode steps are still executing on `st`; the steps of this call wait for them.  `input_ready`
+// (may be null) is an event the contexts depend on; with a null event the CALLER guarantees that the contexts are
+// complete when the call is made (they must not be produced by earlier work queued on `st`).
+static int decode_loop_xbatch(sat_handle* h, const float* contexts, int B, int T, const int32_t* forced, int32_t* tokens,
+                              float* logits_all, cudaStream_t st, cudaEvent_t input_ready) {
+    const sat_dims& d = h->d;
+    if (!h->xb_stream) {
+        CK(cudaStreamCreateWithFlags(&h->xb_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&h->xb[i].ev_prep, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->xb[i].ev_done, cudaEventDisableTiming));
+        }
+        h->xb[0].T1 = h->T1; h->xb[0].c0 = h->st_c[0]; h->xb[0].h0 = h->st_h[0]; h->xb[0].pa_h0 = h->pa_h[0];
+        const size_t R = (size_t)h->max_rows, RP = R + 272;
+        RET(dmalloc(&h->xb[1].T1, R * d.num_ctx * d.dim_attend_layer));
+        RET(dmalloc(&h->xb[1].c0, R * d.num_lstm_units));
+        RET(dmalloc(&h->xb[1].h0, R * d.num_lstm_units));
+        RET(dmalloc(&h->xb[1].pa_h0, RP * d.num_lstm_units * 4));
+    }
+    const int slot = h->xb_next;
+    h->xb_next ^= 1;
+    sat_handle::XbSlot& S = h->xb[slot];
+    if (h->ops_since_xb > 1) {
+        // some other entry point (step, beam search, prepare ...) was called since the last overlapped loop; it
+        // uses the handle's own buffers (= set 0) in `st` order: let the prologue stream see all of `st` once
+        cudaEvent_t ev = h->xb[0].ev_prep;
+        CK(cudaEventRecord(ev, st));
+        CK(cudaStreamWaitEvent(h->xb_stream, ev, 0));
+    }
+    h->ops_since_xb = 0;
+    // this set's previous user (two calls back) must have finished decoding; the one in between uses the other set
+    if (S.used) CK(cudaStreamWaitEvent(h->xb_stream, S.ev_done, 0));
+    if (input_ready) CK(cudaStreamWaitEvent(h->xb_stream, input_ready, 0));
+    // swap the set in: everything enqueued / captured below bakes these pointers in
+    float *T1_keep = h->T1, *c_keep = h->st_c[0], *h_keep = h->st_h[0];
+    uint8_t* pa_keep = h->pa_h[0];
+    h->T1 = S.T1; h->st_c[0] = S.c0; h->st_h[0] = S.h0; h->pa_h[0] = S.pa_h0;
+    int rc = run_graphed(h, {3, (long long)contexts, B, slot}, h->xb_stream, [&]() -> int {
+        return prepare_impl(h, contexts, B, h->st_c[0], h->st_h[0], h->xb_stream, h->pa_h[0]);
+    });
+    if (rc == SAT_OK) {
+        cudaEventRecord(S.ev_prep, h->xb_stream);
+        cudaStreamWaitEvent(st, S.ev_prep, 0);
+        h->prep_ctx = contexts;
+        h->prep_ni = B;
+        rc = run_graphed(h, {4, (long long)contexts, B, T, (long long)forced, (long long)tokens, (long long)logits_all, slot}, st,
+                         [&]() -> int { return loop_enqueue_chain(h, contexts, B, T, forced, tokens, logits_all, st, true); });
+        cudaEventRecord(S.ev_done, st);
+        S.used = true;
+    }
+    h->T1 = T1_keep; h->st_c[0] = c_keep; h->st_h[0] = h_keep; h->pa_h[0] = pa_keep;
+    h->prep_ctx = nullptr;   // the handle's own T1 no longer matches any contexts
+    return rc;
+}
+
 extern "C" int sat_decode_loop(sat_handle* h, const float* contexts, int32_t B, int32_t T, const int32_t* forced_words,
                                int32_t* tokens, float* logits_all, void* stream) {
     RET(require_ready(h));
@@ -1210,6 +1295,8 @@ extern "C" int sat_decode_loop(sat_handle* h, const float* contexts, int32_t B, 
     if (B < 1 || B > h->max_rows) return fail(SAT_ERR_INVALID, "batch %d outside [1, %d]", B, h->max_rows);
     if (T < 1) return fail(SAT_ERR_INVALID, "T must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->opt_xbatch && chain_loop_available(h) && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread)
+        return decode_loop_xbatch(h, contexts, B, T, forced_words, tokens, logits_all, st, nullptr);
     std::vector<long long> key = {1, (long long)contexts, B, T, (long long)forced_words, (long long)tokens,
                                   (long long)logits_all};
     // the graph bakes in the tensor map and T1 validity: force a fresh encode inside the captured work
@@ -1390,8 +1477,11 @@ extern "C" int sat_decode_loop_host_submit(sat_handle* h, const float* contexts_
                        cudaMemcpyHostToDevice, h->pipe_copy));
     if (forced) CK(cudaMemcpyAsync(forced, forced_words_host, TB * sizeof(int32_t), cudaMemcpyHostToDevice, h->pipe_copy));
     CK(cudaEventRecord(h->pipe_up[slot], h->pipe_copy));
-    CK(cudaStreamWaitEvent(st, h->pipe_up[slot], 0));
-    RET(sat_decode_loop(h, h->pipe_ctx[slot], B, T, forced, tok, nullptr, stream));
+    CK(cudaStreamWaitEvent(st, h->pipe_up[slot], 0));      // (forced words; and the contexts when not overlapped)
+    if (chain_loop_available(h) && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread)
+        RET(decode_loop_xbatch(h, h->pipe_ctx[slot], B, T, forced, tok, nullptr, st, h->pipe_up[slot]));
+    else
+        RET(sat_decode_loop(h, h->pipe_ctx[slot], B, T, forced, tok, nullptr, stream));
     CK(cudaMemcpyAsync(tokens_host, tok, TB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->pipe_done[slot], st));
     h->pipe_busy[slot] = true;

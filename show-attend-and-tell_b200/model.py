@@ -95,7 +95,9 @@ class CaptionGenerator(object):
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(self.lib, self.lib.sat_create(C.byref(d), C.byref(self._h)))
-            self.stream = torch.cuda.Stream(self.device)
+            # high priority: with cross-batch overlap ("xbatch") the decode steps must win SMs over the prologue of
+            # the next batch, which the library runs on a default-priority stream of its own
+            self.stream = torch.cuda.Stream(self.device, priority=-1)
         self._shapes = weight_shapes(config)
         self._keep = {}
 

@@ -139,6 +139,19 @@ def test_loop_layouts_agree_and_pipelined_host_api():
             got = m.decode_loop(batches[1], 20)
             assert np.array_equal(got, ref[1]), (overlap, pdl, graphs, rep)
     m.set_option("overlap", 2); m.set_option("pdl", 1); m.set_option("graphs", 1)
+    # cross-batch overlap: the prologue of batch i+1 runs on its own stream under the decode steps of batch i
+    dev = [torch.from_numpy(b).cuda() for b in batches]
+    torch.cuda.synchronize()                                           # "xbatch" wants complete inputs
+    for graphs in (0, 1):
+        m.set_option("graphs", graphs); m.set_option("xbatch", 1)
+        outs = [m.loop_device(dev[i % 4], 20)[0].clone() for i in range(10)]
+        torch.cuda.synchronize()
+        for i, o in enumerate(outs):
+            assert np.array_equal(o.cpu().numpy(), ref[i % 4]), (graphs, i)
+        m.set_option("xbatch", 0)
+        assert np.array_equal(m.decode_step(batches[0], np.zeros(64, np.int32), np.zeros((64, 1024), np.float32),
+                                            np.zeros((64, 1024), np.float32))[2].shape, (64, 10000))
+    m.set_option("graphs", 1)
     host = [torch.from_numpy(b).pin_memory() for b in batches]
     toks = [torch.empty(64, 20, dtype=torch.int32).pin_memory() for _ in range(2)]
     out = []
