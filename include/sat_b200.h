@@ -76,6 +76,10 @@ int sat_version(void);
  *   "overlap"     launch layout of the greedy loop: 2 = one stream, the attention kernel of step t+1 runs beside the
  *                 vocabulary layer of step t without waiting for it [2]; 1 = two streams, fork/join; 0 = in order.
  *                 (the attention grid, hence the split-L merge order, differs between 0 and 1/2)
+ *   "xbatch"      1 = sat_decode_loop runs its prologue (context projection, initialize) on a stream of the library's
+ *                 own into one of two buffer sets, so that it overlaps the decode steps of the previous call [0].
+ *                 Contract: the contexts passed to sat_decode_loop are COMPLETE when the call is made (not produced
+ *                 by earlier work queued on the same stream).  The pipelined host API does this by itself.
  *   "warm"        1 = idle epilogue warps pre-run the epilogue code to warm the instruction caches [1]
  *   "att_wpc"     1 = warp-per-chunk attention kernel for 512-float rows [1]
  *   "att_sms", "att_occ", "att_warps", "l2_w", "l2_vocab", "l2_t", "l2_ctx", "l2_prefetch": grid / cache-policy knobs
