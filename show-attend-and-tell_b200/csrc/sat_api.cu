@@ -141,7 +141,7 @@ struct sat_handle {
     uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0, opt_l2_vocab = -1, opt_l2_prefetch = 0;
+    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0, opt_l2_vocab = -1, opt_l2_prefetch = 0, opt_stages = 0;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -416,6 +416,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "l2_w") h->opt_l2_w = (int)value;
     else if (k == "l2_vocab") h->opt_l2_vocab = (int)value;
     else if (k == "l2_prefetch") h->opt_l2_prefetch = (int)value;
+    else if (k == "stages") h->opt_stages = (int)value;
     else if (k == "l2_t") h->opt_l2_t = (int)value;
     else if (k == "l2_ctx") h->opt_l2_ctx = (int)value;
     else if (k == "profile") {
@@ -649,6 +650,7 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.nprob = n;
     L.layout_mode = h->opt_layout;
     L.stages = lin_pick_stages(max_rt);
+    if (h->opt_stages > 0 && h->opt_stages < L.stages) L.stages = h->opt_stages;   // experiment knob: shallower pipeline
     L.l2_w = (h->cur_tag == kTagDec2 && h->opt_l2_vocab >= 0) ? h->opt_l2_vocab : h->opt_l2_w;   // vocabulary layer: own policy
     L.dbg = nullptr;
     L.tl = nullptr;

@@ -22,7 +22,7 @@ def timeit(n=30):
     torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 m.set_option("graphs", 0)   # options are baked into captured graphs: measure eagerly
-for pf, lw, lv in [(0, 2, -1), (1, 2, -1), (1, 2, 1), (1, 0, -1), (1, 1, -1), (0, 2, -1), (1, 2, -1)]:
-    m.set_option("l2_prefetch", pf); m.set_option("l2_w", lw); m.set_option("l2_vocab", lv)
+for stg in (0, 3, 2, 0):
+    m.set_option("stages", stg)
     ms = min(timeit() for _ in range(2))
-    print("l2_prefetch=%d l2_w=%d l2_vocab=%2d : %.3f ms/loop  %.1f us/step" % (pf, lw, lv, ms, ms * 1e3 / T), flush=True)
+    print("stages=%d : %.3f ms/loop  %.1f us/step" % (stg, ms, ms * 1e3 / T), flush=True)
