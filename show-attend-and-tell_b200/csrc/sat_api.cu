@@ -141,7 +141,7 @@ struct sat_handle {
     uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0, opt_l2_vocab = -1, opt_l2_prefetch = 0, opt_stages = 0;
+    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0, opt_l2_vocab = -1, opt_l2_prefetch = 0, opt_stages = 0, opt_train_tc = 1;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -417,6 +417,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "l2_vocab") h->opt_l2_vocab = (int)value;
     else if (k == "l2_prefetch") h->opt_l2_prefetch = (int)value;
     else if (k == "stages") h->opt_stages = (int)value;
+    else if (k == "train_tc") h->opt_train_tc = (int)value;
     else if (k == "l2_t") h->opt_l2_t = (int)value;
     else if (k == "l2_ctx") h->opt_l2_ctx = (int)value;
     else if (k == "profile") {
@@ -674,6 +675,43 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     }
     h->launches += 1;
     return SAT_OK;
+}
+
+// Dense product on the tcgen05 kernel from operands that are ALREADY in the packed layouts (training path,
+// sat_train.cu): out[rows, n_out] (+)= X * W with X a packed activation of row tile `row_tile` and W a packed weight.
+int sat_handle_layout_mode(sat_handle* h) { return h->opt_layout; }
+int sat_handle_train_tc(sat_handle* h) { return h->opt_train_tc && h->opt_gemm != 0; }
+
+int sat_dense_packed(sat_handle* h, const uint8_t* x_pa, int rows, int row_tile, int K, const uint8_t* wpack,
+                     const float* bias_packed, int n_out, int epi, float* out, int ldo, int accumulate, int splits,
+                     void* stream) {
+    if (!h || !x_pa || !wpack || !out) return fail(SAT_ERR_INVALID, "sat_dense_packed: null argument");
+    if (K % kBK || row_tile % 16 || row_tile > 256 || splits < 1 || splits > 8 || (splits & (splits - 1)))
+        return fail(SAT_ERR_INVALID, "sat_dense_packed: K %d / row tile %d / splits %d", K, row_tile, splits);
+    LinProblem P;
+    memset(&P, 0, sizeof(P));
+    P.seg[0].pa = x_pa;
+    P.seg[0].width = K;
+    P.seg[0].ld = K;
+    P.seg[0].row_div = 1;
+    P.nseg = 1;
+    P.K = K;
+    P.k_blocks = K / kBK;
+    P.rows = rows;
+    P.row_tile = row_tile;
+    P.n_row_tiles = (rows + row_tile - 1) / row_tile;
+    P.n_out = n_out;
+    P.n_tiles = (n_out + kTileN - 1) / kTileN;
+    P.splits = splits;
+    P.cta_count = P.n_tiles * P.n_row_tiles * splits;
+    P.wpack = wpack;
+    P.bias = bias_packed;
+    P.epi = epi;
+    P.out = out;
+    P.ldo = ldo;
+    P.accumulate = accumulate;
+    h->cur_tag = kTagProj;
+    return launch(h, &P, 1, (cudaStream_t)stream);
 }
 
 // --------------------------------------------------------------- contexts

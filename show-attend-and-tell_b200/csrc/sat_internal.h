@@ -6,3 +6,10 @@ int sat_fail(int code, const char* fmt, ...);
 const sat_dims* sat_handle_dims(sat_handle* h);
 void** sat_handle_train_slot(sat_handle* h);
 void sat_handle_set_train_free(sat_handle* h, void (*fn)(void*));
+
+// dense product on the tcgen05 kernel from packed operands (see sat_api.cu); epi = sat::kEpi* of sat_linear.cuh
+int sat_dense_packed(sat_handle* h, const uint8_t* x_pa, int rows, int row_tile, int K, const uint8_t* wpack,
+                     const float* bias_packed, int n_out, int epi, float* out, int ldo, int accumulate, int splits,
+                     void* stream);
+int sat_handle_layout_mode(sat_handle* h);
+int sat_handle_train_tc(sat_handle* h);

@@ -448,7 +448,11 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             float4 g = g4[j];
                             if (!do_am) { g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w; }
                             if (epi == kEpiBiasTanh) { g.x = act_tanh(g.x); g.y = act_tanh(g.y); g.z = act_tanh(g.z); g.w = act_tanh(g.w); }
-                            if (out) *reinterpret_cast<float4*>(out + (size_t)(row0 + (id >> 5)) * ldo + ng) = g;
+                            if (out) {
+                                float4* o = reinterpret_cast<float4*>(out + (size_t)(row0 + (id >> 5)) * ldo + ng);
+                                if (P.accumulate) { const float4 a = *o; g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
+                                *o = g;
+                            }
                         }
                     }
                 }
@@ -502,12 +506,14 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                     if (out) {
                         float* o = out + (size_t)(row0 + bb) * ldo + ng;
                         if (vec_out) {
+                            if (P.accumulate) { const float4 a = *reinterpret_cast<const float4*>(o); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
                             *reinterpret_cast<float4*>(o) = g;
                         } else {
-                            if (ng + 0 < n_out) o[0] = g.x;
-                            if (ng + 1 < n_out) o[1] = g.y;
-                            if (ng + 2 < n_out) o[2] = g.z;
-                            if (ng + 3 < n_out) o[3] = g.w;
+                            const float a = P.accumulate ? 1.f : 0.f;
+                            if (ng + 0 < n_out) o[0] = g.x + a * o[0];
+                            if (ng + 1 < n_out) o[1] = g.y + a * o[1];
+                            if (ng + 2 < n_out) o[2] = g.z + a * o[2];
+                            if (ng + 3 < n_out) o[3] = g.w + a * o[3];
                         }
                     }
                     if (out_pa) {

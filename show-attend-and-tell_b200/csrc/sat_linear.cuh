@@ -58,6 +58,7 @@ struct LinProblem {
     int epi;
     float* out;            // [rows, ldo]
     int ldo;
+    int accumulate;        // out += result instead of out = result (training: gradient accumulated over time steps)
     const float* c_in;     // LSTM: [rows, H]
     float* c_out;
     float* h_out;

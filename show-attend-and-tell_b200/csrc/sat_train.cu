@@ -26,6 +26,7 @@
 
 #include "../../include/sat_b200.h"
 #include "sat_internal.h"
+#include "sat_linear.cuh"
 
 namespace {
 
@@ -520,6 +521,12 @@ struct TrainState {
     float *dtd = nullptr, *dexp = nullptr, *dh_out = nullptr, *dh_state = nullptr, *dh_raw = nullptr, *dc = nullptr, *dG = nullptr,
           *dlin = nullptr, *dz = nullptr, *demb = nullptr, *dalpha = nullptr, *dtemp = nullptr, *dq = nullptr, *dhd = nullptr,
           *dbuf = nullptr;
+    // tensor-core path of attend/fc_1a (forward + weight gradient: ~25 % of the step's time on CUDA cores): the
+    // operands in the packed layouts of the tcgen05 dense kernel
+    uint8_t *tc_xpa = nullptr, *tc_wbig = nullptr, *tc_w1a = nullptr;   // packed rows / packed [BL x A] "weight" / packed W1a
+    float* tc_b1a = nullptr;
+    bool tc_ok = false;
+    sat_handle* handle = nullptr;
     float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2
     // per-call scalars live in device cells (fed from pinned host memory before each launch), so that the
     // ~3500 launches of a step are captured once into a CUDA graph and replayed
@@ -614,6 +621,15 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
     A1(&s->dc, B * H); A1(&s->dG, B * 4 * H); A1(&s->dlin, B * (D + E + H)); A1(&s->dz, B * D); A1(&s->demb, B * E);
     A1(&s->dalpha, BL); A1(&s->dtemp, BL * A); A1(&s->dq, B * A); A1(&s->dhd, B * H); A1(&s->dbuf, B * (D + E + I + H));
     A1(&s->loss_acc, 8);
+    s->handle = h;
+    s->tc_ok = (D % 128 == 0) && (A % 128 == 0) && (BL % 128 == 0);
+    if (s->tc_ok) {
+        float* f = nullptr;   // (sizes in floats: a packed operand takes 4 bytes per element, like fp32)
+        A1(&f, BL * D); s->tc_xpa = reinterpret_cast<uint8_t*>(f);
+        A1(&f, BL * (A > D ? A : D)); s->tc_wbig = reinterpret_cast<uint8_t*>(f);
+        A1(&f, D * A); s->tc_w1a = reinterpret_cast<uint8_t*>(f);
+        A1(&s->tc_b1a, A);
+    }
     float* cells = nullptr;
     A1(&cells, 8);
     if (rc == SAT_OK) {
@@ -688,6 +704,12 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(s->ib1d, I, s->ib1, I, B, I, seed, INIT + 2, kf, 0);
     TRET(dense_fwd(st, s->ib1d, B, I, P(vIb2W), P(vIb2B), H, s->h0, 0));
 
+    const bool tc = s->tc_ok && sat_handle_train_tc(s->handle);
+    const int lmode = sat_handle_layout_mode(s->handle);
+    if (tc) {   // this step's attend/fc_1a weights in the packed layout (they change with every optimizer step)
+        TCK(sat::lin_repack_weight(P(vA1aW), D, A, 0, s->tc_w1a, lmode, st));
+        TCK(sat::lin_repack_bias(P(vA1aB), A, 0, s->tc_b1a, st));
+    }
     // ------------------------------------------------------------ forward through time (model.py:258-312)
     for (int t = 0; t < T; ++t) {
         const float* h_out_prev = t ? s->h_out[t - 1] : s->h0;
@@ -695,7 +717,13 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         const float* c_prev = t ? s->c[t - 1] : s->c0;
         // attend (model.py:395-436)
         dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
-        TRET(dense_fwd(st, s->ctxd, BL, D, P(vA1aW), P(vA1aB), A, s->T1[t], 1));
+        if (tc) {   // T1 = tanh(ctxd W1a + b1a) on the tcgen05 dense kernel: rows packed once, bias + tanh fused
+            sat::PackJob job{s->ctxd, nullptr, D, D, BL, 128, s->tc_xpa};
+            TCK(sat::pack_rows_launch(&job, 1, lmode, st));
+            TRET(sat_dense_packed(s->handle, s->tc_xpa, BL, 128, D, s->tc_w1a, s->tc_b1a, A, sat::kEpiBiasTanh, s->T1[t], A, 0, 1, st));
+        } else {
+            TRET(dense_fwd(st, s->ctxd, BL, D, P(vA1aW), P(vA1aB), A, s->T1[t], 1));
+        }
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
         TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
         att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
@@ -770,7 +798,17 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         segsum_kernel<<<dim3((A + 127) / 128, B), 128, 0, st>>>(s->dq, s->dtemp, B, L, A);
         tanh_bwd_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->T1[t], (size_t)BL * A);
         dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
-        TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));           // contexts are inputs
+        if (tc) {
+            // dW1a[D, A] += ctxd^T[D, BL] * dtemp[BL, A]: the weight repack kernel transposes, so ctxd [BL x D] read
+            // as a "[K x n_out] weight" IS the packed activation ctxd^T (row tile 128), and dtemp [BL x A] is the
+            // packed weight; split-K over an 8-CTA cluster, accumulated into the gradient in the epilogue
+            TCK(sat::lin_repack_weight(s->ctxd, BL, D, 0, s->tc_xpa, lmode, st));
+            TCK(sat::lin_repack_weight(s->dtemp, BL, A, 0, s->tc_wbig, lmode, st));
+            TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, st));
+            colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA1aB), s->dtemp, BL, A);
+        } else {
+            TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));       // contexts are inputs
+        }
         tanh_bwd_kernel<<<GRID1D((size_t)B * A), 256, 0, st>>>(s->dq, s->q[t], (size_t)B * A);
         TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, s->dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
@@ -814,7 +852,8 @@ extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, fl
     auto enqueue = [&]() { return train_enqueue(s, params, grads, contexts, sentences, masks, B, T, global_batch, losses, st); };
     if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return enqueue();
     std::vector<long long> key = {(long long)params, (long long)grads, (long long)contexts, (long long)sentences,
-                                  (long long)masks, (long long)losses, B, T, global_batch};
+                                  (long long)masks, (long long)losses, B, T, global_batch,
+                                  sat_handle_train_tc(h), sat_handle_layout_mode(h)};
     TrainState::GEntry* ent = nullptr;
     for (auto& g : s->graphs)
         if (g.key == key) ent = &g;

@@ -52,6 +52,31 @@ def test_losses_and_gradients_match_autograd(seed):
     grad_check(m, ref_g, 2e-4)
 
 
+TC_DIMS = dict(num_ctx=32, dim_ctx=128, dim_embedding=32, num_lstm_units=32, dim_initalize_layer=16,
+               dim_attend_layer=128, dim_decode_layer=40, vocabulary_size=50, max_caption_length=4)
+
+
+@pytest.mark.parametrize("seed", [0, 31])
+def test_tensor_core_attend_projection_in_training(seed):
+    """Shapes at which attend/fc_1a (forward and weight gradient) runs on the tcgen05 dense kernel
+    (dim_ctx, dim_attend_layer and B*L multiples of 128): same parity bars, and agreement with the CUDA-core path."""
+    ocfg, w, m, ctx, sent, masks = setup(B=4, seed=11, dims=TC_DIMS)
+    ref_l, ref_g = TR.loss_and_grads(ocfg, w, ctx, sent, masks, seed if seed else None, reg_in_grad=False)
+    res = {}
+    for tc in (1, 0):
+        m.set_option("train_tc", tc)
+        losses = m.train_forward_backward(ctx, sent, masks, seed=seed).cpu().numpy()
+        ce, acc, att, reg = [float(x) for x in losses]
+        assert abs(ce - ref_l["cross_entropy_loss"]) < 1e-4 * ref_l["cross_entropy_loss"], tc
+        assert abs(att - ref_l["attention_loss"]) < 1e-4 * ref_l["attention_loss"] + 1e-9, tc
+        grad_check(m, ref_g, 2e-4)
+        res[tc] = {k: v.detach().cpu().numpy().copy() for k, v in m.train_state_dict("grads").items()}
+    m.set_option("train_tc", 1)
+    g1, g0 = res[1]["attend/fc_1a/kernel"], res[0]["attend/fc_1a/kernel"]
+    assert np.abs(g1 - g0).max() <= 1e-4 * np.abs(g0).max()
+    assert np.abs(g1 - g0).max() > 0          # the two paths really differ (bf16x3 tensor cores vs fp32 FMA)
+
+
 def test_adam_update_matches_tf_semantics():
     ocfg, w, m, ctx, sent, masks = setup(seed=5)
     w64 = {k: v.astype(np.float64) for k, v in w.items()}

@@ -1,4 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python tools/l2_sweep.py > gpurun_out/l2_sweep.log 2>&1
-cat gpurun_out/l2_sweep.log
+timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 -k "train" > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -n 15 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu --workload 4 > gpurun_out/bench_train1.log 2>&1
+tail -n 1 gpurun_out/bench_train1.log | cut -c1-260
