@@ -147,6 +147,7 @@ struct sat_handle {
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
     int opt_trace = 0;
     int trace_at = 0;      // with trace == 1: index of the dense launch (counted from the option call) to stamp
+    bool lin_w_dynamic = false;   // next dense launch: its weight operand comes from the preceding kernel
     int att_loop_grid = 0; // CTAs of the last attention launch that ran beside the vocabulary layer (decode loop)
     int tl_count = 0;      // with trace == 3: launches recorded so far ({min start, max end} per launch)
     std::vector<std::string> tl_names;
@@ -657,6 +658,8 @@ static int launch(sat_handle* h, LinProblem* probs, int n, cudaStream_t st) {
     L.tl = nullptr;
     L.warm_epilogue = h->opt_warm;
     L.l2_prefetch = h->opt_l2_prefetch;
+    L.w_dynamic = h->lin_w_dynamic ? 1 : 0;
+    h->lin_w_dynamic = false;
     if (h->opt_trace == 1 && begin <= 1024 && h->trace_at-- == 0) L.dbg = h->trace;
     if (h->opt_trace == 3 && h->tl_count < 4000) {
         L.tl = h->trace + 4 * h->tl_count++;
@@ -684,7 +687,7 @@ int sat_handle_train_tc(sat_handle* h) { return h->opt_train_tc && h->opt_gemm !
 
 int sat_dense_packed(sat_handle* h, const uint8_t* x_pa, int rows, int row_tile, int K, const uint8_t* wpack,
                      const float* bias_packed, int n_out, int epi, float* out, int ldo, int accumulate, int splits,
-                     void* stream) {
+                     void* stream, int weights_dynamic) {
     if (!h || !x_pa || !wpack || !out) return fail(SAT_ERR_INVALID, "sat_dense_packed: null argument");
     if (K % kBK || row_tile % 16 || row_tile > 256 || splits < 1 || splits > 8 || (splits & (splits - 1)))
         return fail(SAT_ERR_INVALID, "sat_dense_packed: K %d / row tile %d / splits %d", K, row_tile, splits);
@@ -697,6 +700,7 @@ int sat_dense_packed(sat_handle* h, const uint8_t* x_pa, int rows, int row_tile,
     P.nseg = 1;
     P.K = K;
     P.k_blocks = K / kBK;
+    while (splits > 1 && splits > P.k_blocks) splits >>= 1;   // every CTA of a split needs at least one K block
     P.rows = rows;
     P.row_tile = row_tile;
     P.n_row_tiles = (rows + row_tile - 1) / row_tile;
@@ -711,6 +715,7 @@ int sat_dense_packed(sat_handle* h, const uint8_t* x_pa, int rows, int row_tile,
     P.ldo = ldo;
     P.accumulate = accumulate;
     h->cur_tag = kTagProj;
+    h->lin_w_dynamic = weights_dynamic != 0;
     return launch(h, &P, 1, (cudaStream_t)stream);
 }
 

@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             const int pre = nkb < S ? nkb : S;
             if (!L.pdl) tl_go(L.tl);
             if (L.pdl) {
+                if (L.w_dynamic) pdl_wait();          // (a second wait further down returns at once)
                 for (int it = 0; it < pre; ++it) load_w(it);
                 // the rest of this CTA's weight stream: into L2 while the predecessor drains
                 if (L.l2_prefetch)

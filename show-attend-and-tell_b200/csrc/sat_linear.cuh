@@ -91,6 +91,7 @@ struct LinLaunch {
     unsigned long long* dbg;  // optional [grid][16] timeline stamps
     unsigned long long* tl;   // optional {min start, max end} of this launch
     int pdl;          // launched with programmatic stream serialization (see pdl_wait)
+    int w_dynamic;    // the weight operand was written by the preceding kernel (training): no weight fetch before the wait
     int l2_prefetch;  // (with pdl) prefetch the CTA's whole weight stream into L2 before waiting for the predecessor
     int warm_epilogue;  // idle epilogue warps pre-run the epilogue code (no side effects) to warm the instruction caches
     int x_mode;       // 0 = producer warps convert X per stage; 1 = cooperative pre-pack + TMA (grid <= #SMs);

@@ -526,6 +526,16 @@ struct TrainState {
     uint8_t *tc_xpa = nullptr, *tc_wbig = nullptr, *tc_w1a = nullptr;   // packed rows / packed [BL x A] "weight" / packed W1a
     float* tc_b1a = nullptr;
     bool tc_ok = false;
+    // batch-row products (rows = B) of the step: y = x W (+ b) forward and dx = dy W^T backward, with this step's
+    // weights packed once (W as the kernel's weight operand, W^T likewise through the row packer)
+    struct TcLayer {
+        int var_w = -1, var_b = -1, K = 0, N = 0;
+        uint8_t *w = nullptr, *wT = nullptr;
+        float* b = nullptr;
+        bool fwd = false, dx = false;
+    } tcl[4];   // 0 attend/fc_1b, 1 lstm, 2 decode/fc_1, 3 decode/fc_2
+    uint8_t* tc_xs = nullptr;   // packed batch rows (scratch)
+    int tc_rt = 0;              // their row tile
     sat_handle* handle = nullptr;
     float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2
     // per-call scalars live in device cells (fed from pinned host memory before each launch), so that the
@@ -630,6 +640,28 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
         A1(&f, D * A); s->tc_w1a = reinterpret_cast<uint8_t*>(f);
         A1(&s->tc_b1a, A);
     }
+    {
+        const size_t XLs = D + E + H, XDs = H + D + E;
+        const int vw[4] = {vA1bW, vLW, vD1W, vD2W}, vb[4] = {vA1bB, vLB, vD1B, vD2B};
+        const size_t Ks[4] = {H, XLs, XDs, Dd}, Ns[4] = {A, 4 * H, Dd, V};
+        size_t kmax = 0;
+        s->tc_rt = (int)((B + 15) / 16 * 16);
+        for (int i = 0; i < 4; ++i) {
+            TrainState::TcLayer& l = s->tcl[i];
+            l.var_w = vw[i]; l.var_b = vb[i]; l.K = (int)Ks[i]; l.N = (int)Ns[i];
+            l.fwd = (Ks[i] % 64 == 0) && s->tc_rt <= 256;
+            l.dx = l.fwd && (Ns[i] % 64 == 0);
+            float* f = nullptr;
+            const size_t npad = (Ns[i] + 127) / 128 * 128, kpad = (Ks[i] + 127) / 128 * 128;
+            if (l.fwd) { A1(&f, Ks[i] * npad); l.w = reinterpret_cast<uint8_t*>(f); A1(&l.b, npad); }
+            if (l.dx) { A1(&f, Ns[i] * kpad); l.wT = reinterpret_cast<uint8_t*>(f); }
+            kmax = Ks[i] > kmax ? Ks[i] : kmax;
+            kmax = (l.dx && Ns[i] > kmax) ? Ns[i] : kmax;
+        }
+        float* f = nullptr;
+        A1(&f, (size_t)(s->tc_rt + 16) * kmax);
+        s->tc_xs = reinterpret_cast<uint8_t*>(f);
+    }
     float* cells = nullptr;
     A1(&cells, 8);
     if (rc == SAT_OK) {
@@ -710,6 +742,47 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         TCK(sat::lin_repack_weight(P(vA1aW), D, A, 0, s->tc_w1a, lmode, st));
         TCK(sat::lin_repack_bias(P(vA1aB), A, 0, s->tc_b1a, st));
     }
+    const bool tcb = sat_handle_train_tc(s->handle) != 0;
+    if (tcb) {
+        for (int i = 0; i < 4; ++i) {
+            TrainState::TcLayer& l = s->tcl[i];
+            if (l.fwd) {
+                TCK(sat::lin_repack_weight(P(l.var_w), l.K, l.N, 0, l.w, lmode, st));
+                TCK(sat::lin_repack_bias(P(l.var_b), l.N, 0, l.b, st));
+            }
+            if (l.dx) {   // W^T as a weight operand: row n of the operand = row k of W ... i.e. W's rows are its K-major rows
+                sat::PackJob job{P(l.var_w), nullptr, l.N, l.N, l.K, 128, l.wT};
+                TCK(sat::pack_rows_launch(&job, 1, lmode, st));
+            }
+        }
+    }
+    auto tc_splits = [&](int n_out, int K) {
+        const int tiles = (n_out + 127) / 128;
+        int sp = 1;
+        while (sp * 2 <= 8 && tiles * sp * 2 <= 148 && sp * 2 <= K / 64) sp *= 2;
+        return sp;
+    };
+    // y[B, N] = epi(x[B, K] W + b) on the tcgen05 kernel; false if this layer / shape stays on the CUDA-core path
+    auto tc_fwd = [&](int li, const float* x, int epi, float* y, int* rc) -> bool {
+        TrainState::TcLayer& l = s->tcl[li];
+        if (!tcb || !l.fwd) return false;
+        sat::PackJob job{x, nullptr, l.K, l.K, B, s->tc_rt, s->tc_xs};
+        cudaError_t ce = sat::pack_rows_launch(&job, 1, lmode, st);
+        if (ce != cudaSuccess) { *rc = sat_fail(SAT_ERR_CUDA, "pack: %s", cudaGetErrorString(ce)); return true; }
+        *rc = sat_dense_packed(s->handle, s->tc_xs, B, s->tc_rt, l.K, l.w, l.b, l.N, epi, y, l.N, 0, tc_splits(l.N, l.K), st);
+        return true;
+    };
+    // dx[B, K] = dy[B, N] W^T
+    auto tc_dx = [&](int li, const float* dy, float* dx, int* rc) -> bool {
+        TrainState::TcLayer& l = s->tcl[li];
+        if (!tcb || !l.dx) return false;
+        sat::PackJob job{dy, nullptr, l.N, l.N, B, s->tc_rt, s->tc_xs};
+        cudaError_t ce = sat::pack_rows_launch(&job, 1, lmode, st);
+        if (ce != cudaSuccess) { *rc = sat_fail(SAT_ERR_CUDA, "pack: %s", cudaGetErrorString(ce)); return true; }
+        *rc = sat_dense_packed(s->handle, s->tc_xs, B, s->tc_rt, l.N, l.wT, nullptr, l.K, sat::kEpiNone, dx, l.K, 0, tc_splits(l.K, l.N), st);
+        return true;
+    };
+    int trc = SAT_OK;
     // ------------------------------------------------------------ forward through time (model.py:258-312)
     for (int t = 0; t < T; ++t) {
         const float* h_out_prev = t ? s->h_out[t - 1] : s->h0;
@@ -725,7 +798,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             TRET(dense_fwd(st, s->ctxd, BL, D, P(vA1aW), P(vA1aB), A, s->T1[t], 1));
         }
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
-        TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
+        if (tc_fwd(0, s->hd[t], sat::kEpiBiasTanh, s->q[t], &trc)) { TRET(trc); }
+        else TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
         att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
         rowdot_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->e, s->temp, P(vA2W), BL, A);
         softmax_rows_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(s->alpha[t], s->e, B, L);
@@ -738,7 +812,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->dlin + D, D + E, s->emb[t], E, B, E, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * (D + E)), 256, 0, st>>>(s->lstm_in[t], XL, s->dlin, D + E, B, D + E, seed, ST(t, 3), kl, 0);
         copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->lstm_in[t] + D + E, XL, h_state_prev, H, B, H, 0);
-        TCK(sgemm(st, false, false, B, 4 * H, XL, s->lstm_in[t], XL, P(vLW), 4 * H, s->acts[t], 4 * H, false));
+        if (tc_fwd(1, s->lstm_in[t], sat::kEpiNone, s->acts[t], &trc)) { TRET(trc); }   // (bias and gates: next kernel)
+        else TCK(sgemm(st, false, false, B, 4 * H, XL, s->lstm_in[t], XL, P(vLW), 4 * H, s->acts[t], 4 * H, false));
         lstm_fwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->acts[t], P(vLB), c_prev, s->c[t], s->h_raw, B, H);
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->h_out[t], H, s->h_raw, H, B, H, seed, ST(t, 5), kl, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->h_state[t], H, s->h_raw, H, B, H, seed, ST(t, 4), kl, 0);
@@ -747,9 +822,11 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dexp + H, XD, s->z[t], D, B, D, 0);
         copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->dexp + H + D, XD, s->emb[t], E, B, E, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->expd[t], XD, s->dexp, XD, B, XD, seed, ST(t, 6), kf, 0);
-        TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), Dd, s->t1[t], 1));
+        if (tc_fwd(2, s->expd[t], sat::kEpiBiasTanh, s->t1[t], &trc)) { TRET(trc); }
+        else TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), Dd, s->t1[t], 1));
         dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->td[t], Dd, s->t1[t], Dd, B, Dd, seed, ST(t, 7), kf, 0);
-        TRET(dense_fwd(st, s->td[t], B, Dd, P(vD2W), P(vD2B), V, s->logits, 0));
+        if (tc_fwd(3, s->td[t], sat::kEpiBias, s->logits, &trc)) { TRET(trc); }
+        else TRET(dense_fwd(st, s->td[t], B, Dd, P(vD2W), P(vD2B), V, s->logits, 0));
         // masked cross entropy + accuracy, and d loss / d logits (model.py:292-305, 316-318, 332-334)
         ce_kernel<<<B, 256, 0, st>>>(s->logits, s->dlogits[t], sentences, T, t, masks, V, inv_msum, s->loss_acc);
     }
@@ -771,7 +848,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), s->dtd));
         dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->dtd, Dd, s->dtd, Dd, B, Dd, seed, ST(t, 7), kf, 0);
         tanh_bwd_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->dtd, s->t1[t], (size_t)B * Dd);
-        TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, s->dtd, Gd(vD1W), Gd(vD1B), s->dexp));
+        if (tc_dx(2, s->dtd, s->dexp, &trc)) { TRET(trc); TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, s->dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
+        else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, s->dtd, Gd(vD1W), Gd(vD1B), s->dexp));
         dropout2d_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->dexp, XD, s->dexp, XD, B, XD, seed, ST(t, 6), kf, 0);
         // dexp = [dh_out | dz | demb]
         copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dexp, XD, B, H, 1);
@@ -781,7 +859,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_out, H, B, H, seed, ST(t, 5), kl, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_state, H, B, H, seed, ST(t, 4), kl, 1);
         lstm_bwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dG, s->dc, s->dh_raw, s->acts[t], s->c[t], c_prev, B, H);
-        TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, s->dG, Gd(vLW), Gd(vLB), s->dlin));
+        if (tc_dx(1, s->dG, s->dlin, &trc)) { TRET(trc); TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, s->dG, Gd(vLW), Gd(vLB), nullptr)); }
+        else TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, s->dG, Gd(vLW), Gd(vLB), s->dlin));
         // dlin = [d xd (D+E) | dh_state_prev]
         copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_state, H, s->dlin + D + E, XL, B, H, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * (D + E)), 256, 0, st>>>(s->dbuf, D + E, s->dlin, XL, B, D + E, seed, ST(t, 3), kl, 0);
@@ -804,13 +883,14 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             // packed weight; split-K over an 8-CTA cluster, accumulated into the gradient in the epilogue
             TCK(sat::lin_repack_weight(s->ctxd, BL, D, 0, s->tc_xpa, lmode, st));
             TCK(sat::lin_repack_weight(s->dtemp, BL, A, 0, s->tc_wbig, lmode, st));
-            TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, st));
+            TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, st, 1));
             colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA1aB), s->dtemp, BL, A);
         } else {
             TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));       // contexts are inputs
         }
         tanh_bwd_kernel<<<GRID1D((size_t)B * A), 256, 0, st>>>(s->dq, s->q[t], (size_t)B * A);
-        TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, s->dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
+        if (tc_dx(0, s->dq, s->dhd, &trc)) { TRET(trc); TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, s->dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
+        else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, s->dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
     }

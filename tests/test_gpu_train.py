@@ -52,14 +52,15 @@ def test_losses_and_gradients_match_autograd(seed):
     grad_check(m, ref_g, 2e-4)
 
 
-TC_DIMS = dict(num_ctx=32, dim_ctx=128, dim_embedding=32, num_lstm_units=32, dim_initalize_layer=16,
-               dim_attend_layer=128, dim_decode_layer=40, vocabulary_size=50, max_caption_length=4)
+TC_DIMS = dict(num_ctx=32, dim_ctx=128, dim_embedding=64, num_lstm_units=64, dim_initalize_layer=16,
+               dim_attend_layer=128, dim_decode_layer=64, vocabulary_size=50, max_caption_length=4)
 
 
 @pytest.mark.parametrize("seed", [0, 31])
 def test_tensor_core_attend_projection_in_training(seed):
-    """Shapes at which attend/fc_1a (forward and weight gradient) runs on the tcgen05 dense kernel
-    (dim_ctx, dim_attend_layer and B*L multiples of 128): same parity bars, and agreement with the CUDA-core path."""
+    """Shapes at which attend/fc_1a (forward and weight gradient; dim_ctx, dim_attend_layer and B*L multiples of 128)
+    and every batch-row product (forward, and dx where the output width is a multiple of 64) run on the tcgen05 dense
+    kernel: same parity bars, and agreement with the CUDA-core path."""
     ocfg, w, m, ctx, sent, masks = setup(B=4, seed=11, dims=TC_DIMS)
     ref_l, ref_g = TR.loss_and_grads(ocfg, w, ctx, sent, masks, seed if seed else None, reg_in_grad=False)
     res = {}
