@@ -536,6 +536,11 @@ struct TrainState {
     } tcl[4];   // 0 attend/fc_1b, 1 lstm, 2 decode/fc_1, 3 decode/fc_2
     uint8_t* tc_xs = nullptr;   // packed batch rows (scratch)
     int tc_rt = 0;              // their row tile
+    // weight gradients of those layers: dW = sum_t x_t^T dy_t = X_all^T dY_all with the T steps stacked ([T*B, .]
+    // matrices: the per-step stashes are contiguous), one tensor-core product per layer after the time loop
+    std::vector<float*> dys[4];            // [t] slices of dY_all per layer (decode/fc_2 uses dlogits)
+    uint8_t *tc_sx = nullptr, *tc_sw = nullptr;   // packed X_all^T / packed dY_all
+    bool tc_stack = false;
     sat_handle* handle = nullptr;
     float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2
     // per-call scalars live in device cells (fed from pinned host memory before each launch), so that the
@@ -617,9 +622,11 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
                  Dd = d.dim_decode_layer, I = d.dim_initalize_layer, V = d.vocabulary_size, L = d.num_ctx;
     int rc = SAT_OK;
     auto A1 = [&](float** p, size_t n) { if (rc == SAT_OK) rc = talloc(s, p, n); };
-    auto AT = [&](std::vector<float*>& v, size_t n) {
+    auto AT = [&](std::vector<float*>& v, size_t n) {   // one block, [t] = slice t: the T slices also form a [T*B, .] matrix
         v.assign(T, nullptr);
-        for (int t = 0; t < T; ++t) A1(&v[t], n);
+        float* base = nullptr;
+        A1(&base, n * T);
+        for (int t = 0; t < T && base; ++t) v[t] = base + (size_t)t * n;
     };
     AT(s->T1, BL * A); AT(s->q, B * A); AT(s->hd, B * H); AT(s->alpha, B * L); AT(s->z, B * D); AT(s->lstm_in, B * (D + E + H));
     AT(s->acts, B * 4 * H); AT(s->c, B * H); AT(s->h_out, B * H); AT(s->h_state, B * H); AT(s->expd, B * (H + D + E));
@@ -661,6 +668,21 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
         float* f = nullptr;
         A1(&f, (size_t)(s->tc_rt + 16) * kmax);
         s->tc_xs = reinterpret_cast<uint8_t*>(f);
+        // stacked weight gradients: T*B rows must fill whole K blocks
+        const size_t TB = (size_t)T * B;
+        s->tc_stack = (TB % 64 == 0);
+        for (int i = 0; i < 4 && s->tc_stack; ++i) s->tc_stack = s->tcl[i].fwd && (i == 3 || s->tcl[i].dx);
+        if (s->tc_stack) {
+            AT(s->dys[0], B * A); AT(s->dys[1], B * 4 * H); AT(s->dys[2], B * Dd);
+            size_t xmax = 0, wmax = 0;
+            for (int i = 0; i < 4; ++i) {
+                const size_t kp = (Ks[i] + 127) / 128 * 128, np = (Ns[i] + 127) / 128 * 128;
+                xmax = TB * kp > xmax ? TB * kp : xmax;
+                wmax = TB * np > wmax ? TB * np : wmax;
+            }
+            A1(&f, xmax); s->tc_sx = reinterpret_cast<uint8_t*>(f);
+            A1(&f, wmax); s->tc_sw = reinterpret_cast<uint8_t*>(f);
+        }
     }
     float* cells = nullptr;
     A1(&cells, 8);
@@ -783,6 +805,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         return true;
     };
     int trc = SAT_OK;
+    const bool stack = tcb && s->tc_stack;   // weight gradients of the four batch-row layers after the time loop
     // ------------------------------------------------------------ forward through time (model.py:258-312)
     for (int t = 0; t < T; ++t) {
         const float* h_out_prev = t ? s->h_out[t - 1] : s->h0;
@@ -845,11 +868,15 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         const float* c_prev = t ? s->c[t - 1] : s->c0;
         (void)h_state_prev;
         // decode fc_2, fc_1
-        TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), s->dtd));
-        dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->dtd, Dd, s->dtd, Dd, B, Dd, seed, ST(t, 7), kf, 0);
-        tanh_bwd_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->dtd, s->t1[t], (size_t)B * Dd);
-        if (tc_dx(2, s->dtd, s->dexp, &trc)) { TRET(trc); TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, s->dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
-        else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, s->dtd, Gd(vD1W), Gd(vD1B), s->dexp));
+        float* dtd = stack ? s->dys[2][t] : s->dtd;
+        float* dG = stack ? s->dys[1][t] : s->dG;
+        float* dq = stack ? s->dys[0][t] : s->dq;
+        if (stack) TCK(sgemm(st, false, true, B, Dd, V, s->dlogits[t], V, P(vD2W), V, dtd, Dd, false));   // dx only (V is not a K-block multiple)
+        else TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), dtd));
+        dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(dtd, Dd, dtd, Dd, B, Dd, seed, ST(t, 7), kf, 0);
+        tanh_bwd_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(dtd, s->t1[t], (size_t)B * Dd);
+        if (tc_dx(2, dtd, s->dexp, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
+        else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), s->dexp));
         dropout2d_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->dexp, XD, s->dexp, XD, B, XD, seed, ST(t, 6), kf, 0);
         // dexp = [dh_out | dz | demb]
         copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dexp, XD, B, H, 1);
@@ -858,9 +885,9 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         // h_out = drop_out(h_raw), h_state = drop_state(h_raw)
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_out, H, B, H, seed, ST(t, 5), kl, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_state, H, B, H, seed, ST(t, 4), kl, 1);
-        lstm_bwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dG, s->dc, s->dh_raw, s->acts[t], s->c[t], c_prev, B, H);
-        if (tc_dx(1, s->dG, s->dlin, &trc)) { TRET(trc); TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, s->dG, Gd(vLW), Gd(vLB), nullptr)); }
-        else TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, s->dG, Gd(vLW), Gd(vLB), s->dlin));
+        lstm_bwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(dG, s->dc, s->dh_raw, s->acts[t], s->c[t], c_prev, B, H);
+        if (tc_dx(1, dG, s->dlin, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), nullptr)); }
+        else TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), s->dlin));
         // dlin = [d xd (D+E) | dh_state_prev]
         copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_state, H, s->dlin + D + E, XL, B, H, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * (D + E)), 256, 0, st>>>(s->dbuf, D + E, s->dlin, XL, B, D + E, seed, ST(t, 3), kl, 0);
@@ -874,7 +901,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
         TCK(sgemm(st, true, false, A, 1, BL, s->temp, A, s->dalpha, 1, Gd(vA2W), 1, true));                  // dw2 += temp^T de
         att_dtemp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
-        segsum_kernel<<<dim3((A + 127) / 128, B), 128, 0, st>>>(s->dq, s->dtemp, B, L, A);
+        segsum_kernel<<<dim3((A + 127) / 128, B), 128, 0, st>>>(dq, s->dtemp, B, L, A);
         tanh_bwd_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->T1[t], (size_t)BL * A);
         dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
         if (tc) {
@@ -888,11 +915,28 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         } else {
             TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));       // contexts are inputs
         }
-        tanh_bwd_kernel<<<GRID1D((size_t)B * A), 256, 0, st>>>(s->dq, s->q[t], (size_t)B * A);
-        if (tc_dx(0, s->dq, s->dhd, &trc)) { TRET(trc); TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, s->dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
-        else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, s->dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
+        tanh_bwd_kernel<<<GRID1D((size_t)B * A), 256, 0, st>>>(dq, s->q[t], (size_t)B * A);
+        if (tc_dx(0, dq, s->dhd, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
+        else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
+    }
+    if (stack) {
+        // dW += X_all^T dY_all, db += colsum(dY_all) for attend/fc_1b, lstm, decode/fc_1, decode/fc_2 (the repack kernel
+        // transposes: X_all [T*B, K] read as a "[K' x n_out'] weight" is the packed operand X_all^T, row tile 128)
+        const int TB = T * B;
+        const float* xs[4] = {s->hd[0], s->lstm_in[0], s->expd[0], s->td[0]};
+        const float* dy[4] = {s->dys[0][0], s->dys[1][0], s->dys[2][0], s->dlogits[0]};
+        for (int i = 0; i < 4; ++i) {
+            TrainState::TcLayer& l = s->tcl[i];
+            TCK(sat::lin_repack_weight(xs[i], TB, l.K, 0, s->tc_sx, lmode, st));
+            TCK(sat::lin_repack_weight(dy[i], TB, l.N, 0, s->tc_sw, lmode, st));
+            int sp = 1;
+            const int tiles = ((l.N + 127) / 128) * ((l.K + 127) / 128);
+            while (sp * 2 <= 8 && tiles * sp * 2 <= 148) sp *= 2;
+            TRET(sat_dense_packed(s->handle, s->tc_sx, l.K, 128, TB, s->tc_sw, nullptr, l.N, sat::kEpiNone, Gd(l.var_w), l.N, 1, sp, st, 1));
+            colsum_kernel<<<dim3((l.N + 127) / 128, (TB + 255) / 256), 128, 0, st>>>(Gd(l.var_b), dy[i], TB, l.N);
+        }
     }
     // ------------------------------------------------------------ initialize backward
     // h0 is both h_out[-1] (attend of step 0) and h_state[-1] (LSTM of step 0); c0 receives dc

@@ -61,7 +61,9 @@ def test_tensor_core_attend_projection_in_training(seed):
     """Shapes at which attend/fc_1a (forward and weight gradient; dim_ctx, dim_attend_layer and B*L multiples of 128)
     and every batch-row product (forward, and dx where the output width is a multiple of 64) run on the tcgen05 dense
     kernel: same parity bars, and agreement with the CUDA-core path."""
-    ocfg, w, m, ctx, sent, masks = setup(B=4, seed=11, dims=TC_DIMS)
+    # B = 16, T = 4: T*B = 64 rows, so the weight gradients of the batch-row layers are also taken as ONE stacked
+    # product per layer after the time loop
+    ocfg, w, m, ctx, sent, masks = setup(B=16, seed=11, dims=TC_DIMS)
     ref_l, ref_g = TR.loss_and_grads(ocfg, w, ctx, sent, masks, seed if seed else None, reg_in_grad=False)
     res = {}
     for tc in (1, 0):

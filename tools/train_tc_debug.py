@@ -3,7 +3,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from test_gpu_train import setup, TC_DIMS
-ocfg, w, m, ctx, sent, masks = setup(B=4, seed=11, dims=TC_DIMS)
+ocfg, w, m, ctx, sent, masks = setup(B=16, seed=11, dims=TC_DIMS)
 res = {}
 for tc in (0, 1):
     m.set_option("train_tc", tc)
