@@ -36,8 +36,8 @@ WORKLOADS = {
             B=256, L=196, D=2048, H=1536, V=10000, T=20),
     # BASELINE.json configs[3]: training step, 64 images per GPU (512 on 8 GPUs), forward + backward + gradient
     # all-reduce + clip + Adam; tokens = teacher-forced words per step
-    4: dict(name="config4: training step B=64/GPU L=196 D=512 H=1024 V=10000 T=20, fwd+bwd+all-reduce+Adam (fp32 "
-                 "CUDA-core kernels, dropout on)", B=64, L=196, D=512, H=1024, V=10000, T=20, train=True),
+    4: dict(name="config4: training step B=64/GPU L=196 D=512 H=1024 V=10000 T=20, fwd+bwd+all-reduce+Adam (large "
+                 "products on the tcgen05 dense kernel as split bf16x3, the rest fp32 CUDA-core kernels; dropout on)", B=64, L=196, D=512, H=1024, V=10000, T=20, train=True),
     # BASELINE.json configs[4]: beam search, 128 images x beam 3, T=30 (tokens = images x T)
     5: dict(name="config5: beam search beam=3, 128 images, L=196 D=512 H=1024 V=10000 T=30 (device-side TopN)",
             B=128, L=196, D=512, H=1024, V=10000, T=30, beam=3),
