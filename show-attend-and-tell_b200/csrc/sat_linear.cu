@@ -510,11 +510,11 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                             if (P.accumulate) { const float4 a = *reinterpret_cast<const float4*>(o); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
                             *reinterpret_cast<float4*>(o) = g;
                         } else {
-                            const float a = P.accumulate ? 1.f : 0.f;
-                            if (ng + 0 < n_out) o[0] = g.x + a * o[0];
-                            if (ng + 1 < n_out) o[1] = g.y + a * o[1];
-                            if (ng + 2 < n_out) o[2] = g.z + a * o[2];
-                            if (ng + 3 < n_out) o[3] = g.w + a * o[3];
+                            const bool acc = P.accumulate != 0;   // (never read `o` otherwise: it may hold anything)
+                            if (ng + 0 < n_out) o[0] = acc ? g.x + o[0] : g.x;
+                            if (ng + 1 < n_out) o[1] = acc ? g.y + o[1] : g.y;
+                            if (ng + 2 < n_out) o[2] = acc ? g.z + o[2] : g.z;
+                            if (ng + 3 < n_out) o[3] = acc ? g.w + o[3] : g.w;
                         }
                     }
                     if (out_pa) {
