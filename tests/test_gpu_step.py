@@ -167,6 +167,33 @@ def test_loop_layouts_agree_and_pipelined_host_api():
         m.loop_host_wait(0)                                            # nothing in flight
 
 
+def test_reference_checkpoint_import(tmp_path):
+    """the reference saves / loads a pickled {tf_variable_name + ':0': ndarray} dict
+    (base_model.py:242-278) that also holds global_step and the optimizer slots.  load() takes that file as is."""
+    ocfg, w, m = make_pair(4)
+    ctx = R.synth_contexts(ocfg, 4)
+    want = m.decode_loop(ctx, 5, None, want_logits=True)[1]
+    import sat_b200
+    cfg = m.config
+    m2 = sat_b200.CaptionGenerator(cfg)
+    ckpt = {k + ":0": v for k, v in w.items()}
+    ckpt["global_step:0"] = np.int64(12345)
+    ckpt["optimizer/beta1_power:0"] = np.float32(0.5)
+    ckpt["OptimizeLoss/lstm/lstm_cell/kernel/Adam:0"] = np.zeros_like(w["lstm/lstm_cell/kernel"])
+    path = str(tmp_path / "289999.npy")
+    np.save(path, ckpt)
+    assert m2.load(None, path) == len(w)                 # every decoder variable found, extras ignored
+    got = m2.decode_loop(ctx, 5, None, want_logits=True)[1]
+    assert np.array_equal(got, want)
+    del ckpt["decode/fc_2/bias:0"]
+    np.save(path, ckpt)
+    m3 = sat_b200.CaptionGenerator(cfg)
+    assert m3.load(None, path) == len(w) - 1             # like the reference: counts what it could assign ...
+    with pytest.raises(sat_b200.SatError) as e:          # ... but a missing variable is an error at first use
+        m3.decode_loop(ctx, 2)
+    assert "decode/fc_2/bias" in str(e.value)
+
+
 def test_error_behaviour():
     import sat_b200
     cfg = sat_b200.Config(batch_size=2, beam_size=1, **SMALL)

@@ -3,3 +3,9 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -n 4 gpurun_out/pytest_gpu.log
+for i in 1 2 3; do
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu --workload 4 > gpurun_out/bench_train1.log 2>&1
+grep "^{" gpurun_out/bench_train1.log | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['e2e']['ms_per_step'])"
+done
