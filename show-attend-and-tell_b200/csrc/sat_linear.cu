@@ -788,7 +788,8 @@ __global__ void pack_rows_kernel(const PackJobs J) {
             uint4 hi, lo;
             split_bf16x8(a, c, hi, lo);
             const int rt = b / jb.row_tile, r = b - rt * jb.row_tile;
-            uint8_t* dst = jb.pa + ((size_t)rt * (jb.width >> 6) + (g >> 3)) * 2 * half + umma_tile_off(J.mode, r, g & 7);
+            const int kbs = jb.k_blocks > 0 ? jb.k_blocks : (jb.width >> 6);
+            uint8_t* dst = jb.pa + ((size_t)rt * kbs + (g >> 3)) * 2 * half + umma_tile_off(J.mode, r, g & 7);
             *reinterpret_cast<uint4*>(dst) = hi;
             *reinterpret_cast<uint4*>(dst + half) = lo;
         }

@@ -152,6 +152,8 @@ struct PackJob {           // fp32 rows (optionally gathered) -> packed activati
     const int32_t* gather;
     int ld, width, rows, row_tile;
     uint8_t* pa;
+    int k_blocks;   // K blocks per row tile of the destination (0 = width / 64).  Larger than width / 64 when the
+                    // consumer rounds a ragged width up; the caller keeps the unwritten tail of the last block zero.
 };
 cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st);
 

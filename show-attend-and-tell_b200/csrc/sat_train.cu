@@ -205,6 +205,24 @@ __global__ void dropout2d_kernel(float* y, int ldy, const float* x, int ldx, int
                                  const unsigned long long* seedp, unsigned long long stream, float keep, int accumulate) {
     const unsigned long long seed = *seedp;
     const size_t n = (size_t)rows * cols;
+    if (ldx == cols && ldy == cols && !accumulate && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+        // dense case (the [B*L, D] contexts): four elements per thread, no index arithmetic beyond the linear index
+        // (the mask of element i depends on i only, exactly as in the general path)
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4* y4 = reinterpret_cast<float4*>(y);
+        for (size_t i4 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i4 < (n >> 2); i4 += (size_t)gridDim.x * blockDim.x) {
+            float4 v = x4[i4];
+            if (seed) {
+                const unsigned long long i = i4 << 2;
+                v.x *= drop_scale(seed, stream, i, keep);
+                v.y *= drop_scale(seed, stream, i + 1, keep);
+                v.z *= drop_scale(seed, stream, i + 2, keep);
+                v.w *= drop_scale(seed, stream, i + 3, keep);
+            }
+            y4[i4] = v;
+        }
+        return;
+    }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
         const float s = seed ? drop_scale(seed, stream, i, keep) : 1.0f;
@@ -223,6 +241,17 @@ __global__ void bias_act_kernel(float* x, const float* b, int rows, int cols, in
 }
 // dx = dy * (1 - y^2) in place on dy
 __global__ void tanh_bwd_kernel(float* dy, const float* y, size_t n) {
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dy);
+        const float4* y4 = reinterpret_cast<const float4*>(y);
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (n >> 2); i += (size_t)gridDim.x * blockDim.x) {
+            float4 d = d4[i];
+            const float4 t = y4[i];
+            d.x *= 1.0f - t.x * t.x; d.y *= 1.0f - t.y * t.y; d.z *= 1.0f - t.z * t.z; d.w *= 1.0f - t.w * t.w;
+            d4[i] = d;
+        }
+        return;
+    }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dy[i] *= 1.0f - y[i] * y[i];
 }
@@ -265,6 +294,24 @@ __global__ void att_temp_kernel(float* temp, const float* T1, const float* q, in
                                 const unsigned long long* seedp, unsigned long long stream, float keep) {
     const unsigned long long seed = *seedp;
     const size_t n = (size_t)B * L * A;
+    if ((A & 3) == 0 && n < (1ull << 33) && ((reinterpret_cast<uintptr_t>(temp) | reinterpret_cast<uintptr_t>(T1) | reinterpret_cast<uintptr_t>(q)) & 15) == 0) {
+        const unsigned A4 = (unsigned)A >> 2, n4 = (unsigned)(n >> 2);
+        for (unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+            const unsigned row = i4 / A4, a4 = i4 - row * A4, b = row / (unsigned)L;
+            const float4 t = reinterpret_cast<const float4*>(T1)[i4];
+            const float4 qq = reinterpret_cast<const float4*>(q)[(size_t)b * A4 + a4];
+            float4 v = make_float4(t.x + qq.x, t.y + qq.y, t.z + qq.z, t.w + qq.w);
+            if (seed) {
+                const unsigned long long i = (unsigned long long)i4 << 2;
+                v.x *= drop_scale(seed, stream, i, keep);
+                v.y *= drop_scale(seed, stream, i + 1, keep);
+                v.z *= drop_scale(seed, stream, i + 2, keep);
+                v.w *= drop_scale(seed, stream, i + 3, keep);
+            }
+            reinterpret_cast<float4*>(temp)[i4] = v;
+        }
+        return;
+    }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int a = (int)(i % A);
         const int b = (int)(i / ((size_t)L * A));
@@ -330,6 +377,24 @@ __global__ void att_dtemp_kernel(float* dtemp, const float* de, const float* w2,
                                  const unsigned long long* seedp, unsigned long long stream, float keep) {
     const unsigned long long seed = *seedp;
     const size_t n = (size_t)rows * A;
+    if ((A & 3) == 0 && n < (1ull << 33) && ((reinterpret_cast<uintptr_t>(dtemp) | reinterpret_cast<uintptr_t>(w2)) & 15) == 0) {
+        const unsigned A4 = (unsigned)A >> 2, n4 = (unsigned)(n >> 2);
+        for (unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+            const unsigned row = i4 / A4, a4 = i4 - row * A4;
+            const float d = de[row];
+            const float4 w = reinterpret_cast<const float4*>(w2)[a4];
+            float4 v = make_float4(d * w.x, d * w.y, d * w.z, d * w.w);
+            if (seed) {
+                const unsigned long long i = (unsigned long long)i4 << 2;
+                v.x *= drop_scale(seed, stream, i, keep);
+                v.y *= drop_scale(seed, stream, i + 1, keep);
+                v.z *= drop_scale(seed, stream, i + 2, keep);
+                v.w *= drop_scale(seed, stream, i + 3, keep);
+            }
+            reinterpret_cast<float4*>(dtemp)[i4] = v;
+        }
+        return;
+    }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int a = (int)(i % A);
         const float s = seed ? drop_scale(seed, stream, i, keep) : 1.0f;
@@ -538,6 +603,10 @@ struct TrainState {
     int tc_rt = 0;              // their row tile
     // weight gradients of those layers: dW = sum_t x_t^T dy_t = X_all^T dY_all with the T steps stacked ([T*B, .]
     // matrices: the per-step stashes are contiguous), one tensor-core product per layer after the time loop
+    // input gradient of decode/fc_2: K = V is not a multiple of the 64-wide K block; its two operands get buffers of
+    // their own, zeroed once, so that the unwritten tail of the last K block stays zero
+    uint8_t *tc_vx = nullptr, *tc_vw = nullptr;
+    int tc_vk = 0;                         // V rounded up to K blocks (0 = path off)
     std::vector<float*> dys[4];            // [t] slices of dY_all per layer (decode/fc_2 uses dlogits)
     uint8_t *tc_sx = nullptr, *tc_sw = nullptr;   // packed X_all^T / packed dY_all
     bool tc_stack = false;
@@ -668,6 +737,16 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
         float* f = nullptr;
         A1(&f, (size_t)(s->tc_rt + 16) * kmax);
         s->tc_xs = reinterpret_cast<uint8_t*>(f);
+        if (s->tcl[3].fwd && V % 8 == 0) {
+            s->tc_vk = (int)((V + 63) / 64 * 64);
+            const size_t ddp = (Dd + 127) / 128 * 128;
+            A1(&f, (size_t)(s->tc_rt + 16) * s->tc_vk); s->tc_vx = reinterpret_cast<uint8_t*>(f);
+            A1(&f, ddp * s->tc_vk); s->tc_vw = reinterpret_cast<uint8_t*>(f);
+            if (rc == SAT_OK) {
+                cudaMemset(s->tc_vx, 0, (size_t)(s->tc_rt + 16) * s->tc_vk * 4);
+                cudaMemset(s->tc_vw, 0, ddp * s->tc_vk * 4);
+            }
+        }
         // stacked weight gradients: T*B rows must fill whole K blocks
         const size_t TB = (size_t)T * B;
         s->tc_stack = (TB % 64 == 0);
@@ -778,6 +857,11 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             }
         }
     }
+    const bool tcv = tcb && s->tc_vk > 0;
+    if (tcv) {   // decode/fc_2's W^T (rows Dd, K = V rounded up) for its input gradient
+        sat::PackJob job{P(vD2W), nullptr, V, V, Dd, 128, s->tc_vw, s->tc_vk / 64};
+        TCK(sat::pack_rows_launch(&job, 1, lmode, st));
+    }
     auto tc_splits = [&](int n_out, int K) {
         const int tiles = (n_out + 127) / 128;
         int sp = 1;
@@ -871,7 +955,16 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         float* dtd = stack ? s->dys[2][t] : s->dtd;
         float* dG = stack ? s->dys[1][t] : s->dG;
         float* dq = stack ? s->dys[0][t] : s->dq;
-        if (stack) TCK(sgemm(st, false, true, B, Dd, V, s->dlogits[t], V, P(vD2W), V, dtd, Dd, false));   // dx only (V is not a K-block multiple)
+        bool vdx = false;
+        if (tcv) {   // dtd = dlogits W2^T on the tensor cores (ragged K = V: zero-padded last K block)
+            sat::PackJob job{s->dlogits[t], nullptr, V, V, B, s->tc_rt, s->tc_vx, s->tc_vk / 64};
+            TCK(sat::pack_rows_launch(&job, 1, lmode, st));
+            TRET(sat_dense_packed(s->handle, s->tc_vx, B, s->tc_rt, s->tc_vk, s->tc_vw, nullptr, Dd, sat::kEpiNone, dtd, Dd, 0,
+                                  tc_splits(Dd, s->tc_vk), st));
+            vdx = true;
+        }
+        if (stack) { if (!vdx) TCK(sgemm(st, false, true, B, Dd, V, s->dlogits[t], V, P(vD2W), V, dtd, Dd, false)); }
+        else if (vdx) TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), nullptr));
         else TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), dtd));
         dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(dtd, Dd, dtd, Dd, B, Dd, seed, ST(t, 7), kf, 0);
         tanh_bwd_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(dtd, s->t1[t], (size_t)B * Dd);

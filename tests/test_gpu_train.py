@@ -53,7 +53,7 @@ def test_losses_and_gradients_match_autograd(seed):
 
 
 TC_DIMS = dict(num_ctx=32, dim_ctx=128, dim_embedding=64, num_lstm_units=64, dim_initalize_layer=16,
-               dim_attend_layer=128, dim_decode_layer=64, vocabulary_size=50, max_caption_length=4)
+               dim_attend_layer=128, dim_decode_layer=64, vocabulary_size=72, max_caption_length=4)
 
 
 @pytest.mark.parametrize("seed", [0, 31])
