@@ -1,11 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -k train > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -n 3 gpurun_out/pytest_gpu.log
-for i in 1 2; do
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu --workload 4 > gpurun_out/bench_train1.log 2>&1
-grep "^{" gpurun_out/bench_train1.log | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['e2e']['ms_per_step'])"
-done
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 8000 -c 3400 --csv \
+    --log-file gpurun_out/launches_train.csv python bench.py --steps 1 --warmup 1 --no-cpu --workload 4 > gpurun_out/ncu_train.log 2>&1
+tail -1 gpurun_out/ncu_train.log | cut -c1-200
