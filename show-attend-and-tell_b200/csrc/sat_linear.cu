@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         const unsigned am_gen0 = (do_am && pt == 0) ? ld_acquire_gpu(P.am_ctr + 1) : 0u;
 #pragma unroll 1
         // (the warm-up pass only pays for short epilogues: a long row loop warms itself)
-        for (int pass = (xtma && L.warm_epilogue && hi - lo <= 4 * kLinProducers) ? 0 : 1; pass < 2; ++pass) {
+        for (int pass = (xtma && L.warm_epilogue && (!row_loop || hi - lo <= 8 * kLinProducers)) ? 0 : 1; pass < 2; ++pass) {
             const bool dry = pass == 0;
             if (!dry) {
                 // ---- part 1: accumulator tile TMEM -> shared memory (two warps per TMEM lane quadrant).
@@ -540,20 +540,23 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                     const int r = r0 + (pt >> 2);
                     const bool live = r < rows_here;
                     const float4* row_t = reinterpret_cast<const float4*>(tile_s + (live ? r : 0) * kTileN) + part * 8;
-                    float bv = -INFINITY;
-                    int bi = 0x7fffffff;
-#pragma unroll 1
+                    // every element becomes an ordered 64-bit key (value bits, then inverted index) and the scan is a
+                    // running 64-bit max: two independent chains of 2-instruction steps instead of one chain of
+                    // compare / compare / select per element
+                    unsigned long long k0 = 0ull, k1 = 0ull;
+#pragma unroll 2
                     for (int j = 0; j < 8; ++j) {
                         const int jj = (j + pt) & 7;
                         const float4 a4 = row_t[jj];
                         const int i0 = n_tile * kTileN + part * 32 + jj * 4;
-                        const float y0 = a4.x, y1 = a4.y, y2 = a4.z, y3 = a4.w;
-                        if (i0 + 0 < n_out && (y0 > bv || (y0 == bv && i0 + 0 < bi))) { bv = y0; bi = i0 + 0; }
-                        if (i0 + 1 < n_out && (y1 > bv || (y1 == bv && i0 + 1 < bi))) { bv = y1; bi = i0 + 1; }
-                        if (i0 + 2 < n_out && (y2 > bv || (y2 == bv && i0 + 2 < bi))) { bv = y2; bi = i0 + 2; }
-                        if (i0 + 3 < n_out && (y3 > bv || (y3 == bv && i0 + 3 < bi))) { bv = y3; bi = i0 + 3; }
+                        const unsigned long long e0 = i0 + 0 < n_out ? argmax_key(a4.x, i0 + 0) : 0ull;
+                        const unsigned long long e1 = i0 + 1 < n_out ? argmax_key(a4.y, i0 + 1) : 0ull;
+                        const unsigned long long e2 = i0 + 2 < n_out ? argmax_key(a4.z, i0 + 2) : 0ull;
+                        const unsigned long long e3 = i0 + 3 < n_out ? argmax_key(a4.w, i0 + 3) : 0ull;
+                        k0 = max(k0, max(e0, e1));
+                        k1 = max(k1, max(e2, e3));
                     }
-                    unsigned long long key = argmax_key(bv, bi);
+                    unsigned long long key = max(k0, k1);
                     key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
                     key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
                     if (live && part == 0 && !dry) am_key[r] = key;
