@@ -255,14 +255,27 @@ __global__ void tanh_bwd_kernel(float* dy, const float* y, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dy[i] *= 1.0f - y[i] * y[i];
 }
-// db[c] += sum_r dx[r, c]
-__global__ void colsum_kernel(float* db, const float* dx, int rows, int cols) {
+// db[c] += sum_r dx[r, c] * (w ? w[r] : 1)   (column sums, optionally row-weighted: the weight gradient of a
+// one-column dense layer is dw[c] = sum_r x[r, c] * dy[r]).  Eight rows in flight per thread.
+__global__ void colsum_kernel(float* db, const float* dx, int rows, int cols, const float* w = nullptr) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     const int r0 = blockIdx.y * 256, r1 = min(rows, r0 + 256);
-    float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += dx[(size_t)r * cols + c];
-    atomicAdd(db + c, s);
+    float s0 = 0.f, s1 = 0.f;
+    int r = r0;
+    for (; r + 8 <= r1; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = dx[(size_t)(r + j) * cols + c];
+        if (w) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= w[r + j];
+        }
+        s0 += (v[0] + v[1]) + (v[2] + v[3]);
+        s1 += (v[4] + v[5]) + (v[6] + v[7]);
+    }
+    for (; r < r1; ++r) s0 += dx[(size_t)r * cols + c] * (w ? w[r] : 1.f);
+    atomicAdd(db + c, s0 + s1);
 }
 __global__ void copy2d_kernel(float* y, int ldy, const float* x, int ldx, int rows, int cols, int accumulate) {
     const size_t n = (size_t)rows * cols;
@@ -992,7 +1005,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         context_bwd_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->dalpha, s->dz, contexts, s->extra, B, L, D);
         softmax_bwd_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
         att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
-        TCK(sgemm(st, true, false, A, 1, BL, s->temp, A, s->dalpha, 1, Gd(vA2W), 1, true));                  // dw2 += temp^T de
+        colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
         att_dtemp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
         segsum_kernel<<<dim3((A + 127) / 128, B), 128, 0, st>>>(dq, s->dtemp, B, L, A);
         tanh_bwd_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->T1[t], (size_t)BL * A);
