@@ -1047,7 +1047,6 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     // ------------------------------------------------------------ initialize backward
     // h0 is both h_out[-1] (attend of step 0) and h_state[-1] (LSTM of step 0); c0 receives dc
     copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dh_state, H, B, H, 1);
-    float* dmean = s->dbuf;                 // [B, D]
     float* dmid = s->dbuf + (size_t)B * D;  // [B, I]
     TRET(dense_bwd(st, s->ib1d, B, I, P(vIb2W), H, s->dh_out, Gd(vIb2W), Gd(vIb2B), dmid));
     dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, I, dmid, I, B, I, seed, INIT + 2, kf, 0);
@@ -1057,7 +1056,6 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, I, dmid, I, B, I, seed, INIT + 1, kf, 0);
     tanh_bwd_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, s->ia1, (size_t)B * I);
     TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), I, dmid, Gd(vIa1W), Gd(vIa1B), nullptr));
-    (void)dmean;
     TCK(cudaGetLastError());
     TCK(cudaMemcpyAsync(losses, s->loss_acc, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return SAT_OK;
