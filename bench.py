@@ -198,7 +198,7 @@ def run_training(args, wl, model, cfg, rank, local_rank, world, dev):
     with torch.cuda.stream(st):
         ev0.record(st)
         for i in range(args.steps):
-            out = model.train_step(ctx_dev[i % pool], sent, masks, seed=100 + i)
+            model.train_step(ctx_dev[i % pool], sent, masks, seed=100 + i, sync=False)   # losses stay on the device
         ev1.record(st)
     barrier()
     ms = parallel.max_over_ranks(ev0.elapsed_time(ev1), dev)

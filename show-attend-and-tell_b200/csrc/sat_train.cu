@@ -625,11 +625,10 @@ struct TrainState {
     bool tc_stack = false;
     sat_handle* handle = nullptr;
     float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2
-    // per-call scalars live in device cells (fed from pinned host memory before each launch), so that the
+    // per-call scalars live in device cells (fed by small stream-ordered copies before each launch), so that the
     // ~3500 launches of a step are captured once into a CUDA graph and replayed
     unsigned long long* seed_d = nullptr;
     float* inv_msum_d = nullptr;
-    unsigned long long* seed_h = nullptr;   // pinned: [0] seed, [1] bits of inv_msum
     struct GEntry { std::vector<long long> key; int seen = 0; cudaGraphExec_t exec = nullptr; };
     std::vector<GEntry> graphs;
     std::vector<void*> all;
@@ -648,7 +647,6 @@ void train_free(void* p) {
     for (void* b : s->all) cudaFree(b);
     for (auto& g : s->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
-    if (s->seed_h) cudaFreeHost(s->seed_h);
     delete s;
 }
 
@@ -781,7 +779,6 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
     if (rc == SAT_OK) {
         s->seed_d = reinterpret_cast<unsigned long long*>(cells);
         s->inv_msum_d = cells + 2;
-        if (cudaMallocHost((void**)&s->seed_h, 16) != cudaSuccess) rc = sat_fail(SAT_ERR_NOMEM, "pinned staging");
     }
     if (rc != SAT_OK) { train_free(s); return rc; }
     *slot = s;
@@ -1070,13 +1067,13 @@ extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, fl
     TrainState* s = (TrainState*)*sat_handle_train_slot(h);
     if (!s || s->B != B || s->T != T) return sat_fail(SAT_ERR_STATE, "call sat_train_init(B=%d, T=%d) first", B, T);
     cudaStream_t st = (cudaStream_t)stream;
-    // per-call scalars -> device cells (the pinned staging must not be overwritten while a copy is in flight)
-    TCK(cudaStreamSynchronize(st));
-    s->seed_h[0] = seed;
-    const float inv = (float)(1.0 / global_mask_sum);
-    memcpy(&s->seed_h[1], &inv, sizeof(float));
-    TCK(cudaMemcpyAsync(s->seed_d, &s->seed_h[0], 8, cudaMemcpyHostToDevice, st));
-    TCK(cudaMemcpyAsync(s->inv_msum_d, &s->seed_h[1], 4, cudaMemcpyHostToDevice, st));
+    // per-call scalars -> device cells, in stream order.  The sources are ordinary (pageable) host variables: such a
+    // copy is staged by the driver before the call returns, so no stream synchronisation is needed to reuse them
+    // and the host can queue the next step while this one runs.
+    unsigned long long seed_v = seed;
+    float inv = (float)(1.0 / global_mask_sum);
+    TCK(cudaMemcpyAsync(s->seed_d, &seed_v, 8, cudaMemcpyHostToDevice, st));
+    TCK(cudaMemcpyAsync(s->inv_msum_d, &inv, 4, cudaMemcpyHostToDevice, st));
     auto enqueue = [&]() { return train_enqueue(s, params, grads, contexts, sentences, masks, B, T, global_batch, losses, st); };
     if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return enqueue();
     std::vector<long long> key = {(long long)params, (long long)grads, (long long)contexts, (long long)sentences,

@@ -246,7 +246,7 @@ class CaptionGenerator(object):
         sent = self._dev(sentences, torch.int32)
         mk = self._dev(masks, torch.float32)
         assert tuple(sent.shape) == (B, T) and tuple(mk.shape) == (B, T) and ctx.shape[0] == B
-        gms = float(mk.sum().item()) if global_mask_sum is None else float(global_mask_sum)
+        gms = self._mask_sum(masks, mk) if global_mask_sum is None else float(global_mask_sum)
         gb = B if global_batch is None else int(global_batch)
         self._sync_in()
         self._check(self.lib.sat_train_forward_backward(self._h, self._p(self.params), self._p(self.grads), self._p(ctx),
@@ -255,6 +255,21 @@ class CaptionGenerator(object):
         self._sync_out()
         self._keep["train_in"] = (ctx, sent, mk)
         return self._train_losses
+
+    def _mask_sum(self, masks, mk):
+        """Sum of the caption masks as a host float without stalling the device when it can be avoided: host arrays are
+        summed on the host; a device tensor is summed once and remembered until it is modified."""
+        torch = self.torch
+        if isinstance(masks, np.ndarray):
+            return float(masks.astype(np.float64).sum())
+        if isinstance(masks, torch.Tensor) and not masks.is_cuda:
+            return float(masks.double().sum())
+        key = (mk.data_ptr(), mk._version, tuple(mk.shape))
+        hit = self._keep.get("mask_sum")
+        if hit is None or hit[0] != key:
+            hit = (key, float(mk.sum().item()))
+            self._keep["mask_sum"] = hit
+        return hit[1]
 
     def train_apply(self):
         """Regulariser gradient + global-norm clip + Adam on self.grads (already summed over ranks)."""
@@ -268,25 +283,31 @@ class CaptionGenerator(object):
         self._sync_out()
         return self._train_norm
 
-    def train_step(self, contexts, sentences, masks, seed=0):
+    def train_step(self, contexts, sentences, masks, seed=0, sync=True):
         """One optimisation step (the sess.run(opt_op) of base_model.py:57-60) on this process's shard; with
         torch.distributed initialised the gradients are summed over the ranks by ONE all-reduce of the flat
-        buffer (NCCL) and the losses are normalised by the global batch."""
+        buffer (NCCL) and the losses are normalised by the global batch.  sync=False returns the device tensors
+        (losses [4], squared gradient norm [1]) without reading them back, so that the host can queue the next step
+        while this one runs (the reference reads its summary every step; a training loop rarely needs to)."""
         import torch.distributed as dist
         torch = self.torch
         B, T = self._train_BT
         mk = self._dev(masks, torch.float32)
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        msum = mk.sum().reshape(1).double()
+        msum = self._mask_sum(masks, mk)
         if world > 1:
-            dist.all_reduce(msum)
+            t = torch.tensor([msum], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t)
+            msum = float(t.item())
             seed = int(seed) + 0x1000003 * dist.get_rank() if seed else 0
-        losses = self.train_forward_backward(contexts, sentences, mk, seed, float(msum.item()), B * world)
+        losses = self.train_forward_backward(contexts, sentences, mk, seed, msum, B * world)
         if world > 1:
             dist.all_reduce(self.grads)                    # the single gradient all-reduce of the step
             losses = losses.clone()
             dist.all_reduce(losses[:3])                    # CE / accuracy / attention are sums of shard parts
         norm2 = self.train_apply()
+        if not sync:
+            return losses, norm2
         ce, acc, att, reg = [float(x) for x in losses.tolist()]
         return dict(cross_entropy_loss=ce, accuracy=acc, attention_loss=att, reg_loss=reg, total_loss=ce + att + reg,
                     gradient_norm=float(norm2.item()) ** 0.5)
