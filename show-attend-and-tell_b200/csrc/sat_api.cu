@@ -141,7 +141,7 @@ struct sat_handle {
     uint8_t* pa_z2[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0, opt_l2_vocab = -1, opt_l2_prefetch = 0, opt_stages = 0, opt_train_tc = 1;
+    int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0, opt_l2_vocab = -1, opt_l2_prefetch = 0, opt_stages = 0, opt_train_tc = 1, opt_dec1_splits = 0;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -419,6 +419,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "l2_prefetch") h->opt_l2_prefetch = (int)value;
     else if (k == "stages") h->opt_stages = (int)value;
     else if (k == "train_tc") h->opt_train_tc = (int)value;
+    else if (k == "dec1_splits") h->opt_dec1_splits = (int)value;
     else if (k == "l2_t") h->opt_l2_t = (int)value;
     else if (k == "l2_ctx") h->opt_l2_ctx = (int)value;
     else if (k == "profile") {
@@ -978,7 +979,7 @@ static int decode_impl(sat_handle* h, const float* h_out, const float* z, const 
                  {seg(h_out, d.num_lstm_units, d.num_lstm_units, nullptr, pa ? h->pa_cur_h_out : nullptr),
                   seg(z, d.dim_ctx, d.dim_ctx, nullptr, pa ? (h->pa_cur_z ? h->pa_cur_z : h->pa_z) : nullptr),
                   seg(h->embedding, d.dim_embedding, d.dim_embedding, last_word, pa ? h->pa_emb : nullptr)},
-                 rows, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st, 0, group));
+                 rows, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st, h->opt_dec1_splits, group));
         P[0].out_pa = pa ? h->pa_t : nullptr;
         int np = 1;
         if (make_next_q) {  // q of the next step depends on the same h_out: share the launch
