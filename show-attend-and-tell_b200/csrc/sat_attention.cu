@@ -23,6 +23,10 @@
 // There is no grid-wide dependency inside the kernel: a single producer thread keeps the
 // ring full across the T1 -> ctx boundary, so the SM never waits on another SM.
 // G rows (beams) of one image share the image's T1/ctx traffic.
+//
+// Two kernels implement this: att_wpc_kernel (further down; rows of exactly 512 floats, the reference's sizes:
+// a TMA chunk of 8 rows belongs to ONE consumer warp, row sums by a transposing butterfly, whole-image CTAs
+// normalise in place) and att_fused_kernel (below; any width, all warps on every chunk) as the general path.
 #include "sat_common.cuh"
 #include "sat_attention.cuh"
 #include "sat_linear.cuh"

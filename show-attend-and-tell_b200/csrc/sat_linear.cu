@@ -29,6 +29,16 @@
 // Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM
 // allocator + MMA issuer (one lane), warps 2..9 = X producers (modes 0/1), then
 // epilogue.
+//
+// Launch chaining: every launch carries the programmatic-dependent-launch attribute.  The TMA lane fills its
+// first stages with weights before griddepcontrol.wait; launch_dependents is called only after the wait (so a
+// kernel never starts before the predecessor of its predecessor has completed).  While the main loop streams,
+// the idle epilogue warps run the (short) epilogue once without side effects to pull its code into the
+// instruction caches: epilogues execute once per launch from cold caches, and that costs microseconds.
+// The vocabulary layer's fused arg-max ends in a grid-wide rendezvous of its one-wave launch; CTA i then merges
+// row i's candidates and packs the embedding row of the chosen word for the next LSTM / decode layers.
+// The training step (sat_train.cu) uses the same kernel through sat_dense_packed(): packed operands of either
+// role, an accumulate epilogue, weights that may come from the preceding kernel (w_dynamic).
 #include "sat_common.cuh"
 #include "sat_linear.cuh"
 
