@@ -277,6 +277,40 @@ __global__ void colsum_kernel(float* db, const float* dx, int rows, int cols, co
     for (; r < r1; ++r) s0 += dx[(size_t)r * cols + c] * (w ? w[r] : 1.f);
     atomicAdd(db + c, s0 + s1);
 }
+// out[r, :] = concat(a[r, :na], b[r, :nb], c[r, :nc]) with dropout on the first `ndrop` columns, mask index
+// r * ndrop + col (= a dropout2d over a dense [rows, ndrop] matrix: one launch instead of three copies + one dropout)
+__global__ void concat3_drop_kernel(float* out, int ldo, const float* a, int na, const float* b, int nb, const float* c, int nc,
+                                    int ndrop, int rows, const unsigned long long* seedp, unsigned long long stream, float keep) {
+    const unsigned long long seed = *seedp;
+    const int cols = na + nb + nc;
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), col = (int)(i - (size_t)r * cols);
+        float v = col < na ? a[(size_t)r * na + col] : col < na + nb ? b[(size_t)r * nb + col - na] : c[(size_t)r * nc + col - na - nb];
+        if (seed && col < ndrop) v *= drop_scale(seed, stream, (unsigned long long)r * ndrop + col, keep);
+        out[(size_t)r * ldo + col] = v;
+    }
+}
+// the transpose of the above: src[r, :] (dropout on the first ndrop columns) is split into three destinations, each
+// either assigned or accumulated
+__global__ void split3_drop_kernel(const float* src, int lds, int rows, float* a, int na, int acc_a, float* b, int nb, int acc_b,
+                                   float* c, int nc, int acc_c, int ndrop, const unsigned long long* seedp,
+                                   unsigned long long stream, float keep) {
+    const unsigned long long seed = *seedp;
+    const int cols = na + nb + nc;
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), col = (int)(i - (size_t)r * cols);
+        float v = src[(size_t)r * lds + col];
+        if (seed && col < ndrop) v *= drop_scale(seed, stream, (unsigned long long)r * ndrop + col, keep);
+        float* o;
+        int acc;
+        if (col < na) { o = a + (size_t)r * na + col; acc = acc_a; }
+        else if (col < na + nb) { o = b + (size_t)r * nb + col - na; acc = acc_b; }
+        else { o = c + (size_t)r * nc + col - na - nb; acc = acc_c; }
+        *o = acc ? *o + v : v;
+    }
+}
 __global__ void copy2d_kernel(float* y, int ldy, const float* x, int ldx, int rows, int cols, int accumulate) {
     const size_t n = (size_t)rows * cols;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -925,20 +959,17 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         // embedding of the previous word: 0 at t = 0, then teacher forcing (model.py:254, 310)
         gather_rows_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->emb[t], E, P(vEmb), E, t ? sentences + (t - 1) : nullptr, T, B);
         // LSTM with DropoutWrapper (model.py:228-236, 276-279)
-        copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dlin, D + E, s->z[t], D, B, D, 0);
-        copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->dlin + D, D + E, s->emb[t], E, B, E, 0);
-        dropout2d_kernel<<<GRID1D((size_t)B * (D + E)), 256, 0, st>>>(s->lstm_in[t], XL, s->dlin, D + E, B, D + E, seed, ST(t, 3), kl, 0);
-        copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->lstm_in[t] + D + E, XL, h_state_prev, H, B, H, 0);
+        // lstm_in = [ drop_in(concat(z, emb)) | h_state_prev ]
+        concat3_drop_kernel<<<GRID1D((size_t)B * XL), 256, 0, st>>>(s->lstm_in[t], XL, s->z[t], D, s->emb[t], E, h_state_prev, H, D + E, B,
+                                                                    seed, ST(t, 3), kl);
         if (tc_fwd(1, s->lstm_in[t], sat::kEpiNone, s->acts[t], &trc)) { TRET(trc); }   // (bias and gates: next kernel)
         else TCK(sgemm(st, false, false, B, 4 * H, XL, s->lstm_in[t], XL, P(vLW), 4 * H, s->acts[t], 4 * H, false));
         lstm_fwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->acts[t], P(vLB), c_prev, s->c[t], s->h_raw, B, H);
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->h_out[t], H, s->h_raw, H, B, H, seed, ST(t, 5), kl, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->h_state[t], H, s->h_raw, H, B, H, seed, ST(t, 4), kl, 0);
         // decode (model.py:282-287, 438-459)
-        copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dexp, XD, s->h_out[t], H, B, H, 0);
-        copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dexp + H, XD, s->z[t], D, B, D, 0);
-        copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->dexp + H + D, XD, s->emb[t], E, B, E, 0);
-        dropout2d_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->expd[t], XD, s->dexp, XD, B, XD, seed, ST(t, 6), kf, 0);
+        concat3_drop_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->expd[t], XD, s->h_out[t], H, s->z[t], D, s->emb[t], E, XD, B,
+                                                                    seed, ST(t, 6), kf);
         if (tc_fwd(2, s->expd[t], sat::kEpiBiasTanh, s->t1[t], &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), Dd, s->t1[t], 1));
         dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->td[t], Dd, s->t1[t], Dd, B, Dd, seed, ST(t, 7), kf, 0);
@@ -980,11 +1011,9 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         tanh_bwd_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(dtd, s->t1[t], (size_t)B * Dd);
         if (tc_dx(2, dtd, s->dexp, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
         else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), s->dexp));
-        dropout2d_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->dexp, XD, s->dexp, XD, B, XD, seed, ST(t, 6), kf, 0);
-        // dexp = [dh_out | dz | demb]
-        copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dexp, XD, B, H, 1);
-        copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dz, D, s->dexp + H, XD, B, D, 0);
-        copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->demb, E, s->dexp + H + D, XD, B, E, 0);
+        // drop(dexp) = [dh_out (+=) | dz (=) | demb (=)]
+        split3_drop_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, s->demb, E, 0, XD, seed,
+                                                                   ST(t, 6), kf);
         // h_out = drop_out(h_raw), h_state = drop_state(h_raw)
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_out, H, B, H, seed, ST(t, 5), kl, 0);
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_state, H, B, H, seed, ST(t, 4), kl, 1);
@@ -992,10 +1021,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         if (tc_dx(1, dG, s->dlin, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), nullptr)); }
         else TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), s->dlin));
         // dlin = [d xd (D+E) | dh_state_prev]
-        copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_state, H, s->dlin + D + E, XL, B, H, 0);
-        dropout2d_kernel<<<GRID1D((size_t)B * (D + E)), 256, 0, st>>>(s->dbuf, D + E, s->dlin, XL, B, D + E, seed, ST(t, 3), kl, 0);
-        copy2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->dz, D, s->dbuf, D + E, B, D, 1);
-        copy2d_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->demb, E, s->dbuf + D, D + E, B, E, 1);
+        split3_drop_kernel<<<GRID1D((size_t)B * XL), 256, 0, st>>>(s->dlin, XL, B, s->dz, D, 1, s->demb, E, 1, s->dh_state, H, 0, D + E, seed,
+                                                                   ST(t, 3), kl);
         scatter_add_rows_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(Gd(vEmb), E, t ? sentences + (t - 1) : nullptr, T, s->demb, E, B);
         // attention: context vector, softmax, scorer
         coverage_grad_kernel<<<(BL + 255) / 256, 256, 0, st>>>(s->extra, s->datt, masks, T, t, B, L);
