@@ -742,7 +742,8 @@ __global__ void __launch_bounds__(128) lin_simt_kernel(const __grid_constant__ L
 // packed bf16 hi/lo UMMA tiles.  perm_H > 0 selects the LSTM gate interleave:
 // packed output p = unit*4 + gate  <->  TF column gate*H + unit (split order i,j,f,o).
 __global__ void repack_weight_kernel(const float* __restrict__ w, int K, int n_out, int perm_H, uint8_t* wpack,
-                                     int k_blocks, int n_tiles, int mode) {
+                                     int k_blocks, int n_tiles, int mode, DropSpec drop) {
+    const unsigned long long seed = drop.seedp ? *drop.seedp : 0ull;
     const size_t total = (size_t)n_tiles * k_blocks * kTileN * 8;  // 16-byte groups
     for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(g % kTileN);
@@ -759,6 +760,7 @@ __global__ void repack_weight_kernel(const float* __restrict__ w, int K, int n_o
         for (int e = 0; e < 8; ++e) {
             const int k = kb * kBK + kg * 8 + e;
             x[e] = (col >= 0 && k < K) ? w[(size_t)k * n_out + col] : 0.f;
+            if (seed && col >= 0 && k < K) x[e] *= drop_scale(seed, drop.stream, (unsigned long long)k * n_out + col, drop.keep);
         }
         uint4 hi, lo;
         split_bf16x8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), hi, lo);
@@ -781,8 +783,10 @@ __global__ void repack_bias_kernel(const float* __restrict__ b, int n_out, int p
 struct PackJobs {
     PackJob j[2];
     int n, mode;
+    DropSpec drop;
 };
 __global__ void pack_rows_kernel(const PackJobs J) {
+    const unsigned long long seed = J.drop.seedp ? *J.drop.seedp : 0ull;
     for (int q = 0; q < J.n; ++q) {
         const PackJob& jb = J.j[q];
         const int groups = jb.width >> 3;
@@ -797,6 +801,17 @@ __global__ void pack_rows_kernel(const PackJobs J) {
                 const float4* src = reinterpret_cast<const float4*>(jb.src + (size_t)row * jb.ld + g * 8);
                 a = src[0];
                 c = src[1];
+                if (seed) {
+                    const unsigned long long i0 = (unsigned long long)row * jb.width + g * 8;
+                    a.x *= drop_scale(seed, J.drop.stream, i0, J.drop.keep);
+                    a.y *= drop_scale(seed, J.drop.stream, i0 + 1, J.drop.keep);
+                    a.z *= drop_scale(seed, J.drop.stream, i0 + 2, J.drop.keep);
+                    a.w *= drop_scale(seed, J.drop.stream, i0 + 3, J.drop.keep);
+                    c.x *= drop_scale(seed, J.drop.stream, i0 + 4, J.drop.keep);
+                    c.y *= drop_scale(seed, J.drop.stream, i0 + 5, J.drop.keep);
+                    c.z *= drop_scale(seed, J.drop.stream, i0 + 6, J.drop.keep);
+                    c.w *= drop_scale(seed, J.drop.stream, i0 + 7, J.drop.keep);
+                }
             }
             uint4 hi, lo;
             split_bf16x8(a, c, hi, lo);
@@ -809,10 +824,11 @@ __global__ void pack_rows_kernel(const PackJobs J) {
     }
 }
 
-cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st) {
+cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st, const DropSpec* drop) {
     PackJobs J;
     J.n = njobs;
     J.mode = layout_mode;
+    J.drop = drop ? *drop : DropSpec{nullptr, 0ull, 1.0f};
     int total = 0;
     for (int i = 0; i < njobs; ++i) {
         J.j[i] = jobs[i];
@@ -902,9 +918,10 @@ cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt) {
 }
 
 cudaError_t lin_repack_weight(const float* w_tf, int K, int n_out, int perm_H, uint8_t* wpack, int layout_mode,
-                              cudaStream_t st) {
+                              cudaStream_t st, const DropSpec* drop) {
     const int k_blocks = (K + kBK - 1) / kBK, n_tiles = (n_out + kTileN - 1) / kTileN;
-    repack_weight_kernel<<<1184, 256, 0, st>>>(w_tf, K, n_out, perm_H, wpack, k_blocks, n_tiles, layout_mode);
+    repack_weight_kernel<<<1184, 256, 0, st>>>(w_tf, K, n_out, perm_H, wpack, k_blocks, n_tiles, layout_mode,
+                                               drop ? *drop : DropSpec{nullptr, 0ull, 1.0f});
     return cudaGetLastError();
 }
 

@@ -147,6 +147,28 @@ __device__ __forceinline__ int argmax_key_index(unsigned long long key) { return
 
 constexpr int kAmSmemWords = 1024;   // rows whose chosen word the last CTA keeps in shared memory
 
+// Counter-based dropout masks of the training path (sat_train.cu): element `idx` of mask stream `stream` is kept
+// when floor(keep + U) == 1, U = rng_u24(seed, stream, idx) in [0, 1).  The packing kernels below can apply such a
+// mask while they convert, so a dropped copy of a large operand is never materialised in fp32.
+__host__ __device__ inline float rng_u24(unsigned long long seed, unsigned long long stream, unsigned long long idx) {
+    unsigned long long x = (seed ^ (stream * 0x9E3779B97F4A7C15ull)) + idx * 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (float)(x >> 40) * 5.9604644775390625e-08f;  // 2^-24
+}
+__host__ __device__ inline float drop_scale(unsigned long long seed, unsigned long long stream, unsigned long long idx, float keep) {
+    // x / keep * floor(keep + U)
+    return floorf(keep + rng_u24(seed, stream, idx)) / keep;
+}
+struct DropSpec {          // seedp == nullptr or *seedp == 0: no dropout
+    const unsigned long long* seedp;
+    unsigned long long stream;
+    float keep;
+};
+
 struct PackJob {           // fp32 rows (optionally gathered) -> packed activation
     const float* src;
     const int32_t* gather;
@@ -155,13 +177,15 @@ struct PackJob {           // fp32 rows (optionally gathered) -> packed activati
     int k_blocks;   // K blocks per row tile of the destination (0 = width / 64).  Larger than width / 64 when the
                     // consumer rounds a ragged width up; the caller keeps the unwritten tail of the last block zero.
 };
-cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st);
+// drop (optional) applies to every job: mask index = row * width + column of the (un-gathered) source row
+cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st, const DropSpec* drop = nullptr);
 
 size_t lin_smem_bytes(int row_tile, int stages);
 int lin_pick_stages(int row_tile);
 cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt);
+// drop (optional): mask index = k * n_out + column of the source
 cudaError_t lin_repack_weight(const float* w_tf, int K, int n_out, int perm_H, uint8_t* wpack, int layout_mode,
-                              cudaStream_t st);
+                              cudaStream_t st, const DropSpec* drop = nullptr);
 cudaError_t lin_repack_bias(const float* b_tf, int n_out, int perm_H, float* bias_packed, cudaStream_t st);
 cudaError_t lin_init_attrs();
 

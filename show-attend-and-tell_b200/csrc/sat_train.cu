@@ -42,19 +42,9 @@ namespace {
     } while (0)
 
 // ------------------------------------------------------------------------------------------ RNG
-__host__ __device__ inline float rng_u24(unsigned long long seed, unsigned long long stream, unsigned long long idx) {
-    unsigned long long x = (seed ^ (stream * 0x9E3779B97F4A7C15ull)) + idx * 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 30;
-    x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27;
-    x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    return (float)(x >> 40) * 5.9604644775390625e-08f;  // 2^-24
-}
-__device__ inline float drop_scale(unsigned long long seed, unsigned long long stream, unsigned long long idx, float keep) {
-    // x / keep * floor(keep + U)
-    return floorf(keep + rng_u24(seed, stream, idx)) / keep;
-}
+// counter-based dropout masks: sat::rng_u24 / sat::drop_scale of sat_linear.cuh (shared with the packing kernels)
+using sat::drop_scale;
+using sat::rng_u24;
 
 // ------------------------------------------------------------------------------------------ SGEMM
 // C[M,N] = op(A)[M,K] * op(B)[K,N] (+ C if accumulate).  Row-major.  TA: A is stored [K,M]; TB: B is stored [N,K].
@@ -364,6 +354,98 @@ __global__ void att_temp_kernel(float* temp, const float* T1, const float* q, in
         const int b = (int)(i / ((size_t)L * A));
         const float s = seed ? drop_scale(seed, stream, i, keep) : 1.0f;
         temp[i] = (T1[i] + q[(size_t)b * A + a]) * s;
+    }
+}
+// e[b*L + l] = sum_a (T1[b*L + l, a] + q[b, a]) * drop(att_mid) * w2[a]: att_temp + rowdot in one pass over T1 (temp is
+// not stored; the backward pass rebuilds it from T1, q and the mask).  One warp per row, A % 4 == 0.
+__global__ void att_logits_kernel(float* e, const float* T1, const float* q, const float* w2, int B, int L, int A,
+                                  const unsigned long long* seedp, unsigned long long stream, float keep) {
+    const unsigned long long seed = *seedp;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= B * L) return;
+    const int A4 = A >> 2, b = row / L;
+    const float4* t4 = reinterpret_cast<const float4*>(T1) + (size_t)row * A4;
+    const float4* q4 = reinterpret_cast<const float4*>(q) + (size_t)b * A4;
+    const float4* w4 = reinterpret_cast<const float4*>(w2);
+    float s = 0.f;
+#pragma unroll 4
+    for (int a4 = lane; a4 < A4; a4 += 32) {
+        const float4 t = t4[a4], qq = q4[a4], w = w4[a4];
+        float4 v = make_float4(t.x + qq.x, t.y + qq.y, t.z + qq.z, t.w + qq.w);
+        if (seed) {
+            const unsigned long long i = ((unsigned long long)row * A4 + a4) << 2;
+            v.x *= drop_scale(seed, stream, i, keep);
+            v.y *= drop_scale(seed, stream, i + 1, keep);
+            v.z *= drop_scale(seed, stream, i + 2, keep);
+            v.w *= drop_scale(seed, stream, i + 3, keep);
+        }
+        s = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, s))));
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) e[row] = s;
+}
+// The backward pass of the scorer in one pass over T1 (A % 4 == 0).  With m = drop(att_mid) and de the logit gradient:
+//   dtemp[r, a] = de[r] * w2[a] * m[r, a] * (1 - T1[r, a]^2)        (written: the gradient at the fc_1a pre-activation)
+//   dq[b, a]   += sum_l de[r] * w2[a] * m[r, a]                      (dq zeroed by the caller)
+//   dw2[a]     += sum_r (T1[r, a] + q[b, a]) * m[r, a] * de[r]
+//   db[a]      += sum_r dtemp[r, a]                                  (db may be null)
+// grid (ceil(A/256), row chunks, B), 256 threads = 4 row groups x 64 float4 columns.
+constexpr int kAbRG = 4, kAbCT = 64;
+__global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(float* dtemp, float* dq, float* dw2, float* db, const float* T1,
+                                                                      const float* q, const float* de, const float* w2, int L, int A,
+                                                                      int chunk_rows, const unsigned long long* seedp,
+                                                                      unsigned long long stream, float keep) {
+    __shared__ float4 red[3][kAbRG - 1][kAbCT];
+    const unsigned long long seed = *seedp;
+    const int ct = threadIdx.x % kAbCT, rg = threadIdx.x / kAbCT;
+    const int A4 = A >> 2, c4 = blockIdx.x * kAbCT + ct, b = blockIdx.z;
+    const int l0 = blockIdx.y * chunk_rows, l1 = min(L, l0 + chunk_rows);
+    const bool on = c4 < A4;
+    float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), aw = aq, ab = aq;
+    if (on) {
+        const float4 w = reinterpret_cast<const float4*>(w2)[c4];
+        const float4 qq = reinterpret_cast<const float4*>(q)[(size_t)b * A4 + c4];
+#pragma unroll 4
+        for (int l = l0 + rg; l < l1; l += kAbRG) {
+            const size_t r = (size_t)b * L + l;
+            const float4 t = reinterpret_cast<const float4*>(T1)[r * A4 + c4];
+            const float d = de[r];
+            float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (seed) {
+                const unsigned long long i = (r * A4 + c4) << 2;
+                m.x = drop_scale(seed, stream, i, keep);
+                m.y = drop_scale(seed, stream, i + 1, keep);
+                m.z = drop_scale(seed, stream, i + 2, keep);
+                m.w = drop_scale(seed, stream, i + 3, keep);
+            }
+            const float4 dm = make_float4(d * m.x, d * m.y, d * m.z, d * m.w);          // de * mask
+            const float4 g = make_float4(dm.x * w.x, dm.y * w.y, dm.z * w.z, dm.w * w.w);  // d temp (before the mask: d (T1 + q))
+            aq.x += g.x; aq.y += g.y; aq.z += g.z; aq.w += g.w;
+            aw.x = fmaf(t.x + qq.x, dm.x, aw.x); aw.y = fmaf(t.y + qq.y, dm.y, aw.y);
+            aw.z = fmaf(t.z + qq.z, dm.z, aw.z); aw.w = fmaf(t.w + qq.w, dm.w, aw.w);
+            const float4 o = make_float4(g.x * (1.0f - t.x * t.x), g.y * (1.0f - t.y * t.y), g.z * (1.0f - t.z * t.z), g.w * (1.0f - t.w * t.w));
+            ab.x += o.x; ab.y += o.y; ab.z += o.z; ab.w += o.w;
+            reinterpret_cast<float4*>(dtemp)[r * A4 + c4] = o;
+        }
+    }
+    if (rg > 0) { red[0][rg - 1][ct] = aq; red[1][rg - 1][ct] = aw; red[2][rg - 1][ct] = ab; }
+    __syncthreads();
+    if (rg == 0 && on) {
+#pragma unroll
+        for (int g = 0; g < kAbRG - 1; ++g) {
+            const float4 x = red[0][g][ct], y = red[1][g][ct], z = red[2][g][ct];
+            aq.x += x.x; aq.y += x.y; aq.z += x.z; aq.w += x.w;
+            aw.x += y.x; aw.y += y.y; aw.z += y.z; aw.w += y.w;
+            ab.x += z.x; ab.y += z.y; ab.z += z.z; ab.w += z.w;
+        }
+        float* pq = dq + ((size_t)b * A4 + c4) * 4;
+        float* pw = dw2 + (size_t)c4 * 4;
+        atomicAdd(pq, aq.x); atomicAdd(pq + 1, aq.y); atomicAdd(pq + 2, aq.z); atomicAdd(pq + 3, aq.w);
+        atomicAdd(pw, aw.x); atomicAdd(pw + 1, aw.y); atomicAdd(pw + 2, aw.z); atomicAdd(pw + 3, aw.w);
+        if (db) {
+            float* pb = db + (size_t)c4 * 4;
+            atomicAdd(pb, ab.x); atomicAdd(pb + 1, ab.y); atomicAdd(pb + 2, ab.z); atomicAdd(pb + 3, ab.w);
+        }
     }
 }
 // e[r] = sum_a temp[r, a] * w2[a]       (one warp per row)
@@ -934,25 +1016,43 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     };
     int trc = SAT_OK;
     const bool stack = tcb && s->tc_stack;   // weight gradients of the four batch-row layers after the time loop
+    // scorer: fused one-pass kernels when the rows are float4-addressable (every buffer involved is a cudaMalloc'd
+    // [rows, A] matrix or an A-vector, so A % 4 == 0 gives 16-byte alignment)
+    const bool att_fused = (A & 3) == 0 && ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads)) & 15) == 0;
+    int ab_chunks = 1, ab_rows = L;
+    {
+        const int gx = (A / 4 + kAbCT - 1) / kAbCT;
+        ab_chunks = (148 * 4 + B * gx - 1) / (B * gx > 0 ? B * gx : 1);   // about four CTAs per SM
+        if (ab_chunks > (L + 15) / 16) ab_chunks = (L + 15) / 16;
+        if (ab_chunks < 1) ab_chunks = 1;
+        ab_rows = (L + ab_chunks - 1) / ab_chunks;
+        ab_chunks = (L + ab_rows - 1) / ab_rows;
+    }
     // ------------------------------------------------------------ forward through time (model.py:258-312)
     for (int t = 0; t < T; ++t) {
         const float* h_out_prev = t ? s->h_out[t - 1] : s->h0;
         const float* h_state_prev = t ? s->h_state[t - 1] : s->h0;
         const float* c_prev = t ? s->c[t - 1] : s->c0;
         // attend (model.py:395-436)
-        dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
-        if (tc) {   // T1 = tanh(ctxd W1a + b1a) on the tcgen05 dense kernel: rows packed once, bias + tanh fused
-            sat::PackJob job{s->ctxd, nullptr, D, D, BL, 128, s->tc_xpa};
-            TCK(sat::pack_rows_launch(&job, 1, lmode, st));
+        if (tc) {   // T1 = tanh(drop(ctx) W1a + b1a) on the tcgen05 dense kernel: the context dropout is applied while the
+                    // rows are packed (no fp32 dropped copy), bias + tanh fused in the epilogue
+            sat::PackJob job{contexts, nullptr, D, D, BL, 128, s->tc_xpa};
+            const sat::DropSpec drop{seed, ST(t, 0), kf};
+            TCK(sat::pack_rows_launch(&job, 1, lmode, st, &drop));
             TRET(sat_dense_packed(s->handle, s->tc_xpa, BL, 128, D, s->tc_w1a, s->tc_b1a, A, sat::kEpiBiasTanh, s->T1[t], A, 0, 1, st));
         } else {
+            dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
             TRET(dense_fwd(st, s->ctxd, BL, D, P(vA1aW), P(vA1aB), A, s->T1[t], 1));
         }
         dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
         if (tc_fwd(0, s->hd[t], sat::kEpiBiasTanh, s->q[t], &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
-        att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
-        rowdot_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->e, s->temp, P(vA2W), BL, A);
+        if (att_fused) {
+            att_logits_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->e, s->T1[t], s->q[t], P(vA2W), B, L, A, seed, ST(t, 2), kf);
+        } else {
+            att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
+            rowdot_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->e, s->temp, P(vA2W), BL, A);
+        }
         softmax_rows_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(s->alpha[t], s->e, B, L);
         context_fwd_kernel<<<dim3((D + 127) / 128, B), 128, 0, st>>>(s->z[t], s->alpha[t], contexts, B, L, D);   // un-dropped ctx
         coverage_acc_kernel<<<(BL + 255) / 256, 256, 0, st>>>(s->att, s->alpha[t], masks, T, t, B, L);
@@ -1028,21 +1128,29 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         coverage_grad_kernel<<<(BL + 255) / 256, 256, 0, st>>>(s->extra, s->datt, masks, T, t, B, L);
         context_bwd_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->dalpha, s->dz, contexts, s->extra, B, L, D);
         softmax_bwd_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
-        att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
-        colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
-        att_dtemp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
-        segsum_kernel<<<dim3((A + 127) / 128, B), 128, 0, st>>>(dq, s->dtemp, B, L, A);
-        tanh_bwd_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->T1[t], (size_t)BL * A);
-        dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
+        if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
+            TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));
+            att_bwd_fused_kernel<<<dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B), kAbRG * kAbCT, 0, st>>>(
+                s->dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A, ab_rows, seed, ST(t, 2), kf);
+        } else {
+            att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
+            colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
+            att_dtemp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
+            segsum_kernel<<<dim3((A + 127) / 128, B), 128, 0, st>>>(dq, s->dtemp, B, L, A);
+            tanh_bwd_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->T1[t], (size_t)BL * A);
+        }
         if (tc) {
             // dW1a[D, A] += ctxd^T[D, BL] * dtemp[BL, A]: the weight repack kernel transposes, so ctxd [BL x D] read
             // as a "[K x n_out] weight" IS the packed activation ctxd^T (row tile 128), and dtemp [BL x A] is the
             // packed weight; split-K over an 8-CTA cluster, accumulated into the gradient in the epilogue
-            TCK(sat::lin_repack_weight(s->ctxd, BL, D, 0, s->tc_xpa, lmode, st));
+            // (the context dropout mask is re-applied while ctx is packed: mask index row * D + column, as in the forward pass)
+            const sat::DropSpec drop{seed, ST(t, 0), kf};
+            TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, st, &drop));
             TCK(sat::lin_repack_weight(s->dtemp, BL, A, 0, s->tc_wbig, lmode, st));
             TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, st, 1));
-            colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA1aB), s->dtemp, BL, A);
+            if (!att_fused) colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA1aB), s->dtemp, BL, A);
         } else {
+            dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
             TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));       // contexts are inputs
         }
         tanh_bwd_kernel<<<GRID1D((size_t)B * A), 256, 0, st>>>(dq, s->q[t], (size_t)B * A);
