@@ -17,11 +17,11 @@ import numpy as np
 from . import ref_step as R
 
 # ------------------------------------------------------------------ counter-based dropout RNG
-# u = 24 high bits of splitmix64(seed ^ stream*GOLDEN + idx*C1), mask = floor(keep + u) in float32
-_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+# u = 24 high bits of a 32-bit integer hash of idx keyed by K = seed ^ stream*GOLDEN (low word xor-ed in before the
+# first multiply, high word added between the two multiplies); mask = floor(keep + u) in float32.  The CUDA side
+# (sat_linear.cuh: rng_bits24 / rng_u24) is the same function.
 _GOLD = np.uint64(0x9E3779B97F4A7C15)
-_C1 = np.uint64(0xBF58476D1CE4E5B9)
-_C2 = np.uint64(0x94D049BB133111EB)
+_M32 = np.uint64(0xFFFFFFFF)
 
 # mask streams of time step t: t * 16 + k
 ATT_CTX, ATT_OUT, ATT_MID, LSTM_IN, LSTM_STATE, LSTM_OUT, DEC_IN, DEC_MID = range(8)
@@ -30,21 +30,26 @@ INIT_BASE = 0xFFFF0   # + 0 init_mean, + 1 init_a, + 2 init_b
 
 def uniform24(seed: int, stream: int, n: int) -> np.ndarray:
     with np.errstate(over="ignore"):
+        K = np.uint64(seed) ^ (np.uint64(stream) * _GOLD)
+        k0, k1 = np.uint32(K & _M32), np.uint32(K >> np.uint64(32))
         idx = np.arange(n, dtype=np.uint64)
-        x = (np.uint64(seed) ^ (np.uint64(stream) * _GOLD)) + idx * _C1
-        x ^= x >> np.uint64(30)
-        x *= _C1
-        x ^= x >> np.uint64(27)
-        x *= _C2
-        x ^= x >> np.uint64(31)
-    return ((x >> np.uint64(40)).astype(np.float32)) * np.float32(2.0 ** -24)
+        lo, hi = (idx & _M32).astype(np.uint32), (idx >> np.uint64(32)).astype(np.uint32)
+        x = lo ^ k0
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(0x21F0AAAD)
+        x ^= x >> np.uint32(15)
+        x += k1 ^ (hi * np.uint32(0x9E3779B1))
+        x *= np.uint32(0x735A2D97)
+        x ^= x >> np.uint32(15)
+    return ((x >> np.uint32(8)).astype(np.float32)) * np.float32(2.0 ** -24)
 
 
 def dropout_mask(seed: int, stream: int, shape, keep: float) -> np.ndarray:
     """0/1 mask = floor(keep + U[0,1)) (graph fixture */dropout/{Floor}), float32 arithmetic."""
     n = int(np.prod(shape))
     u = uniform24(seed, stream, n)
-    return np.floor(np.float32(keep) + u).astype(np.float32).reshape(shape)
+    # (min: with keep == 1 the float32 sum can round up to 2.0 for the largest u)
+    return np.minimum(np.floor(np.float32(keep) + u), 1.0).astype(np.float32).reshape(shape)
 
 
 def step_masks(cfg: R.OracleConfig, seed: int, t: int, B: int):

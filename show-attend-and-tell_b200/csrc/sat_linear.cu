@@ -744,6 +744,7 @@ __global__ void __launch_bounds__(128) lin_simt_kernel(const __grid_constant__ L
 __global__ void repack_weight_kernel(const float* __restrict__ w, int K, int n_out, int perm_H, uint8_t* wpack,
                                      int k_blocks, int n_tiles, int mode, DropSpec drop) {
     const unsigned long long seed = drop.seedp ? *drop.seedp : 0ull;
+    const DropGen gen = drop_gen(seed, drop.stream, drop.keep);
     const size_t total = (size_t)n_tiles * k_blocks * kTileN * 8;  // 16-byte groups
     for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(g % kTileN);
@@ -760,7 +761,7 @@ __global__ void repack_weight_kernel(const float* __restrict__ w, int K, int n_o
         for (int e = 0; e < 8; ++e) {
             const int k = kb * kBK + kg * 8 + e;
             x[e] = (col >= 0 && k < K) ? w[(size_t)k * n_out + col] : 0.f;
-            if (seed && col >= 0 && k < K) x[e] *= drop_scale(seed, drop.stream, (unsigned long long)k * n_out + col, drop.keep);
+            if (seed && col >= 0 && k < K) x[e] *= gen.scale((unsigned long long)k * n_out + col);
         }
         uint4 hi, lo;
         split_bf16x8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), hi, lo);
@@ -787,6 +788,7 @@ struct PackJobs {
 };
 __global__ void pack_rows_kernel(const PackJobs J) {
     const unsigned long long seed = J.drop.seedp ? *J.drop.seedp : 0ull;
+    const DropGen gen = drop_gen(seed, J.drop.stream, J.drop.keep);
     for (int q = 0; q < J.n; ++q) {
         const PackJob& jb = J.j[q];
         const int groups = jb.width >> 3;
@@ -803,14 +805,14 @@ __global__ void pack_rows_kernel(const PackJobs J) {
                 c = src[1];
                 if (seed) {
                     const unsigned long long i0 = (unsigned long long)row * jb.width + g * 8;
-                    a.x *= drop_scale(seed, J.drop.stream, i0, J.drop.keep);
-                    a.y *= drop_scale(seed, J.drop.stream, i0 + 1, J.drop.keep);
-                    a.z *= drop_scale(seed, J.drop.stream, i0 + 2, J.drop.keep);
-                    a.w *= drop_scale(seed, J.drop.stream, i0 + 3, J.drop.keep);
-                    c.x *= drop_scale(seed, J.drop.stream, i0 + 4, J.drop.keep);
-                    c.y *= drop_scale(seed, J.drop.stream, i0 + 5, J.drop.keep);
-                    c.z *= drop_scale(seed, J.drop.stream, i0 + 6, J.drop.keep);
-                    c.w *= drop_scale(seed, J.drop.stream, i0 + 7, J.drop.keep);
+                    a.x *= gen.scale(i0);
+                    a.y *= gen.scale(i0 + 1);
+                    a.z *= gen.scale(i0 + 2);
+                    a.w *= gen.scale(i0 + 3);
+                    c.x *= gen.scale(i0 + 4);
+                    c.y *= gen.scale(i0 + 5);
+                    c.z *= gen.scale(i0 + 6);
+                    c.w *= gen.scale(i0 + 7);
                 }
             }
             uint4 hi, lo;

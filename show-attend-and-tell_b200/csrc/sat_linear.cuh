@@ -148,20 +148,55 @@ __device__ __forceinline__ int argmax_key_index(unsigned long long key) { return
 constexpr int kAmSmemWords = 1024;   // rows whose chosen word the last CTA keeps in shared memory
 
 // Counter-based dropout masks of the training path (sat_train.cu): element `idx` of mask stream `stream` is kept
-// when floor(keep + U) == 1, U = rng_u24(seed, stream, idx) in [0, 1).  The packing kernels below can apply such a
-// mask while they convert, so a dropped copy of a large operand is never materialised in fp32.
+// when floor(keep + U) == 1, U = rng_u24(seed, stream, idx) in [0, 1) with 24 bits (oracle/train_ref.py:uniform24 is
+// the same function in numpy).  A 32-bit integer hash (two multiplies, three xor-shifts; the stream key enters before
+// the first and between the two multiplies) — the masks are regenerated wherever they are needed instead of being
+// stored, so the generator is on the critical path of the element-wise kernels.  The packing kernels below can
+// apply such a mask while they convert, so a dropped copy of a large operand is never materialised in fp32.
+struct DropKey {
+    uint32_t k0, k1;
+};
+__host__ __device__ inline DropKey drop_key(unsigned long long seed, unsigned long long stream) {
+    const unsigned long long K = seed ^ (stream * 0x9E3779B97F4A7C15ull);
+    return DropKey{(uint32_t)K, (uint32_t)(K >> 32)};
+}
+__host__ __device__ inline uint32_t rng_bits24(DropKey k, unsigned long long idx) {
+    uint32_t x = (uint32_t)idx ^ k.k0;
+    x ^= x >> 16;
+    x *= 0x21F0AAADu;
+    x ^= x >> 15;
+    x += k.k1 ^ ((uint32_t)(idx >> 32) * 0x9E3779B1u);
+    x *= 0x735A2D97u;
+    x ^= x >> 15;
+    return x >> 8;
+}
 __host__ __device__ inline float rng_u24(unsigned long long seed, unsigned long long stream, unsigned long long idx) {
-    unsigned long long x = (seed ^ (stream * 0x9E3779B97F4A7C15ull)) + idx * 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 30;
-    x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27;
-    x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    return (float)(x >> 40) * 5.9604644775390625e-08f;  // 2^-24
+    return (float)rng_bits24(drop_key(seed, stream), idx) * 5.9604644775390625e-08f;  // 2^-24
 }
 __host__ __device__ inline float drop_scale(unsigned long long seed, unsigned long long stream, unsigned long long idx, float keep) {
-    // x / keep * floor(keep + U)
-    return floorf(keep + rng_u24(seed, stream, idx)) / keep;
+    // x / keep * floor(keep + U), floor(keep + U) in {0, 1}
+    return keep + rng_u24(seed, stream, idx) >= 1.0f ? 1.0f / keep : 0.0f;
+}
+// The same mask with the per-element work reduced to the hash and one integer compare: kt is the smallest 24-bit
+// count k with fl32(keep + k * 2^-24) >= 1 (the sum is monotone in k), so "kept" <=> rng_bits24 >= kt, bit for bit
+// the float formula above.  Built once per thread.
+struct DropGen {
+    DropKey k;
+    uint32_t kt;
+    float inv;
+    __device__ __forceinline__ float scale(unsigned long long idx) const { return rng_bits24(k, idx) >= kt ? inv : 0.0f; }
+};
+__host__ __device__ inline DropGen drop_gen(unsigned long long seed, unsigned long long stream, float keep) {
+    DropGen g;
+    g.k = drop_key(seed, stream);
+    g.inv = 1.0f / keep;
+    const float c = ceilf((1.0f - keep) * 16777216.0f);
+    uint32_t kt = c > 0.0f ? (uint32_t)c : 0u;
+    if (kt > (1u << 24)) kt = 1u << 24;
+    while (kt > 0 && keep + (float)(kt - 1) * 5.9604644775390625e-08f >= 1.0f) --kt;
+    while (kt < (1u << 24) && keep + (float)kt * 5.9604644775390625e-08f < 1.0f) ++kt;
+    g.kt = kt;
+    return g;
 }
 struct DropSpec {          // seedp == nullptr or *seedp == 0: no dropout
     const unsigned long long* seedp;

@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -43,8 +44,45 @@ namespace {
 
 // ------------------------------------------------------------------------------------------ RNG
 // counter-based dropout masks: sat::rng_u24 / sat::drop_scale of sat_linear.cuh (shared with the packing kernels)
+using sat::drop_gen;
 using sat::drop_scale;
+using sat::DropGen;
 using sat::rng_u24;
+
+// ------------------------------------------------------------------------------------------ launches
+// Every kernel of this file starts with "wait for the predecessor grid, then let the successor launch"
+// (griddepcontrol.wait ; griddepcontrol.launch_dependents) and is launched with the programmatic-serialization
+// attribute: the next kernel's launch latency (a few microseconds, comparable to the run time of the many small
+// element-wise kernels of a time step) overlaps this kernel's execution, while the data dependency stays a full
+// one — nothing is read or written before the wait returns, and because the trigger comes after the kernel's own
+// wait, a kernel never starts before the predecessor of its predecessor has completed (the convention of
+// sat_common.cuh, which the dense kernel's early weight prefetch relies on).  SAT_TRAIN_PDL=0 turns the attribute off.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static int train_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SAT_TRAIN_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+template <typename... KA, typename... A>
+static cudaError_t launch_k(void (*kernel)(KA...), dim3 grid, dim3 block, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = train_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------ SGEMM
 // C[M,N] = op(A)[M,K] * op(B)[K,N] (+ C if accumulate).  Row-major.  TA: A is stored [K,M]; TB: B is stored [N,K].
@@ -97,6 +135,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                     const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                     int accumulate, int kchunk) {
+    pdl_enter();
     __shared__ float As[2][GK][GM + 4];
     __shared__ float Bs[2][GK][GN + 4];
     const int tid = threadIdx.x;
@@ -180,10 +219,10 @@ cudaError_t sgemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const 
         }
     }
     const int acc = accumulate ? 1 : 0;
-    if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
-    else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
-    else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
-    else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
+    if (!ta && !tb) launch_k(sgemm_kernel<false, false>, grid, 256, st, M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
+    else if (ta && !tb) launch_k(sgemm_kernel<true, false>, grid, 256, st, M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
+    else if (!ta && tb) launch_k(sgemm_kernel<false, true>, grid, 256, st, M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
+    else launch_k(sgemm_kernel<true, true>, grid, 256, st, M, N, K, A, lda, B, ldb, C, ldc, acc, kchunk);
     return cudaGetLastError();
 }
 
@@ -193,6 +232,7 @@ cudaError_t sgemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const 
 // y[r, c] = x[r, c] * drop(seed, stream, r * cols + c) ; x / y may have different leading dimensions
 __global__ void dropout2d_kernel(float* y, int ldy, const float* x, int ldx, int rows, int cols,
                                  const unsigned long long* seedp, unsigned long long stream, float keep, int accumulate) {
+    pdl_enter();
     const unsigned long long seed = *seedp;
     const size_t n = (size_t)rows * cols;
     if (ldx == cols && ldy == cols && !accumulate && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
@@ -223,6 +263,7 @@ __global__ void dropout2d_kernel(float* y, int ldy, const float* x, int ldx, int
 }
 // y = act(x + b[c]) in place ; act 0 none, 1 tanh
 __global__ void bias_act_kernel(float* x, const float* b, int rows, int cols, int act) {
+    pdl_enter();
     const size_t n = (size_t)rows * cols;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float v = x[i] + b[i % cols];
@@ -231,6 +272,7 @@ __global__ void bias_act_kernel(float* x, const float* b, int rows, int cols, in
 }
 // dx = dy * (1 - y^2) in place on dy
 __global__ void tanh_bwd_kernel(float* dy, const float* y, size_t n) {
+    pdl_enter();
     if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
         float4* d4 = reinterpret_cast<float4*>(dy);
         const float4* y4 = reinterpret_cast<const float4*>(y);
@@ -248,6 +290,7 @@ __global__ void tanh_bwd_kernel(float* dy, const float* y, size_t n) {
 // db[c] += sum_r dx[r, c] * (w ? w[r] : 1)   (column sums, optionally row-weighted: the weight gradient of a
 // one-column dense layer is dw[c] = sum_r x[r, c] * dy[r]).  Eight rows in flight per thread.
 __global__ void colsum_kernel(float* db, const float* dx, int rows, int cols, const float* w = nullptr) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     const int r0 = blockIdx.y * 256, r1 = min(rows, r0 + 256);
@@ -271,6 +314,7 @@ __global__ void colsum_kernel(float* db, const float* dx, int rows, int cols, co
 // r * ndrop + col (= a dropout2d over a dense [rows, ndrop] matrix: one launch instead of three copies + one dropout)
 __global__ void concat3_drop_kernel(float* out, int ldo, const float* a, int na, const float* b, int nb, const float* c, int nc,
                                     int ndrop, int rows, const unsigned long long* seedp, unsigned long long stream, float keep) {
+    pdl_enter();
     const unsigned long long seed = *seedp;
     const int cols = na + nb + nc;
     const size_t n = (size_t)rows * cols;
@@ -286,6 +330,7 @@ __global__ void concat3_drop_kernel(float* out, int ldo, const float* a, int na,
 __global__ void split3_drop_kernel(const float* src, int lds, int rows, float* a, int na, int acc_a, float* b, int nb, int acc_b,
                                    float* c, int nc, int acc_c, int ndrop, const unsigned long long* seedp,
                                    unsigned long long stream, float keep) {
+    pdl_enter();
     const unsigned long long seed = *seedp;
     const int cols = na + nb + nc;
     const size_t n = (size_t)rows * cols;
@@ -302,6 +347,7 @@ __global__ void split3_drop_kernel(const float* src, int lds, int rows, float* a
     }
 }
 __global__ void copy2d_kernel(float* y, int ldy, const float* x, int ldx, int rows, int cols, int accumulate) {
+    pdl_enter();
     const size_t n = (size_t)rows * cols;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
@@ -311,6 +357,7 @@ __global__ void copy2d_kernel(float* y, int ldy, const float* x, int ldx, int ro
     }
 }
 __global__ void gather_rows_kernel(float* y, int ldy, const float* table, int E, const int32_t* idx, int idx_ld, int rows) {
+    pdl_enter();
     const size_t n = (size_t)rows * E;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / E), c = (int)(i - (size_t)r * E);
@@ -319,6 +366,7 @@ __global__ void gather_rows_kernel(float* y, int ldy, const float* table, int E,
     }
 }
 __global__ void scatter_add_rows_kernel(float* dtable, int E, const int32_t* idx, int idx_ld, const float* dx, int ldx, int rows) {
+    pdl_enter();
     const size_t n = (size_t)rows * E;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / E), c = (int)(i - (size_t)r * E);
@@ -329,6 +377,7 @@ __global__ void scatter_add_rows_kernel(float* dtable, int E, const int32_t* idx
 // temp[b*L + l, a] = (T1[b*L + l, a] + q[b, a]) * drop(att_mid)
 __global__ void att_temp_kernel(float* temp, const float* T1, const float* q, int B, int L, int A,
                                 const unsigned long long* seedp, unsigned long long stream, float keep) {
+    pdl_enter();
     const unsigned long long seed = *seedp;
     const size_t n = (size_t)B * L * A;
     if ((A & 3) == 0 && n < (1ull << 33) && ((reinterpret_cast<uintptr_t>(temp) | reinterpret_cast<uintptr_t>(T1) | reinterpret_cast<uintptr_t>(q)) & 15) == 0) {
@@ -358,9 +407,12 @@ __global__ void att_temp_kernel(float* temp, const float* T1, const float* q, in
 }
 // e[b*L + l] = sum_a (T1[b*L + l, a] + q[b, a]) * drop(att_mid) * w2[a]: att_temp + rowdot in one pass over T1 (temp is
 // not stored; the backward pass rebuilds it from T1, q and the mask).  One warp per row, A % 4 == 0.
-__global__ void att_logits_kernel(float* e, const float* T1, const float* q, const float* w2, int B, int L, int A,
+__global__ void att_logits_kernel(float* __restrict__ e, const float* __restrict__ T1, const float* __restrict__ q,
+                                  const float* __restrict__ w2, int B, int L, int A,
                                   const unsigned long long* seedp, unsigned long long stream, float keep) {
+    pdl_enter();
     const unsigned long long seed = *seedp;
+    const DropGen gen = drop_gen(seed, stream, keep);
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= B * L) return;
     const int A4 = A >> 2, b = row / L;
@@ -374,10 +426,10 @@ __global__ void att_logits_kernel(float* e, const float* T1, const float* q, con
         float4 v = make_float4(t.x + qq.x, t.y + qq.y, t.z + qq.z, t.w + qq.w);
         if (seed) {
             const unsigned long long i = ((unsigned long long)row * A4 + a4) << 2;
-            v.x *= drop_scale(seed, stream, i, keep);
-            v.y *= drop_scale(seed, stream, i + 1, keep);
-            v.z *= drop_scale(seed, stream, i + 2, keep);
-            v.w *= drop_scale(seed, stream, i + 3, keep);
+            v.x *= gen.scale(i);
+            v.y *= gen.scale(i + 1);
+            v.z *= gen.scale(i + 2);
+            v.w *= gen.scale(i + 3);
         }
         s = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, s))));
     }
@@ -391,12 +443,15 @@ __global__ void att_logits_kernel(float* e, const float* T1, const float* q, con
 //   db[a]      += sum_r dtemp[r, a]                                  (db may be null)
 // grid (ceil(A/256), row chunks, B), 256 threads = 4 row groups x 64 float4 columns.
 constexpr int kAbRG = 4, kAbCT = 64;
-__global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(float* dtemp, float* dq, float* dw2, float* db, const float* T1,
-                                                                      const float* q, const float* de, const float* w2, int L, int A,
+__global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(float* __restrict__ dtemp, float* dq, float* dw2, float* db,
+                                                                      const float* __restrict__ T1, const float* __restrict__ q,
+                                                                      const float* __restrict__ de, const float* __restrict__ w2, int L, int A,
                                                                       int chunk_rows, const unsigned long long* seedp,
                                                                       unsigned long long stream, float keep) {
+    pdl_enter();
     __shared__ float4 red[3][kAbRG - 1][kAbCT];
     const unsigned long long seed = *seedp;
+    const DropGen gen = drop_gen(seed, stream, keep);
     const int ct = threadIdx.x % kAbCT, rg = threadIdx.x / kAbCT;
     const int A4 = A >> 2, c4 = blockIdx.x * kAbCT + ct, b = blockIdx.z;
     const int l0 = blockIdx.y * chunk_rows, l1 = min(L, l0 + chunk_rows);
@@ -413,10 +468,10 @@ __global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(float* dtem
             float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
             if (seed) {
                 const unsigned long long i = (r * A4 + c4) << 2;
-                m.x = drop_scale(seed, stream, i, keep);
-                m.y = drop_scale(seed, stream, i + 1, keep);
-                m.z = drop_scale(seed, stream, i + 2, keep);
-                m.w = drop_scale(seed, stream, i + 3, keep);
+                m.x = gen.scale(i);
+                m.y = gen.scale(i + 1);
+                m.z = gen.scale(i + 2);
+                m.w = gen.scale(i + 3);
             }
             const float4 dm = make_float4(d * m.x, d * m.y, d * m.z, d * m.w);          // de * mask
             const float4 g = make_float4(dm.x * w.x, dm.y * w.y, dm.z * w.z, dm.w * w.w);  // d temp (before the mask: d (T1 + q))
@@ -450,6 +505,7 @@ __global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(float* dtem
 }
 // e[r] = sum_a temp[r, a] * w2[a]       (one warp per row)
 __global__ void rowdot_kernel(float* e, const float* temp, const float* w2, int rows, int A) {
+    pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     float s = 0.f;
@@ -459,6 +515,7 @@ __global__ void rowdot_kernel(float* e, const float* temp, const float* w2, int 
 }
 // softmax over L per row (one warp per row)
 __global__ void softmax_rows_kernel(float* alpha, const float* e, int rows, int L) {
+    pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const float* x = e + (size_t)warp * L;
@@ -472,6 +529,7 @@ __global__ void softmax_rows_kernel(float* alpha, const float* e, int rows, int 
 }
 // de = alpha * (dalpha - sum_l alpha*dalpha)   (one warp per row), written over dalpha
 __global__ void softmax_bwd_kernel(float* dalpha, const float* alpha, int rows, int L) {
+    pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     float s = 0.f;
@@ -484,6 +542,7 @@ __global__ void softmax_bwd_kernel(float* dalpha, const float* alpha, int rows, 
 }
 // z[b, d] = sum_l alpha[b, l] * ctx[b, l, d]
 __global__ void context_fwd_kernel(float* z, const float* alpha, const float* ctx, int B, int L, int D) {
+    pdl_enter();
     const int b = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
     const float* c = ctx + (size_t)b * L * D + d;
@@ -491,8 +550,39 @@ __global__ void context_fwd_kernel(float* z, const float* alpha, const float* ct
     for (int l = 0; l < L; ++l) s = fmaf(alpha[(size_t)b * L + l], c[(size_t)l * D], s);
     z[(size_t)b * D + d] = s;
 }
+// the same on float4 columns with eight rows in flight per column: grid (ceil(D / 128), B), 256 threads =
+// 8 row groups x 32 float4 columns, row groups summed through shared memory (D % 4 == 0, 16-byte aligned)
+__global__ void __launch_bounds__(256) context_fwd4_kernel(float* __restrict__ z, const float* __restrict__ alpha,
+                                                            const float* __restrict__ ctx, int L, int D) {
+    pdl_enter();
+    __shared__ float4 red[7][32];
+    const int ct = threadIdx.x & 31, rg = threadIdx.x >> 5, b = blockIdx.y;
+    const int D4 = D >> 2, c4 = blockIdx.x * 32 + ct;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < D4) {
+        const float4* c = reinterpret_cast<const float4*>(ctx) + (size_t)b * L * D4 + c4;
+        const float* al = alpha + (size_t)b * L;
+#pragma unroll 4
+        for (int l = rg; l < L; l += 8) {
+            const float4 v = c[(size_t)l * D4];
+            const float w = al[l];
+            a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+        }
+    }
+    if (rg > 0) red[rg - 1][ct] = a;
+    __syncthreads();
+    if (rg == 0 && c4 < D4) {
+#pragma unroll
+        for (int g = 0; g < 7; ++g) {
+            const float4 v = red[g][ct];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        reinterpret_cast<float4*>(z)[(size_t)b * D4 + c4] = a;
+    }
+}
 // dalpha[b, l] = sum_d dz[b, d] * ctx[b, l, d]  (+ extra[b, l] if given)   (one warp per (b, l))
 __global__ void context_bwd_kernel(float* dalpha, const float* dz, const float* ctx, const float* extra, int B, int L, int D) {
+    pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * L) return;
     const int b = warp / L;
@@ -504,6 +594,7 @@ __global__ void context_bwd_kernel(float* dalpha, const float* dz, const float* 
 // dtemp[r, a] = de[r] * w2[a] * drop(att_mid)   and  (1 - T1^2) applied later
 __global__ void att_dtemp_kernel(float* dtemp, const float* de, const float* w2, int rows, int A,
                                  const unsigned long long* seedp, unsigned long long stream, float keep) {
+    pdl_enter();
     const unsigned long long seed = *seedp;
     const size_t n = (size_t)rows * A;
     if ((A & 3) == 0 && n < (1ull << 33) && ((reinterpret_cast<uintptr_t>(dtemp) | reinterpret_cast<uintptr_t>(w2)) & 15) == 0) {
@@ -532,6 +623,7 @@ __global__ void att_dtemp_kernel(float* dtemp, const float* de, const float* w2,
 }
 // dq[b, a] = sum_l dtemp[b*L + l, a]
 __global__ void segsum_kernel(float* dq, const float* dtemp, int B, int L, int A) {
+    pdl_enter();
     const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= A) return;
     float s = 0.f;
@@ -541,6 +633,7 @@ __global__ void segsum_kernel(float* dq, const float* dtemp, int B, int L, int A
 __device__ inline float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 // gates G [B, 4H] (blocks i, j, f, o) -> activated gates (in place), c, h_raw
 __global__ void lstm_fwd_kernel(float* G, const float* bias, const float* c_prev, float* c, float* h_raw, int B, int H) {
+    pdl_enter();
     const size_t n = (size_t)B * H;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / H), u = (int)(i - (size_t)b * H);
@@ -558,6 +651,7 @@ __global__ void lstm_fwd_kernel(float* G, const float* bias, const float* c_prev
 // dh_raw, dc (in/out: on entry dc = gradient flowing into c_t from step t+1) -> dG (pre-activation), dc_prev
 __global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_raw, const float* acts, const float* c,
                                 const float* c_prev, int B, int H) {
+    pdl_enter();
     const size_t n = (size_t)B * H;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / H), u = (int)(i - (size_t)b * H);
@@ -577,6 +671,7 @@ __global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_raw, const
 // masked cross entropy of one time step + its gradient; one block per row
 __global__ void __launch_bounds__(256) ce_kernel(const float* logits, float* dlogits, const int32_t* sent, int sent_ld, int t,
                                                  const float* masks, int V, const float* inv_msum_p, float* loss_acc) {
+    pdl_enter();
     const float inv_msum = *inv_msum_p;
     __shared__ float red[8];
     __shared__ int redi[8];
@@ -621,12 +716,14 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* logits, float* dlo
 }
 // att[b, l] += alpha[b, l] * mask[b, t]
 __global__ void coverage_acc_kernel(float* att, const float* alpha, const float* masks, int mld, int t, int B, int L) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * L) return;
     att[i] += alpha[i] * masks[(size_t)(i / L) * mld + t];
 }
 // loss = factor * sum (1 - att)^2 / 2 / (GB * L);  datt = -factor * (1 - att) / (GB * L)
 __global__ void coverage_loss_kernel(float* datt, const float* att, int n, float factor, float inv_gbl, float* loss_acc) {
+    pdl_enter();
     __shared__ float red[8];
     float s = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -645,11 +742,13 @@ __global__ void coverage_loss_kernel(float* datt, const float* att, int n, float
 }
 // extra[b, l] = datt[b, l] * mask[b, t]
 __global__ void coverage_grad_kernel(float* extra, const float* datt, const float* masks, int mld, int t, int B, int L) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * L) return;
     extra[i] = datt[i] * masks[(size_t)(i / L) * mld + t];
 }
 __global__ void mean_L_kernel(float* out, const float* ctx, int L, int D) {
+    pdl_enter();
     const int b = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
     float s = 0.f;
@@ -658,9 +757,24 @@ __global__ void mean_L_kernel(float* out, const float* ctx, int L, int D) {
 }
 // out[0] += scale * sum x^2
 __global__ void sumsq_kernel(const float* x, size_t n, float scale, float* out) {
+    pdl_enter();
     __shared__ float red[8];
     float s = 0.f;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s = fmaf(x[i], x[i], s);
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    size_t head = 0;   // elements covered by the float4 loop
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const size_t n4 = n >> 2;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (size_t i = tid; i < n4; i += nth) {
+            const float4 v = x4[i];
+            a.x = fmaf(v.x, v.x, a.x); a.y = fmaf(v.y, v.y, a.y); a.z = fmaf(v.z, v.z, a.z); a.w = fmaf(v.w, v.w, a.w);
+        }
+        s = (a.x + a.y) + (a.z + a.w);
+        head = n4 << 2;
+    }
+    for (size_t i = head + tid; i < n; i += nth) s = fmaf(x[i], x[i], s);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -671,11 +785,13 @@ __global__ void sumsq_kernel(const float* x, size_t n, float scale, float* out) 
     }
 }
 __global__ void axpy_kernel(float* y, const float* x, float a, size_t n) {
+    pdl_enter();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = fmaf(a, x[i], y[i]);
 }
 // clip_by_global_norm + TF Adam.  norm2 = sum of squares of the (already reduced, regularised) gradient
 __global__ void adam_kernel(float* w, const float* g, float* m, float* v, size_t n, const float* norm2, float clip, float lr_t,
                             float b1, float b2, float eps) {
+    pdl_enter();
     const float norm = sqrtf(*norm2);
     const float scale = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -921,14 +1037,14 @@ extern "C" int sat_train_var(sat_handle* h, int32_t i, const char** name, int64_
 // y = act(dropout?(x) W + b)
 static int dense_fwd(cudaStream_t st, const float* x, int rows, int K, const float* W, const float* b, int N, float* y, int act) {
     TCK(sgemm(st, false, false, rows, N, K, x, K, W, N, y, N, false));
-    bias_act_kernel<<<GRID1D((size_t)rows * N), 256, 0, st>>>(y, b, rows, N, act);
+    launch_k(bias_act_kernel, GRID1D((size_t)rows * N), 256, st, y, b, rows, N, act);
     return SAT_OK;
 }
 // given dy (w.r.t. pre-activation): dW += x^T dy, db += colsum(dy), dx = dy W^T (if dx)
 static int dense_bwd(cudaStream_t st, const float* x, int rows, int K, const float* W, int N, const float* dy, float* dW,
                      float* db, float* dx) {
     TCK(sgemm(st, true, false, K, N, rows, x, K, dy, N, dW, N, true));
-    if (db) colsum_kernel<<<dim3((N + 127) / 128, (rows + 255) / 256), 128, 0, st>>>(db, dy, rows, N);
+    if (db) launch_k(colsum_kernel, dim3((N + 127) / 128, (rows + 255) / 256), 128, st, db, dy, rows, N, nullptr);
     if (dx) TCK(sgemm(st, false, true, rows, K, N, dy, N, W, N, dx, K, false));
     return SAT_OK;
 }
@@ -954,13 +1070,13 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     TCK(cudaMemsetAsync(s->att, 0, (size_t)BL * sizeof(float), st));
 
     // ------------------------------------------------------------ initialize (model.py:239-242, 358-393)
-    mean_L_kernel<<<dim3((D + 127) / 128, B), 128, 0, st>>>(s->mean, contexts, L, D);
-    dropout2d_kernel<<<GRID1D((size_t)B * D), 256, 0, st>>>(s->meand, D, s->mean, D, B, D, seed, INIT + 0, kf, 0);
+    launch_k(mean_L_kernel, dim3((D + 127) / 128, B), 128, st, s->mean, contexts, L, D);
+    launch_k(dropout2d_kernel, GRID1D((size_t)B * D), 256, st, s->meand, D, s->mean, D, B, D, seed, INIT + 0, kf, 0);
     TRET(dense_fwd(st, s->meand, B, D, P(vIa1W), P(vIa1B), I, s->ia1, 1));
-    dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(s->ia1d, I, s->ia1, I, B, I, seed, INIT + 1, kf, 0);
+    launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, s->ia1d, I, s->ia1, I, B, I, seed, INIT + 1, kf, 0);
     TRET(dense_fwd(st, s->ia1d, B, I, P(vIa2W), P(vIa2B), H, s->c0, 0));
     TRET(dense_fwd(st, s->meand, B, D, P(vIb1W), P(vIb1B), I, s->ib1, 1));
-    dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(s->ib1d, I, s->ib1, I, B, I, seed, INIT + 2, kf, 0);
+    launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, s->ib1d, I, s->ib1, I, B, I, seed, INIT + 2, kf, 0);
     TRET(dense_fwd(st, s->ib1d, B, I, P(vIb2W), P(vIb2B), H, s->h0, 0));
 
     const bool tc = s->tc_ok && sat_handle_train_tc(s->handle);
@@ -1041,48 +1157,54 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             TCK(sat::pack_rows_launch(&job, 1, lmode, st, &drop));
             TRET(sat_dense_packed(s->handle, s->tc_xpa, BL, 128, D, s->tc_w1a, s->tc_b1a, A, sat::kEpiBiasTanh, s->T1[t], A, 0, 1, st));
         } else {
-            dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
+            launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
             TRET(dense_fwd(st, s->ctxd, BL, D, P(vA1aW), P(vA1aB), A, s->T1[t], 1));
         }
-        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
         if (tc_fwd(0, s->hd[t], sat::kEpiBiasTanh, s->q[t], &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
         if (att_fused) {
-            att_logits_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->e, s->T1[t], s->q[t], P(vA2W), B, L, A, seed, ST(t, 2), kf);
+            launch_k(att_logits_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->T1[t], s->q[t], P(vA2W), B, L, A, seed, ST(t, 2), kf);
         } else {
-            att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
-            rowdot_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->e, s->temp, P(vA2W), BL, A);
+            launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
+            launch_k(rowdot_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->temp, P(vA2W), BL, A);
         }
-        softmax_rows_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(s->alpha[t], s->e, B, L);
-        context_fwd_kernel<<<dim3((D + 127) / 128, B), 128, 0, st>>>(s->z[t], s->alpha[t], contexts, B, L, D);   // un-dropped ctx
-        coverage_acc_kernel<<<(BL + 255) / 256, 256, 0, st>>>(s->att, s->alpha[t], masks, T, t, B, L);
+        launch_k(softmax_rows_kernel, (B * 32 + 255) / 256, 256, st, s->alpha[t], s->e, B, L);
+        if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(contexts) & 15) == 0)   // un-dropped ctx
+            launch_k(context_fwd4_kernel, dim3((D / 4 + 31) / 32, B), 256, st, s->z[t], s->alpha[t], contexts, L, D);
+        else
+            launch_k(context_fwd_kernel, dim3((D + 127) / 128, B), 128, st, s->z[t], s->alpha[t], contexts, B, L, D);
+        launch_k(coverage_acc_kernel, (BL + 255) / 256, 256, st, s->att, s->alpha[t], masks, T, t, B, L);
         // embedding of the previous word: 0 at t = 0, then teacher forcing (model.py:254, 310)
-        gather_rows_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(s->emb[t], E, P(vEmb), E, t ? sentences + (t - 1) : nullptr, T, B);
+        launch_k(gather_rows_kernel, GRID1D((size_t)B * E), 256, st, s->emb[t], E, P(vEmb), E, t ? sentences + (t - 1) : nullptr, T, B);
         // LSTM with DropoutWrapper (model.py:228-236, 276-279)
         // lstm_in = [ drop_in(concat(z, emb)) | h_state_prev ]
-        concat3_drop_kernel<<<GRID1D((size_t)B * XL), 256, 0, st>>>(s->lstm_in[t], XL, s->z[t], D, s->emb[t], E, h_state_prev, H, D + E, B,
+        launch_k(concat3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->lstm_in[t], XL, s->z[t], D, s->emb[t], E, h_state_prev, H, D + E, B,
                                                                     seed, ST(t, 3), kl);
         if (tc_fwd(1, s->lstm_in[t], sat::kEpiNone, s->acts[t], &trc)) { TRET(trc); }   // (bias and gates: next kernel)
         else TCK(sgemm(st, false, false, B, 4 * H, XL, s->lstm_in[t], XL, P(vLW), 4 * H, s->acts[t], 4 * H, false));
-        lstm_fwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->acts[t], P(vLB), c_prev, s->c[t], s->h_raw, B, H);
-        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->h_out[t], H, s->h_raw, H, B, H, seed, ST(t, 5), kl, 0);
-        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->h_state[t], H, s->h_raw, H, B, H, seed, ST(t, 4), kl, 0);
+        launch_k(lstm_fwd_kernel, GRID1D((size_t)B * H), 256, st, s->acts[t], P(vLB), c_prev, s->c[t], s->h_raw, B, H);
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->h_out[t], H, s->h_raw, H, B, H, seed, ST(t, 5), kl, 0);
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->h_state[t], H, s->h_raw, H, B, H, seed, ST(t, 4), kl, 0);
         // decode (model.py:282-287, 438-459)
-        concat3_drop_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->expd[t], XD, s->h_out[t], H, s->z[t], D, s->emb[t], E, XD, B,
+        launch_k(concat3_drop_kernel, GRID1D((size_t)B * XD), 256, st, s->expd[t], XD, s->h_out[t], H, s->z[t], D, s->emb[t], E, XD, B,
                                                                     seed, ST(t, 6), kf);
         if (tc_fwd(2, s->expd[t], sat::kEpiBiasTanh, s->t1[t], &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), Dd, s->t1[t], 1));
-        dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(s->td[t], Dd, s->t1[t], Dd, B, Dd, seed, ST(t, 7), kf, 0);
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * Dd), 256, st, s->td[t], Dd, s->t1[t], Dd, B, Dd, seed, ST(t, 7), kf, 0);
         if (tc_fwd(3, s->td[t], sat::kEpiBias, s->logits, &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->td[t], B, Dd, P(vD2W), P(vD2B), V, s->logits, 0));
         // masked cross entropy + accuracy, and d loss / d logits (model.py:292-305, 316-318, 332-334)
-        ce_kernel<<<B, 256, 0, st>>>(s->logits, s->dlogits[t], sentences, T, t, masks, V, inv_msum, s->loss_acc);
+        launch_k(ce_kernel, B, 256, st, s->logits, s->dlogits[t], sentences, T, t, masks, V, inv_msum, s->loss_acc);
     }
     // attention coverage loss (model.py:320-326) and L2 regulariser (model.py:328)
-    coverage_loss_kernel<<<64, 256, 0, st>>>(s->datt, s->att, BL, s->att_factor, inv_gbl, s->loss_acc);
+    launch_k(coverage_loss_kernel, 64, 256, st, s->datt, s->att, BL, s->att_factor, inv_gbl, s->loss_acc);
     for (int v = 0; v < kNumVars; ++v)
-        if (s->regularised[v])
-            sumsq_kernel<<<128, 256, 0, st>>>(P(v), (size_t)s->rows[v] * s->cols[v], 0.5f * s->reg_scale, s->loss_acc + 3);
+        if (s->regularised[v]) {
+            const size_t n = (size_t)s->rows[v] * s->cols[v];
+            const int g = (int)((n / 4 + 1023) / 1024);   // about four float4 per thread
+            launch_k(sumsq_kernel, g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g), 256, st, P(v), n, 0.5f * s->reg_scale, s->loss_acc + 3);
+        }
 
     // ------------------------------------------------------------ backward through time
     TCK(cudaMemsetAsync(s->dh_out, 0, (size_t)B * H * sizeof(float), st));    // d loss / d h_out[t] from step t+1's attend
@@ -1107,37 +1229,37 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         if (stack) { if (!vdx) TCK(sgemm(st, false, true, B, Dd, V, s->dlogits[t], V, P(vD2W), V, dtd, Dd, false)); }
         else if (vdx) TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), nullptr));
         else TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), dtd));
-        dropout2d_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(dtd, Dd, dtd, Dd, B, Dd, seed, ST(t, 7), kf, 0);
-        tanh_bwd_kernel<<<GRID1D((size_t)B * Dd), 256, 0, st>>>(dtd, s->t1[t], (size_t)B * Dd);
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, Dd, dtd, Dd, B, Dd, seed, ST(t, 7), kf, 0);
+        launch_k(tanh_bwd_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, s->t1[t], (size_t)B * Dd);
         if (tc_dx(2, dtd, s->dexp, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
         else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), s->dexp));
         // drop(dexp) = [dh_out (+=) | dz (=) | demb (=)]
-        split3_drop_kernel<<<GRID1D((size_t)B * XD), 256, 0, st>>>(s->dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, s->demb, E, 0, XD, seed,
+        launch_k(split3_drop_kernel, GRID1D((size_t)B * XD), 256, st, s->dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, s->demb, E, 0, XD, seed,
                                                                    ST(t, 6), kf);
         // h_out = drop_out(h_raw), h_state = drop_state(h_raw)
-        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_out, H, B, H, seed, ST(t, 5), kl, 0);
-        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_raw, H, s->dh_state, H, B, H, seed, ST(t, 4), kl, 1);
-        lstm_bwd_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(dG, s->dc, s->dh_raw, s->acts[t], s->c[t], c_prev, B, H);
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_raw, H, s->dh_out, H, B, H, seed, ST(t, 5), kl, 0);
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_raw, H, s->dh_state, H, B, H, seed, ST(t, 4), kl, 1);
+        launch_k(lstm_bwd_kernel, GRID1D((size_t)B * H), 256, st, dG, s->dc, s->dh_raw, s->acts[t], s->c[t], c_prev, B, H);
         if (tc_dx(1, dG, s->dlin, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), nullptr)); }
         else TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), s->dlin));
         // dlin = [d xd (D+E) | dh_state_prev]
-        split3_drop_kernel<<<GRID1D((size_t)B * XL), 256, 0, st>>>(s->dlin, XL, B, s->dz, D, 1, s->demb, E, 1, s->dh_state, H, 0, D + E, seed,
+        launch_k(split3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->dlin, XL, B, s->dz, D, 1, s->demb, E, 1, s->dh_state, H, 0, D + E, seed,
                                                                    ST(t, 3), kl);
-        scatter_add_rows_kernel<<<GRID1D((size_t)B * E), 256, 0, st>>>(Gd(vEmb), E, t ? sentences + (t - 1) : nullptr, T, s->demb, E, B);
+        launch_k(scatter_add_rows_kernel, GRID1D((size_t)B * E), 256, st, Gd(vEmb), E, t ? sentences + (t - 1) : nullptr, T, s->demb, E, B);
         // attention: context vector, softmax, scorer
-        coverage_grad_kernel<<<(BL + 255) / 256, 256, 0, st>>>(s->extra, s->datt, masks, T, t, B, L);
-        context_bwd_kernel<<<(BL * 32 + 255) / 256, 256, 0, st>>>(s->dalpha, s->dz, contexts, s->extra, B, L, D);
-        softmax_bwd_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
+        launch_k(coverage_grad_kernel, (BL + 255) / 256, 256, st, s->extra, s->datt, masks, T, t, B, L);
+        launch_k(context_bwd_kernel, (BL * 32 + 255) / 256, 256, st, s->dalpha, s->dz, contexts, s->extra, B, L, D);
+        launch_k(softmax_bwd_kernel, (B * 32 + 255) / 256, 256, st, s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
         if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
             TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));
-            att_bwd_fused_kernel<<<dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B), kAbRG * kAbCT, 0, st>>>(
+            launch_k(att_bwd_fused_kernel, dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B), kAbRG * kAbCT, st, 
                 s->dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A, ab_rows, seed, ST(t, 2), kf);
         } else {
-            att_temp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
-            colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
-            att_dtemp_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
-            segsum_kernel<<<dim3((A + 127) / 128, B), 128, 0, st>>>(dq, s->dtemp, B, L, A);
-            tanh_bwd_kernel<<<GRID1D((size_t)BL * A), 256, 0, st>>>(s->dtemp, s->T1[t], (size_t)BL * A);
+            launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
+            launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
+            launch_k(att_dtemp_kernel, GRID1D((size_t)BL * A), 256, st, s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
+            launch_k(segsum_kernel, dim3((A + 127) / 128, B), 128, st, dq, s->dtemp, B, L, A);
+            launch_k(tanh_bwd_kernel, GRID1D((size_t)BL * A), 256, st, s->dtemp, s->T1[t], (size_t)BL * A);
         }
         if (tc) {
             // dW1a[D, A] += ctxd^T[D, BL] * dtemp[BL, A]: the weight repack kernel transposes, so ctxd [BL x D] read
@@ -1148,16 +1270,16 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, st, &drop));
             TCK(sat::lin_repack_weight(s->dtemp, BL, A, 0, s->tc_wbig, lmode, st));
             TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, st, 1));
-            if (!att_fused) colsum_kernel<<<dim3((A + 127) / 128, (BL + 255) / 256), 128, 0, st>>>(Gd(vA1aB), s->dtemp, BL, A);
+            if (!att_fused) launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aB), s->dtemp, BL, A, nullptr);
         } else {
-            dropout2d_kernel<<<GRID1D((size_t)BL * D), 256, 0, st>>>(s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
+            launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
             TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));       // contexts are inputs
         }
-        tanh_bwd_kernel<<<GRID1D((size_t)B * A), 256, 0, st>>>(dq, s->q[t], (size_t)B * A);
+        launch_k(tanh_bwd_kernel, GRID1D((size_t)B * A), 256, st, dq, s->q[t], (size_t)B * A);
         if (tc_dx(0, dq, s->dhd, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
         else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
-        dropout2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
     }
     if (stack) {
         // dW += X_all^T dY_all, db += colsum(dY_all) for attend/fc_1b, lstm, decode/fc_1, decode/fc_2 (the repack kernel
@@ -1173,20 +1295,20 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             const int tiles = ((l.N + 127) / 128) * ((l.K + 127) / 128);
             while (sp * 2 <= 8 && tiles * sp * 2 <= 148) sp *= 2;
             TRET(sat_dense_packed(s->handle, s->tc_sx, l.K, 128, TB, s->tc_sw, nullptr, l.N, sat::kEpiNone, Gd(l.var_w), l.N, 1, sp, st, 1));
-            colsum_kernel<<<dim3((l.N + 127) / 128, (TB + 255) / 256), 128, 0, st>>>(Gd(l.var_b), dy[i], TB, l.N);
+            launch_k(colsum_kernel, dim3((l.N + 127) / 128, (TB + 255) / 256), 128, st, Gd(l.var_b), dy[i], TB, l.N, nullptr);
         }
     }
     // ------------------------------------------------------------ initialize backward
     // h0 is both h_out[-1] (attend of step 0) and h_state[-1] (LSTM of step 0); c0 receives dc
-    copy2d_kernel<<<GRID1D((size_t)B * H), 256, 0, st>>>(s->dh_out, H, s->dh_state, H, B, H, 1);
+    launch_k(copy2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dh_state, H, B, H, 1);
     float* dmid = s->dbuf + (size_t)B * D;  // [B, I]
     TRET(dense_bwd(st, s->ib1d, B, I, P(vIb2W), H, s->dh_out, Gd(vIb2W), Gd(vIb2B), dmid));
-    dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, I, dmid, I, B, I, seed, INIT + 2, kf, 0);
-    tanh_bwd_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, s->ib1, (size_t)B * I);
+    launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, dmid, I, dmid, I, B, I, seed, INIT + 2, kf, 0);
+    launch_k(tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ib1, (size_t)B * I);
     TRET(dense_bwd(st, s->meand, B, D, P(vIb1W), I, dmid, Gd(vIb1W), Gd(vIb1B), nullptr));
     TRET(dense_bwd(st, s->ia1d, B, I, P(vIa2W), H, s->dc, Gd(vIa2W), Gd(vIa2B), dmid));
-    dropout2d_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, I, dmid, I, B, I, seed, INIT + 1, kf, 0);
-    tanh_bwd_kernel<<<GRID1D((size_t)B * I), 256, 0, st>>>(dmid, s->ia1, (size_t)B * I);
+    launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, dmid, I, dmid, I, B, I, seed, INIT + 1, kf, 0);
+    launch_k(tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ia1, (size_t)B * I);
     TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), I, dmid, Gd(vIa1W), Gd(vIa1B), nullptr));
     TCK(cudaGetLastError());
     TCK(cudaMemcpyAsync(losses, s->loss_acc, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1253,12 +1375,12 @@ extern "C" int sat_train_apply(sat_handle* h, float* params, float* grads, float
     for (int v = 0; v < kNumVars; ++v)
         if (s->regularised[v]) {
             const size_t n = (size_t)s->rows[v] * s->cols[v];
-            axpy_kernel<<<GRID1D(n), 256, 0, st>>>(grads + s->off[v], params + s->off[v], s->reg_scale, n);
+            launch_k(axpy_kernel, GRID1D(n), 256, st, grads + s->off[v], params + s->off[v], s->reg_scale, n);
         }
     TCK(cudaMemsetAsync(s->loss_acc + 4, 0, sizeof(float), st));
-    sumsq_kernel<<<296, 256, 0, st>>>(grads, s->off[kNumVars], 1.0f, s->loss_acc + 4);   // padding entries are zero
+    launch_k(sumsq_kernel, 148 * 8, 256, st, grads, s->off[kNumVars], 1.0f, s->loss_acc + 4);   // padding entries are zero
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
-    adam_kernel<<<GRID1D(s->off[kNumVars]), 256, 0, st>>>(params, grads, adam_m, adam_v, s->off[kNumVars], s->loss_acc + 4, clip,
+    launch_k(adam_kernel, GRID1D(s->off[kNumVars]), 256, st, params, grads, adam_m, adam_v, s->off[kNumVars], s->loss_acc + 4, clip,
                                                           (float)lr_t, beta1, beta2, epsilon);
     TCK(cudaGetLastError());
     if (grad_norm) TCK(cudaMemcpyAsync(grad_norm, s->loss_acc + 4, sizeof(float), cudaMemcpyDeviceToDevice, st));  // norm^2
