@@ -742,7 +742,8 @@ __global__ void __launch_bounds__(128) lin_simt_kernel(const __grid_constant__ L
 // packed bf16 hi/lo UMMA tiles.  perm_H > 0 selects the LSTM gate interleave:
 // packed output p = unit*4 + gate  <->  TF column gate*H + unit (split order i,j,f,o).
 __global__ void repack_weight_kernel(const float* __restrict__ w, int K, int n_out, int perm_H, uint8_t* wpack,
-                                     int k_blocks, int n_tiles, int mode, DropSpec drop) {
+                                     int k_blocks, int n_tiles, int mode, DropSpec drop, int pdl) {
+    if (pdl) { pdl_wait(); pdl_launch_dependents(); }   // launched with programmatic serialization (training path)
     const unsigned long long seed = drop.seedp ? *drop.seedp : 0ull;
     const DropGen gen = drop_gen(seed, drop.stream, drop.keep);
     const size_t total = (size_t)n_tiles * k_blocks * kTileN * 8;  // 16-byte groups
@@ -785,8 +786,10 @@ struct PackJobs {
     PackJob j[2];
     int n, mode;
     DropSpec drop;
+    int pdl;
 };
 __global__ void pack_rows_kernel(const PackJobs J) {
+    if (J.pdl) { pdl_wait(); pdl_launch_dependents(); }   // launched with programmatic serialization (training path)
     const unsigned long long seed = J.drop.seedp ? *J.drop.seedp : 0ull;
     const DropGen gen = drop_gen(seed, J.drop.stream, J.drop.keep);
     for (int q = 0; q < J.n; ++q) {
@@ -826,8 +829,24 @@ __global__ void pack_rows_kernel(const PackJobs J) {
     }
 }
 
-cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st, const DropSpec* drop) {
+// launch with the programmatic-serialization attribute: the kernel waits for its predecessor itself (first statement)
+template <typename... KA, typename... A>
+static cudaError_t launch_serialized(void (*kernel)(KA...), int grid, int block, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
+
+cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st, const DropSpec* drop, int pdl) {
     PackJobs J;
+    J.pdl = pdl;
     J.n = njobs;
     J.mode = layout_mode;
     J.drop = drop ? *drop : DropSpec{nullptr, 0ull, 1.0f};
@@ -840,6 +859,7 @@ cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cu
     int grid = (total + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;   // every thread converts a few 32-byte groups: short dependent chains
     if (grid < 1) grid = 1;
+    if (pdl) return launch_serialized(pack_rows_kernel, grid, 256, st, J);
     pack_rows_kernel<<<grid, 256, 0, st>>>(J);
     return cudaGetLastError();
 }
@@ -920,10 +940,11 @@ cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt) {
 }
 
 cudaError_t lin_repack_weight(const float* w_tf, int K, int n_out, int perm_H, uint8_t* wpack, int layout_mode,
-                              cudaStream_t st, const DropSpec* drop) {
+                              cudaStream_t st, const DropSpec* drop, int pdl) {
     const int k_blocks = (K + kBK - 1) / kBK, n_tiles = (n_out + kTileN - 1) / kTileN;
-    repack_weight_kernel<<<1184, 256, 0, st>>>(w_tf, K, n_out, perm_H, wpack, k_blocks, n_tiles, layout_mode,
-                                               drop ? *drop : DropSpec{nullptr, 0ull, 1.0f});
+    const DropSpec ds = drop ? *drop : DropSpec{nullptr, 0ull, 1.0f};
+    if (pdl) return launch_serialized(repack_weight_kernel, 1184, 256, st, w_tf, K, n_out, perm_H, wpack, k_blocks, n_tiles, layout_mode, ds, 1);
+    repack_weight_kernel<<<1184, 256, 0, st>>>(w_tf, K, n_out, perm_H, wpack, k_blocks, n_tiles, layout_mode, ds, 0);
     return cudaGetLastError();
 }
 

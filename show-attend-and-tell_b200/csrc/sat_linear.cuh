@@ -213,14 +213,17 @@ struct PackJob {           // fp32 rows (optionally gathered) -> packed activati
                     // consumer rounds a ragged width up; the caller keeps the unwritten tail of the last block zero.
 };
 // drop (optional) applies to every job: mask index = row * width + column of the (un-gathered) source row
-cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st, const DropSpec* drop = nullptr);
+// pdl: launch with the programmatic-serialization attribute (the kernel then waits for its predecessor itself and
+// lets its successor launch early; used by the training step, whose neighbours all follow that convention)
+cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st, const DropSpec* drop = nullptr,
+                             int pdl = 0);
 
 size_t lin_smem_bytes(int row_tile, int stages);
 int lin_pick_stages(int row_tile);
 cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt);
 // drop (optional): mask index = k * n_out + column of the source
 cudaError_t lin_repack_weight(const float* w_tf, int K, int n_out, int perm_H, uint8_t* wpack, int layout_mode,
-                              cudaStream_t st, const DropSpec* drop = nullptr);
+                              cudaStream_t st, const DropSpec* drop = nullptr, int pdl = 0);
 cudaError_t lin_repack_bias(const float* b_tf, int n_out, int perm_H, float* bias_packed, cudaStream_t st);
 cudaError_t lin_init_attrs();
 

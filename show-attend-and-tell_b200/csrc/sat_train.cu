@@ -69,6 +69,7 @@ static int train_pdl_enabled() {
     }
     return v;
 }
+#define PDLK train_pdl_enabled()
 template <typename... KA, typename... A>
 static cudaError_t launch_k(void (*kernel)(KA...), dim3 grid, dim3 block, cudaStream_t st, A... args) {
     cudaLaunchConfig_t cfg = {};
@@ -268,6 +269,17 @@ __global__ void bias_act_kernel(float* x, const float* b, int rows, int cols, in
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float v = x[i] + b[i % cols];
         x[i] = act ? tanhf(v) : v;
+    }
+}
+// dx = drop(dy) * (1 - y^2) in place on dy (dense [rows, cols]: mask index = linear index): the backward of
+// y = tanh(.) followed by dropout
+__global__ void drop_tanh_bwd_kernel(float* dy, const float* y, size_t n, const unsigned long long* seedp, unsigned long long stream,
+                                     float keep) {
+    pdl_enter();
+    const unsigned long long seed = *seedp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float d = seed ? dy[i] * drop_scale(seed, stream, i, keep) : dy[i];
+        dy[i] = d * (1.0f - y[i] * y[i]);
     }
 }
 // dx = dy * (1 - y^2) in place on dy
@@ -514,7 +526,8 @@ __global__ void rowdot_kernel(float* e, const float* temp, const float* w2, int 
     if (lane == 0) e[warp] = s;
 }
 // softmax over L per row (one warp per row)
-__global__ void softmax_rows_kernel(float* alpha, const float* e, int rows, int L) {
+// and the attention coverage accumulator att[b, l] += alpha[b, l] * mask[b, t] (att == nullptr: skipped)
+__global__ void softmax_rows_kernel(float* alpha, const float* e, int rows, int L, float* att, const float* masks, int mld, int t) {
     pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -525,7 +538,12 @@ __global__ void softmax_rows_kernel(float* alpha, const float* e, int rows, int 
     float s = 0.f;
     for (int l = lane; l < L; l += 32) s += expf(x[l] - m);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    for (int l = lane; l < L; l += 32) alpha[(size_t)warp * L + l] = expf(x[l] - m) / s;
+    const float mk = att ? masks[(size_t)warp * mld + t] : 0.f;
+    for (int l = lane; l < L; l += 32) {
+        const float a = expf(x[l] - m) / s;
+        alpha[(size_t)warp * L + l] = a;
+        if (att) att[(size_t)warp * L + l] += a * mk;
+    }
 }
 // de = alpha * (dalpha - sum_l alpha*dalpha)   (one warp per row), written over dalpha
 __global__ void softmax_bwd_kernel(float* dalpha, const float* alpha, int rows, int L) {
@@ -580,8 +598,9 @@ __global__ void __launch_bounds__(256) context_fwd4_kernel(float* __restrict__ z
         reinterpret_cast<float4*>(z)[(size_t)b * D4 + c4] = a;
     }
 }
-// dalpha[b, l] = sum_d dz[b, d] * ctx[b, l, d]  (+ extra[b, l] if given)   (one warp per (b, l))
-__global__ void context_bwd_kernel(float* dalpha, const float* dz, const float* ctx, const float* extra, int B, int L, int D) {
+// dalpha[b, l] = sum_d dz[b, d] * ctx[b, l, d]  (+ extra[b, l] * mask[b, t] if given)   (one warp per (b, l))
+__global__ void context_bwd_kernel(float* dalpha, const float* dz, const float* ctx, const float* extra, int B, int L, int D,
+                                   const float* masks, int mld, int t) {
     pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * L) return;
@@ -589,7 +608,8 @@ __global__ void context_bwd_kernel(float* dalpha, const float* dz, const float* 
     float s = 0.f;
     for (int d = lane; d < D; d += 32) s = fmaf(dz[(size_t)b * D + d], ctx[(size_t)warp * D + d], s);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) dalpha[warp] = s + (extra ? extra[warp] : 0.f);
+    // extra = d coverage loss / d att (datt); it reaches alpha[b, l] of step t through att += alpha * mask[b, t]
+    if (lane == 0) dalpha[warp] = s + (extra ? extra[warp] * masks[(size_t)b * mld + t] : 0.f);
 }
 // dtemp[r, a] = de[r] * w2[a] * drop(att_mid)   and  (1 - T1^2) applied later
 __global__ void att_dtemp_kernel(float* dtemp, const float* de, const float* w2, int rows, int A,
@@ -631,9 +651,12 @@ __global__ void segsum_kernel(float* dq, const float* dtemp, int B, int L, int A
     dq[(size_t)b * A + a] = s;
 }
 __device__ inline float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
-// gates G [B, 4H] (blocks i, j, f, o) -> activated gates (in place), c, h_raw
-__global__ void lstm_fwd_kernel(float* G, const float* bias, const float* c_prev, float* c, float* h_raw, int B, int H) {
+// gates G [B, 4H] (blocks i, j, f, o) -> activated gates (in place), c, and the two dropped copies of
+// h_raw = o * tanh(c): h_out = drop_out(h_raw) (mask stream st_out), h_state = drop_state(h_raw) (st_state)
+__global__ void lstm_fwd_kernel(float* G, const float* bias, const float* c_prev, float* c, float* h_out, float* h_state, int B, int H,
+                                const unsigned long long* seedp, unsigned long long st_out, unsigned long long st_state, float keep) {
     pdl_enter();
+    const unsigned long long seed = *seedp;
     const size_t n = (size_t)B * H;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / H), u = (int)(i - (size_t)b * H);
@@ -645,20 +668,26 @@ __global__ void lstm_fwd_kernel(float* G, const float* bias, const float* c_prev
         const float cc = gf * c_prev[i] + gi * gj;
         g[u] = gi; g[H + u] = gj; g[2 * H + u] = gf; g[3 * H + u] = go;
         c[i] = cc;
-        h_raw[i] = go * tanhf(cc);
+        const float hr = go * tanhf(cc);
+        h_out[i] = seed ? hr * drop_scale(seed, st_out, i, keep) : hr;
+        h_state[i] = seed ? hr * drop_scale(seed, st_state, i, keep) : hr;
     }
 }
-// dh_raw, dc (in/out: on entry dc = gradient flowing into c_t from step t+1) -> dG (pre-activation), dc_prev
-__global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_raw, const float* acts, const float* c,
-                                const float* c_prev, int B, int H) {
+// dh_raw = drop_out(dh_out) + drop_state(dh_state) (the masks of the forward pass), dc (in/out: on entry dc = gradient
+// flowing into c_t from step t+1) -> dG (pre-activation), dc_prev
+__global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_out, const float* dh_state, const float* acts, const float* c,
+                                const float* c_prev, int B, int H, const unsigned long long* seedp, unsigned long long st_out,
+                                unsigned long long st_state, float keep) {
     pdl_enter();
+    const unsigned long long seed = *seedp;
     const size_t n = (size_t)B * H;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / H), u = (int)(i - (size_t)b * H);
         const float* a = acts + (size_t)b * 4 * H;
         const float gi = a[u], gj = a[H + u], gf = a[2 * H + u], go = a[3 * H + u];
         const float tc = tanhf(c[i]);
-        const float dh = dh_raw[i];
+        const float dh = seed ? dh_out[i] * drop_scale(seed, st_out, i, keep) + dh_state[i] * drop_scale(seed, st_state, i, keep)
+                              : dh_out[i] + dh_state[i];
         const float dcc = dh * go * (1.0f - tc * tc) + dc[i];
         float* d = dG + (size_t)b * 4 * H;
         d[u] = dcc * gj * gi * (1.0f - gi);
@@ -669,17 +698,20 @@ __global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_raw, const
     }
 }
 // masked cross entropy of one time step + its gradient; one block per row
-__global__ void __launch_bounds__(256) ce_kernel(const float* logits, float* dlogits, const int32_t* sent, int sent_ld, int t,
-                                                 const float* masks, int V, const float* inv_msum_p, float* loss_acc) {
+constexpr int kCeThreads = 1024;   // one CTA per batch row: the three passes over the V logits are latency bound
+__global__ void __launch_bounds__(kCeThreads) ce_kernel(const float* logits, float* dlogits, const int32_t* sent, int sent_ld, int t,
+                                                        const float* masks, int V, const float* inv_msum_p, float* loss_acc) {
     pdl_enter();
+    constexpr int NW = kCeThreads / 32;
     const float inv_msum = *inv_msum_p;
-    __shared__ float red[8];
-    __shared__ int redi[8];
+    __shared__ float red[NW];
+    __shared__ int redi[NW];
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* x = logits + (size_t)b * V;
+    float* d = dlogits + (size_t)b * V;
     float m = -INFINITY;
     int mi = 0x7fffffff;
-    for (int i = threadIdx.x; i < V; i += 256) {
+    for (int i = threadIdx.x; i < V; i += kCeThreads) {
         const float v = x[i];
         if (v > m || (v == m && i < mi)) { m = v; mi = i; }
     }
@@ -691,22 +723,26 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* logits, float* dlo
     if (lane == 0) { red[warp] = m; redi[warp] = mi; }
     __syncthreads();
     m = red[0]; mi = redi[0];
-    for (int w = 1; w < 8; ++w)
+    for (int w = 1; w < NW; ++w)
         if (red[w] > m || (red[w] == m && redi[w] < mi)) { m = red[w]; mi = redi[w]; }
     __syncthreads();
     float s = 0.f;
-    for (int i = threadIdx.x; i < V; i += 256) s += expf(x[i] - m);
+    for (int i = threadIdx.x; i < V; i += kCeThreads) {   // e^{x - m} is kept in dlogits for the last pass (same thread, same i)
+        const float e = expf(x[i] - m);
+        d[i] = e;
+        s += e;
+    }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) red[warp] = s;
     __syncthreads();
     s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w];
+    for (int w = 0; w < NW; ++w) s += red[w];
     const int y = sent[(size_t)b * sent_ld + t];
     const float mk = masks[(size_t)b * sent_ld + t];
     const float scale = mk * inv_msum;
-    for (int i = threadIdx.x; i < V; i += 256) {
-        const float p = expf(x[i] - m) / s;
-        dlogits[(size_t)b * V + i] = (p - (i == y ? 1.0f : 0.0f)) * scale;
+    for (int i = threadIdx.x; i < V; i += kCeThreads) {
+        const float p = d[i] / s;
+        d[i] = (p - (i == y ? 1.0f : 0.0f)) * scale;
     }
     if (threadIdx.x == 0) {
         const float ce = logf(s) + m - x[y];
@@ -1082,7 +1118,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     const bool tc = s->tc_ok && sat_handle_train_tc(s->handle);
     const int lmode = sat_handle_layout_mode(s->handle);
     if (tc) {   // this step's attend/fc_1a weights in the packed layout (they change with every optimizer step)
-        TCK(sat::lin_repack_weight(P(vA1aW), D, A, 0, s->tc_w1a, lmode, st));
+        TCK(sat::lin_repack_weight(P(vA1aW), D, A, 0, s->tc_w1a, lmode, st, nullptr, PDLK));
         TCK(sat::lin_repack_bias(P(vA1aB), A, 0, s->tc_b1a, st));
     }
     const bool tcb = sat_handle_train_tc(s->handle) != 0;
@@ -1090,19 +1126,19 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         for (int i = 0; i < 4; ++i) {
             TrainState::TcLayer& l = s->tcl[i];
             if (l.fwd) {
-                TCK(sat::lin_repack_weight(P(l.var_w), l.K, l.N, 0, l.w, lmode, st));
+                TCK(sat::lin_repack_weight(P(l.var_w), l.K, l.N, 0, l.w, lmode, st, nullptr, PDLK));
                 TCK(sat::lin_repack_bias(P(l.var_b), l.N, 0, l.b, st));
             }
             if (l.dx) {   // W^T as a weight operand: row n of the operand = row k of W ... i.e. W's rows are its K-major rows
                 sat::PackJob job{P(l.var_w), nullptr, l.N, l.N, l.K, 128, l.wT};
-                TCK(sat::pack_rows_launch(&job, 1, lmode, st));
+                TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
             }
         }
     }
     const bool tcv = tcb && s->tc_vk > 0;
     if (tcv) {   // decode/fc_2's W^T (rows Dd, K = V rounded up) for its input gradient
         sat::PackJob job{P(vD2W), nullptr, V, V, Dd, 128, s->tc_vw, s->tc_vk / 64};
-        TCK(sat::pack_rows_launch(&job, 1, lmode, st));
+        TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
     }
     auto tc_splits = [&](int n_out, int K) {
         const int tiles = (n_out + 127) / 128;
@@ -1115,7 +1151,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         TrainState::TcLayer& l = s->tcl[li];
         if (!tcb || !l.fwd) return false;
         sat::PackJob job{x, nullptr, l.K, l.K, B, s->tc_rt, s->tc_xs};
-        cudaError_t ce = sat::pack_rows_launch(&job, 1, lmode, st);
+        cudaError_t ce = sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK);
         if (ce != cudaSuccess) { *rc = sat_fail(SAT_ERR_CUDA, "pack: %s", cudaGetErrorString(ce)); return true; }
         *rc = sat_dense_packed(s->handle, s->tc_xs, B, s->tc_rt, l.K, l.w, l.b, l.N, epi, y, l.N, 0, tc_splits(l.N, l.K), st);
         return true;
@@ -1125,7 +1161,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         TrainState::TcLayer& l = s->tcl[li];
         if (!tcb || !l.dx) return false;
         sat::PackJob job{dy, nullptr, l.N, l.N, B, s->tc_rt, s->tc_xs};
-        cudaError_t ce = sat::pack_rows_launch(&job, 1, lmode, st);
+        cudaError_t ce = sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK);
         if (ce != cudaSuccess) { *rc = sat_fail(SAT_ERR_CUDA, "pack: %s", cudaGetErrorString(ce)); return true; }
         *rc = sat_dense_packed(s->handle, s->tc_xs, B, s->tc_rt, l.N, l.wT, nullptr, l.K, sat::kEpiNone, dx, l.K, 0, tc_splits(l.K, l.N), st);
         return true;
@@ -1154,7 +1190,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
                     // rows are packed (no fp32 dropped copy), bias + tanh fused in the epilogue
             sat::PackJob job{contexts, nullptr, D, D, BL, 128, s->tc_xpa};
             const sat::DropSpec drop{seed, ST(t, 0), kf};
-            TCK(sat::pack_rows_launch(&job, 1, lmode, st, &drop));
+            TCK(sat::pack_rows_launch(&job, 1, lmode, st, &drop, PDLK));
             TRET(sat_dense_packed(s->handle, s->tc_xpa, BL, 128, D, s->tc_w1a, s->tc_b1a, A, sat::kEpiBiasTanh, s->T1[t], A, 0, 1, st));
         } else {
             launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
@@ -1169,12 +1205,11 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
             launch_k(rowdot_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->temp, P(vA2W), BL, A);
         }
-        launch_k(softmax_rows_kernel, (B * 32 + 255) / 256, 256, st, s->alpha[t], s->e, B, L);
+        launch_k(softmax_rows_kernel, (B * 32 + 255) / 256, 256, st, s->alpha[t], s->e, B, L, s->att, masks, T, t);   // + coverage
         if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(contexts) & 15) == 0)   // un-dropped ctx
             launch_k(context_fwd4_kernel, dim3((D / 4 + 31) / 32, B), 256, st, s->z[t], s->alpha[t], contexts, L, D);
         else
             launch_k(context_fwd_kernel, dim3((D + 127) / 128, B), 128, st, s->z[t], s->alpha[t], contexts, B, L, D);
-        launch_k(coverage_acc_kernel, (BL + 255) / 256, 256, st, s->att, s->alpha[t], masks, T, t, B, L);
         // embedding of the previous word: 0 at t = 0, then teacher forcing (model.py:254, 310)
         launch_k(gather_rows_kernel, GRID1D((size_t)B * E), 256, st, s->emb[t], E, P(vEmb), E, t ? sentences + (t - 1) : nullptr, T, B);
         // LSTM with DropoutWrapper (model.py:228-236, 276-279)
@@ -1183,9 +1218,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
                                                                     seed, ST(t, 3), kl);
         if (tc_fwd(1, s->lstm_in[t], sat::kEpiNone, s->acts[t], &trc)) { TRET(trc); }   // (bias and gates: next kernel)
         else TCK(sgemm(st, false, false, B, 4 * H, XL, s->lstm_in[t], XL, P(vLW), 4 * H, s->acts[t], 4 * H, false));
-        launch_k(lstm_fwd_kernel, GRID1D((size_t)B * H), 256, st, s->acts[t], P(vLB), c_prev, s->c[t], s->h_raw, B, H);
-        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->h_out[t], H, s->h_raw, H, B, H, seed, ST(t, 5), kl, 0);
-        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->h_state[t], H, s->h_raw, H, B, H, seed, ST(t, 4), kl, 0);
+        launch_k(lstm_fwd_kernel, GRID1D((size_t)B * H), 256, st, s->acts[t], P(vLB), c_prev, s->c[t], s->h_out[t], s->h_state[t], B, H, seed,
+                 ST(t, 5), ST(t, 4), kl);
         // decode (model.py:282-287, 438-459)
         launch_k(concat3_drop_kernel, GRID1D((size_t)B * XD), 256, st, s->expd[t], XD, s->h_out[t], H, s->z[t], D, s->emb[t], E, XD, B,
                                                                     seed, ST(t, 6), kf);
@@ -1195,7 +1229,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         if (tc_fwd(3, s->td[t], sat::kEpiBias, s->logits, &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->td[t], B, Dd, P(vD2W), P(vD2B), V, s->logits, 0));
         // masked cross entropy + accuracy, and d loss / d logits (model.py:292-305, 316-318, 332-334)
-        launch_k(ce_kernel, B, 256, st, s->logits, s->dlogits[t], sentences, T, t, masks, V, inv_msum, s->loss_acc);
+        launch_k(ce_kernel, B, kCeThreads, st, s->logits, s->dlogits[t], sentences, T, t, masks, V, inv_msum, s->loss_acc);
     }
     // attention coverage loss (model.py:320-326) and L2 regulariser (model.py:328)
     launch_k(coverage_loss_kernel, 64, 256, st, s->datt, s->att, BL, s->att_factor, inv_gbl, s->loss_acc);
@@ -1221,7 +1255,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         bool vdx = false;
         if (tcv) {   // dtd = dlogits W2^T on the tensor cores (ragged K = V: zero-padded last K block)
             sat::PackJob job{s->dlogits[t], nullptr, V, V, B, s->tc_rt, s->tc_vx, s->tc_vk / 64};
-            TCK(sat::pack_rows_launch(&job, 1, lmode, st));
+            TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
             TRET(sat_dense_packed(s->handle, s->tc_vx, B, s->tc_rt, s->tc_vk, s->tc_vw, nullptr, Dd, sat::kEpiNone, dtd, Dd, 0,
                                   tc_splits(Dd, s->tc_vk), st));
             vdx = true;
@@ -1229,17 +1263,15 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         if (stack) { if (!vdx) TCK(sgemm(st, false, true, B, Dd, V, s->dlogits[t], V, P(vD2W), V, dtd, Dd, false)); }
         else if (vdx) TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), nullptr));
         else TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), dtd));
-        launch_k(dropout2d_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, Dd, dtd, Dd, B, Dd, seed, ST(t, 7), kf, 0);
-        launch_k(tanh_bwd_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, s->t1[t], (size_t)B * Dd);
+        launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, s->t1[t], (size_t)B * Dd, seed, ST(t, 7), kf);
         if (tc_dx(2, dtd, s->dexp, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
         else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), s->dexp));
         // drop(dexp) = [dh_out (+=) | dz (=) | demb (=)]
         launch_k(split3_drop_kernel, GRID1D((size_t)B * XD), 256, st, s->dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, s->demb, E, 0, XD, seed,
                                                                    ST(t, 6), kf);
         // h_out = drop_out(h_raw), h_state = drop_state(h_raw)
-        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_raw, H, s->dh_out, H, B, H, seed, ST(t, 5), kl, 0);
-        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_raw, H, s->dh_state, H, B, H, seed, ST(t, 4), kl, 1);
-        launch_k(lstm_bwd_kernel, GRID1D((size_t)B * H), 256, st, dG, s->dc, s->dh_raw, s->acts[t], s->c[t], c_prev, B, H);
+        launch_k(lstm_bwd_kernel, GRID1D((size_t)B * H), 256, st, dG, s->dc, s->dh_out, s->dh_state, s->acts[t], s->c[t], c_prev, B, H, seed,
+                 ST(t, 5), ST(t, 4), kl);
         if (tc_dx(1, dG, s->dlin, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), nullptr)); }
         else TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), s->dlin));
         // dlin = [d xd (D+E) | dh_state_prev]
@@ -1247,8 +1279,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
                                                                    ST(t, 3), kl);
         launch_k(scatter_add_rows_kernel, GRID1D((size_t)B * E), 256, st, Gd(vEmb), E, t ? sentences + (t - 1) : nullptr, T, s->demb, E, B);
         // attention: context vector, softmax, scorer
-        launch_k(coverage_grad_kernel, (BL + 255) / 256, 256, st, s->extra, s->datt, masks, T, t, B, L);
-        launch_k(context_bwd_kernel, (BL * 32 + 255) / 256, 256, st, s->dalpha, s->dz, contexts, s->extra, B, L, D);
+        launch_k(context_bwd_kernel, (BL * 32 + 255) / 256, 256, st, s->dalpha, s->dz, contexts, s->datt, B, L, D, masks, T, t);
         launch_k(softmax_bwd_kernel, (B * 32 + 255) / 256, 256, st, s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
         if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
             TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));
@@ -1267,8 +1298,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             // packed weight; split-K over an 8-CTA cluster, accumulated into the gradient in the epilogue
             // (the context dropout mask is re-applied while ctx is packed: mask index row * D + column, as in the forward pass)
             const sat::DropSpec drop{seed, ST(t, 0), kf};
-            TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, st, &drop));
-            TCK(sat::lin_repack_weight(s->dtemp, BL, A, 0, s->tc_wbig, lmode, st));
+            TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, st, &drop, PDLK));
+            TCK(sat::lin_repack_weight(s->dtemp, BL, A, 0, s->tc_wbig, lmode, st, nullptr, PDLK));
             TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, st, 1));
             if (!att_fused) launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aB), s->dtemp, BL, A, nullptr);
         } else {
@@ -1289,8 +1320,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         const float* dy[4] = {s->dys[0][0], s->dys[1][0], s->dys[2][0], s->dlogits[0]};
         for (int i = 0; i < 4; ++i) {
             TrainState::TcLayer& l = s->tcl[i];
-            TCK(sat::lin_repack_weight(xs[i], TB, l.K, 0, s->tc_sx, lmode, st));
-            TCK(sat::lin_repack_weight(dy[i], TB, l.N, 0, s->tc_sw, lmode, st));
+            TCK(sat::lin_repack_weight(xs[i], TB, l.K, 0, s->tc_sx, lmode, st, nullptr, PDLK));
+            TCK(sat::lin_repack_weight(dy[i], TB, l.N, 0, s->tc_sw, lmode, st, nullptr, PDLK));
             int sp = 1;
             const int tiles = ((l.N + 127) / 128) * ((l.K + 127) / 128);
             while (sp * 2 <= 8 && tiles * sp * 2 <= 148) sp *= 2;
@@ -1303,12 +1334,10 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     launch_k(copy2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dh_state, H, B, H, 1);
     float* dmid = s->dbuf + (size_t)B * D;  // [B, I]
     TRET(dense_bwd(st, s->ib1d, B, I, P(vIb2W), H, s->dh_out, Gd(vIb2W), Gd(vIb2B), dmid));
-    launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, dmid, I, dmid, I, B, I, seed, INIT + 2, kf, 0);
-    launch_k(tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ib1, (size_t)B * I);
+    launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ib1, (size_t)B * I, seed, INIT + 2, kf);
     TRET(dense_bwd(st, s->meand, B, D, P(vIb1W), I, dmid, Gd(vIb1W), Gd(vIb1B), nullptr));
     TRET(dense_bwd(st, s->ia1d, B, I, P(vIa2W), H, s->dc, Gd(vIa2W), Gd(vIa2B), dmid));
-    launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, dmid, I, dmid, I, B, I, seed, INIT + 1, kf, 0);
-    launch_k(tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ia1, (size_t)B * I);
+    launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ia1, (size_t)B * I, seed, INIT + 1, kf);
     TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), I, dmid, Gd(vIa1W), Gd(vIa1B), nullptr));
     TCK(cudaGetLastError());
     TCK(cudaMemcpyAsync(losses, s->loss_acc, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
