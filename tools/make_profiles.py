@@ -34,6 +34,34 @@ with open(os.path.join(P, tag + "_launches_summary.csv"), "w") as f:
     for (k, g), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write('%s,"%s",%d,%.2f,%.2f,%.2f,%.3f\n' % (k, g, len(v), sum(v) / len(v), min(v), max(v), sum(v) / tot))
 
+# ---- launch list of the training step (tools/gpu_train_list.sh)
+tp = os.path.join(G, "train_launches.csv")
+if os.path.exists(tp):
+    rows = list(csv.reader(open(tp)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
+    tseq = []
+    for r in rows[hi + 1:]:
+        try:
+            name = r[ki].split("(")[0].replace("void ", "").replace("<unnamed>::", "").strip()
+            tseq.append((name, r[gi], float(r[vi].replace(",", "")) / 1e3))
+        except Exception:
+            pass
+    ends = [i for i, (k, _, _) in enumerate(tseq) if k.startswith("adam_kernel")]
+    one = tseq[ends[0] + 1:ends[1] + 1] if len(ends) >= 2 else tseq   # exactly one optimizer step
+    agg = collections.OrderedDict()
+    for k, g, u in one:
+        agg.setdefault((k, g), []).append(u)
+    tot = sum(u for _, _, u in one)
+    with open(os.path.join(P, tag + "_train_launches_summary.csv"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 6000 -c 3000 python bench.py --steps 1 --warmup 1 --no-cpu --workload 4\n")
+        f.write("# training step, config 4 (B=64 L=196 D=512 H=1024 V=10000 T=20): the %d launches of ONE step (between two adam_kernel "
+                "launches), %.1f us in total; cold-cache and serialised (the real step overlaps launch latencies)\n" % (len(one), tot))
+        f.write("kernel,grid,launches,mean_us,total_us,share_of_total\n")
+        for (k, g), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write('%s,"%s",%d,%.2f,%.1f,%.3f\n' % (k, g, len(v), sum(v) / len(v), sum(v), sum(v) / tot))
+
 # ---- full captures
 def pick(rep, out, title):
     raw = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
