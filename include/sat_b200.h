@@ -190,6 +190,11 @@ int sat_train_var(sat_handle* h, int32_t i, const char** name, int64_t* offset, 
 int sat_train_forward_backward(sat_handle* h, const float* params, float* grads, const float* contexts,
                                const int32_t* sentences, const float* masks, int32_t B, int32_t T, uint64_t seed,
                                double global_mask_sum, int32_t global_batch, float* losses, void* stream);
+/* the same with the whole-batch mask sum read from DEVICE memory (one double, e.g. the output of an all-reduce
+ * queued on `stream` just before): nothing of a data-parallel step then waits for the host. */
+int sat_train_forward_backward_dsum(sat_handle* h, const float* params, float* grads, const float* contexts,
+                                    const int32_t* sentences, const float* masks, int32_t B, int32_t T, uint64_t seed,
+                                    const double* global_mask_sum_dev, int32_t global_batch, float* losses, void* stream);
 /* adds the L2-regulariser gradient, clips by the global norm (clip_gradients, config.py:36) and applies TF Adam
  * (config.py:32-43).  step counts from 1.  grad_norm (device, 1 float, may be NULL) receives the squared norm. */
 int sat_train_apply(sat_handle* h, float* params, float* grads, float* adam_m, float* adam_v, int64_t step, float lr,

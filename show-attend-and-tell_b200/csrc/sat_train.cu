@@ -1344,10 +1344,14 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     return SAT_OK;
 }
 
-extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, float* grads, const float* contexts,
-                                          const int32_t* sentences, const float* masks, int32_t B, int32_t T,
-                                          uint64_t seed, double global_mask_sum, int32_t global_batch, float* losses,
-                                          void* stream) {
+namespace {
+__global__ void reciprocal_kernel(float* out, const double* in) { *out = (float)(1.0 / *in); }
+}  // namespace
+
+static int train_forward_backward(sat_handle* h, const float* params, float* grads, const float* contexts,
+                                  const int32_t* sentences, const float* masks, int32_t B, int32_t T, uint64_t seed,
+                                  double global_mask_sum, const double* global_mask_sum_dev, int32_t global_batch, float* losses,
+                                  void* stream) {
     if (!h || !params || !grads || !contexts || !sentences || !masks || !losses)
         return sat_fail(SAT_ERR_INVALID, "sat_train_forward_backward: null argument");
     TrainState* s = (TrainState*)*sat_handle_train_slot(h);
@@ -1359,7 +1363,8 @@ extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, fl
     unsigned long long seed_v = seed;
     float inv = (float)(1.0 / global_mask_sum);
     TCK(cudaMemcpyAsync(s->seed_d, &seed_v, 8, cudaMemcpyHostToDevice, st));
-    TCK(cudaMemcpyAsync(s->inv_msum_d, &inv, 4, cudaMemcpyHostToDevice, st));
+    if (global_mask_sum_dev) reciprocal_kernel<<<1, 1, 0, st>>>(s->inv_msum_d, global_mask_sum_dev);   // the sum never visits the host
+    else TCK(cudaMemcpyAsync(s->inv_msum_d, &inv, 4, cudaMemcpyHostToDevice, st));
     auto enqueue = [&]() { return train_enqueue(s, params, grads, contexts, sentences, masks, B, T, global_batch, losses, st); };
     if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return enqueue();
     std::vector<long long> key = {(long long)params, (long long)grads, (long long)contexts, (long long)sentences,
@@ -1390,6 +1395,24 @@ extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, fl
     if (ce != cudaSuccess) { ent->exec = nullptr; return sat_fail(SAT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
     TCK(cudaGraphLaunch(ent->exec, st));
     return SAT_OK;
+}
+
+extern "C" int sat_train_forward_backward(sat_handle* h, const float* params, float* grads, const float* contexts,
+                                          const int32_t* sentences, const float* masks, int32_t B, int32_t T,
+                                          uint64_t seed, double global_mask_sum, int32_t global_batch, float* losses,
+                                          void* stream) {
+    return train_forward_backward(h, params, grads, contexts, sentences, masks, B, T, seed, global_mask_sum, nullptr, global_batch,
+                                  losses, stream);
+}
+// the same with the global mask sum in device memory (one double, e.g. the result of an all-reduce still in flight
+// on `stream`): a data-parallel loop then has no host synchronisation per step
+extern "C" int sat_train_forward_backward_dsum(sat_handle* h, const float* params, float* grads, const float* contexts,
+                                               const int32_t* sentences, const float* masks, int32_t B, int32_t T,
+                                               uint64_t seed, const double* global_mask_sum_dev, int32_t global_batch,
+                                               float* losses, void* stream) {
+    if (!global_mask_sum_dev) return sat_fail(SAT_ERR_INVALID, "sat_train_forward_backward_dsum: null mask sum");
+    return train_forward_backward(h, params, grads, contexts, sentences, masks, B, T, seed, 1.0, global_mask_sum_dev, global_batch,
+                                  losses, stream);
 }
 
 // grads: the (all-reduced) sum over data-parallel shards.  Adds the L2-regulariser gradient once, clips by the

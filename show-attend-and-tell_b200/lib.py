@@ -54,6 +54,7 @@ SIGNATURES = {
     "sat_train_var": (C.c_int, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L),
                                 C.POINTER(_I), C.POINTER(_L)]),
     "sat_train_forward_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, C.c_uint64, C.c_double, _I, _P, _P]),
+    "sat_train_forward_backward_dsum": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, C.c_uint64, _P, _I, _P, _P]),
     "sat_train_apply": (C.c_int, [_P, _P, _P, _P, _P, _L, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P,
                                   _P]),
 }

@@ -246,8 +246,18 @@ class CaptionGenerator(object):
         sent = self._dev(sentences, torch.int32)
         mk = self._dev(masks, torch.float32)
         assert tuple(sent.shape) == (B, T) and tuple(mk.shape) == (B, T) and ctx.shape[0] == B
-        gms = self._mask_sum(masks, mk) if global_mask_sum is None else float(global_mask_sum)
         gb = B if global_batch is None else int(global_batch)
+        if isinstance(global_mask_sum, torch.Tensor):    # device scalar (float64 [1]): no host round trip
+            gsum = global_mask_sum
+            assert gsum.is_cuda and gsum.dtype == torch.float64 and gsum.numel() == 1
+            self._sync_in()
+            self._check(self.lib.sat_train_forward_backward_dsum(self._h, self._p(self.params), self._p(self.grads), self._p(ctx),
+                                                                 self._p(sent), self._p(mk), B, T, int(seed), self._p(gsum), gb,
+                                                                 self._p(self._train_losses), self._st()))
+            self._sync_out()
+            self._keep["train_in"] = (ctx, sent, mk, gsum)
+            return self._train_losses
+        gms = self._mask_sum(masks, mk) if global_mask_sum is None else float(global_mask_sum)
         self._sync_in()
         self._check(self.lib.sat_train_forward_backward(self._h, self._p(self.params), self._p(self.grads), self._p(ctx),
                                                         self._p(sent), self._p(mk), B, T, int(seed), gms, gb,
@@ -294,12 +304,14 @@ class CaptionGenerator(object):
         B, T = self._train_BT
         mk = self._dev(masks, torch.float32)
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        msum = self._mask_sum(masks, mk)
         if world > 1:
-            t = torch.tensor([msum], dtype=torch.float64, device=self.device)
-            dist.all_reduce(t)
-            msum = float(t.item())
+            # the whole-batch mask sum stays on the device: summed, all-reduced and consumed in stream order, so the
+            # host can queue step i+1 while step i runs
+            msum = mk.sum(dtype=torch.float64).reshape(1)
+            dist.all_reduce(msum)
             seed = int(seed) + 0x1000003 * dist.get_rank() if seed else 0
+        else:
+            msum = self._mask_sum(masks, mk)
         losses = self.train_forward_backward(contexts, sentences, mk, seed, msum, B * world)
         if world > 1:
             dist.all_reduce(self.grads)                    # the single gradient all-reduce of the step

@@ -125,6 +125,18 @@ def test_training_reduces_the_loss_and_feeds_the_decoder():
     assert toks.shape == (4, ocfg.max_caption_length)
 
 
+def test_mask_sum_from_device_memory():
+    """sat_train_forward_backward_dsum: the whole-batch mask sum as a device scalar gives the same step."""
+    import torch
+    ocfg, w, m, ctx, sent, masks = setup(seed=5)
+    a = m.train_forward_backward(ctx, sent, masks, seed=9, global_mask_sum=float(masks.sum()) * 2, global_batch=8).cpu().numpy().copy()
+    ga = m.grads.detach().cpu().numpy().copy()
+    dsum = torch.tensor([float(masks.sum()) * 2], dtype=torch.float64, device=m.device)
+    b = m.train_forward_backward(ctx, sent, masks, seed=9, global_mask_sum=dsum, global_batch=8).cpu().numpy()
+    assert np.allclose(a, b, rtol=1e-6, atol=0)
+    assert np.allclose(ga, m.grads.detach().cpu().numpy(), rtol=1e-5, atol=1e-9)
+
+
 def test_reference_shapes_one_step():
     """default reference graph (L=196, D=512, H=512, V=5000), B=8, T=4: losses against the oracle forward."""
     dims = dict(max_caption_length=4)
