@@ -174,7 +174,10 @@ int sat_dense_fwd(sat_handle* h, const float* x, const float* w_tf, const float*
  * (TF variable name, offset in floats, TF shape).  A data-parallel step is
  *     sat_train_forward_backward  ->  all-reduce(sum) of `grads` across ranks (NCCL)  ->  sat_train_apply
  * Dropout masks come from a counter-based generator keyed by `seed` (0 = dropout off), so a step is
- * reproducible; ranks must use different seeds. */
+ * reproducible; ranks must use different seeds.
+ * Knobs: sat_set_option "train_tc" 1 = the large products of the step run on the tcgen05 dense kernel [1], 0 = fp32
+ * CUDA-core SGEMM everywhere; environment SAT_TRAIN_PDL=0 launches the step's kernels without the programmatic-
+ * serialization attribute (read once per process; for A/B timing only, results are identical). */
 int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop_rate, float lstm_drop_rate,
                    float attention_loss_factor, float fc_kernel_regularizer_scale);
 int sat_train_num_vars(sat_handle* h);

@@ -750,13 +750,6 @@ __global__ void __launch_bounds__(kCeThreads) ce_kernel(const float* logits, flo
         atomicAdd(loss_acc + 1, (mi == y ? mk : 0.0f) * inv_msum);  // accuracy
     }
 }
-// att[b, l] += alpha[b, l] * mask[b, t]
-__global__ void coverage_acc_kernel(float* att, const float* alpha, const float* masks, int mld, int t, int B, int L) {
-    pdl_enter();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * L) return;
-    att[i] += alpha[i] * masks[(size_t)(i / L) * mld + t];
-}
 // loss = factor * sum (1 - att)^2 / 2 / (GB * L);  datt = -factor * (1 - att) / (GB * L)
 __global__ void coverage_loss_kernel(float* datt, const float* att, int n, float factor, float inv_gbl, float* loss_acc) {
     pdl_enter();
@@ -775,13 +768,6 @@ __global__ void coverage_loss_kernel(float* datt, const float* att, int n, float
         for (int w = 0; w < (int)blockDim.x / 32; ++w) t += red[w];
         atomicAdd(loss_acc + 2, t * 0.5f * factor * inv_gbl);
     }
-}
-// extra[b, l] = datt[b, l] * mask[b, t]
-__global__ void coverage_grad_kernel(float* extra, const float* datt, const float* masks, int mld, int t, int B, int L) {
-    pdl_enter();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * L) return;
-    extra[i] = datt[i] * masks[(size_t)(i / L) * mld + t];
 }
 __global__ void mean_L_kernel(float* out, const float* ctx, int L, int D) {
     pdl_enter();
@@ -859,12 +845,12 @@ struct TrainState {
     bool regularised[kNumVars];
     // stashes (index [t])
     std::vector<float*> T1, q, hd, alpha, z, lstm_in, acts, c, h_out, h_state, expd, t1, td, dlogits, emb;
-    float *ctxd = nullptr, *temp = nullptr, *e = nullptr, *G = nullptr, *h_raw = nullptr, *logits = nullptr;
+    float *ctxd = nullptr, *temp = nullptr, *e = nullptr, *G = nullptr, *logits = nullptr;
     float *mean = nullptr, *meand = nullptr, *ia1 = nullptr, *ia1d = nullptr, *ib1 = nullptr, *ib1d = nullptr, *c0 = nullptr,
           *h0 = nullptr;
-    float *att = nullptr, *datt = nullptr, *extra = nullptr;
+    float *att = nullptr, *datt = nullptr;
     // backward scratch
-    float *dtd = nullptr, *dexp = nullptr, *dh_out = nullptr, *dh_state = nullptr, *dh_raw = nullptr, *dc = nullptr, *dG = nullptr,
+    float *dtd = nullptr, *dexp = nullptr, *dh_out = nullptr, *dh_state = nullptr, *dc = nullptr, *dG = nullptr,
           *dlin = nullptr, *dz = nullptr, *demb = nullptr, *dalpha = nullptr, *dtemp = nullptr, *dq = nullptr, *dhd = nullptr,
           *dbuf = nullptr;
     // tensor-core path of attend/fc_1a (forward + weight gradient: ~25 % of the step's time on CUDA cores): the
@@ -979,10 +965,10 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
     AT(s->T1, BL * A); AT(s->q, B * A); AT(s->hd, B * H); AT(s->alpha, B * L); AT(s->z, B * D); AT(s->lstm_in, B * (D + E + H));
     AT(s->acts, B * 4 * H); AT(s->c, B * H); AT(s->h_out, B * H); AT(s->h_state, B * H); AT(s->expd, B * (H + D + E));
     AT(s->t1, B * Dd); AT(s->td, B * Dd); AT(s->dlogits, B * V); AT(s->emb, B * E);
-    A1(&s->ctxd, BL * D); A1(&s->temp, BL * A); A1(&s->e, BL); A1(&s->G, B * 4 * H); A1(&s->h_raw, B * H); A1(&s->logits, B * V);
+    A1(&s->ctxd, BL * D); A1(&s->temp, BL * A); A1(&s->e, BL); A1(&s->G, B * 4 * H); A1(&s->logits, B * V);
     A1(&s->mean, B * D); A1(&s->meand, B * D); A1(&s->ia1, B * I); A1(&s->ia1d, B * I); A1(&s->ib1, B * I); A1(&s->ib1d, B * I);
-    A1(&s->c0, B * H); A1(&s->h0, B * H); A1(&s->att, BL); A1(&s->datt, BL); A1(&s->extra, BL);
-    A1(&s->dtd, B * Dd); A1(&s->dexp, B * (H + D + E)); A1(&s->dh_out, B * H); A1(&s->dh_state, B * H); A1(&s->dh_raw, B * H);
+    A1(&s->c0, B * H); A1(&s->h0, B * H); A1(&s->att, BL); A1(&s->datt, BL);
+    A1(&s->dtd, B * Dd); A1(&s->dexp, B * (H + D + E)); A1(&s->dh_out, B * H); A1(&s->dh_state, B * H);
     A1(&s->dc, B * H); A1(&s->dG, B * 4 * H); A1(&s->dlin, B * (D + E + H)); A1(&s->dz, B * D); A1(&s->demb, B * E);
     A1(&s->dalpha, BL); A1(&s->dtemp, BL * A); A1(&s->dq, B * A); A1(&s->dhd, B * H); A1(&s->dbuf, B * (D + E + I + H));
     A1(&s->loss_acc, 8);

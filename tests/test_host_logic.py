@@ -56,6 +56,24 @@ def test_dropout_generator_matches_the_numpy_copy(built_lib):
     assert lib.sat_train_rng_uniform(9, 1, (1 << 20) - 1) == big[-1]
 
 
+def test_dropout_keep_threshold_is_the_float_formula(tmp_path):
+    """The training kernels decide "kept" with one integer compare (sat::DropGen); the threshold must reproduce
+    floor(keep + u) in float32 for every 24-bit u.  Exhaustive, on the host (nvcc compiles the header for the CPU)."""
+    import shutil, subprocess
+    from oracle import train_ref as TR
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "drop_threshold_check.cu")
+    exe = str(tmp_path / "drop_threshold_check")
+    subprocess.run([nvcc, "-O2", "-o", exe, src], check=True, capture_output=True)
+    keeps = ["0.5", "0.7", "0.3", "0.9", "1.0", "0.1", "0.999", "0.33333334"]
+    out = subprocess.run([exe] + keeps, check=True, capture_output=True, text=True).stdout.splitlines()
+    assert len(out) == len(keeps) + 1 and all(l.endswith("mismatches 0") for l in out[:-1]), out
+    u = np.array([float(x) for x in out[-1].split()[1:]], np.float32)   # printed with 9 significant digits: exact in float32
+    assert np.array_equal(u[:2], TR.uniform24(1234, 5, 2))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
