@@ -455,11 +455,11 @@ __global__ void att_logits_kernel(float* __restrict__ e, const float* __restrict
 //   db[a]      += sum_r dtemp[r, a]                                  (db may be null)
 // grid (ceil(A/256), row chunks, B), 256 threads = 4 row groups x 64 float4 columns.
 constexpr int kAbRG = 4, kAbCT = 64;
-__global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(float* __restrict__ dtemp, float* dq, float* dw2, float* db,
-                                                                      const float* __restrict__ T1, const float* __restrict__ q,
-                                                                      const float* __restrict__ de, const float* __restrict__ w2, int L, int A,
-                                                                      int chunk_rows, const unsigned long long* seedp,
-                                                                      unsigned long long stream, float keep) {
+__device__ __forceinline__ void att_bwd_fused_body(float* __restrict__ dtemp, float* dq, float* dw2, float* db,
+                                                   const float* __restrict__ T1, const float* __restrict__ q,
+                                                   const float* __restrict__ de, const float* __restrict__ w2, int L, int A,
+                                                   int chunk_rows, const unsigned long long* seedp,
+                                                   unsigned long long stream, float keep) {
     pdl_enter();
     __shared__ float4 red[3][kAbRG - 1][kAbCT];
     const unsigned long long seed = *seedp;
@@ -515,6 +515,18 @@ __global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(float* __re
         }
     }
 }
+#define ATT_BWD_ARGS                                                                                                      \
+    float *__restrict__ dtemp, float *dq, float *dw2, float *db, const float *__restrict__ T1, const float *__restrict__ q, \
+        const float *__restrict__ de, const float *__restrict__ w2, int L, int A, int chunk_rows,                         \
+        const unsigned long long *seedp, unsigned long long stream, float keep
+__global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(ATT_BWD_ARGS) {
+    att_bwd_fused_body(dtemp, dq, dw2, db, T1, q, de, w2, L, A, chunk_rows, seedp, stream, keep);
+}
+// the same held to 64 registers (4 CTAs per SM), for the one-resident-wave experiment (SAT_TRAIN_ATTBWD_WAVE=1)
+__global__ void __launch_bounds__(kAbRG* kAbCT, 4) att_bwd_fused_wave_kernel(ATT_BWD_ARGS) {
+    att_bwd_fused_body(dtemp, dq, dw2, db, T1, q, de, w2, L, A, chunk_rows, seedp, stream, keep);
+}
+#undef ATT_BWD_ARGS
 // e[r] = sum_a temp[r, a] * w2[a]       (one warp per row)
 __global__ void rowdot_kernel(float* e, const float* temp, const float* w2, int rows, int A) {
     pdl_enter();
@@ -1157,12 +1169,25 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     // scorer: fused one-pass kernels when the rows are float4-addressable (every buffer involved is a cudaMalloc'd
     // [rows, A] matrix or an A-vector, so A % 4 == 0 gives 16-byte alignment)
     const bool att_fused = (A & 3) == 0 && ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads)) & 15) == 0;
-    int ab_chunks = 1, ab_rows = L;
+    int ab_chunks = 1, ab_rows = L, ab_wave = 0;
     {
         const int gx = (A / 4 + kAbCT - 1) / kAbCT;
         ab_chunks = (148 * 4 + B * gx - 1) / (B * gx > 0 ? B * gx : 1);   // about four CTAs per SM
         if (ab_chunks > (L + 15) / 16) ab_chunks = (L + 15) / 16;
         if (ab_chunks < 1) ab_chunks = 1;
+        // SAT_TRAIN_ATTBWD_WAVE=1 (experiment): the 64-register build of the kernel and as many row
+        // chunks as fit ONE resident wave (the default shape is 1.44 waves of 3 CTAs per SM at config 4)
+        static const int one_wave = []() { const char* e = getenv("SAT_TRAIN_ATTBWD_WAVE"); return (e && e[0] == '1') ? 1 : 0; }();
+        ab_wave = one_wave;
+        if (one_wave) {
+            int occ = 0, sms = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, att_bwd_fused_wave_kernel, kAbRG * kAbCT, 0) != cudaSuccess || occ < 1) occ = 1;
+            ab_chunks = (occ * sms) / (B * gx > 0 ? B * gx : 1);
+            if (ab_chunks > (L + 7) / 8) ab_chunks = (L + 7) / 8;
+            if (ab_chunks < 1) ab_chunks = 1;
+        }
         ab_rows = (L + ab_chunks - 1) / ab_chunks;
         ab_chunks = (L + ab_rows - 1) / ab_rows;
     }
@@ -1269,8 +1294,9 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         launch_k(softmax_bwd_kernel, (B * 32 + 255) / 256, 256, st, s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
         if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
             TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));
-            launch_k(att_bwd_fused_kernel, dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B), kAbRG * kAbCT, st, 
-                s->dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A, ab_rows, seed, ST(t, 2), kf);
+            launch_k(ab_wave ? att_bwd_fused_wave_kernel : att_bwd_fused_kernel, dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B),
+                     kAbRG * kAbCT, st, s->dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A,
+                     ab_rows, seed, ST(t, 2), kf);
         } else {
             launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
             launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
