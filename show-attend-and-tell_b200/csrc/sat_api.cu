@@ -221,6 +221,7 @@ int sat_fail(int code, const char* fmt, ...) {
     return code;
 }
 const sat_dims* sat_handle_dims(sat_handle* h) { return &h->d; }
+int sat_handle_device(sat_handle* h) { return h->dev; }
 void** sat_handle_train_slot(sat_handle* h) { return &h->train; }
 void sat_handle_set_train_free(sat_handle* h, void (*fn)(void*)) { h->train_free = fn; }
 
@@ -469,7 +470,11 @@ extern "C" int sat_get_info(sat_handle* h, const char* key, int64_t* value) {
         size_t b = 0;
         for (Layer* ly : h->layers) b += (size_t)ly->n_tiles * ly->k_blocks * kWStageBytes;
         *value = (int64_t)b;
-    } else return fail(SAT_ERR_INVALID, "unknown info key '%s'", key);
+    } else {
+        int rc = SAT_OK;
+        if (sat_train_info(h, key, value, &rc)) return rc;
+        return fail(SAT_ERR_INVALID, "unknown info key '%s'", key);
+    }
     return SAT_OK;
 }
 
@@ -478,6 +483,7 @@ extern "C" int sat_set_weight(sat_handle* h, const char* tf_var_name, const floa
                               void* stream) {
     if (!h || !tf_var_name || !dev) return fail(SAT_ERR_INVALID, "sat_set_weight: null argument");
     cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->dev));
     std::string name(tf_var_name);
     if (name.size() > 2 && name.compare(name.size() - 2, 2, ":0") == 0) name.resize(name.size() - 2);
     h->weights_locked = true;
@@ -536,6 +542,7 @@ extern "C" int sat_weights_missing(sat_handle* h) {
 
 static int require_ready(sat_handle* h) {
     if (!h) return fail(SAT_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->dev));   // lazily allocated buffers and every launch belong to the handle's device
     ++h->ops_since_xb;
     for (Layer* ly : h->layers) {
         if (!ly->w_set) return fail(SAT_ERR_STATE, "variable %s/kernel was never set", ly->name.c_str());
@@ -1083,6 +1090,12 @@ extern "C" int sat_decode_step(sat_handle* h, const float* contexts, const int32
 }
 
 // ------------------------------------------------------------ CUDA graphs
+// host-side record of which contexts the hoisted projection T1 currently holds (nullptr: none / unknown)
+static void note_projected(sat_handle* h, const float* ctx, int n_img) {
+    if (ctx && h->opt_hoist && h->d.num_attend_layers == 2) { h->prep_ctx = ctx; h->prep_ni = n_img; }
+    else { h->prep_ctx = nullptr; h->prep_ni = 0; }
+}
+
 template <typename F>
 static int run_graphed(sat_handle* h, const std::vector<long long>& key, cudaStream_t st, F&& enqueue) {
     if (!h->opt_graphs || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return enqueue();
@@ -1345,10 +1358,14 @@ extern "C" int sat_decode_loop(sat_handle* h, const float* contexts, int32_t B, 
         return decode_loop_xbatch(h, contexts, B, T, forced_words, tokens, logits_all, st, nullptr);
     std::vector<long long> key = {1, (long long)contexts, B, T, (long long)forced_words, (long long)tokens,
                                   (long long)logits_all};
-    // the graph bakes in the tensor map and T1 validity: force a fresh encode inside the captured work
-    return run_graphed(h, key, st, [&]() -> int {
+    const int rc = run_graphed(h, key, st, [&]() -> int {
         return loop_enqueue(h, contexts, B, T, forced_words, tokens, logits_all, st);
     });
+    // A replayed graph re-projects `contexts` into T1 on the device without passing through prepare_impl: the host-side
+    // record of what T1 holds must follow in every case (eager, capture, replay), or a later single step on other
+    // contexts would skip its projection.
+    note_projected(h, rc == SAT_OK ? contexts : nullptr, B);
+    return rc;
 }
 
 // ------------------------------------------------------------ beam search
@@ -1407,10 +1424,12 @@ extern "C" int sat_beam_search(sat_handle* h, const float* contexts, int32_t n_i
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<long long> key = {2, (long long)contexts, n_img, beam_size, T, eos_id, (long long)sentences,
                                   (long long)lengths, (long long)scores, (long long)n_results, (long long)is_complete};
-    return run_graphed(h, key, st, [&]() -> int {
+    const int rc = run_graphed(h, key, st, [&]() -> int {
         return beam_enqueue(h, contexts, n_img, beam_size, T, eos_id, sentences, lengths, scores, n_results,
                             is_complete, st);
     });
+    note_projected(h, rc == SAT_OK ? contexts : nullptr, n_img);   // (see sat_decode_loop)
+    return rc;
 }
 
 // ---------------------------------------------------------- host-buffer forms

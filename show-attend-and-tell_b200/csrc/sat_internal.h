@@ -15,3 +15,8 @@ int sat_dense_packed(sat_handle* h, const uint8_t* x_pa, int rows, int row_tile,
                      void* stream, int weights_dynamic = 0);
 int sat_handle_layout_mode(sat_handle* h);
 int sat_handle_train_tc(sat_handle* h);
+// device the handle is bound to (entry points re-select it: the caller may have switched devices since sat_create)
+int sat_handle_device(sat_handle* h);
+// training-side keys of sat_get_info ("train_bad_ids": word ids outside [0, V) met by the last forward pass);
+// returns 1 if the key was handled
+int sat_train_info(sat_handle* h, const char* key, int64_t* value, int* rc);

@@ -368,22 +368,29 @@ __global__ void copy2d_kernel(float* y, int ldy, const float* x, int ldx, int ro
         *o = accumulate ? *o + v : v;
     }
 }
-__global__ void gather_rows_kernel(float* y, int ldy, const float* table, int E, const int32_t* idx, int idx_ld, int rows) {
+// Word ids index the embedding table and its gradient: an id outside [0, V) (TF's embedding_lookup / sparse softmax
+// raise InvalidArgument on those) reads as a zero row, contributes no gradient and is counted in *bad (reported by
+// sat_get_info "train_bad_ids"; the facade raises), instead of reading / corrupting neighbouring memory.
+__global__ void gather_rows_kernel(float* y, int ldy, const float* table, int E, const int32_t* idx, int idx_ld, int rows, int V,
+                                   float* bad) {
     pdl_enter();
     const size_t n = (size_t)rows * E;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / E), c = (int)(i - (size_t)r * E);
         const int w = idx ? idx[(size_t)r * idx_ld] : 0;
-        y[(size_t)r * ldy + c] = table[(size_t)w * E + c];
+        const bool ok = (unsigned)w < (unsigned)V;
+        if (!ok && c == 0) atomicAdd(bad, 1.0f);
+        y[(size_t)r * ldy + c] = ok ? table[(size_t)w * E + c] : 0.f;
     }
 }
-__global__ void scatter_add_rows_kernel(float* dtable, int E, const int32_t* idx, int idx_ld, const float* dx, int ldx, int rows) {
+__global__ void scatter_add_rows_kernel(float* dtable, int E, const int32_t* idx, int idx_ld, const float* dx, int ldx, int rows,
+                                        int V) {
     pdl_enter();
     const size_t n = (size_t)rows * E;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / E), c = (int)(i - (size_t)r * E);
         const int w = idx ? idx[(size_t)r * idx_ld] : 0;
-        atomicAdd(dtable + (size_t)w * E + c, dx[(size_t)r * ldx + c]);
+        if ((unsigned)w < (unsigned)V) atomicAdd(dtable + (size_t)w * E + c, dx[(size_t)r * ldx + c]);
     }
 }
 // temp[b*L + l, a] = (T1[b*L + l, a] + q[b, a]) * drop(att_mid)
@@ -749,14 +756,17 @@ __global__ void __launch_bounds__(kCeThreads) ce_kernel(const float* logits, flo
     __syncthreads();
     s = 0.f;
     for (int w = 0; w < NW; ++w) s += red[w];
-    const int y = sent[(size_t)b * sent_ld + t];
-    const float mk = masks[(size_t)b * sent_ld + t];
+    const int y_raw = sent[(size_t)b * sent_ld + t];
+    const bool y_ok = (unsigned)y_raw < (unsigned)V;      // (an id outside the vocabulary: no target, counted as bad)
+    const int y = y_ok ? y_raw : 0;
+    const float mk = y_ok ? masks[(size_t)b * sent_ld + t] : 0.f;
     const float scale = mk * inv_msum;
     for (int i = threadIdx.x; i < V; i += kCeThreads) {
         const float p = d[i] / s;
         d[i] = (p - (i == y ? 1.0f : 0.0f)) * scale;
     }
     if (threadIdx.x == 0) {
+        if (!y_ok) atomicAdd(loss_acc + 5, 1.0f);
         const float ce = logf(s) + m - x[y];
         atomicAdd(loss_acc + 0, ce * scale);                       // cross entropy (already / sum of masks)
         atomicAdd(loss_acc + 1, (mi == y ? mk : 0.0f) * inv_msum);  // accuracy
@@ -890,7 +900,8 @@ struct TrainState {
     uint8_t *tc_sx = nullptr, *tc_sw = nullptr;   // packed X_all^T / packed dY_all
     bool tc_stack = false;
     sat_handle* handle = nullptr;
-    float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2
+    float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2, [5] out-of-vocabulary ids seen
+                                 // by the last forward pass ([6] the same, accumulated since sat_train_init)
     // per-call scalars live in device cells (fed by small stream-ordered copies before each launch), so that the
     // ~3500 launches of a step are captured once into a CUDA graph and replayed
     unsigned long long* seed_d = nullptr;
@@ -952,6 +963,7 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
     if (dp->num_attend_layers != 2 || dp->num_decode_layers != 2 || dp->num_initalize_layers != 2)
         return sat_fail(SAT_ERR_UNSUPPORTED, "the training step supports the 2-layer attend/decode/initialize graph only");
     if (B < 1 || T < 1) return sat_fail(SAT_ERR_INVALID, "bad B/T");
+    TCK(cudaSetDevice(sat_handle_device(h)));
     void** slot = sat_handle_train_slot(h);
     if (*slot) { train_free(*slot); *slot = nullptr; }
     TrainState* s = new TrainState();
@@ -1050,6 +1062,19 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
     *slot = s;
     sat_handle_set_train_free(h, train_free);
     return SAT_OK;
+}
+
+int sat_train_info(sat_handle* h, const char* key, int64_t* value, int* rc) {
+    if (strcmp(key, "train_bad_ids") != 0) return 0;
+    TrainState* s = (TrainState*)*sat_handle_train_slot(h);
+    *value = 0;
+    *rc = SAT_OK;
+    if (!s) return 1;
+    float v = 0.f;
+    cudaError_t e = cudaMemcpy(&v, s->loss_acc + 5, sizeof(float), cudaMemcpyDeviceToHost);   // (synchronises)
+    if (e != cudaSuccess) { *rc = sat_fail(SAT_ERR_CUDA, "train_bad_ids: %s", cudaGetErrorString(e)); return 1; }
+    *value = (int64_t)v;
+    return 1;
 }
 
 extern "C" int sat_train_var(sat_handle* h, int32_t i, const char** name, int64_t* offset, int64_t* rows, int64_t* cols,
@@ -1222,7 +1247,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         else
             launch_k(context_fwd_kernel, dim3((D + 127) / 128, B), 128, st, s->z[t], s->alpha[t], contexts, B, L, D);
         // embedding of the previous word: 0 at t = 0, then teacher forcing (model.py:254, 310)
-        launch_k(gather_rows_kernel, GRID1D((size_t)B * E), 256, st, s->emb[t], E, P(vEmb), E, t ? sentences + (t - 1) : nullptr, T, B);
+        launch_k(gather_rows_kernel, GRID1D((size_t)B * E), 256, st, s->emb[t], E, P(vEmb), E, t ? sentences + (t - 1) : nullptr, T, B, V,
+                 s->loss_acc + 5);
         // LSTM with DropoutWrapper (model.py:228-236, 276-279)
         // lstm_in = [ drop_in(concat(z, emb)) | h_state_prev ]
         launch_k(concat3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->lstm_in[t], XL, s->z[t], D, s->emb[t], E, h_state_prev, H, D + E, B,
@@ -1288,7 +1314,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         // dlin = [d xd (D+E) | dh_state_prev]
         launch_k(split3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->dlin, XL, B, s->dz, D, 1, s->demb, E, 1, s->dh_state, H, 0, D + E, seed,
                                                                    ST(t, 3), kl);
-        launch_k(scatter_add_rows_kernel, GRID1D((size_t)B * E), 256, st, Gd(vEmb), E, t ? sentences + (t - 1) : nullptr, T, s->demb, E, B);
+        launch_k(scatter_add_rows_kernel, GRID1D((size_t)B * E), 256, st, Gd(vEmb), E, t ? sentences + (t - 1) : nullptr, T, s->demb, E, B, V);
         // attention: context vector, softmax, scorer
         launch_k(context_bwd_kernel, (BL * 32 + 255) / 256, 256, st, s->dalpha, s->dz, contexts, s->datt, B, L, D, masks, T, t);
         launch_k(softmax_bwd_kernel, (B * 32 + 255) / 256, 256, st, s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
@@ -1368,6 +1394,7 @@ static int train_forward_backward(sat_handle* h, const float* params, float* gra
         return sat_fail(SAT_ERR_INVALID, "sat_train_forward_backward: null argument");
     TrainState* s = (TrainState*)*sat_handle_train_slot(h);
     if (!s || s->B != B || s->T != T) return sat_fail(SAT_ERR_STATE, "call sat_train_init(B=%d, T=%d) first", B, T);
+    TCK(cudaSetDevice(sat_handle_device(h)));
     cudaStream_t st = (cudaStream_t)stream;
     // per-call scalars -> device cells, in stream order.  The sources are ordinary (pageable) host variables: such a
     // copy is staged by the driver before the call returns, so no stream synchronisation is needed to reuse them

@@ -166,8 +166,12 @@ class CaptionGenerator(object):
             if name not in given:
                 continue
             w = self._dev(given[name], torch.float32)
-            if tuple(w.shape) != tuple(shp) and int(np.prod(w.shape)) != int(np.prod(shp)):
-                raise ValueError("%s: expected shape %s, got %s" % (name, shp, tuple(w.shape)))
+            got = tuple(w.shape)
+            # like tf.assign: the shape must match.  The only tolerated differences are a vector given as a
+            # one-row / one-column matrix or the reverse (biases [n] vs [1,n]; attend/fc_2, fc_a [n,1] vs [n]).
+            vec_ok = (len(shp) == 1 or 1 in shp) and sorted(d for d in got if d != 1) == sorted(d for d in shp if d != 1)
+            if got != tuple(shp) and not vec_ok:
+                raise ValueError("%s: expected shape %s, got %s" % (name, shp, got))
             rows, cols = (shp[0], shp[1]) if len(shp) == 2 else (1, shp[0])
             torch.cuda.synchronize(self.device)
             self._check(self.lib.sat_set_weight(self._h, name.encode(), self._p(w), rows, cols, self._st()))
@@ -237,9 +241,10 @@ class CaptionGenerator(object):
         """Repack the trained parameters for the decode kernels (so beam_search / decode_step use them)."""
         return self.set_weights(self.train_state_dict("params"))
 
-    def train_forward_backward(self, contexts, sentences, masks, seed=0, global_mask_sum=None, global_batch=None):
-        """Forward + backward of one batch shard; fills self.grads (no regulariser term) and returns the losses
-        {cross_entropy_loss, accuracy, attention_loss, reg_loss, total_loss} as floats."""
+    def train_forward_backward(self, contexts, sentences, masks, seed=None, global_mask_sum=None, global_batch=None):
+        """Forward + backward of one batch shard; fills self.grads (no regulariser term) and returns the device
+        tensor of the four losses (cross_entropy, accuracy, attention, reg).  seed: see _step_seed."""
+        seed = self._step_seed(seed)
         torch = self.torch
         B, T = self._train_BT
         ctx = self._dev(contexts, torch.float32)
@@ -293,12 +298,23 @@ class CaptionGenerator(object):
         self._sync_out()
         return self._train_norm
 
-    def train_step(self, contexts, sentences, masks, seed=0, sync=True):
+    def _step_seed(self, seed):
+        """Dropout seed of the next optimisation step.  None (default): fresh masks every step, derived from the
+        step counter and `config.dropout_seed` (the reference draws new unseeded masks every step with
+        fc_drop_rate / lstm_drop_rate, model.py:231-236, nn.py:111-114); an explicit 0 switches dropout OFF (the C ABI's
+        convention); any other value is used as given."""
+        if seed is None:
+            base = int(getattr(self.config, "dropout_seed", 0x5A17B200)) & 0xFFFFFFFF
+            return ((base << 20) ^ (self.global_step + 1)) or 1
+        return int(seed)
+
+    def train_step(self, contexts, sentences, masks, seed=None, sync=True):
         """One optimisation step (the sess.run(opt_op) of base_model.py:57-60) on this process's shard; with
         torch.distributed initialised the gradients are summed over the ranks by ONE all-reduce of the flat
         buffer (NCCL) and the losses are normalised by the global batch.  sync=False returns the device tensors
         (losses [4], squared gradient norm [1]) without reading them back, so that the host can queue the next step
-        while this one runs (the reference reads its summary every step; a training loop rarely needs to)."""
+        while this one runs (the reference reads its summary every step; a training loop rarely needs to).
+        seed: see _step_seed (None = new dropout masks every step, 0 = dropout off)."""
         import torch.distributed as dist
         torch = self.torch
         B, T = self._train_BT
@@ -309,8 +325,10 @@ class CaptionGenerator(object):
             # host can queue step i+1 while step i runs
             msum = mk.sum(dtype=torch.float64).reshape(1)
             dist.all_reduce(msum)
-            seed = int(seed) + 0x1000003 * dist.get_rank() if seed else 0
+            seed = self._step_seed(seed)
+            seed = seed + 0x1000003 * dist.get_rank() if seed else 0   # rank-offset mask streams (0 stays "off")
         else:
+            seed = self._step_seed(seed)
             msum = self._mask_sum(masks, mk)
         losses = self.train_forward_backward(contexts, sentences, mk, seed, msum, B * world)
         if world > 1:
