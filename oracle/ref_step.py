@@ -180,8 +180,11 @@ def initialize(cfg: OracleConfig, w, contexts, dtype=np.float32, masks: Optional
 # --------------------------------------------------------------------------
 # model.py:395-436  attend
 # --------------------------------------------------------------------------
-def attend(cfg: OracleConfig, w, contexts, output, dtype=np.float32, masks: Optional[dict] = None):
-    """alpha [B, L] = softmax over locations.  model.py:395-436."""
+def attend(cfg: OracleConfig, w, contexts, output, dtype=np.float32, masks: Optional[dict] = None, t1=None):
+    """alpha [B, L] = softmax over locations.  model.py:395-436.
+
+    t1 (2-layer inference only): the fc_1a branch tanh(ctx2d @ W1a + b1a) computed by an earlier call on the same
+    contexts (it does not depend on the state: the reference recomputes it every step, the result is the same array)."""
     masks = masks or {}
     keep = 1.0 - cfg.fc_drop_rate
     B, L, D = contexts.shape
@@ -193,7 +196,8 @@ def attend(cfg: OracleConfig, w, contexts, output, dtype=np.float32, masks: Opti
         l2 = _dense(out, w, "attend/fc_b", None, use_bias=False)                     # model.py:409-413
         logits = l1 + l2                                                             # model.py:414
     else:
-        t1 = _dense(ctx2d, w, "attend/fc_1a", np.tanh)                   # model.py:417-420
+        if t1 is None:
+            t1 = _dense(ctx2d, w, "attend/fc_1a", np.tanh)               # model.py:417-420
         t2 = _dense(out, w, "attend/fc_1b", np.tanh)                     # model.py:421-424
         t2 = np.repeat(t2[:, None, :], L, axis=1).reshape(B * L, -1)     # model.py:425-426 (tile)
         t = t1 + t2                                                      # model.py:427
@@ -241,7 +245,7 @@ def decode(cfg: OracleConfig, w, expanded_output, masks: Optional[dict] = None):
 # model.py:258-290  one decode step (inference graph: num_steps = 1, model.py:255)
 # --------------------------------------------------------------------------
 def decode_step(cfg: OracleConfig, w, contexts, last_word, last_memory, last_output,
-                dtype=np.float32):
+                dtype=np.float32, t1=None):
     """One inference step: the sess.run of base_model.py:207-212.
 
     feeds: contexts [B,L,D] f32, last_word [B] i32, last_memory (=c) [B,H],
@@ -251,7 +255,7 @@ def decode_step(cfg: OracleConfig, w, contexts, last_word, last_memory, last_out
     ctx = contexts.astype(dtype)
     c_prev = last_memory.astype(dtype)
     h_prev = last_output.astype(dtype)
-    alpha = attend(cfg, w, ctx, h_prev, dtype)                            # model.py:262
+    alpha = attend(cfg, w, ctx, h_prev, dtype, None, t1)                  # model.py:262
     context = (ctx * alpha[:, :, None]).sum(axis=1)                       # model.py:263-264
     word_embed = w["word_embedding/weights"].astype(dtype)[np.asarray(last_word)]  # model.py:273
     current_input = np.concatenate([context, word_embed], axis=1)         # model.py:277
@@ -282,6 +286,23 @@ def decode_loop(cfg: OracleConfig, w, contexts, num_steps: int,
         toks.append(pred); steps.append(r)
         word = forced_words[:, t].astype(np.int32) if forced_words is not None else pred
     return np.stack(toks, axis=1), steps
+
+
+class HoistedStepper:
+    """decode_step on fixed contexts with the state-independent fc_1a branch of `attend` computed once (the SAME numpy
+    expression the step would evaluate, so the results are bit-identical to decode_step's): makes full-size beam
+    searches (128 images x 3 beams x 30 steps) affordable for the parity tests."""
+
+    def __init__(self, cfg: OracleConfig, w, contexts, dtype=np.float32):
+        self.cfg, self.w, self.dtype = cfg, w, dtype
+        self.ctx = contexts.astype(dtype)
+        B, L, D = contexts.shape
+        self.t1 = (_dense(self.ctx.reshape(B * L, D), w, "attend/fc_1a", np.tanh)
+                   if cfg.num_attend_layers == 2 else None)
+
+    def step(self, contexts, last_word, last_memory, last_output):
+        r = decode_step(self.cfg, self.w, self.ctx, last_word, last_memory, last_output, self.dtype, self.t1)
+        return r["memory"], r["output"], r["probs"]
 
 
 # --------------------------------------------------------------------------
@@ -327,7 +348,7 @@ class TopN:
 
 
 def beam_search(cfg: OracleConfig, w, contexts, eos_id: int, dtype=np.float32,
-                step_fn=None):
+                step_fn=None, fast_topk=False):
     """base_model.py:163-240 with precomputed contexts in place of images.
 
     `vocabulary.words[w] == '.'` (base_model.py:229) is `w == eos_id`.
@@ -336,6 +357,9 @@ def beam_search(cfg: OracleConfig, w, contexts, eos_id: int, dtype=np.float32,
     Returns, per image, the list of CaptionData sorted by descending score.
     `step_fn(contexts, last_word, last_memory, last_output) -> (memory, output,
     probs)` lets the tests drive this host loop with the CUDA step.
+    fast_topk: take the beam+1 best words with a stable numpy argsort instead of sorting the
+    Python list of (word, score) pairs (base_model.py:216-219) — the same order, ties included
+    (a stable sort on -score keeps equal scores in index order, like list.sort with that key).
     """
     B = contexts.shape[0]
     if step_fn is None:
@@ -363,8 +387,12 @@ def beam_search(cfg: OracleConfig, w, contexts, eos_id: int, dtype=np.float32,
             memory, output, scores = step_fn(contexts, last_word, last_memory, last_output)
             for k in range(B):                                             # base_model.py:215-232
                 cd = lists[k][b]
-                ws = list(enumerate(scores[k]))
-                ws.sort(key=lambda x: -x[1])
+                if fast_topk:
+                    order = np.argsort(-np.asarray(scores[k]), kind="stable")[:cfg.beam_size + 1]
+                    ws = [(int(i), scores[k][i]) for i in order]
+                else:
+                    ws = list(enumerate(scores[k]))
+                    ws.sort(key=lambda x: -x[1])
                 for wd, s in ws[:cfg.beam_size + 1]:
                     beam = CaptionData(cd.sentence + [wd], memory[k], output[k],
                                        float(cd.score) * float(s))

@@ -142,6 +142,13 @@ struct sat_handle {
     cudaStream_t side = nullptr;           // second stream of the decode loop (attention of step t+1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_overlap = 2, opt_att_sms = 0, opt_att_occ = 1, opt_att_warps = 8, opt_pdl = 1, opt_warm = 1, opt_att_wpc = 1, opt_att_reuse_q = 0, opt_l2_vocab = -1, opt_l2_prefetch = 0, opt_stages = 0, opt_train_tc = 1, opt_dec1_splits = 0;
+    // chained dense launch of the greedy loop (sat_chain.cu): arrival counters, split-K scratch, per-row arg-max keys
+    unsigned* chain_ctr = nullptr;         // [kChainMaxPhase + kChainMaxPhase * kChainMaxTiles]
+    float* chain_scratch = nullptr;
+    unsigned long long* chain_best = nullptr;
+    int opt_chain = 1;
+    const unsigned* att_qflag = nullptr;   // set around the attention launch that runs beside a chained launch
+    unsigned att_qtarget = 0;
     void* train = nullptr;                 // training state (sat_train.cu)
     void (*train_free)(void*) = nullptr;
     unsigned long long* trace = nullptr;   // [1024][16] timeline stamps of the last traced launch
@@ -254,7 +261,8 @@ extern "C" void sat_destroy(sat_handle* h) {
     void* bufs[] = {h->att_vec.dev, h->embedding, h->T1, h->q, h->e, h->alpha, h->z, h->mean, h->tmp_a, h->tmp_b,
                     h->t_dec, h->logits, h->st_c[0], h->st_c[1], h->st_h[0], h->st_h[1], h->word, h->zero_word,
                     h->rowcnt, h->topk_idx, h->part_n, h->comp_n, h->comp_sent, h->sent[0], h->sent[1], h->topk_p,
-                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part, h->trace, h->pa_h[0], h->pa_h[1], h->pa_z, h->pa_emb, h->pa_t, h->pa_z2[1], h->z2[1]};
+                    h->part_score, h->comp_heap, h->stage_ctx, h->stage_misc, h->att_part, h->trace, h->pa_h[0], h->pa_h[1], h->pa_z, h->pa_emb, h->pa_t, h->pa_z2[1], h->z2[1],
+                    h->chain_ctr, h->chain_scratch, h->chain_best};
     for (void* b : bufs) cudaFree(b);
     delete h;
 }
@@ -402,6 +410,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "att_wpc") h->opt_att_wpc = (int)value;
     else if (k == "att_reuse_q") h->opt_att_reuse_q = (int)value;
     else if (k == "xbatch") h->opt_xbatch = (int)value;
+    else if (k == "chain") h->opt_chain = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -910,6 +919,11 @@ static int attention_impl(sat_handle* h, const float* ctx, int n_img, int G, con
     }
     ap.pdl = h->opt_pdl ? 1 : 0;
     ap.nowait = (nowait && ap.pdl) ? 1 : 0;
+    if (h->att_qflag) {
+        if (!ap.nowait || !ap.wpc) return fail(SAT_ERR_STATE, "attention beside a chained launch needs the warp-per-chunk kernel");
+        ap.qflag = h->att_qflag;
+        ap.qtarget = h->att_qtarget;
+    }
     if (q_ready && !h->opt_att_reuse_q) h->att_loop_grid = ap.grid;
     ap.dbg = h->opt_trace == 2 ? h->trace : nullptr;
     ap.tl = nullptr;
@@ -1253,9 +1267,150 @@ static int loop_enqueue_chain(sat_handle* h, const float* ctx, int B, int T, con
     return SAT_OK;
 }
 
+// The same step sequence with the three dense layers of a step as the phases of ONE persistent launch (sat_chain.cu):
+//   chain(t) = { LSTM(t) -> [decode fc_1(t) || q(t+1)] -> vocabulary layer(t) + arg-max }  ->  attention(t+1)
+// The attention kernel of step t+1 starts beside the chained launch, spins on the counter of its phase 1 (q(t+1) and
+// everything older are complete then) and runs beside the vocabulary phase on the SMs whose CTAs have exited.
+static bool fused_loop_available(sat_handle* h, int B) {
+    return h->opt_chain && h->pa_ok && h->opt_pa && h->opt_gemm != 0 && h->opt_overlap == 2 && h->opt_pdl &&
+           h->d.num_decode_layers == 2 && h->d.num_attend_layers == 2 && h->opt_hoist && h->opt_att_wpc &&
+           h->d.dim_attend_layer == 512 && h->d.dim_ctx == 512 && row_tile_for(B) <= 64 && B <= h->num_sms &&
+           (h->opt_trace == 0 || h->opt_trace >= 3) && h->opt_profile == 0;
+}
+
+static int loop_enqueue_fused(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
+                              float* logits_all, cudaStream_t st, bool prepared) {
+    const sat_dims& d = h->d;
+    const size_t nctr = (size_t)kChainMaxPhase + (size_t)kChainMaxPhase * kChainMaxTiles;
+    if (!h->chain_ctr) {
+        if (stream_capturing(st)) return fail(SAT_ERR_STATE, "chained loop: workspace growth during graph capture");
+        RET(dmalloc(&h->chain_ctr, nctr));
+        RET(dmalloc(&h->chain_scratch, (size_t)h->num_sms * 64 * kTileN));
+        RET(dmalloc(&h->chain_best, (size_t)h->max_rows));
+        CK(cudaMemset(h->chain_best, 0, (size_t)h->max_rows * sizeof(unsigned long long)));
+    }
+    if (!prepared) RET(prepare_impl(h, ctx, B, h->st_c[0], h->st_h[0], st, h->pa_h[0]));
+    CK(cudaMemsetAsync(h->word, 0, (size_t)B * sizeof(int32_t), st));  // <start> = 0 (model.py:254)
+    CK(cudaMemsetAsync(h->chain_ctr, 0, nctr * sizeof(unsigned), st)); // counters are relative to the start of the loop
+    int budget = h->opt_att_sms > 0 ? h->opt_att_sms : h->num_sms - h->dec_2.n_tiles;
+    if (budget < B) budget = B;
+    const int rtile = row_tile_for(B);
+    const int stages = lin_chain_pick_stages(rtile);
+    if (stages < 2) return fail(SAT_ERR_UNSUPPORTED, "chained loop: row tile %d does not fit", rtile);
+    unsigned cta_sum[kChainMaxPhase] = {0, 0, 0}, split_sum[kChainMaxPhase] = {0, 0, 0};   // counter values after each launch
+    for (int t = 0; t < T; ++t) {
+        const float *c_in = h->st_c[t & 1], *h_in = h->st_h[t & 1];
+        float *c_out = h->st_c[(t + 1) & 1], *h_out = h->st_h[(t + 1) & 1];
+        h->pa_on = true;
+        h->pa_cur_h_in = h->pa_h[t & 1];
+        h->pa_cur_h_out = h->pa_h[(t + 1) & 1];
+        h->pa_cur_z = h->pa_z;
+        if (t == 0)   // q(0), attention(0) and the embedding of <start>
+            RET(attention_impl(h, ctx, B, 1, h_in, nullptr, h->z, st, false, h->word));
+        float* logits = logits_all ? logits_all + (size_t)t * B * d.vocabulary_size : nullptr;
+        LinChain C;
+        memset(&C, 0, sizeof(C));
+        C.nphase = 3;
+        // phase 0: current_input = concat([context, word_embed]) (model.py:277); LSTMCell concat([x, h]) (TF)
+        {
+            LinProblem& P = C.ph[0].p[0];
+            RET(plan(h, h->lstm, P,
+                     {seg(h->z, d.dim_ctx, d.dim_ctx, nullptr, h->pa_z),
+                      seg(h->embedding, d.dim_embedding, d.dim_embedding, h->word, h->pa_emb),
+                      seg(h_in, d.num_lstm_units, d.num_lstm_units, nullptr, h->pa_cur_h_in)},
+                     B, kEpiLstm, nullptr, 0, st));
+            P.out_pa = h->pa_cur_h_out;
+            P.c_in = c_in; P.c_out = c_out; P.h_out = h_out; P.H = d.num_lstm_units;
+            C.ph[0].nprob = 1;
+        }
+        // phase 1: expanded_output = concat([output, context, word_embed]) (model.py:283-286) -> fc_1; q of step t+1
+        {
+            const bool nq = t + 1 < T;
+            LinProblem& P = C.ph[1].p[0];
+            RET(plan(h, h->dec_1, P,
+                     {seg(h_out, d.num_lstm_units, d.num_lstm_units, nullptr, h->pa_cur_h_out),
+                      seg(h->z, d.dim_ctx, d.dim_ctx, nullptr, h->pa_z),
+                      seg(h->embedding, d.dim_embedding, d.dim_embedding, h->word, h->pa_emb)},
+                     B, kEpiBiasTanh, h->t_dec, d.dim_decode_layer, st, h->opt_dec1_splits, nq ? 2 : 1));
+            P.out_pa = h->pa_t;
+            C.ph[1].nprob = 1;
+            if (nq) {
+                RET(plan_att_state(h, C.ph[1].p[1], h_out, B, st, 2, h->pa_cur_h_out));
+                C.ph[1].nprob = 2;
+                // one split factor for the pair, like the grouped launch of the per-layer path (bit-identical sums)
+                const int sm = C.ph[1].p[0].splits < C.ph[1].p[1].splits ? C.ph[1].p[0].splits : C.ph[1].p[1].splits;
+                C.ph[1].p[0].splits = C.ph[1].p[1].splits = sm;
+            }
+        }
+        // phase 2: logits = t * Wd2 + b, arg-max, embedding of the word fed to step t+1
+        {
+            LinProblem& P = C.ph[2].p[0];
+            RET(plan(h, h->dec_2, P, {seg(h->t_dec, d.dim_decode_layer, d.dim_decode_layer, nullptr, h->pa_t)}, B, kEpiBias,
+                     logits, d.vocabulary_size, st, 1));
+            P.am_key = h->chain_best;
+            P.am_tokens = tokens; P.am_tokens_ld = T; P.am_step = t;
+            P.am_next_word = h->word; P.am_forced = forced; P.am_forced_ld = T;
+            if (t + 1 < T) { P.am_emb = h->embedding; P.am_E = d.dim_embedding; P.am_emb_pa = h->pa_emb; }
+            C.ph[2].nprob = 1;
+        }
+        int grid = 0;
+        for (int ph = 0; ph < C.nphase; ++ph) {
+            int begin = 0, tiles = 0;
+            for (int i = 0; i < C.ph[ph].nprob; ++i) {
+                LinProblem& P = C.ph[ph].p[i];
+                if (P.n_row_tiles != 1 || P.row_tile != rtile) return fail(SAT_ERR_UNSUPPORTED, "chained loop: one row tile per layer");
+                for (int sgi = 0; sgi < P.nseg; ++sgi)
+                    if (!P.seg[sgi].pa) return fail(SAT_ERR_STATE, "chained loop: operands must arrive packed");
+                P.cta_begin = begin;
+                P.cta_count = P.n_tiles * P.splits;
+                begin += P.cta_count;
+                tiles += P.n_tiles;
+            }
+            if (tiles > kChainMaxTiles || begin > h->num_sms) return fail(SAT_ERR_UNSUPPORTED, "chained loop: %d tiles / %d CTAs in one phase", tiles, begin);
+            for (int i = 1; i < C.ph[ph].nprob; ++i)
+                if (C.ph[ph].p[i].splits != C.ph[ph].p[0].splits) return fail(SAT_ERR_STATE, "chained loop: one split factor per phase");
+            C.ph[ph].ctas = begin;
+            cta_sum[ph] += (unsigned)begin;                     // (the last step has no q tiles: sums, not multiples)
+            split_sum[ph] += (unsigned)C.ph[ph].p[0].splits;
+            C.target[ph] = cta_sum[ph];
+            C.tile_target[ph] = split_sum[ph];
+            if (begin > grid) grid = begin;
+        }
+        C.layout_mode = h->opt_layout;
+        C.stages = stages;
+        C.l2_w = h->opt_l2_w;
+        C.pdl = 1;
+        C.row_tile = rtile;
+        C.ctr = h->chain_ctr;
+        C.tile_ctr = h->chain_ctr + kChainMaxPhase;
+        C.scratch = h->chain_scratch;
+        if (h->opt_trace == 3 && h->tl_count + 4 <= 4000) {   // four timeline entries: the launch, then its phases
+            C.tl = h->trace + 4 * h->tl_count;
+            h->tl_count += 4;
+            h->tl_names.push_back("chain/" + std::to_string(grid));
+            for (int ph = 0; ph < 3; ++ph) h->tl_names.push_back("  phase" + std::to_string(ph) + "/" + std::to_string(C.ph[ph].ctas));
+        }
+        if (h->opt_trace >= 4 && h->opt_trace <= 7 && h->trace_at-- == 0) { C.dbg = h->trace; C.dbg_mode = h->opt_trace - 4; }   // per-CTA stamps of this one launch
+        CK(lin_chain_launch(C, grid, st));
+        h->launches += 1;
+        if (t + 1 < T) {
+            h->pa_cur_h_in = h->pa_h[(t + 1) & 1];
+            h->att_qflag = h->chain_ctr + 1;          // phase 1 of the launch above
+            h->att_qtarget = C.target[1];
+            const int rc = attention_impl(h, ctx, B, 1, h_out, nullptr, h->z, st, true, nullptr, budget, true);
+            h->att_qflag = nullptr;
+            RET(rc);
+        }
+    }
+    h->pa_on = false;
+    h->pa_cur_z = nullptr;
+    return SAT_OK;
+}
+
 static int loop_enqueue(sat_handle* h, const float* ctx, int B, int T, const int32_t* forced, int32_t* tokens,
                         float* logits_all, cudaStream_t st) {
     const bool pa = h->pa_ok && h->opt_pa && h->opt_gemm != 0;
+    if (fused_loop_available(h, B)) return loop_enqueue_fused(h, ctx, B, T, forced, tokens, logits_all, st, false);
     if (pa && h->opt_overlap == 2 && h->opt_pdl && h->d.num_decode_layers == 2)
         return loop_enqueue_chain(h, ctx, B, T, forced, tokens, logits_all, st);
     if (pa && h->opt_overlap && h->d.num_decode_layers == 2 && st != nullptr && st != cudaStreamLegacy)
@@ -1338,7 +1493,10 @@ static int decode_loop_xbatch(sat_handle* h, const float* contexts, int B, int T
         h->prep_ctx = contexts;
         h->prep_ni = B;
         rc = run_graphed(h, {4, (long long)contexts, B, T, (long long)forced, (long long)tokens, (long long)logits_all, slot}, st,
-                         [&]() -> int { return loop_enqueue_chain(h, contexts, B, T, forced, tokens, logits_all, st, true); });
+                         [&]() -> int {
+                             return fused_loop_available(h, B) ? loop_enqueue_fused(h, contexts, B, T, forced, tokens, logits_all, st, true)
+                                                               : loop_enqueue_chain(h, contexts, B, T, forced, tokens, logits_all, st, true);
+                         });
         cudaEventRecord(S.ev_done, st);
         S.used = true;
     }

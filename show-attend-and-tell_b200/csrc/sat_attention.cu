@@ -662,6 +662,10 @@ __global__ void __launch_bounds__(10 * 32, 1) att_wpc_kernel(const __grid_consta
     // q / the fed words come from earlier kernels of the step; with `nowait` the immediate predecessor produced
     // none of them (and everything older is complete, see pdl_wait), so this kernel runs beside it
     if (p.pdl) { if (!p.nowait) pdl_wait(); pdl_launch_dependents(); }
+    if (p.qflag) {   // q comes from a phase of the predecessor launch, which is still running: wait for that phase only
+        if (lane == 0) { wait_counter(p.qflag, p.qtarget, "attention: state branch of the running dense launch"); __threadfence(); }
+        __syncwarp();
+    }
     if (threadIdx.x == 0) tl_go(p.tl);
     if (p.emb_pa) att_pack_embedding(p, c * NT + ct, P * NT, G);
     if (ct == 0) trace_stamp(p.dbg, 1);
@@ -682,7 +686,7 @@ __global__ void __launch_bounds__(10 * 32, 1) att_wpc_kernel(const __grid_consta
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                qreg[g][k] = p.q ? __ldg(reinterpret_cast<const float4*>(p.q + ((size_t)img * G + g) * RW) + lane + 32 * k)
+                qreg[g][k] = p.q ? __ldcg(reinterpret_cast<const float4*>(p.q + ((size_t)img * G + g) * RW) + lane + 32 * k)
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         if (!first_seg) named_bar_sync(1, NT);      // previous segment's w_s / zred fully consumed
 

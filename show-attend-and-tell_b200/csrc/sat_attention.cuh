@@ -38,6 +38,8 @@ struct AttParams {
     int pdl;             // launched with programmatic stream serialization
     int nowait;          // (with pdl, warp-per-chunk kernel) nothing of the immediate predecessor is read: run beside it
                          // and wait for it only before exiting
+    const unsigned* qflag;   // (with nowait) q is produced by a phase of the STILL RUNNING predecessor (the chained dense
+    unsigned qtarget;        // launch, sat_chain.cu): spin until *qflag has reached qtarget before reading q
 };
 
 bool att_plan(AttParams& p, int smem_optin, int num_sms);

@@ -45,6 +45,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time; a polling loop that also
+// watches something else wants test_wait)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -125,6 +138,17 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // generic-proxy global writes (possibly by other SMs, already acquired) -> visible to TMA reads
 __device__ __forceinline__ void fence_proxy_async_global() {
     asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// One lane of a CONVERGED warp (elect.sync).  The async-unit instructions (cp.async.bulk, tcgen05.mma / commit) take their
+// operands from the uniform register file: issued from `if (lane == 0)` code their addresses live in per-thread registers
+// and every instruction costs a handful of register->uniform moves plus an elect/branch loop (~70 cycles per MMA measured
+// on the chained dense launch); issued as `if (elect_one()) ...` from a loop the whole warp runs, the operands are
+// computed in uniform registers to begin with.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 // ------------------------------------------------------------------- tcgen05
@@ -274,6 +298,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// spin until a monotonic arrival counter has reached `target` (wrap-safe); traps instead of hanging the GPU box
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p);
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, const char* what) {
+    if ((int)(ld_acquire_gpu(ctr) - target) >= 0) return;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
+        if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
+            printf("sat_b200: %s timed out (block %d)\n", what, (int)blockIdx.x);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

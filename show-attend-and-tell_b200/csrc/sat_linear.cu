@@ -41,26 +41,11 @@
 // role, an accumulate epilogue, weights that may come from the preceding kernel (w_dynamic).
 #include "sat_common.cuh"
 #include "sat_linear.cuh"
+#include "sat_linear_dev.cuh"
 
 namespace sat {
 
-// ---------------------------------------------------------------- helpers
-__device__ __forceinline__ void split_bf16x8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
-    float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]);
-        __nv_bfloat16 h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-        __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
+// (split_bf16x8, lstm_gates: sat_linear_dev.cuh)
 // fp32 source of the 8 consecutive K elements starting at k0 of activation row b (zeros outside).
 __device__ __forceinline__ void load_x8(const LinProblem& P, int b, int k0, float4& a, float4& c) {
     a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -92,18 +77,6 @@ __device__ __forceinline__ float epi_scalar(const LinProblem& P, float acc, int 
     if (P.epi == kEpiNone) return acc;
     acc += P.bias[n];
     return P.epi == kEpiBiasTanh ? act_tanh(acc) : acc;
-}
-
-// TF LSTMCell (un-vendored TF 1.7 dependency; gate order i, j, f, o and forget_bias 1.0
-// confirmed on the reference's recorded GraphDef, tests/golden/graph_fixture.json):
-//   c = sigmoid(f + 1) * c_prev + sigmoid(i) * tanh(j);  h = sigmoid(o) * tanh(c)
-__device__ __forceinline__ void lstm_gates(const LinProblem& P, float4 g, float cp, int b, int unit, int mode, bool dry) {
-    const float c = act_sigmoid(g.z + 1.0f) * cp + act_sigmoid(g.x) * act_tanh(g.y);
-    const float h = act_sigmoid(g.w) * act_tanh(c);
-    if (dry) return;   // instruction-cache warm-up pass: no side effects
-    P.c_out[(size_t)b * P.H + unit] = c;
-    P.h_out[(size_t)b * P.H + unit] = h;
-    if (P.out_pa) pa_store(P.out_pa, mode, P.row_tile, P.H >> 6, b, unit, h);   // h feeds the next dense layers
 }
 
 // ------------------------------------------------------------- UMMA kernel
@@ -183,7 +156,77 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     // blocking wait issued by the idle lanes of warp 0 would stall the TMA lane's weight prefetch with them.
     if (L.pdl && warp >= 2) { pdl_wait(); pdl_launch_dependents(); }
 
-    if (warp == 0) {
+    if (warp == 0 && xpa) {
+        // ===================== TMA producer, every operand packed (the steady state of loops and of the training
+        // step's products): the WHOLE warp runs the loop, converged, and one elected lane issues (see elect_one in
+        // sat_common.cuh) — issued from `if (lane == 0)` code each bulk copy paid several register->uniform moves and
+        // an indexed walk over the launch descriptor, and this loop paces the tile.  Running cursors: no divisions.
+        const uint64_t wpol = l2_policy(L.l2_w);
+        const int l2w = L.l2_w;
+        const uint32_t stage0 = smem_u32(stage_base);
+        const uint32_t bar_w0 = smem_u32(full_w), bar_x0 = smem_u32(full_x);
+        const uint8_t* wptr = P.wpack + ((size_t)n_tile * P.k_blocks + kb0) * kWStageBytes;
+        int xsg = 0, xkb = kb0;      // the K block lives in the packed activation of the segment that covers it
+        while (xsg + 1 < P.nseg && xkb >= (P.seg[xsg].width >> 6)) { xkb -= P.seg[xsg].width >> 6; ++xsg; }
+        const uint8_t* xptr = P.seg[xsg].pa + ((size_t)rt * (P.seg[xsg].width >> 6) + xkb) * x_stage_bytes;
+        int xseg_left = (P.seg[xsg].width >> 6) - xkb;
+        int sw = 0, sx = 0;
+        auto load_w = [&]() {
+            if (elect_one()) {
+                const uint32_t bar = bar_w0 + 8u * (uint32_t)sw;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kWStageBytes) : "memory");
+                const uint32_t dst = stage0 + (uint32_t)sw * stage_bytes;
+                if (l2w == 0)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                                 "l"(wptr), "r"((uint32_t)kWStageBytes), "r"(bar) : "memory");
+                else
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                                 "l"(wptr), "r"((uint32_t)kWStageBytes), "r"(bar), "l"(wpol) : "memory");
+            }
+            wptr += kWStageBytes;
+            if (++sw == S) sw = 0;
+        };
+        auto load_x = [&]() {
+            if (elect_one()) {
+                const uint32_t bar = bar_x0 + 8u * (uint32_t)sx;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(x_stage_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 stage0 + (uint32_t)sx * stage_bytes + (uint32_t)kWStageBytes),
+                             "l"(xptr), "r"(x_stage_bytes), "r"(bar) : "memory");
+            }
+            xptr += x_stage_bytes;
+            if (++sx == S) sx = 0;
+            if (--xseg_left == 0 && xsg + 1 < P.nseg) {
+                ++xsg;
+                xptr = P.seg[xsg].pa + (size_t)rt * (P.seg[xsg].width >> 6) * x_stage_bytes;
+                xseg_left = P.seg[xsg].width >> 6;
+            }
+        };
+        const int pre = nkb < S ? nkb : S;
+        if (!L.pdl) {
+            if (lane == 0) tl_go(L.tl);
+            for (int it = 0; it < pre; ++it) { load_w(); load_x(); }
+        } else {
+            if (L.w_dynamic) pdl_wait();          // (a second wait further down returns at once)
+            for (int it = 0; it < pre; ++it) load_w();
+            // the rest of this CTA's weight stream: into L2 while the predecessor drains
+            if (L.l2_prefetch && elect_one())
+                for (int it = pre; it < nkb; ++it) prefetch_l2_bulk(wptr + (size_t)(it - pre) * kWStageBytes, kWStageBytes);
+            pdl_wait();
+            pdl_launch_dependents();
+            if (lane == 0) tl_go(L.tl);
+            for (int it = 0; it < pre; ++it) load_x();
+        }
+        uint32_t par = 1u;            // parity of empty[] that means "free"; blocks [0, S) found fresh barriers
+        int se = 0;
+        for (int it = pre; it < nkb; ++it) {
+            if (it == S) par = 0u;
+            mbar_wait(&empty[se], par);
+            load_w();
+            load_x();
+            if (++se == S) { se = 0; par ^= 1u; }
+        }
+    } else if (warp == 0) {
         // ===================== TMA producer: one 32 KB bulk copy per stage =====================
         if (lane == 0) {
             const uint8_t* src = P.wpack + ((size_t)n_tile * P.k_blocks + kb0) * kWStageBytes;
@@ -246,36 +289,48 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp runs the loop (converged: all lanes wait on the stage barriers) and one elected lane issues the
+        // MMAs and the commits: their descriptors then live in uniform registers (see elect_one in sat_common.cuh).
+        {
             const uint32_t idesc = umma_idesc_bf16(kTileN, N);
             const uint32_t lbo = mode == 0 ? 128u : 16u;
             const uint32_t layout = mode == 0 ? 0u : 2u;
-            const uint32_t kstep = mode == 0 ? 256u : 32u;  // bytes per UMMA K (=16 bf16) inside a stage tile
+            const uint32_t kstep16 = (mode == 0 ? 256u : 32u) >> 4;  // descriptor address units (16 B) per UMMA K (=16 bf16)
+            const uint64_t dzero = umma_smem_desc(0u, lbo, 1024, layout);   // descriptor of byte address 0; the start address is added
+            const uint32_t stage0 = smem_u32(stage_base);
+            const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_d, 0);
+            int s = 0;
+            uint32_t ph = 0u;
+#pragma unroll 1
             for (int it = 0; it < nkb; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(&full_w[s], ph);
-                if (it == 0) trace_stamp(L.dbg, 4);
+                if (it == 0 && lane == 0) trace_stamp(L.dbg, 4);
                 mbar_wait(&full_x[s], ph);
-                if (it == 0) trace_stamp(L.dbg, 5);
+                if (it == 0 && lane == 0) trace_stamp(L.dbg, 5);
                 tc_fence_after();
-                const uint32_t wb = smem_u32(stage_base + (size_t)s * stage_bytes);
-                const uint32_t xb = wb + kWStageBytes;
+                if (elect_one()) {
+                    const uint32_t wb = stage0 + (uint32_t)s * stage_bytes;
+                    uint64_t a_hi = dzero + (uint64_t)(wb >> 4);
+                    uint64_t a_lo = dzero + (uint64_t)((wb + kWHalfBytes) >> 4);
+                    uint64_t b_hi = dzero + (uint64_t)((wb + kWStageBytes) >> 4);
+                    uint64_t b_lo = dzero + (uint64_t)((wb + kWStageBytes + x_half_bytes) >> 4);
 #pragma unroll
-                for (int kk = 0; kk < kBK / 16; ++kk) {
-                    const uint64_t a_hi = umma_smem_desc(wb + kk * kstep, lbo, 1024, layout);
-                    const uint64_t a_lo = umma_smem_desc(wb + kWHalfBytes + kk * kstep, lbo, 1024, layout);
-                    const uint64_t b_hi = umma_smem_desc(xb + kk * kstep, lbo, 1024, layout);
-                    const uint64_t b_lo = umma_smem_desc(xb + x_half_bytes + kk * kstep, lbo, 1024, layout);
-                    umma_f16(tmem_d, a_hi, b_hi, idesc, (it | kk) != 0 ? 1u : 0u);
-                    umma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
-                    umma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
+                    for (int kk = 0; kk < kBK / 16; ++kk) {
+                        umma_f16(tmem_acc, a_hi, b_hi, idesc, (it | kk) != 0 ? 1u : 0u);
+                        umma_f16(tmem_acc, a_lo, b_hi, idesc, 1u);
+                        umma_f16(tmem_acc, a_hi, b_lo, idesc, 1u);
+                        a_hi += kstep16; a_lo += kstep16; b_hi += kstep16; b_lo += kstep16;
+                    }
+                    umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+                    if (it == nkb - 1) {
+                        umma_commit(tmem_full);
+                        trace_stamp(L.dbg, 6);
+                    }
                 }
-                umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
             }
-            umma_commit(tmem_full);
-            trace_stamp(L.dbg, 6);
-            if (L.tl) { mbar_wait(tmem_full, 0); tl_main_done(L.tl); }
+            if (L.tl) { mbar_wait(tmem_full, 0); if (lane == 0) tl_main_done(L.tl); }
         }
     } else {
         // ===================== X producers (warps 2..9), then epilogue =====================

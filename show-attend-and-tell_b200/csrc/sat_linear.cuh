@@ -218,6 +218,45 @@ struct PackJob {           // fp32 rows (optionally gathered) -> packed activati
 cudaError_t pack_rows_launch(const PackJob* jobs, int njobs, int layout_mode, cudaStream_t st, const DropSpec* drop = nullptr,
                              int pdl = 0);
 
+// ------------------------------------------------------------------------------------------------------------
+// Chained launch (sat_chain.cu): the dense layers of ONE decode step of the greedy loop — LSTM -> [decode fc_1 ||
+// attend fc_1b of the next step] -> vocabulary layer + arg-max — as the phases of one persistent launch (one CTA per
+// SM).  A phase needs the outputs of ALL CTAs of the phase before it (h, then t = tanh(fc_1)), so phases meet at
+// grid-wide arrival counters in global memory; what a separate launch per layer cannot do and this does: every CTA is
+// resident from the start, and its TMA lane streams the (immutable) weights of its next tile into the pipeline
+// stages as they free up, i.e. under the epilogue and the rendezvous of the current phase.
+//   * all operands arrive packed (x_mode 2 of lin_umma_kernel), one row tile (rows <= row_tile <= 64);
+//   * split-K partial tiles meet in a global (L2 resident) scratch buffer behind a per-tile arrival counter, summed in
+//     fixed split order (bit-identical to the cluster / DSMEM reduction of lin_umma_kernel);
+//   * arg-max of the vocabulary phase: one atomicMax per (row, tile) on the ordered 64-bit key; every CTA but the
+//     last to arrive exits at once (its SM is free for the next launch); the last arriver records the words and packs
+//     their embedding rows for the next step.
+// Counters are monotonic: the host zeroes them at the start of a loop and passes the expected values per launch.
+constexpr int kChainMaxPhase = 3;
+constexpr int kChainMaxTiles = 128;
+struct ChainPhase {
+    LinProblem p[2];
+    int nprob;
+    int ctas;              // CTAs with a tile in this phase (blockIdx.x < ctas)
+};
+struct LinChain {
+    ChainPhase ph[kChainMaxPhase];
+    int nphase;
+    int layout_mode, stages, l2_w, pdl, row_tile;
+    unsigned* ctr;         // [kChainMaxPhase] CTAs that finished phase i (since the counters were zeroed)
+    unsigned target[kChainMaxPhase];   // value of ctr[i] that means "phase i of THIS launch is complete"
+    unsigned* tile_ctr;    // [kChainMaxPhase][kChainMaxTiles] split-K arrivals per (phase, tile)
+    unsigned tile_target[kChainMaxPhase];   // value of a tile counter of phase i that means "every split of THIS launch arrived"
+                                            // (= split factors of the phase summed over the launches since the zeroing)
+    float* scratch;        // [grid][row_tile x 128] split-K partial tiles
+    unsigned long long* tl;   // optional timeline cells (see tl_begin)
+    unsigned long long* dbg;  // optional [grid][16] per-CTA stamps (tools/trace_chain.py)
+    int dbg_mode;             // 0: phase milestones; 1: phase 0 per K block (slots 0-7 operands landed, 8-15 weight copy issued)
+};
+size_t lin_chain_smem_bytes(int row_tile, int stages);
+int lin_chain_pick_stages(int row_tile);
+cudaError_t lin_chain_launch(const LinChain& C, int grid, cudaStream_t st);
+
 size_t lin_smem_bytes(int row_tile, int stages);
 int lin_pick_stages(int row_tile);
 cudaError_t lin_launch(const LinLaunch& L, cudaStream_t st, bool use_simt);

@@ -62,3 +62,39 @@ def test_beam_one_equals_greedy_loop():
     res = m.beam_search(ctx, eos_id=-1)
     for k in range(6):
         assert res[k][0].sentence == [int(x) for x in toks[k]]
+
+
+def test_config5_as_stated():
+    """BASELINE config 5 as stated: 128 images x beam 3, T=30, L=196, D=512, H=1024, V=10000 (bench.py --workload 5).
+
+    With random weights the word distribution is almost flat, so over 128 x 3 x 30 top-(beam+1) selections a few
+    decisions are numerical ties (relative gap below the GPU path's ~5e-6 error).  The oracle is therefore run twice —
+    exact fp64, and fp64 with every probability perturbed by 3e-5 relative noise — and an image counts as decidable
+    when both runs give the same captions; decidable images (>= 90 %) must match the GPU exactly, scores to 1e-3."""
+    ocfg, w, m = make_pair(128, beam=3, num_lstm_units=1024, vocabulary_size=10000, max_caption_length=30)
+    ctx = R.synth_contexts(ocfg, 128)
+    stepper = R.HoistedStepper(ocfg, w, ctx, np.float64)
+    eos = pick_eos_fast(ocfg, w, ctx[:8])
+    ref = R.beam_search(ocfg, w, ctx, eos_id=eos, dtype=np.float64, step_fn=stepper.step, fast_topk=True)
+    rng = np.random.RandomState(5)
+
+    def noisy(cx, lw, lm, lo):
+        mem, out, probs = stepper.step(cx, lw, lm, lo)
+        return mem, out, probs * (1.0 + 3e-5 * rng.standard_normal(probs.shape))
+    ref2 = R.beam_search(ocfg, w, ctx, eos_id=eos, dtype=np.float64, step_fn=noisy, fast_topk=True)
+    got = m.beam_search(ctx, eos_id=eos)
+    decidable = 0
+    for k in range(128):
+        same = len(ref[k]) == len(ref2[k]) and all(a.sentence == b.sentence for a, b in zip(ref[k], ref2[k]))
+        if not same:
+            continue
+        decidable += 1
+        compare([got[k]], [ref[k]])
+    assert decidable >= 115, decidable
+    assert any(c.complete for caps in got for c in caps)
+
+
+def pick_eos_fast(ocfg, w, ctx):
+    import dataclasses
+    sub = dataclasses.replace(ocfg, max_caption_length=6)
+    return pick_eos(sub, w, ctx)

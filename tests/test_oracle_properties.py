@@ -102,3 +102,33 @@ def test_train_forward_dropout_off_equals_inference_steps():
     _, steps = R.decode_loop(cfg, w, ctx, 6, sent, np.float64)
     for a, b in zip(out["logits"], steps):
         np.testing.assert_allclose(a, b["logits"], rtol=1e-10, atol=1e-12)
+
+
+def test_hoisted_stepper_and_fast_topk_equal_the_literal_restatement():
+    """The two shortcuts the full-size beam-search parity test uses are exact: the hoisted fc_1a branch gives
+    bit-identical steps, and the stable argsort picks the same words in the same order as the reference's list sort."""
+    import numpy as np
+    from oracle import ref_step as R
+    cfg = R.OracleConfig(batch_size=3, beam_size=3, num_ctx=25, dim_ctx=32, dim_embedding=16, num_lstm_units=32,
+                         dim_initalize_layer=16, dim_attend_layer=24, dim_decode_layer=32, vocabulary_size=40,
+                         max_caption_length=6)
+    w = R.init_weights(cfg, seed=4)
+    ctx = R.synth_contexts(cfg, 3, seed=4)
+    rng = np.random.RandomState(1)
+    lw = rng.randint(0, 40, 3).astype(np.int32)
+    c = rng.uniform(-0.5, 0.5, (3, 32)).astype(np.float32)
+    h = rng.uniform(-0.5, 0.5, (3, 32)).astype(np.float32)
+    for dt in (np.float32, np.float64):
+        st = R.HoistedStepper(cfg, w, ctx, dt)
+        a = R.decode_step(cfg, w, ctx, lw, c, h, dt)
+        mem, out, probs = st.step(ctx, lw, c, h)
+        assert np.array_equal(mem, a["memory"]) and np.array_equal(out, a["output"]) and np.array_equal(probs, a["probs"])
+    # ties included: quantised probabilities produce many equal scores
+    def coarse(cx, lw_, lm, lo):
+        r = R.decode_step(cfg, w, cx, lw_, lm, lo, np.float64)
+        return r["memory"], r["output"], np.round(r["probs"], 2)
+    a = R.beam_search(cfg, w, ctx, eos_id=2, step_fn=coarse)
+    b = R.beam_search(cfg, w, ctx, eos_id=2, step_fn=coarse, fast_topk=True)
+    for x, y in zip(a, b):
+        assert [c_.sentence for c_ in x] == [c_.sentence for c_ in y]
+        assert [c_.score for c_ in x] == [c_.score for c_ in y]
