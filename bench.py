@@ -90,6 +90,66 @@ class ClockSampler(threading.Thread):
                     samples=len(sm))
 
 
+def loop_kernel_times(model, ctx, T, work, pk):
+    """Per-kernel durations of the greedy loop measured on the device (option "trace" = 3: every launch stamps
+    min CTA start / min dependency-release / max accumulator-ready / max end with %globaltimer).  Returns the list
+    for roofline.kernels[].  `work`: name -> (algorithmic bytes, flops incl. the 3 passes of the bf16x3 split)."""
+    import numpy as np
+    import torch
+    import cuda.bindings.runtime as cr
+    model.set_option("graphs", 0)
+    for _ in range(2):
+        model.loop_device(ctx, T)
+    torch.cuda.synchronize()
+    model.set_option("trace", 3)
+    model.loop_device(ctx, T)
+    torch.cuda.synchronize()
+    n = model.info("tl_count")
+    host = np.zeros(1024 * 16, np.uint64)
+    cr.cudaMemcpy(host.ctypes.data, model.info("trace_ptr"), host.nbytes, cr.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    names = []
+    for i in range(n):
+        model.info("tl_tag_%d" % i)
+        names.append(model.lib.sat_last_error().decode().strip())
+    model.set_option("trace", 0)
+    model.set_option("graphs", 1)
+    cell = lambda i, k: float(int(host[4 * i + k])) if 0 < int(host[4 * i + k]) < 2 ** 62 else float("nan")
+    groups = {}
+    for i, nm in enumerate(names):
+        start, end, go, acc = cell(i, 0), cell(i, 1), cell(i, 2), cell(i, 3)
+        groups.setdefault(nm, []).append(((end - go) / 1e3, (end - start) / 1e3, (acc - go) / 1e3))
+    med = lambda v: float(np.nanmedian(np.array(v))) if len(v) else float("nan")
+    out = []
+    label = {"lstm": "LSTM cell", "dec1": "decode fc_1 || attend fc_1b", "dec2": "vocabulary layer + arg-max", "attention": "attention"}
+    for nm, rows in groups.items():
+        if len(rows) < T // 2:
+            continue                                   # prologue launches (projection, initialize)
+        fam, grid = nm.split("/")[0], nm.split("/")[-1]
+        # (phases of the chained launch stamp: phase opened -> last CTA arrived)
+        us = med([r[1] for r in rows]) if fam.startswith("phase") else med([r[0] for r in rows])
+        ent = dict(kernel=nm, launches=len(rows), us_in_loop=us, us_first_cta_start_to_end=med([r[1] for r in rows]),
+                   timing="device %globaltimer inside one eager loop: first CTA through its dependency wait -> last CTA done (median)")
+        key = {"phase0": "lstm", "phase1": "dec1", "phase2": "dec2"}.get(fam, fam)
+        if key in work:
+            by, fl = work[key]
+            ent.update(what=label[key], algorithmic_bytes=by, achieved_gbs=by / (us * 1e3), frac_hbm=by / (us * 1e3) / pk["hbm"])
+            if fl:
+                ent.update(flops_bf16x3=fl, tflops=fl / (us * 1e6), frac_tensor=fl / (us * 1e6) / pk["tf_sust"])
+        elif fam == "chain":
+            by = sum(work[k][0] for k in ("lstm", "dec1", "dec2"))
+            fl = sum(work[k][1] for k in ("lstm", "dec1", "dec2"))
+            ent.update(what="chained dense launch: LSTM -> fc_1 || q -> vocabulary layer (sat_chain.cu)", algorithmic_bytes=by,
+                       achieved_gbs=by / (us * 1e3), frac_hbm=by / (us * 1e3) / pk["hbm"], flops_bf16x3=fl,
+                       tflops=fl / (us * 1e6), frac_tensor=fl / (us * 1e6) / pk["tf_sust"])
+        out.append(ent)
+    tops = [e for e in out if not e["kernel"].startswith("phase")]
+    if tops:
+        top = max(tops, key=lambda e: e["us_in_loop"])
+        for e in out:
+            e["dominant"] = e is top
+    return out
+
+
 def oracle_setup(wl, seed=1234):
     from oracle import ref_step as R
     ocfg = R.OracleConfig(batch_size=wl["B"], num_ctx=wl["L"], dim_ctx=wl["D"], num_lstm_units=wl["H"],
@@ -145,7 +205,27 @@ def time_cpu_oracle(wl, steps, warmup, budget_s=25.0):
                 sample="%d x (initialize + %d of %d decode steps) at B=%d, numpy/BLAS fp32 oracle restating "
                        "model.py (not TensorFlow: not installable here); %d BLAS threads (fastest of the counts "
                        "tried on %d host cores)" % (len(times), T_s, wl["T"], wl["B"], best_t, ncpu),
-                ms_per_step=1e3 * total / len(times) * (wl["T"] / T_s), steps_sampled=T_s)
+                ms_per_step=1e3 * total / len(times),              # of the MEASURED sample (T_s decode steps per bench step)
+                ms_per_full_step=1e3 * total / len(times) * (wl["T"] / T_s), steps_sampled=T_s, host_cores=ncpu)
+
+
+def bench_config(wl, world, pool=None, pool_mb=None):
+    """The `config` object of a bench line: the same keys for the sat arm and the reference arm."""
+    B, T = wl["B"], wl["T"]
+    beam = wl.get("beam", 1)
+    if wl.get("train"):
+        step = "one optimisation step: forward + backward + gradient all-reduce + clip + Adam on %d images per GPU" % B
+    elif beam > 1:
+        step = "beam search: %d images x beam %d, %d steps, device-side TopN; tokens = images x steps" % (B, beam, T)
+    else:
+        step = ("project contexts + initialize + %d decode steps (greedy) for %d images; consecutive batches overlap: "
+                "the prologue of batch i+1 runs under the decode steps of batch i" % (T, B))
+    return {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world,
+            "parallelism": "dp%d (batch sharded, replicated weights, no data-path collective in decoding)" % world,
+            "precision": "fp32 in/out; GEMMs as split bf16x3 on tcgen05 with fp32 TMEM accumulation",
+            "l2": ("inputs rotate over %d context batches (%.0f MB + 137 MB weights/activations) > 126 MB L2" % (pool, pool_mb))
+                  if pool else "inputs larger than L2 (context batches rotate)",
+            "step": step}
 
 
 def run_reference(args, wl, rank, world):
@@ -153,10 +233,13 @@ def run_reference(args, wl, rank, world):
         return
     cb = time_cpu_oracle(wl, args.steps, max(args.warmup, 1))
     line = {"impl": "reference", "metric": "decode tokens/sec", "value": cb["value"], "unit": "tokens/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "note": "CPU restatement of the reference path (TensorFlow 1.x "
-                       "cannot be installed offline); bounded sample extrapolated to the full T-step loop"},
+            "config": dict(bench_config(wl, args.gpus),
+                           note="reference arm: CPU restatement of the reference path (TensorFlow 1.x cannot be installed "
+                                "offline), rank 0 only; each timed step is a bounded sample of the workload: initialize + "
+                                "%d of its %d decode steps for the full batch (ms_per_step is that sample's own time; "
+                                "tokens/s counts the tokens it produced)" % (cb["steps_sampled"], wl["T"])),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -468,13 +551,17 @@ def main():
         model.set_option("profile", 0)
         att_bytes = 4 * (B * L * (D + A) + B * A + A + B * L + B * D)
         achieved = att_bytes / att_ns                                       # bytes/ns == GB/s
-        traffic = None
+        # DRAM traffic is NOT measured by this run (it needs ncu): the figure below is read from the committed ncu capture
+        # and labelled as such
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "att_traffic.json")   # dram__bytes_read+write of one ncu --set full capture
         if os.path.exists(tp) and args.workload == 2:
             tj = json.load(open(tp))
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_src = "not measured in this run: " + tj["source"]
         roof = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
-                    traffic=traffic, kernel=("att_wpc_kernel<1>" if (D == 512 and A == 512) else "att_fused_kernel<1>"),
+                    traffic=traffic, traffic_source=traffic_src,
+                    kernel=("att_wpc_kernel<1>" if (D == 512 and A == 512) else "att_fused_kernel<1>"),
                     grid=loop_grid, us_per_launch=att_ns / 1e3, us_per_launch_whole_gpu=att_ns_full / 1e3,
                     achieved_whole_gpu=att_bytes / att_ns_full,
                     algorithmic_bytes=att_bytes, peak_source=pk["src"] + " HBM copy, burst",
@@ -485,6 +572,19 @@ def main():
         Dd = cfg.dim_decode_layer
         lstm_bytes = 4 * ((D + E + H) * 4 * H + 4 * H)
         dec2_bytes = 4 * (Dd * V + V)
+        dec1_bytes = 4 * ((H + D + E) * Dd + Dd + H * A + A)
+        # ---- the other kernels of a step, timed INSIDE the loop on the device clock (%globaltimer stamps of every launch
+        # of one eager loop: first CTA through its dependency -> last CTA done; CUDA events cannot bracket one kernel of
+        # a programmatic-dependent-launch chain).  Weight-stream fraction against the HBM peak and tensor fraction
+        # (2*M*N*K x 3 passes of the bf16x3 split) against the sustained bf16 peak, per kernel; `dominant` = longest.
+        kernels = loop_kernel_times(model, ctx_dev[0], T, dict(
+            lstm=(lstm_bytes, 3 * 2 * B * (D + E + H) * 4 * H), dec1=(dec1_bytes, 3 * 2 * B * ((H + D + E) * Dd + H * A)),
+            dec2=(dec2_bytes, 3 * 2 * B * Dd * V), attention=(att_bytes, 0)), pk)
+        roof["kernels"] = kernels
+        step_bytes = att_bytes + lstm_bytes + dec1_bytes + dec2_bytes
+        roof["step"] = dict(algorithmic_bytes=step_bytes, us=1e3 * ms / args.steps / T,
+                            achieved=step_bytes / (1e6 * ms / args.steps / T), frac=step_bytes / (1e6 * ms / args.steps / T) / pk["hbm"],
+                            note="whole decode step (all kernels): algorithmic bytes / (timed loop / T)")
         extra = dict(kernel_us_cold=fam,
                      lstm_weight_stream_gbs=lstm_bytes / (fam["lstm"] * 1e3) if fam["lstm"] else None,
                      vocab_weight_stream_gbs=dec2_bytes / (fam["dec2"] * 1e3) if fam["dec2"] else None,
@@ -502,15 +602,7 @@ def main():
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world,
-                           "parallelism": "dp%d (batch sharded, replicated weights, no collective)" % world,
-                           "precision": "fp32 in/out; GEMMs as split bf16x3 on tcgen05 with fp32 TMEM accumulation",
-                           "l2": "inputs rotate over %d context batches (%.0f MB + 137 MB weights/activations) > 126 MB L2"
-                                 % (pool, pool_mb),
-                           "step": ("project contexts + initialize + %d decode steps (greedy) for %d images; consecutive "
-                                    "batches overlap: the prologue of batch i+1 runs under the decode steps of batch i" % (T, B))
-                           if beam == 1 else ("beam search: %d images x beam %d, %d steps, device-side TopN; tokens = "
-                                              "images x steps" % (B, beam, T))},
+                "config": bench_config(wl, world, pool, pool_mb),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "detail": extra}
         print(json.dumps(line), flush=True)

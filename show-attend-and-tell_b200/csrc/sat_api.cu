@@ -146,7 +146,8 @@ struct sat_handle {
     unsigned* chain_ctr = nullptr;         // [kChainMaxPhase + kChainMaxPhase * kChainMaxTiles]
     float* chain_scratch = nullptr;
     unsigned long long* chain_best = nullptr;
-    int opt_chain = 1;
+    int opt_chain = 0, opt_chain_cluster = 0;   // (measured slower than the per-layer launches so far: opt-in)
+    int chain_clusters[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // resident clusters of the chained kernel per cluster size
     const unsigned* att_qflag = nullptr;   // set around the attention launch that runs beside a chained launch
     unsigned att_qtarget = 0;
     void* train = nullptr;                 // training state (sat_train.cu)
@@ -411,6 +412,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
     else if (k == "att_reuse_q") h->opt_att_reuse_q = (int)value;
     else if (k == "xbatch") h->opt_xbatch = (int)value;
     else if (k == "chain") h->opt_chain = (int)value;
+    else if (k == "chain_cluster") h->opt_chain_cluster = (int)value;
     else if (k == "trace") {
         h->opt_trace = (int)value;
         if (value && !h->trace) RET(dmalloc(&h->trace, (size_t)1024 * 16));
@@ -1271,10 +1273,14 @@ static int loop_enqueue_chain(sat_handle* h, const float* ctx, int B, int T, con
 //   chain(t) = { LSTM(t) -> [decode fc_1(t) || q(t+1)] -> vocabulary layer(t) + arg-max }  ->  attention(t+1)
 // The attention kernel of step t+1 starts beside the chained launch, spins on the counter of its phase 1 (q(t+1) and
 // everything older are complete then) and runs beside the vocabulary phase on the SMs whose CTAs have exited.
+// OPT-IN (option "chain" = 1; default 0): measured SLOWER than the per-layer launches at config 2 (50 us against 38 us per
+// step: its three epilogues and the last arriver's tail run from cold instruction caches and cost 7 - 9 us each, see
+// DESIGN.md), and only validated for a 64-row tile (at B = 4 an eager, fully serialised run of it was seen to give wrong
+// logits from the second step on while the replayed graph was right: unresolved, so smaller batches are refused).
 static bool fused_loop_available(sat_handle* h, int B) {
     return h->opt_chain && h->pa_ok && h->opt_pa && h->opt_gemm != 0 && h->opt_overlap == 2 && h->opt_pdl &&
            h->d.num_decode_layers == 2 && h->d.num_attend_layers == 2 && h->opt_hoist && h->opt_att_wpc &&
-           h->d.dim_attend_layer == 512 && h->d.dim_ctx == 512 && row_tile_for(B) <= 64 && B <= h->num_sms &&
+           h->d.dim_attend_layer == 512 && h->d.dim_ctx == 512 && row_tile_for(B) == 64 && B <= h->num_sms &&
            (h->opt_trace == 0 || h->opt_trace >= 3) && h->opt_profile == 0;
 }
 
@@ -1384,13 +1390,36 @@ static int loop_enqueue_fused(sat_handle* h, const float* ctx, int B, int T, con
         C.ctr = h->chain_ctr;
         C.tile_ctr = h->chain_ctr + kChainMaxPhase;
         C.scratch = h->chain_scratch;
+        // split-K partials through distributed shared memory when the splits of every tile fall inside one cluster
+        // (option "chain_cluster" 0: through the L2 scratch buffer instead)
+        {
+            int cs = 1;
+            bool ok = h->opt_chain_cluster != 0;
+            for (int ph = 0; ph < C.nphase; ++ph)
+                for (int i = 0; i < C.ph[ph].nprob; ++i) {
+                    const LinProblem& P = C.ph[ph].p[i];
+                    if (P.splits > cs) cs = P.splits;
+                }
+            for (int ph = 0; ph < C.nphase && ok; ++ph)
+                for (int i = 0; i < C.ph[ph].nprob; ++i) {
+                    const LinProblem& P = C.ph[ph].p[i];
+                    if (P.splits > 1 && (P.cta_begin % P.splits || cs % P.splits)) ok = false;
+                }
+            C.cluster = 1;
+            if (ok && cs > 1 && cs <= 8) {
+                const int padded = (grid + cs - 1) / cs * cs;   // (CTAs past the last tile have no work and exit)
+                // every cluster of the launch must be resident at once (the phases meet at grid-wide counters)
+                if (h->chain_clusters[cs] < 0) h->chain_clusters[cs] = lin_chain_max_clusters(rtile, stages, cs);
+                if (padded <= h->num_sms && h->chain_clusters[cs] * cs >= padded) { C.cluster = cs; grid = padded; }
+            }
+        }
         if (h->opt_trace == 3 && h->tl_count + 4 <= 4000) {   // four timeline entries: the launch, then its phases
             C.tl = h->trace + 4 * h->tl_count;
             h->tl_count += 4;
             h->tl_names.push_back("chain/" + std::to_string(grid));
             for (int ph = 0; ph < 3; ++ph) h->tl_names.push_back("  phase" + std::to_string(ph) + "/" + std::to_string(C.ph[ph].ctas));
         }
-        if (h->opt_trace >= 4 && h->opt_trace <= 7 && h->trace_at-- == 0) { C.dbg = h->trace; C.dbg_mode = h->opt_trace - 4; }   // per-CTA stamps of this one launch
+        if (h->opt_trace >= 4 && h->opt_trace <= 8 && h->trace_at-- == 0) { C.dbg = h->trace; C.dbg_mode = h->opt_trace - 4; }   // per-CTA stamps of this one launch
         CK(lin_chain_launch(C, grid, st));
         h->launches += 1;
         if (t + 1 < T) {

@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
     uint64_t* empty = full_x + 8;
     uint64_t* tmem_full = empty + 8;
     uint64_t* gather_bar = tmem_full + 1;                        // embedding rows of the last arriver's tail
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(gather_bar + 1);
+    uint64_t* peer_ready = gather_bar + 1;                       // [kChainMaxPhase] every split of my tile has parked its partial
+    uint64_t* peer_done = peer_ready + kChainMaxPhase;           // [kChainMaxPhase] every split of my tile has read mine
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(peer_done + kChainMaxPhase);
     unsigned* flag_s = reinterpret_cast<unsigned*>(smem_raw + 256);
     int* word_s = reinterpret_cast<int*>(smem_raw + 512);      // [<= 64] words picked by the last arriver
     uint8_t* stage_base = smem_raw + 1024;
@@ -86,10 +88,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
     unsigned long long* const dbg0 = C.dbg_mode == 0 ? C.dbg : nullptr;   // phase milestones
     unsigned long long* const dbg1 = (C.dbg_mode == 1 || C.dbg_mode == 2) ? C.dbg : nullptr;   // per-K-block stamps of phase 0
     unsigned long long* const dbg3 = C.dbg_mode == 3 ? C.dbg : nullptr;   // fine stamps of K blocks 0..3 of phase 0
+    unsigned long long* const dbg4 = C.dbg_mode == 4 ? C.dbg : nullptr;   // epilogue internals: phase 0 (6..12), last arriver's tail (0..5)
     const bool hi_only = C.dbg_mode == 2;   // timing experiment only (WRONG results): one MMA per K step instead of three
 
     if (threadIdx.x == 0) {
-        if (C.dbg_mode != 3) trace_stamp(C.dbg_mode == 0 ? C.dbg : nullptr, 0);
+        trace_stamp(dbg0, 0);
         tl_begin(C.tl);
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_w[s], 1);
@@ -98,6 +101,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
         }
         mbar_init(tmem_full, 2);                // one arrival per MMA warp and tile
         mbar_init(gather_bar, 1);
+#pragma unroll
+        for (int ph = 0; ph < kChainMaxPhase; ++ph) {            // (used once each: one tile per phase and launch)
+            const int sp = job[ph].nkb ? job[ph].P->splits : 1;
+            mbar_init(&peer_ready[ph], (uint32_t)sp);
+            mbar_init(&peer_done[ph], (uint32_t)sp);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -107,6 +116,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // (cluster mode: a peer may arrive on this CTA's peer_ready / peer_done barriers as soon as it runs: they must be
+    // initialised cluster-wide first.  All threads, once, before anything waits for the predecessor launch.)
+    if (C.cluster > 1) cluster_sync_all();
     const uint32_t tmem_d = *tmem_ptr;
 
     if (warp == 0 || warp == kChainXWarp) {
@@ -185,27 +197,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
             }
             ready_ph = 0;                          // activations of phases <= ready_ph may be fetched
         }
-        long long t0 = 0;
-        int idle = 0;
+        // (no busy polling: these warps share their schedulers with the epilogue warps, and a spinning warp takes issue
+        // slots from them — the stage wait suspends in hardware (mbarrier.try_wait), the phase wait sleeps between polls)
         while (ph < kChainMaxPhase) {
-            bool progress = false;
-            if (ph > ready_ph && __all_sync(0xffffffffu, (int)(ld_acquire_gpu(C.ctr + ph - 1) - C.target[ph - 1]) >= 0)) {
+            if (ph > ready_ph) {
+                long long t0 = 0;
+                int spins = 0;
+                while (!__all_sync(0xffffffffu, (int)(ld_acquire_gpu(C.ctr + ph - 1) - C.target[ph - 1]) >= 0)) {
+                    __nanosleep(128);
+                    if ((++spins & 1023) == 0) {
+                        if (spins == 1024) t0 = clock64();
+                        else if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
+                            if (lane == 0) printf("sat_b200: chained dense launch: phase %d never completed (block %d)\n", ph - 1, (int)blockIdx.x);
+                            __trap();
+                        }
+                    }
+                }
                 fence_proxy_async_global();        // other SMs' (generic-proxy) stores -> visible to the TMA reads below
                 ready_ph = ph;
                 if (C.tl && lane == 0) tl_begin(C.tl + 4 * (1 + ph));   // (timeline) first CTA that saw the phase open
             }
-            if (ph <= ready_ph && __all_sync(0xffffffffu, mbar_test_wait(&empty[st], par))) {
-                issue();
-                progress = true;
-            }
-            if (progress) idle = 0;
-            else if ((++idle & 1023) == 0) {       // (the clock is only read once in a while: it is a slow instruction)
-                if (idle == 1024) t0 = clock64();
-                else if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
-                    if (lane == 0) printf("sat_b200: chained dense launch stalled (block %d, %s block %d)\n", (int)blockIdx.x, wside ? "weight" : "activation", g);
-                    __trap();
-                }
-            }
+            mbar_wait(&empty[st], par);
+            issue();
         }
     } else if (warp == 1 || warp == kChainMma2Warp) {
         // ===================== MMA warps: warp 1 takes the even K blocks of a tile, warp 11 the odd ones =====================
@@ -246,11 +259,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                         }
                         tc_fence_after();
                         if (elect_one()) {
+                            // (14-bit start-address field: in a cluster launch a shared-memory address carries the
+                            // CTA's rank in its high bits, which must not leak into the descriptor's other fields)
                             const uint32_t wb = stage0 + (uint32_t)s * stage_bytes;
-                            uint64_t a_hi = dzero + (uint64_t)(wb >> 4);
-                            uint64_t a_lo = dzero + (uint64_t)((wb + kWHalfBytes) >> 4);
-                            uint64_t b_hi = dzero + (uint64_t)((wb + kWStageBytes) >> 4);
-                            uint64_t b_lo = dzero + (uint64_t)((wb + kWStageBytes + x_half_bytes) >> 4);
+                            uint64_t a_hi = dzero + (uint64_t)((wb >> 4) & 0x3FFFu);
+                            uint64_t a_lo = dzero + (uint64_t)(((wb + kWHalfBytes) >> 4) & 0x3FFFu);
+                            uint64_t b_hi = dzero + (uint64_t)(((wb + kWStageBytes) >> 4) & 0x3FFFu);
+                            uint64_t b_lo = dzero + (uint64_t)(((wb + kWStageBytes + x_half_bytes) >> 4) & 0x3FFFu);
 #pragma unroll
                             for (int kk = 0; kk < kBK / 16; ++kk) {
                                 umma_f16(tmem_acc, a_hi, b_hi, idesc, (it >= 2 || kk != 0) ? 1u : 0u);   // first own block starts the sum
@@ -283,6 +298,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
         const int u = pt & 31;
         if (C.pdl) { pdl_wait(); pdl_launch_dependents(); }
         int jc = 0;                        // tiles finished by this CTA: parity of tmem_full
+        int wait_done_ph = -1;             // cluster mode: phase whose peer_done barrier guards tile_s
 #pragma unroll 1
         for (int ph = 0; ph < C.nphase; ++ph) {
             // (selected by VALUE: a reference into job[] with a run-time index would put the array in local memory)
@@ -302,6 +318,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
             const int lo = (int)(((long long)rows_here * split) / splits) * 32;
             const int hi = (int)(((long long)rows_here * (split + 1)) / splits) * 32;
             const bool do_am = P.am_key != nullptr;           // (host: splits == 1 for the arg-max phase)
+            const bool csplit = splits > 1 && C.cluster > 1;  // partial tiles meet in distributed shared memory
+            const bool gsplit = splits > 1 && C.cluster <= 1; // ... or in the L2 scratch buffer
             const int ng = n_tile * kTileN + 4 * u;           // first of this thread's 4 outputs (all rows)
             const int unit = n_tile * 32 + u;                 // LSTM: the unit whose 4 gates this thread holds
             const bool vec_out = ng + 3 < n_out && (ldo & 3) == 0;
@@ -326,8 +344,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                 tc_fence_after();
                 if (C.tl && pt == 0) { tl_main_done(C.tl); tl_go(C.tl + 4 * (1 + ph)); tl_main_done(C.tl + 4 * (1 + ph)); }
                 if (dbg0 && pt == 0) trace_stamp(dbg0, ph == 0 ? 4 : ph == 1 ? 10 : 12);
+                if (dbg4 && pt == 0 && ph == 0) trace_stamp(dbg4, 6);
                 const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
                 float* const my_part = C.scratch + (size_t)blockIdx.x * N * kTileN;
+                // (cluster mode: the peers of my PREVIOUS split tile must have finished reading tile_s before it is rewritten)
+                if (wait_done_ph >= 0) { mbar_wait_cluster(&peer_done[wait_done_ph], 0u); wait_done_ph = -1; }
 #pragma unroll 1
                 for (int c0 = half * 16; c0 < N; c0 += 32) {
                     float v[16];
@@ -342,21 +363,39 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                     for (int j = 0; j < 16; ++j) {
                         const int row = c0 + j;
                         tile_s[row * kTileN + nl] = v[j] + bias_fold;
-                        if (splits > 1 && row < rows_here && (row * 32 < lo || row * 32 >= hi)) __stcg(my_part + row * kTileN + nl, v[j]);
+                        if (gsplit && row < rows_here && (row * 32 < lo || row * 32 >= hi)) __stcg(my_part + row * kTileN + nl, v[j]);
                     }
                 }
                 tc_fence_before();
+                if (dbg4 && pt == 0 && ph == 0) trace_stamp(dbg4, 7);
             }
-            if (splits > 1) {
+            const uint32_t tile_addr = smem_u32(tile_s);
+            uint32_t peer[8];
+            if (csplit) {
+                // the `splits` CTAs of the tile are consecutive ranks of one cluster: tell every one of them (and myself)
+                // that my partial tile is parked, wait until all of theirs are (mbarrier, cluster scope: no
+                // barrier.cluster, so the TMA / MMA warps are not involved), then CTA `split` sums rows [lo, hi) of
+                // the partial tiles read through distributed shared memory, in fixed split order
+                const uint32_t rank0 = cluster_ctarank() - (uint32_t)split;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) peer[r] = r < splits ? dsmem_map(tile_addr, rank0 + (uint32_t)r) : tile_addr;
+                named_bar_sync(1, kLinProducers);
+                if (dbg4 && pt == 0 && ph == 0) trace_stamp(dbg4, 8);
+                if (pt < splits) mbar_arrive_remote(&peer_ready[ph], rank0 + (uint32_t)pt);
+                mbar_wait_cluster(&peer_ready[ph], 0u);
+                if (pt == 0 && ph == 0) { trace_stamp(dbg0, 6); trace_stamp(dbg4, 9); }
+            } else if (gsplit) {
                 // the `splits` CTAs of the tile meet at its arrival counter; afterwards CTA `split` sums rows [lo, hi)
                 __threadfence();
                 named_bar_sync(1, kLinProducers);
+                if (dbg4 && pt == 0 && ph == 0) trace_stamp(dbg4, 8);
                 if (pt == 0) {
                     unsigned* tc = C.tile_ctr + ph * kChainMaxTiles + j_tile_id;
                     atomicAdd(tc, 1u);
                     wait_counter(tc, C.tile_target[ph], "split-K rendezvous of a chained dense launch");
                     __threadfence();
                     if (ph == 0) trace_stamp(dbg0, 6);
+                    if (ph == 0) trace_stamp(dbg4, 9);
                 }
                 named_bar_sync(1, kLinProducers);
             } else {
@@ -367,6 +406,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                 // split-K: the other splits' partial rows come from L2 (one round trip).  A thread has at most two rows at
                 // the batch sizes this launch serves; the loads of BOTH are issued before the first is consumed.
                 auto remote = [&](int r, int bb) {
+                    if (csplit) return ld_dsmem_f4(peer[r] + (uint32_t)(bb * kTileN + 4 * u) * 4u);
                     return __ldcg(reinterpret_cast<const float4*>(C.scratch + (size_t)(j_cta0 + r) * N * kTileN + bb * kTileN + 4 * u));
                 };
                 // (eight registers-quads in all: splits <= 4 -> pfa = first row, pfb = second row; splits == 8 -> one row,
@@ -409,6 +449,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                             if (r < splits) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
                     }
                     if (!do_am) { g.x += bias4.x; g.y += bias4.y; g.z += bias4.z; g.w += bias4.w; }
+                    if (dbg4 && pt == 0 && ph == 0 && idx == idx0 && g.x != 12345.678f) trace_stamp(dbg4, 10);   // first row's partials arrived
                     if (epi == kEpiLstm) {
                         float cprev = idx == lo + pt ? cpre[0] : cpre[1];
                         if (unit < Hh && idx >= lo + pt + 2 * kLinProducers) cprev = c_in[(size_t)bb * Hh + unit];
@@ -468,7 +509,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                     if (live && part == 0) atomicMax(P.am_key + r, key);
                 }
             }
+            if (csplit) {
+                // my reads of the peers' tiles are complete (the loads above returned their data): every peer may reuse
+                // its tile buffer or exit; mine is guarded by my own peer_done barrier until all of them said the same
+                named_bar_sync(1, kLinProducers);
+                const uint32_t rank0 = cluster_ctarank() - (uint32_t)split;
+                if (pt < splits) mbar_arrive_remote(&peer_done[ph], rank0 + (uint32_t)pt);
+                wait_done_ph = ph;
+            }
             if (dbg0 && pt == 0 && ph == 0) trace_stamp(dbg0, 7);
+            if (dbg4 && pt == 0 && ph == 0) trace_stamp(dbg4, 11);
             // ---- this CTA's part of the phase is complete and visible (also to the TMA reads of the CTAs that fetch
             // the packed outputs): arrive at the phase counter
             __threadfence();
@@ -479,6 +529,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                 const unsigned old = atomicAdd(C.ctr + ph, 1u);
                 flag_s[0] = (do_am && old + 1u == C.target[ph]) ? 1u : 0u;
                 if (dbg0) trace_stamp(dbg0, ph == 0 ? 8 : ph == 1 ? 15 : 13);
+                if (dbg4 && ph == 0) trace_stamp(dbg4, 12);
+                if (dbg4 && flag_s[0]) trace_stamp(dbg4, 0);
             }
             if (do_am) {
                 named_bar_sync(1, kLinProducers);
@@ -498,6 +550,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                     }
                     named_bar_sync(1, kLinProducers);
                     if (dbg0 && pt == 0) trace_stamp(dbg0, 14);
+                    if (dbg4 && pt == 0) trace_stamp(dbg4, 1);
                     if (P.am_emb_pa) {
                         // 64 rows x 2 KB from a 20 MB table: mostly HBM misses, and one SM sustains too few outstanding
                         // loads to fetch 128 KB with ld.global in less than ~7 us (measured).  The pipeline stages are
@@ -506,49 +559,56 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                         const int E = P.am_E, G8 = E >> 3, total = rows * G8;
                         const size_t halfb = (size_t)N * kBK * 2;
                         const uint32_t row_bytes = (uint32_t)E * 4u;
-                        const bool fits = (size_t)rows * row_bytes <= (size_t)S * stage_bytes && (row_bytes & 15u) == 0;
-                        float* const rows_s = reinterpret_cast<float*>(stage_base);
+                        // (row pitch = row + 16 bytes: the conversion below reads 8 rows at the same column at once)
+                        const uint32_t row_pitch = row_bytes + 16u;
+                        const bool fits = (size_t)rows * row_pitch <= (size_t)S * stage_bytes && (row_bytes & 15u) == 0;
+                        const uint8_t* const rows_s = stage_base;
                         if (fits) {
                             if (pt == 0) mbar_arrive_expect_tx(gather_bar, (uint32_t)rows * row_bytes);
                             named_bar_sync(1, kLinProducers);                 // (armed before any copy can complete)
                             const int w8 = pt >> 5;
                             for (int r = w8; r < rows; r += kLinProducers / 32)
                                 if (elect_one())
-                                    tma_bulk_g2s(stage_base + (size_t)r * row_bytes, P.am_emb + (size_t)word_s[r] * E, row_bytes, gather_bar);
+                                    tma_bulk_g2s(stage_base + (size_t)r * row_pitch, P.am_emb + (size_t)word_s[r] * E, row_bytes, gather_bar);
+                            if (dbg4 && pt == 0) trace_stamp(dbg4, 2);
                             mbar_wait(gather_bar, 0);
+                            if (dbg4 && pt == 0) trace_stamp(dbg4, 3);
                         }
                         // conversion fp32 -> packed bf16 hi / lo.  Task t = one 16-byte group of the destination; the low
                         // task bits run over (row & 7, k-group & 3) so that a warp's stores fill whole 128-byte lines of
                         // the operand image (row-major task order made every 16-byte store its own sector: ~4 us)
                         const int KB8 = E >> 6;                                     // K blocks of the operand
-                        const int ttot = ((rows + 7) >> 3) * KB8 * 64;              // 8 rows x 8 k-groups per (row block, K block)
+                        const int nrb = (rows + 7) >> 3;                            // 8-row blocks
                         (void)total;
+                        // thread-constant low bits (the stride of 256 tasks keeps them), the rest advances by 4 per step:
+                        // no division in the loop
+                        const int r7 = pt & 7, kg = ((pt >> 3) & 3) | (((pt >> 5) & 1) << 2);
+                        int kb = (pt >> 6) % KB8, rblk = (pt >> 6) / KB8;
                         constexpr int GB = 4;
 #pragma unroll 1
-                        for (int t0 = pt; t0 < ttot; t0 += kLinProducers * GB) {
+                        while (rblk < nrb) {
                             float4 a4[GB], c4[GB];
+                            int kbs[GB], rs[GB];
 #pragma unroll
                             for (int j = 0; j < GB; ++j) {
-                                const int t = t0 + j * kLinProducers;
-                                const int r7 = t & 7, kg = ((t >> 3) & 3) | (((t >> 5) & 1) << 2), rest = t >> 6;
-                                const int kb = rest % KB8, r = (rest / KB8) * 8 + r7;
-                                if (t < ttot && r < rows) {
+                                kbs[j] = kb;
+                                rs[j] = rblk < nrb ? rblk * 8 + r7 : rows;          // (rows: nothing to do)
+                                if (rs[j] < rows) {
                                     const int g8 = kb * 8 + kg;
-                                    const float4* src = fits ? reinterpret_cast<const float4*>(rows_s + (size_t)r * E + g8 * 8)
-                                                             : reinterpret_cast<const float4*>(P.am_emb + (size_t)word_s[r] * E + g8 * 8);
+                                    const float4* src = fits ? reinterpret_cast<const float4*>(rows_s + (size_t)rs[j] * row_pitch + (size_t)g8 * 32)
+                                                             : reinterpret_cast<const float4*>(P.am_emb + (size_t)word_s[rs[j]] * E + g8 * 8);
                                     a4[j] = src[0];
                                     c4[j] = src[1];
                                 }
+                                kb += 4;
+                                while (kb >= KB8) { kb -= KB8; ++rblk; }
                             }
 #pragma unroll
                             for (int j = 0; j < GB; ++j) {
-                                const int t = t0 + j * kLinProducers;
-                                const int r7 = t & 7, kg = ((t >> 3) & 3) | (((t >> 5) & 1) << 2), rest = t >> 6;
-                                const int kb = rest % KB8, r = (rest / KB8) * 8 + r7;
-                                if (t < ttot && r < rows) {
+                                if (rs[j] < rows) {
                                     uint4 hi4, lo4;
                                     split_bf16x8(a4[j], c4[j], hi4, lo4);
-                                    uint8_t* dst = P.am_emb_pa + (size_t)kb * 2 * halfb + umma_tile_off(mode, r, kg);
+                                    uint8_t* dst = P.am_emb_pa + (size_t)kbs[j] * 2 * halfb + umma_tile_off(mode, rs[j], kg);
                                     *reinterpret_cast<uint4*>(dst) = hi4;
                                     *reinterpret_cast<uint4*>(dst + halfb) = lo4;
                                 }
@@ -557,11 +617,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) lin_chain_kernel(const __gri
                     }
                 }
             }
+            if (dbg4 && pt == 0 && do_am && flag_s[0]) trace_stamp(dbg4, 4);
             ++jc;
         }
+        // (cluster mode: a CTA's shared memory must outlive the peers' reads of it)
+        if (wait_done_ph >= 0) mbar_wait_cluster(&peer_done[wait_done_ph], 0u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { trace_stamp(dbg0, 5); tl_end(C.tl); }
+    if (threadIdx.x == 0) { trace_stamp(dbg0, 5); trace_stamp(dbg4, 5); tl_end(C.tl); }
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -590,6 +653,25 @@ int lin_chain_pick_stages(int row_tile) {
     return s < 0 ? 0 : (int)s;
 }
 
+// clusters of `cluster` CTAs of this kernel that can be resident at once (0 on error): a chained launch waits on
+// grid-wide counters, so ALL its clusters must be
+int lin_chain_max_clusters(int row_tile, int stages, int cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster * 64);
+    cfg.blockDim = dim3(kChainThreads);
+    cfg.dynamicSmemBytes = lin_chain_smem_bytes(row_tile, stages);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lin_chain_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 cudaError_t lin_chain_launch(const LinChain& C, int grid, cudaStream_t st) {
     if (C.stages < 2 || C.row_tile > 64 || C.row_tile % 16) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg = {};
@@ -597,11 +679,23 @@ cudaError_t lin_chain_launch(const LinChain& C, int grid, cudaStream_t st) {
     cfg.blockDim = dim3(kChainThreads);
     cfg.dynamicSmemBytes = lin_chain_smem_bytes(C.row_tile, C.stages);
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (C.cluster > 1) {
+        if (grid % C.cluster) return cudaErrorInvalidValue;
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)C.cluster;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (C.pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = C.pdl ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, lin_chain_kernel, C);
 }
 

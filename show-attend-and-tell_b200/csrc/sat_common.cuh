@@ -247,6 +247,42 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
     return v;
 }
 
+// mbarrier signalling between the CTAs of a cluster (no barrier.cluster: only the threads that need it take part)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// arrive on an mbarrier in the shared memory of CTA `cta_rank` of this cluster; release at cluster scope: the writes of
+// this thread (and, through a preceding bar.sync, of its CTA) are visible to whoever acquires the barrier's phase
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t cta_rank) {
+    const uint32_t raddr = dsmem_map(smem_u32(local_bar), cta_rank);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok = 0;
+    long long t0 = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((++spins & 255) == 0) {
+            if (spins == 256) t0 = clock64();
+            else if (clock64() - t0 > SAT_SPIN_LIMIT_CYCLES) {
+                printf("sat_b200: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+                __trap();
+            }
+        }
+    }
+}
+
 // in-kernel timeline stamps (debug option "trace"): ns since an arbitrary origin, one row of 16 per CTA
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;

@@ -156,76 +156,59 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     // blocking wait issued by the idle lanes of warp 0 would stall the TMA lane's weight prefetch with them.
     if (L.pdl && warp >= 2) { pdl_wait(); pdl_launch_dependents(); }
 
-    if (warp == 0 && xpa) {
-        // ===================== TMA producer, every operand packed (the steady state of loops and of the training
-        // step's products): the WHOLE warp runs the loop, converged, and one elected lane issues (see elect_one in
-        // sat_common.cuh) — issued from `if (lane == 0)` code each bulk copy paid several register->uniform moves and
-        // an indexed walk over the launch descriptor, and this loop paces the tile.  Running cursors: no divisions.
+    // ---- TMA production when every operand arrives packed (x_mode 2: the steady state of loops and of the training
+    // step's products).  Two warps: warp 0 streams the weight halves of the stages (immutable: it starts before the
+    // dependency wait), the last epilogue warp streams the activation halves before it joins the epilogue — the two
+    // wait -> arm -> issue chains overlap, and this production paces the tile.  Each is a WHOLE warp running the loop
+    // converged with one elected lane issuing (see elect_one in sat_common.cuh): issued from `if (lane == 0)` code each
+    // bulk copy paid register->uniform moves and an indexed walk over the launch descriptor.  Running cursors: no divisions.
+    auto stream_half = [&](const bool wside) {
         const uint64_t wpol = l2_policy(L.l2_w);
-        const int l2w = L.l2_w;
-        const uint32_t stage0 = smem_u32(stage_base);
-        const uint32_t bar_w0 = smem_u32(full_w), bar_x0 = smem_u32(full_x);
-        const uint8_t* wptr = P.wpack + ((size_t)n_tile * P.k_blocks + kb0) * kWStageBytes;
-        int xsg = 0, xkb = kb0;      // the K block lives in the packed activation of the segment that covers it
-        while (xsg + 1 < P.nseg && xkb >= (P.seg[xsg].width >> 6)) { xkb -= P.seg[xsg].width >> 6; ++xsg; }
-        const uint8_t* xptr = P.seg[xsg].pa + ((size_t)rt * (P.seg[xsg].width >> 6) + xkb) * x_stage_bytes;
-        int xseg_left = (P.seg[xsg].width >> 6) - xkb;
-        int sw = 0, sx = 0;
-        auto load_w = [&]() {
+        const int l2w = wside ? L.l2_w : 0;
+        const uint32_t stage0 = smem_u32(stage_base) + (wside ? 0u : (uint32_t)kWStageBytes);
+        const uint32_t bar0 = smem_u32(wside ? full_w : full_x);
+        const uint32_t bytes = wside ? (uint32_t)kWStageBytes : x_stage_bytes;
+        const uint8_t* ptr;
+        int sg = 0, seg_left = nkb + 1;        // (weights: one contiguous run)
+        if (wside) {
+            ptr = P.wpack + ((size_t)n_tile * P.k_blocks + kb0) * kWStageBytes;
+        } else {
+            int kb = kb0;                       // the K block lives in the packed activation of the segment that covers it
+            while (sg + 1 < P.nseg && kb >= (P.seg[sg].width >> 6)) { kb -= P.seg[sg].width >> 6; ++sg; }
+            ptr = P.seg[sg].pa + ((size_t)rt * (P.seg[sg].width >> 6) + kb) * x_stage_bytes;
+            seg_left = (P.seg[sg].width >> 6) - kb;
+        }
+        int st = 0;
+        uint32_t par = 1u;                      // parity of empty[st] that means "free" (fresh barrier: the first pass is free)
+        if (wside && L.pdl && L.w_dynamic) pdl_wait();   // the weight operand was written by the preceding kernel
+        for (int it = 0; it < nkb; ++it) {
+            if (it >= S) mbar_wait(&empty[st], par);
             if (elect_one()) {
-                const uint32_t bar = bar_w0 + 8u * (uint32_t)sw;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kWStageBytes) : "memory");
-                const uint32_t dst = stage0 + (uint32_t)sw * stage_bytes;
+                const uint32_t bar = bar0 + 8u * (uint32_t)st;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                const uint32_t dst = stage0 + (uint32_t)st * stage_bytes;
                 if (l2w == 0)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                                 "l"(wptr), "r"((uint32_t)kWStageBytes), "r"(bar) : "memory");
+                                 "l"(ptr), "r"(bytes), "r"(bar) : "memory");
                 else
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                                 "l"(wptr), "r"((uint32_t)kWStageBytes), "r"(bar), "l"(wpol) : "memory");
+                                 "l"(ptr), "r"(bytes), "r"(bar), "l"(wpol) : "memory");
+                // (option) the rest of this CTA's weight stream: into L2 while the predecessor drains
+                if (wside && L.pdl && L.l2_prefetch && it + 1 == (nkb < S ? nkb : S))
+                    for (int j = it + 1; j < nkb; ++j) prefetch_l2_bulk(ptr + (size_t)(j - it) * kWStageBytes, kWStageBytes);
             }
-            wptr += kWStageBytes;
-            if (++sw == S) sw = 0;
-        };
-        auto load_x = [&]() {
-            if (elect_one()) {
-                const uint32_t bar = bar_x0 + 8u * (uint32_t)sx;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(x_stage_bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 stage0 + (uint32_t)sx * stage_bytes + (uint32_t)kWStageBytes),
-                             "l"(xptr), "r"(x_stage_bytes), "r"(bar) : "memory");
+            ptr += bytes;
+            if (++st == S) { st = 0; if (it >= S) par ^= 1u; else par = 0u; }
+            if (--seg_left == 0 && !wside && sg + 1 < P.nseg) {
+                ++sg;
+                ptr = P.seg[sg].pa + (size_t)rt * (P.seg[sg].width >> 6) * x_stage_bytes;
+                seg_left = P.seg[sg].width >> 6;
             }
-            xptr += x_stage_bytes;
-            if (++sx == S) sx = 0;
-            if (--xseg_left == 0 && xsg + 1 < P.nseg) {
-                ++xsg;
-                xptr = P.seg[xsg].pa + (size_t)rt * (P.seg[xsg].width >> 6) * x_stage_bytes;
-                xseg_left = P.seg[xsg].width >> 6;
-            }
-        };
-        const int pre = nkb < S ? nkb : S;
-        if (!L.pdl) {
-            if (lane == 0) tl_go(L.tl);
-            for (int it = 0; it < pre; ++it) { load_w(); load_x(); }
-        } else {
-            if (L.w_dynamic) pdl_wait();          // (a second wait further down returns at once)
-            for (int it = 0; it < pre; ++it) load_w();
-            // the rest of this CTA's weight stream: into L2 while the predecessor drains
-            if (L.l2_prefetch && elect_one())
-                for (int it = pre; it < nkb; ++it) prefetch_l2_bulk(wptr + (size_t)(it - pre) * kWStageBytes, kWStageBytes);
-            pdl_wait();
-            pdl_launch_dependents();
-            if (lane == 0) tl_go(L.tl);
-            for (int it = 0; it < pre; ++it) load_x();
         }
-        uint32_t par = 1u;            // parity of empty[] that means "free"; blocks [0, S) found fresh barriers
-        int se = 0;
-        for (int it = pre; it < nkb; ++it) {
-            if (it == S) par = 0u;
-            mbar_wait(&empty[se], par);
-            load_w();
-            load_x();
-            if (++se == S) { se = 0; par ^= 1u; }
-        }
+    };
+    constexpr int kXWarp = kLinThreads / 32 - 1;   // warp 9
+    if (warp == 0 && xpa) {
+        stream_half(true);
     } else if (warp == 0) {
         // ===================== TMA producer: one 32 KB bulk copy per stage =====================
         if (lane == 0) {
@@ -309,11 +292,13 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 if (it == 0 && lane == 0) trace_stamp(L.dbg, 5);
                 tc_fence_after();
                 if (elect_one()) {
+                    // (14-bit start-address field: in a cluster launch a shared-memory address carries the CTA's rank in
+                    // its high bits, which must not leak into the descriptor's other fields)
                     const uint32_t wb = stage0 + (uint32_t)s * stage_bytes;
-                    uint64_t a_hi = dzero + (uint64_t)(wb >> 4);
-                    uint64_t a_lo = dzero + (uint64_t)((wb + kWHalfBytes) >> 4);
-                    uint64_t b_hi = dzero + (uint64_t)((wb + kWStageBytes) >> 4);
-                    uint64_t b_lo = dzero + (uint64_t)((wb + kWStageBytes + x_half_bytes) >> 4);
+                    uint64_t a_hi = dzero + (uint64_t)((wb >> 4) & 0x3FFFu);
+                    uint64_t a_lo = dzero + (uint64_t)(((wb + kWHalfBytes) >> 4) & 0x3FFFu);
+                    uint64_t b_hi = dzero + (uint64_t)(((wb + kWStageBytes) >> 4) & 0x3FFFu);
+                    uint64_t b_lo = dzero + (uint64_t)(((wb + kWStageBytes + x_half_bytes) >> 4) & 0x3FFFu);
 #pragma unroll
                     for (int kk = 0; kk < kBK / 16; ++kk) {
                         umma_f16(tmem_acc, a_hi, b_hi, idesc, (it | kk) != 0 ? 1u : 0u);
@@ -338,6 +323,10 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
         // NEXT chunk in flight while the current one is converted and stored.
         const int pt = threadIdx.x - 64;  // 0..255
         if (pt == 0) trace_stamp(L.dbg, 1);
+        if (xpa && warp == kXWarp) {      // (this warp waited for the predecessor above, like every epilogue warp)
+            if (lane == 0) tl_go(L.tl);
+            stream_half(false);
+        }
         if (xpre) {
             // ---- cooperative pre-pass: this problem's CTAs convert X (fp32 -> bf16 hi/lo UMMA tiles) ONCE
             // into global scratch; consecutive threads take consecutive 8-element groups of a row (coalesced).

@@ -248,13 +248,17 @@ struct LinChain {
     unsigned* tile_ctr;    // [kChainMaxPhase][kChainMaxTiles] split-K arrivals per (phase, tile)
     unsigned tile_target[kChainMaxPhase];   // value of a tile counter of phase i that means "every split of THIS launch arrived"
                                             // (= split factors of the phase summed over the launches since the zeroing)
-    float* scratch;        // [grid][row_tile x 128] split-K partial tiles
+    float* scratch;        // [grid][row_tile x 128] split-K partial tiles (cluster == 1 only)
+    int cluster;           // > 1: the launch is cut into thread-block clusters of this size and the splits of a tile (all in
+                           // one cluster) exchange their partial tiles through distributed shared memory behind a pair
+                           // of mbarriers per phase; 1: through `scratch` in L2 behind the tile counters
     unsigned long long* tl;   // optional timeline cells (see tl_begin)
     unsigned long long* dbg;  // optional [grid][16] per-CTA stamps (tools/trace_chain.py)
     int dbg_mode;             // 0: phase milestones; 1: phase 0 per K block (slots 0-7 operands landed, 8-15 weight copy issued)
 };
 size_t lin_chain_smem_bytes(int row_tile, int stages);
 int lin_chain_pick_stages(int row_tile);
+int lin_chain_max_clusters(int row_tile, int stages, int cluster);
 cudaError_t lin_chain_launch(const LinChain& C, int grid, cudaStream_t st);
 
 size_t lin_smem_bytes(int row_tile, int stages);

@@ -247,15 +247,12 @@ def test_replayed_loop_then_step_on_other_contexts():
         assert_close(got["alpha"].cpu().numpy(), ref["alpha"], "alpha after %d beam searches" % loops)
 
 
-@pytest.mark.parametrize("shape", ["config2", "config1"])
+@pytest.mark.parametrize("shape", ["config2"])
 def test_chained_launch_agrees_with_the_per_layer_launches(shape):
     """sat_chain.cu (LSTM -> fc_1 || q -> vocabulary layer as phases of one persistent launch) against one launch per
     layer: the same MMAs on the same operands; the chained launch sums even and odd K blocks in two accumulators, so the
     results agree to fp32 round-off (not bit for bit), teacher forced and greedy, eager and replayed."""
-    if shape == "config2":
-        B, T, dims = 64, 20, dict(num_lstm_units=1024, vocabulary_size=10000)
-    else:
-        B, T, dims = 4, 6, dict()
+    B, T, dims = 64, 20, dict(num_lstm_units=1024, vocabulary_size=10000)   # (the opt-in path serves 64-row tiles only)
     ocfg, w, m = make_pair(B, **dims)
     ctx = R.synth_contexts(ocfg, B)
     rng = np.random.RandomState(8)
@@ -266,7 +263,7 @@ def test_chained_launch_agrees_with_the_per_layer_launches(shape):
         greedy = [m.decode_loop(ctx, T) for _ in range(3)]           # eager, capture, replay
         assert all(np.array_equal(greedy[0], g) for g in greedy[1:]), chain
         out[chain] = (greedy[0],) + m.decode_loop(ctx, T, forced, want_logits=True)
-    m.set_option("chain", 1)
+    m.set_option("chain", 0)
     for t in range(T):
         assert_close(out[1][2][t], out[0][2][t], "logits step %d, chained vs per-layer" % t, tol=2e-5)
     lg = out[0][2]
