@@ -246,9 +246,9 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_training(args, wl, model, cfg, rank, local_rank, world, dev):
-    """config 4: one optimisation step per bench step (forward + backward + ONE NCCL all-reduce of the flat
-    gradient + clip + Adam); weak scaling, 64 images per GPU."""
+def measure_training(wl, model, rank, local_rank, world, dev, steps, warmup, e2e=True, sample_clocks=True):
+    """config 4: one optimisation step per bench step (forward + backward + gradient all-reduce + clip + Adam); weak
+    scaling, 64 images per GPU.  Returns the record (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from sat_b200 import parallel
@@ -268,52 +268,78 @@ def run_training(args, wl, model, cfg, rank, local_rank, world, dev):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3 * pool)):   # eager pass + graph capture + first replay per context buffer
+    for i in range(max(warmup, 3 * pool)):   # eager pass + graph capture + first replay per context buffer
         out = model.train_step(ctx_dev[i % pool], sent, masks, seed=1 + i)
     barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
         time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    t0 = time.perf_counter()
     with torch.cuda.stream(st):
         ev0.record(st)
-        for i in range(args.steps):
+        for i in range(steps):
             model.train_step(ctx_dev[i % pool], sent, masks, seed=100 + i, sync=False)   # losses stay on the device
         ev1.record(st)
     barrier()
     ms = parallel.max_over_ranks(ev0.elapsed_time(ev1), dev)
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * B * T * args.steps / (ms / 1e3)
-    # end to end: contexts come from pinned host memory every step (into two device staging buffers, as an input
-    # pipeline would: the captured step graph is keyed by the buffer addresses), the losses go back to the host
-    stage = [torch.empty_like(ctx_dev[0]) for _ in range(2)]
-    for i in range(4):
-        stage[i % 2].copy_(ctx_host[i % pool], non_blocking=True)
-        model.train_step(stage[i % 2], sent, masks, seed=7)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        stage[i % 2].copy_(ctx_host[i % pool], non_blocking=True)
-        out = model.train_step(stage[i % 2], sent, masks, seed=200 + i)
-    torch.cuda.synchronize()
-    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+    value = world * B * T * steps / (ms / 1e3)
+    # the collective alone: the flat gradient buffer (+ the packed scalars) all-reduced back to back, CUDA events, max over ranks
+    ar_ms = None
+    if world > 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            model.allreduce_gradients()
+        barrier()
+        with torch.cuda.stream(st):
+            e0.record(st)
+            for _ in range(5):
+                model.allreduce_gradients()
+            e1.record(st)
+        barrier()
+        ar_ms = parallel.max_over_ranks(e0.elapsed_time(e1) / 5, dev)
+    rec_e2e = None
+    if e2e:
+        # end to end: contexts come from pinned host memory every step (into two device staging buffers, as an input
+        # pipeline would: the captured step graph is keyed by the buffer addresses), the losses go back to the host
+        stage = [torch.empty_like(ctx_dev[0]) for _ in range(2)]
+        for i in range(4):
+            stage[i % 2].copy_(ctx_host[i % pool], non_blocking=True)
+            model.train_step(stage[i % 2], sent, masks, seed=7)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            stage[i % 2].copy_(ctx_host[i % pool], non_blocking=True)
+            out = model.train_step(stage[i % 2], sent, masks, seed=200 + i)
+        torch.cuda.synchronize()
+        e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+        rec_e2e = {"value": world * B * T * steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": B * L * D * 4,
+                   "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * e2e_s / steps}
+    if rank != 0:
+        return None
+    nparams = int(model.params.numel())
+    return {"metric": "training tokens/sec (teacher-forced words per second, fwd+bwd+all-reduce+Adam)",
+            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3 * pool),
+            "ms_per_step": ms / steps, "allreduce_ms": ar_ms,
+            "collective": ("ONE NCCL all-reduce per step over the flat fp32 gradient buffer (%d floats = %.1f MB) with the "
+                           "whole-batch mask sum and the loss scalars packed into its tail" % (nparams, nparams * 4 / 1e6))
+                          if world > 1 else None,
+            "per_gpu_batch": B, "global_batch": B * world, "e2e": rec_e2e, "clocks": clocks, "last_losses": out}
+
+
+def run_training(args, wl, model, cfg, rank, local_rank, world, dev):
+    import torch.distributed as dist
+    rec = measure_training(wl, model, rank, local_rank, world, dev, args.steps, args.warmup)
     if rank == 0:
-        nparams = int(model.params.numel())
-        line = {"metric": "training tokens/sec (teacher-forced words per second, fwd+bwd+all-reduce+Adam)",
-                "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world,
-                           "parallelism": "dp%d: batch sharded, replicated weights, one NCCL all-reduce of the flat "
-                                          "fp32 gradient (%d floats) per step" % (world, nparams),
-                           "l2": "activations of a step (>1.5 GB stashed) exceed L2"},
-                "e2e": {"value": world * B * T * args.steps / e2e_s, "unit": "tokens/s",
-                        "h2d_bytes_per_step": B * L * D * 4, "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": None, "clocks": clocks, "roofline": None, "cpu_baseline": None,
-                "detail": {"last_losses": out}}
+        line = {"metric": rec["metric"], "value": rec["value"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": rec["warmup"], "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(bench_config(wl, world), l2="activations of a step (>1.5 GB stashed) exceed L2",
+                               parallelism="dp%d: batch sharded, replicated weights; %s" % (world, rec["collective"] or "single GPU")),
+                "e2e": rec["e2e"], "gpu_launches": None, "clocks": rec["clocks"], "roofline": None, "cpu_baseline": None,
+                "detail": {"last_losses": rec["last_losses"], "allreduce_ms": rec["allreduce_ms"]}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -328,6 +354,7 @@ def main():
     ap.add_argument("--impl", default="sat", choices=["sat", "reference"])
     ap.add_argument("--workload", type=int, default=2, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training sub-record of the default line")
     ap.add_argument("--pool", type=int, default=6, help="distinct context batches rotated through")
     ap.add_argument("--profile-run", action="store_true",
                     help="for runs under ncu: only the device-resident timed loop (no clock pre/post roll, no e2e, no roofline legs)")
@@ -597,6 +624,18 @@ def main():
         cpu = time_cpu_oracle(wl, 3, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # ---------------------------------------------------------------- training sub-record (BASELINE config 4)
+    # The default run also takes a short measurement of the data-parallel training step at the same per-GPU shapes
+    # (64 images per GPU, weak scaling), so that the driver's 1/2/4/8-GPU scaling runs record the step that contains
+    # the design's only collective.  Its own line: `python bench.py --workload 4`.
+    train_rec = None
+    if beam == 1 and args.workload == 2 and not args.no_train:
+        try:
+            train_rec = measure_training(WORKLOADS[4], model, rank, local_rank, world, dev, max(4, args.steps // 2), 3,
+                                         e2e=False, sample_clocks=False)
+        except Exception as exc:                      # never lose the decode line over the sub-record
+            train_rec = {"error": repr(exc)} if rank == 0 else None
+
     if rank == 0:
         line = {"metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -604,7 +643,7 @@ def main():
                 "data": "synthetic",
                 "config": bench_config(wl, world, pool, pool_mb),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "detail": extra}
+                "train": train_rec, "detail": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

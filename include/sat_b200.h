@@ -203,6 +203,32 @@ int sat_train_forward_backward_dsum(sat_handle* h, const float* params, float* g
 int sat_train_apply(sat_handle* h, float* params, float* grads, float* adam_m, float* adam_v, int64_t step, float lr,
                     float beta1, float beta2, float epsilon, float clip, float* grad_norm, void* stream);
 
+/* The optimizer of model.py:479-503 as plain data (field names of config.py:30-43).  kind: SAT_OPT_*.
+ *   Adam      tf.train.AdamOptimizer(learning_rate, beta1, beta2, epsilon)              slots: m, v
+ *   RMSProp   tf.train.RMSPropOptimizer(learning_rate, decay, momentum, epsilon, centered)
+ *                                                   slots: rms (STARTS AT ONE: sat_train_fill), mg (centered only), momentum
+ *   Momentum  tf.train.MomentumOptimizer(learning_rate, momentum, use_nesterov)        slots: accumulator
+ *   SGD       tf.train.GradientDescentOptimizer(learning_rate)                          slots: none
+ * clip_gradients: optimize_loss(clip_gradients=...) = clip_by_global_norm, applied for every optimizer.
+ * (The reference passes an Optimizer INSTANCE to tf.contrib.layers.optimize_loss, so its learning_rate_decay_fn only feeds
+ * the "learning_rate" summary: the optimizer keeps initial_learning_rate.  The facade reproduces that and offers the
+ * decayed rate as an option; this ABI simply takes the rate to use.) */
+#define SAT_OPT_ADAM 0
+#define SAT_OPT_RMSPROP 1
+#define SAT_OPT_MOMENTUM 2
+#define SAT_OPT_SGD 3
+typedef struct sat_optimizer {
+    int32_t kind;
+    float learning_rate, beta1, beta2, epsilon, decay, momentum;
+    int32_t centered, use_nesterov;
+    float clip_gradients;
+} sat_optimizer;
+/* sat_train_apply for any of the four optimizers; slot0..2 in the order listed above (unused ones may be NULL). */
+int sat_train_apply_opt(sat_handle* h, float* params, float* grads, float* slot0, float* slot1, float* slot2, int64_t step,
+                        const sat_optimizer* opt, float* grad_norm, void* stream);
+/* buf[0..n) = value on the device (initial value of an optimizer slot) */
+int sat_train_fill(sat_handle* h, float* buf, float value, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -409,6 +409,21 @@ def beam_search(cfg: OracleConfig, w, contexts, eos_id: int, dtype=np.float32,
 
 
 # --------------------------------------------------------------------------
+# utils/vocabulary.py:53-63  Vocabulary.get_sentence
+# --------------------------------------------------------------------------
+def get_sentence(words: Sequence[str], idxs: Sequence[int]) -> str:
+    """Word ids -> caption text, utils/vocabulary.py:53-63: append '.' unless the last word is one, cut after
+    the first '.', join with a space before every token that is neither punctuation nor starts with "'"."""
+    import string
+    ws = [words[i] for i in idxs]
+    if ws[-1] != '.':
+        ws.append('.')
+    length = int(np.argmax(np.array(ws) == '.')) + 1
+    ws = ws[:length]
+    return "".join([" " + w if not w.startswith("'") and w not in string.punctuation else w for w in ws]).strip()
+
+
+# --------------------------------------------------------------------------
 # model.py:250-334  training forward (teacher forcing, injected dropout masks)
 # --------------------------------------------------------------------------
 def regularized_names(w) -> List[str]:

@@ -179,3 +179,46 @@ def clip_and_adam(weights, grads, m, v, step, lr=1e-4, beta1=0.9, beta2=0.999, e
         nv[k] = beta2 * v[k] + (1 - beta2) * g * g
         nw[k] = weights[k].astype(np.float64) - lr_t * nm[k] / (np.sqrt(nv[k]) + eps)
     return nw, nm, nv, norm
+
+
+def apply_optimizer(kind, weights, grads, slots, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-6, clip=5.0, decay=0.9,
+                    momentum=0.0, centered=True, use_nesterov=True):
+    """The four optimizers of model.py:479-503 behind optimize_loss(clip_gradients=clip): TF 1.x update rules in fp64.
+
+    slots: list of dicts (name -> array) in the order Adam [m, v]; RMSProp [rms (initialised to ONES), mg, mom];
+    Momentum [accumulator]; SGD [].  Returns (new_weights, new_slots, global_norm).
+      RMSProp (training_ops ApplyCenteredRMSProp / ApplyRMSProp):
+          ms = decay*ms + (1-decay)*g^2 ; mg = decay*mg + (1-decay)*g ; mom = momentum*mom + lr*g/sqrt(ms - mg^2 + eps) ; w -= mom
+      Momentum (ApplyMomentum): acc = momentum*acc + g ; w -= lr*g + lr*momentum*acc (nesterov) | lr*acc
+      SGD: w -= lr*g
+    """
+    if kind == "Adam":
+        nw, nm, nv, norm = clip_and_adam(weights, grads, slots[0], slots[1], step, lr, beta1, beta2, eps, clip)
+        return nw, [nm, nv], norm
+    norm = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
+    scale = clip / max(norm, clip)
+    nw, ns = {}, [dict() for _ in slots]
+    for k in weights:
+        g = grads[k].astype(np.float64) * scale
+        w = weights[k].astype(np.float64)
+        if kind == "RMSProp":
+            ms = decay * slots[0][k] + (1 - decay) * g * g
+            denom = ms
+            if centered:
+                mg = decay * slots[1][k] + (1 - decay) * g
+                ns[1][k] = mg
+                denom = ms - mg * mg
+            else:
+                ns[1][k] = slots[1][k]
+            mom = momentum * slots[2][k] + lr * g / np.sqrt(denom + eps)
+            ns[0][k], ns[2][k] = ms, mom
+            nw[k] = w - mom
+        elif kind == "Momentum":
+            acc = momentum * slots[0][k] + g
+            ns[0][k] = acc
+            nw[k] = w - (lr * g + lr * momentum * acc if use_nesterov else lr * acc)
+        elif kind == "SGD":
+            nw[k] = w - lr * g
+        else:
+            raise ValueError(kind)
+    return nw, ns, norm

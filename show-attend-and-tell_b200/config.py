@@ -29,12 +29,26 @@ class Config(object):
         self.attention_loss_factor = 0.01
         # about the optimization (config.py:30-43)
         self.batch_size = 20
-        self.optimizer = 'Adam'
+        self.optimizer = 'Adam'          # 'Adam', 'RMSProp', 'Momentum' or 'SGD' (model.py:479-503)
         self.initial_learning_rate = 0.0001
+        self.learning_rate_decay_factor = 1.0
+        self.num_steps_per_decay = 100000
         self.clip_gradients = 5.0
+        self.momentum = 0.0
+        self.use_nesterov = True
+        self.decay = 0.9
+        self.centered = True
         self.beta1 = 0.9
         self.beta2 = 0.999
         self.epsilon = 1e-6
+        # The reference hands an Optimizer INSTANCE to tf.contrib.layers.optimize_loss, so its staircase decay
+        # (model.py:466-476) only reaches the "learning_rate" summary and the optimizer keeps initial_learning_rate.
+        # False reproduces that; True feeds the decayed rate to the optimizer.
+        self.apply_learning_rate_decay = False
+        # about the saver (config.py:46-49, base_model.py:242-255)
+        self.save_period = 1000
+        self.save_dir = './models/'
+        self.dropout_seed = 0x5A17B200
         # about the vocabulary (config.py:67) and beam search (main.py:35)
         self.vocabulary_size = 5000
         self.beam_size = 3

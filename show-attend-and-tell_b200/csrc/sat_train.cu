@@ -848,6 +848,48 @@ __global__ void adam_kernel(float* w, const float* g, float* m, float* v, size_t
     }
 }
 
+// The other optimizers of model.py:486-503 (TF 1.x update rules), after the same global-norm clip:
+//   RMSProp   ms = decay ms + (1-decay) g^2 ; [centered: mg = decay mg + (1-decay) g] ;
+//             mom = momentum mom + lr g / sqrt(ms [- mg^2] + eps) ; w -= mom            (slots: ms starts at ONE)
+//   Momentum  acc = momentum acc + g ; w -= nesterov ? lr (g + momentum acc) : lr acc
+//   SGD       w -= lr g
+__global__ void rmsprop_kernel(float* w, const float* g, float* ms, float* mg, float* mom, size_t n, const float* norm2, float clip,
+                               float lr, float decay, float momentum, float eps, int centered) {
+    pdl_enter();
+    const float norm = sqrtf(*norm2);
+    const float scale = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * scale;
+        const float msi = decay * ms[i] + (1.0f - decay) * gi * gi;
+        ms[i] = msi;
+        float denom = msi;
+        if (centered) {
+            const float mgi = decay * mg[i] + (1.0f - decay) * gi;
+            mg[i] = mgi;
+            denom = msi - mgi * mgi;
+        }
+        const float mi = momentum * mom[i] + lr * gi / sqrtf(denom + eps);
+        mom[i] = mi;
+        w[i] -= mi;
+    }
+}
+__global__ void momentum_kernel(float* w, const float* g, float* acc, size_t n, const float* norm2, float clip, float lr, float momentum,
+                                int nesterov, int plain_sgd) {
+    pdl_enter();
+    const float norm = sqrtf(*norm2);
+    const float scale = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * scale;
+        if (plain_sgd) { w[i] -= lr * gi; continue; }
+        const float a = momentum * acc[i] + gi;
+        acc[i] = a;
+        w[i] -= nesterov ? lr * gi + lr * momentum * a : lr * a;
+    }
+}
+__global__ void fill_kernel(float* x, float v, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------ state
 enum Var { vEmb = 0, vIa1W, vIa1B, vIa2W, vIa2B, vIb1W, vIb1B, vIb2W, vIb2B, vA1aW, vA1aB, vA1bW, vA1bB, vA2W, vLW, vLB,
            vD1W, vD1B, vD2W, vD2B, kNumVars };
@@ -1455,25 +1497,59 @@ extern "C" int sat_train_forward_backward_dsum(sat_handle* h, const float* param
 }
 
 // grads: the (all-reduced) sum over data-parallel shards.  Adds the L2-regulariser gradient once, clips by the
-// global norm (clip_gradients = 5.0, model.py:505-510) and applies TF Adam (model.py:480-485).  step counts from 1.
-extern "C" int sat_train_apply(sat_handle* h, float* params, float* grads, float* adam_m, float* adam_v, int64_t step, float lr,
-                               float beta1, float beta2, float epsilon, float clip, float* grad_norm, void* stream) {
-    if (!h || !params || !grads || !adam_m || !adam_v) return sat_fail(SAT_ERR_INVALID, "sat_train_apply: null argument");
+// global norm (clip_gradients = 5.0, model.py:505-510) and applies the optimizer (model.py:479-503).  step counts from 1.
+extern "C" int sat_train_apply_opt(sat_handle* h, float* params, float* grads, float* slot0, float* slot1, float* slot2,
+                                   int64_t step, const sat_optimizer* opt, float* grad_norm, void* stream) {
+    if (!h || !params || !grads || !opt) return sat_fail(SAT_ERR_INVALID, "sat_train_apply_opt: null argument");
     TrainState* s = (TrainState*)*sat_handle_train_slot(h);
     if (!s) return sat_fail(SAT_ERR_STATE, "call sat_train_init first");
     if (step < 1) return sat_fail(SAT_ERR_INVALID, "step counts from 1");
+    const int kind = opt->kind;
+    if (kind < SAT_OPT_ADAM || kind > SAT_OPT_SGD) return sat_fail(SAT_ERR_INVALID, "unknown optimizer kind %d", kind);
+    if ((kind == SAT_OPT_ADAM && (!slot0 || !slot1)) || (kind == SAT_OPT_RMSPROP && (!slot0 || !slot2 || (opt->centered && !slot1))) ||
+        (kind == SAT_OPT_MOMENTUM && !slot0))
+        return sat_fail(SAT_ERR_INVALID, "sat_train_apply_opt: optimizer slot buffer missing");
+    TCK(cudaSetDevice(sat_handle_device(h)));
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = s->off[kNumVars];
     for (int v = 0; v < kNumVars; ++v)
         if (s->regularised[v]) {
-            const size_t n = (size_t)s->rows[v] * s->cols[v];
-            launch_k(axpy_kernel, GRID1D(n), 256, st, grads + s->off[v], params + s->off[v], s->reg_scale, n);
+            const size_t nv = (size_t)s->rows[v] * s->cols[v];
+            launch_k(axpy_kernel, GRID1D(nv), 256, st, grads + s->off[v], params + s->off[v], s->reg_scale, nv);
         }
     TCK(cudaMemsetAsync(s->loss_acc + 4, 0, sizeof(float), st));
-    launch_k(sumsq_kernel, 148 * 8, 256, st, grads, s->off[kNumVars], 1.0f, s->loss_acc + 4);   // padding entries are zero
-    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
-    launch_k(adam_kernel, GRID1D(s->off[kNumVars]), 256, st, params, grads, adam_m, adam_v, s->off[kNumVars], s->loss_acc + 4, clip,
-                                                          (float)lr_t, beta1, beta2, epsilon);
+    launch_k(sumsq_kernel, 148 * 8, 256, st, grads, n, 1.0f, s->loss_acc + 4);   // padding entries are zero
+    const float clip = opt->clip_gradients, lr = opt->learning_rate;
+    if (kind == SAT_OPT_ADAM) {
+        const double lr_t = (double)lr * sqrt(1.0 - pow((double)opt->beta2, (double)step)) / (1.0 - pow((double)opt->beta1, (double)step));
+        launch_k(adam_kernel, GRID1D(n), 256, st, params, grads, slot0, slot1, n, s->loss_acc + 4, clip, (float)lr_t, opt->beta1, opt->beta2,
+                 opt->epsilon);
+    } else if (kind == SAT_OPT_RMSPROP) {
+        launch_k(rmsprop_kernel, GRID1D(n), 256, st, params, grads, slot0, slot1, slot2, n, s->loss_acc + 4, clip, lr, opt->decay,
+                 opt->momentum, opt->epsilon, opt->centered ? 1 : 0);
+    } else {
+        launch_k(momentum_kernel, GRID1D(n), 256, st, params, grads, slot0, n, s->loss_acc + 4, clip, lr, opt->momentum,
+                 opt->use_nesterov ? 1 : 0, kind == SAT_OPT_SGD ? 1 : 0);
+    }
     TCK(cudaGetLastError());
     if (grad_norm) TCK(cudaMemcpyAsync(grad_norm, s->loss_acc + 4, sizeof(float), cudaMemcpyDeviceToDevice, st));  // norm^2
     return SAT_OK;
+}
+
+// TF's RMSProp starts its `rms` slot at one (the other slots of every optimizer start at zero)
+extern "C" int sat_train_fill(sat_handle* h, float* buf, float value, int64_t n, void* stream) {
+    if (!h || !buf || n < 0) return sat_fail(SAT_ERR_INVALID, "sat_train_fill: bad argument");
+    TCK(cudaSetDevice(sat_handle_device(h)));
+    fill_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(buf, value, (size_t)n);
+    TCK(cudaGetLastError());
+    return SAT_OK;
+}
+
+extern "C" int sat_train_apply(sat_handle* h, float* params, float* grads, float* adam_m, float* adam_v, int64_t step, float lr,
+                               float beta1, float beta2, float epsilon, float clip, float* grad_norm, void* stream) {
+    if (!adam_m || !adam_v) return sat_fail(SAT_ERR_INVALID, "sat_train_apply: null argument");
+    sat_optimizer o;
+    memset(&o, 0, sizeof(o));
+    o.kind = SAT_OPT_ADAM; o.learning_rate = lr; o.beta1 = beta1; o.beta2 = beta2; o.epsilon = epsilon; o.clip_gradients = clip;
+    return sat_train_apply_opt(h, params, grads, adam_m, adam_v, nullptr, step, &o, grad_norm, stream);
 }

@@ -13,6 +13,16 @@ class SatError(RuntimeError):
         self.code = code
 
 
+class Optimizer(C.Structure):
+    """sat_optimizer of include/sat_b200.h"""
+    _fields_ = [("kind", C.c_int32), ("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("epsilon", C.c_float), ("decay", C.c_float), ("momentum", C.c_float), ("centered", C.c_int32),
+                ("use_nesterov", C.c_int32), ("clip_gradients", C.c_float)]
+
+
+OPTIMIZER_KINDS = {"Adam": 0, "RMSProp": 1, "Momentum": 2, "SGD": 3}
+
+
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "max_batch", "num_ctx", "dim_ctx", "num_lstm_units", "dim_embedding", "dim_attend_layer",
@@ -57,6 +67,8 @@ SIGNATURES = {
     "sat_train_forward_backward_dsum": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, C.c_uint64, _P, _I, _P, _P]),
     "sat_train_apply": (C.c_int, [_P, _P, _P, _P, _P, _L, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P,
                                   _P]),
+    "sat_train_apply_opt": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, C.POINTER(Optimizer), _P, _P]),
+    "sat_train_fill": (C.c_int, [_P, _P, C.c_float, _L, _P]),
 }
 
 

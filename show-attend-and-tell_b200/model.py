@@ -22,7 +22,7 @@ import ctypes as C
 
 import numpy as np
 
-from .lib import Dims, check, load_library
+from .lib import OPTIMIZER_KINDS, Dims, Optimizer, check, load_library
 
 
 def weight_shapes(config):
@@ -205,9 +205,25 @@ class CaptionGenerator(object):
                                                C.byref(reg), C.byref(total)))
             self._train_vars.append((name.value.decode(), off.value, rows.value, cols.value, bool(reg.value)))
         self.params = torch.zeros(total.value, device=self.device)
-        self.grads = torch.zeros_like(self.params)
-        self.adam_m = torch.zeros_like(self.params)
-        self.adam_v = torch.zeros_like(self.params)
+        # gradients + an 8-float tail in ONE buffer: the data-parallel step all-reduces it as a whole, so the loss sums
+        # and the next batch's mask sum travel inside the gradient collective (tail: ce, accuracy, attention,
+        # mask sum of the next batch)
+        self._flat = torch.zeros(total.value + 8, device=self.device)
+        self.grads = self._flat[:total.value]
+        self._tail = self._flat[total.value:]
+        self._msum_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._msum_key = None
+        # optimizer slots (model.py:479-503): Adam m, v; RMSProp rms (starts at ONE like TF's), mg (centered), momentum;
+        # Momentum accumulator; SGD none
+        kind = getattr(cfg, "optimizer", "Adam")
+        if kind not in OPTIMIZER_KINDS:
+            raise ValueError("config.optimizer %r: expected one of %s" % (kind, sorted(OPTIMIZER_KINDS)))
+        nslots = {"Adam": 2, "RMSProp": 3, "Momentum": 1, "SGD": 0}[kind]
+        self.opt_slots = [torch.zeros_like(self.params) for _ in range(nslots)]
+        if kind == "RMSProp":
+            self._check(self.lib.sat_train_fill(self._h, self._p(self.opt_slots[0]), 1.0, self.params.numel(), self._st()))
+            torch.cuda.synchronize(self.device)
+        self.adam_m, self.adam_v = (self.opt_slots + [None, None])[:2] if kind == "Adam" else (None, None)
         self._train_losses = torch.zeros(4, device=self.device)
         self._train_norm = torch.zeros(1, device=self.device)
         self.global_step = 0
@@ -286,17 +302,83 @@ class CaptionGenerator(object):
             self._keep["mask_sum"] = hit
         return hit[1]
 
-    def train_apply(self):
-        """Regulariser gradient + global-norm clip + Adam on self.grads (already summed over ranks)."""
+    def learning_rate(self, step=None):
+        """The staircase-decayed rate of model.py:466-476 at global step `step` (what the reference writes to its
+        "learning_rate" summary): initial * factor ** floor(step / num_steps_per_decay)."""
         cfg = self.config
+        step = self.global_step if step is None else int(step)
+        f = float(getattr(cfg, "learning_rate_decay_factor", 1.0))
+        if f >= 1.0:
+            return float(cfg.initial_learning_rate)
+        return float(cfg.initial_learning_rate) * f ** (step // int(cfg.num_steps_per_decay))
+
+    def train_apply(self):
+        """Regulariser gradient + global-norm clip + the configured optimizer (model.py:479-503) on self.grads (already
+        summed over ranks).  See Config.apply_learning_rate_decay for which rate the optimizer gets."""
+        cfg = self.config
+        lr = self.learning_rate(self.global_step) if getattr(cfg, "apply_learning_rate_decay", False) \
+            else float(cfg.initial_learning_rate)
         self.global_step += 1
+        o = Optimizer(OPTIMIZER_KINDS[getattr(cfg, "optimizer", "Adam")], lr, float(cfg.beta1), float(cfg.beta2),
+                      float(cfg.epsilon), float(getattr(cfg, "decay", 0.9)), float(getattr(cfg, "momentum", 0.0)),
+                      int(bool(getattr(cfg, "centered", True))), int(bool(getattr(cfg, "use_nesterov", True))),
+                      float(cfg.clip_gradients))
+        slots = [self._p(t) for t in self.opt_slots] + [C.c_void_p(0)] * 3
         self._sync_in()
-        self._check(self.lib.sat_train_apply(self._h, self._p(self.params), self._p(self.grads), self._p(self.adam_m),
-                                             self._p(self.adam_v), self.global_step, float(cfg.initial_learning_rate),
-                                             float(cfg.beta1), float(cfg.beta2), float(cfg.epsilon),
-                                             float(cfg.clip_gradients), self._p(self._train_norm), self._st()))
+        self._check(self.lib.sat_train_apply_opt(self._h, self._p(self.params), self._p(self.grads), slots[0], slots[1],
+                                                 slots[2], self.global_step, C.byref(o), self._p(self._train_norm), self._st()))
         self._sync_out()
         return self._train_norm
+
+    # TF names of the optimizer slot variables, in slot order (graph fixture: optimizer/OptimizeLoss/<var>/Adam, .../Adam_1)
+    _SLOT_SUFFIX = {"Adam": ["Adam", "Adam_1"], "RMSProp": ["RMSProp", "RMSProp_1", "RMSProp_2"], "Momentum": ["Momentum"],
+                    "SGD": []}
+
+    def save(self, save_dir=None):
+        """base_model.py:242-255: np.save of {variable name + ':0': ndarray} over the global variables (the decoder's 20
+        trainable tensors, global_step, the optimizer slots under their TF names, beta powers for Adam) to
+        <save_dir>/<global_step>.npy, plus config.pickle with the step.  The file loads back through load() here and
+        through the reference's own load() (which assigns by variable name)."""
+        import copy
+        import os
+        import pickle
+        cfg = self.config
+        kind = getattr(cfg, "optimizer", "Adam")
+        d = save_dir or getattr(cfg, "save_dir", "./models/")
+        os.makedirs(d, exist_ok=True)
+        self.torch.cuda.synchronize(self.device)
+        data = {nm + ":0": self._var_view(self.params, nm).detach().cpu().numpy().copy() for nm, *_ in self._train_vars}
+        data["global_step:0"] = np.int32(self.global_step)
+        for slot, suffix in zip(self.opt_slots, self._SLOT_SUFFIX[kind]):
+            for nm, *_ in self._train_vars:
+                data["optimizer/OptimizeLoss/%s/%s:0" % (nm, suffix)] = self._var_view(slot, nm).detach().cpu().numpy().copy()
+        if kind == "Adam":
+            data["optimizer/OptimizeLoss/beta1_power:0"] = np.float32(float(cfg.beta1) ** (self.global_step + 1))
+            data["optimizer/OptimizeLoss/beta2_power:0"] = np.float32(float(cfg.beta2) ** (self.global_step + 1))
+        path = os.path.join(d, "%d.npy" % self.global_step)
+        np.save(path, data, allow_pickle=True)
+        cfg_ = copy.copy(cfg)
+        cfg_.global_step = self.global_step
+        with open(os.path.join(d, "config.pickle"), "wb") as f:
+            pickle.dump(cfg_, f)
+        return path
+
+    def train_restore(self, model_file):
+        """Resume training from a file written by save() (or by the reference: same keys): parameters, optimizer slots
+        and global_step.  Returns the number of tensors restored."""
+        data = np.load(model_file, encoding="latin1", allow_pickle=True).item()
+        kind = getattr(self.config, "optimizer", "Adam")
+        n = 0
+        for nm, off, r, c, _ in self._train_vars:
+            if nm + ":0" in data:
+                self.params[off:off + r * c].copy_(self._dev(data[nm + ":0"], self.torch.float32).reshape(-1)); n += 1
+            for slot, suffix in zip(self.opt_slots, self._SLOT_SUFFIX[kind]):
+                k = "optimizer/OptimizeLoss/%s/%s:0" % (nm, suffix)
+                if k in data:
+                    slot[off:off + r * c].copy_(self._dev(data[k], self.torch.float32).reshape(-1)); n += 1
+        if "global_step:0" in data:
+            self.global_step = int(data["global_step:0"])
+        return n
 
     def _step_seed(self, seed):
         """Dropout seed of the next optimisation step.  None (default): fresh masks every step, derived from the
@@ -308,39 +390,59 @@ class CaptionGenerator(object):
             return ((base << 20) ^ (self.global_step + 1)) or 1
         return int(seed)
 
-    def train_step(self, contexts, sentences, masks, seed=None, sync=True):
+    def allreduce_gradients(self):
+        """Sum the flat gradient buffer (with its scalar tail) over the ranks: the one collective of a data-parallel step."""
+        import torch.distributed as dist
+        dist.all_reduce(self._flat)
+
+    def train_step(self, contexts, sentences, masks, seed=None, sync=True, next_masks=None):
         """One optimisation step (the sess.run(opt_op) of base_model.py:57-60) on this process's shard; with
         torch.distributed initialised the gradients are summed over the ranks by ONE all-reduce of the flat
         buffer (NCCL) and the losses are normalised by the global batch.  sync=False returns the device tensors
         (losses [4], squared gradient norm [1]) without reading them back, so that the host can queue the next step
         while this one runs (the reference reads its summary every step; a training loop rarely needs to).
-        seed: see _step_seed (None = new dropout masks every step, 0 = dropout off)."""
+        seed: see _step_seed (None = new dropout masks every step, 0 = dropout off).
+        next_masks (data parallel): the masks of the NEXT batch, if the input pipeline already has them: their sum then
+        rides in this step's gradient collective (default: the same masks tensor is expected again)."""
         import torch.distributed as dist
         torch = self.torch
         B, T = self._train_BT
         mk = self._dev(masks, torch.float32)
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if world > 1:
-            # the whole-batch mask sum stays on the device: summed, all-reduced and consumed in stream order, so the
-            # host can queue step i+1 while step i runs
-            msum = mk.sum(dtype=torch.float64).reshape(1)
-            dist.all_reduce(msum)
+            # ONE collective per step: the flat buffer [gradients | ce, accuracy, attention sums | mask sum of the NEXT
+            # batch].  The whole-batch mask sum (model.py:316-318 divides by it, so it is needed BEFORE the backward
+            # pass) of this batch therefore arrived with the previous step's collective; only the first step of a run —
+            # or a batch whose masks were not announced (`next_masks`) — pays a separate 8-byte all-reduce.  Everything
+            # stays on the device and in stream order: the host can queue step i+1 while step i runs.
+            nxt = mk if next_masks is None else self._dev(next_masks, torch.float32)
+            key = (mk.data_ptr(), mk._version, tuple(mk.shape))
+            if self._msum_key != key:
+                self._msum_dev.copy_(mk.sum(dtype=torch.float64).reshape(1))
+                dist.all_reduce(self._msum_dev)
             seed = self._step_seed(seed)
             seed = seed + 0x1000003 * dist.get_rank() if seed else 0   # rank-offset mask streams (0 stays "off")
+            losses = self.train_forward_backward(contexts, sentences, mk, seed, self._msum_dev, B * world)
+            self._tail[:3].copy_(losses[:3])               # CE / accuracy / attention are sums of shard parts
+            self._tail[3:4].copy_(nxt.sum().reshape(1))    # (exact in fp32: at most batch x steps ones per rank)
+            self.allreduce_gradients()                     # the single collective of the step
+            losses = torch.cat([self._tail[:3], losses[3:4]])
+            self._msum_dev.copy_(self._tail[3:4])
+            self._msum_key = (nxt.data_ptr(), nxt._version, tuple(nxt.shape))
         else:
             seed = self._step_seed(seed)
             msum = self._mask_sum(masks, mk)
-        losses = self.train_forward_backward(contexts, sentences, mk, seed, msum, B * world)
-        if world > 1:
-            dist.all_reduce(self.grads)                    # the single gradient all-reduce of the step
-            losses = losses.clone()
-            dist.all_reduce(losses[:3])                    # CE / accuracy / attention are sums of shard parts
+            losses = self.train_forward_backward(contexts, sentences, mk, seed, msum, B * world)
         norm2 = self.train_apply()
         if not sync:
             return losses, norm2
         ce, acc, att, reg = [float(x) for x in losses.tolist()]
+        bad = self.info("train_bad_ids")
+        if bad:    # (TF's embedding_lookup / sparse softmax raise InvalidArgumentError on such ids)
+            raise ValueError("%d word ids outside [0, %d) in `sentences`" % (bad, self.config.vocabulary_size))
         return dict(cross_entropy_loss=ce, accuracy=acc, attention_loss=att, reg_loss=reg, total_loss=ce + att + reg,
-                    gradient_norm=float(norm2.item()) ** 0.5)
+                    gradient_norm=float(norm2.item()) ** 0.5, learning_rate=self.learning_rate(self.global_step - 1),
+                    global_step=self.global_step)
 
     # ------------------------------------------------------------------ device API
     def prepare(self, contexts, want_state=True):

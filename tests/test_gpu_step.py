@@ -110,7 +110,8 @@ def test_hoisted_and_per_step_projection_agree():
 
 def test_packed_activation_and_prepass_paths_agree():
     """Operands packed by their producer kernels (default) vs the cooperative pre-pass vs per-stage producer
-    warps: the same bf16 hi/lo split feeds the same MMAs, so the three paths must agree bit for bit."""
+    warps: the same bf16 hi/lo split feeds the same MMAs.  The two conversion paths agree bit for bit; the packed path
+    sums even and odd K blocks in two TMEM accumulators (two MMA warps), so it agrees with them to fp32 round-off."""
     ocfg, w, m = make_pair(4)
     ctx = R.synth_contexts(ocfg, 4)
     toks = {}
@@ -120,9 +121,10 @@ def test_packed_activation_and_prepass_paths_agree():
             m.set_option(k, v)
         toks[name] = m.decode_loop(ctx, 6, None, want_logits=True)
     m.set_option("pa", 1); m.set_option("xpack", 1); m.set_option("overlap", 2)
-    for name in ("prepass", "warps"):
-        assert np.array_equal(toks["pa"][0], toks[name][0])
-        assert np.array_equal(toks["pa"][1], toks[name][1]), name
+    assert np.array_equal(toks["prepass"][0], toks["warps"][0])
+    assert np.array_equal(toks["prepass"][1], toks["warps"][1])
+    for t in range(6):
+        assert_close(toks["pa"][1][t], toks["warps"][1][t], "packed vs converted operands, step %d" % t, tol=2e-5)
 
 
 def test_loop_layouts_agree_and_pipelined_host_api():

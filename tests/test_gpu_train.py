@@ -189,3 +189,65 @@ def test_out_of_vocabulary_ids_are_counted_not_dereferenced():
     assert bool(m.grads.isfinite().all())
     m.train_forward_backward(ctx, sent, masks, seed=0)
     assert m.info("train_bad_ids") == 0
+
+
+@pytest.mark.parametrize("kind,extra", [("RMSProp", dict(momentum=0.9, centered=True)), ("RMSProp", dict(momentum=0.0, centered=False)),
+                                        ("Momentum", dict(momentum=0.9, use_nesterov=True)),
+                                        ("Momentum", dict(momentum=0.5, use_nesterov=False)), ("SGD", dict())])
+def test_other_optimizers_match_tf_semantics(kind, extra):
+    """model.py:486-503: RMSProp (centered or not, rms slot starting at one), Momentum (Nesterov or not), SGD — behind the
+    same global-norm clip as Adam, three steps against the fp64 restatement of the TF 1.x update rules."""
+    ocfg, w, m, ctx, sent, masks = setup(seed=5)
+    m.config.optimizer = kind
+    m.config.initial_learning_rate = 1e-2
+    for k, v in extra.items():
+        setattr(m.config, k, v)
+    m.train_setup(4, ocfg.max_caption_length, weights=w)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    zeros = lambda: {k: np.zeros_like(v) for k, v in w64.items()}
+    slots = {"RMSProp": [{k: np.ones_like(v) for k, v in w64.items()}, zeros(), zeros()], "Momentum": [zeros()], "SGD": []}[kind]
+    for step in (1, 2, 3):
+        _, g = TR.loss_and_grads(ocfg, w64, ctx, sent, masks, 100 + step, reg_in_grad=True)
+        clip = 5.0 if step != 2 else 1e-3                      # the clip is active on step 2
+        w64, slots, norm = TR.apply_optimizer(kind, w64, g, slots, step, lr=1e-2, clip=clip, eps=m.config.epsilon,
+                                              decay=m.config.decay, momentum=m.config.momentum, centered=m.config.centered,
+                                              use_nesterov=m.config.use_nesterov)
+        m.config.clip_gradients = clip
+        out = m.train_step(ctx, sent, masks, seed=100 + step)
+        assert abs(out["gradient_norm"] - norm) < 2e-4 * norm
+        got = {k: v.detach().cpu().numpy() for k, v in m.train_state_dict("params").items()}
+        for k in w64:
+            upd = np.abs(w64[k] - w[k].astype(np.float64)).max()
+            np.testing.assert_allclose(got[k].reshape(w64[k].shape), w64[k], rtol=0, atol=max(2e-3 * upd, 3e-6), err_msg=k)
+    m.config.clip_gradients = 5.0
+
+
+def test_save_in_the_reference_format_and_resume(tmp_path):
+    """base_model.py:242-255: {tf variable name + ':0': array} incl. global_step and the Adam slots under their TF names;
+    the file resumes training bit for bit and loads into the decode path like a reference checkpoint."""
+    import sat_b200
+    ocfg, w, m, ctx, sent, masks = setup(seed=8)
+    for it in range(3):
+        m.train_step(ctx, sent, masks, seed=10 + it)
+    path = m.save(str(tmp_path))
+    assert path.endswith("3.npy") and (tmp_path / "config.pickle").exists()
+    data = np.load(path, allow_pickle=True, encoding="latin1").item()
+    assert int(data["global_step:0"]) == 3
+    for k in ("word_embedding/weights:0", "lstm/lstm_cell/kernel:0", "optimizer/OptimizeLoss/lstm/lstm_cell/kernel/Adam:0",
+              "optimizer/OptimizeLoss/decode/fc_2/bias/Adam_1:0", "optimizer/OptimizeLoss/beta1_power:0"):
+        assert k in data, k
+    assert data["lstm/lstm_cell/kernel:0"].shape == w["lstm/lstm_cell/kernel"].shape
+    assert len([k for k in data if k.startswith("optimizer/OptimizeLoss/") and k.endswith("/Adam:0")]) == 20
+    nxt = m.train_step(ctx, sent, masks, seed=99)
+    after = m.params.clone()
+    # resume in a fresh model
+    m2 = sat_b200.CaptionGenerator(m.config)
+    m2.train_setup(4, ocfg.max_caption_length)
+    assert m2.train_restore(path) == 60 and m2.global_step == 3           # 20 variables + 2 x 20 Adam slots
+    nxt2 = m2.train_step(ctx, sent, masks, seed=99)
+    assert nxt2["global_step"] == 4 and abs(nxt2["total_loss"] - nxt["total_loss"]) < 1e-6 * abs(nxt["total_loss"])
+    assert bool((m2.params == after).all())
+    # and as an inference checkpoint (base_model.py:257-278 assigns by name, ignoring what it does not know)
+    m3 = sat_b200.CaptionGenerator(m.config)
+    assert m3.load(None, path) == 20
+    assert m3.decode_loop(ctx, ocfg.max_caption_length).shape == (4, ocfg.max_caption_length)
