@@ -624,6 +624,28 @@ def main():
         cpu = time_cpu_oracle(wl, 3, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # ---------------------------------------------------------------- strong scaling (next to the weak number)
+    # the SAME 64-image batch cut into contiguous shards of B / N images per GPU (no collective): what one caption batch
+    # gains from N GPUs.  Weight-bound layers lose efficiency as the per-GPU batch shrinks; reported, not optimised for.
+    strong = None
+    if beam == 1 and world > 1 and B % world == 0:
+        Bs = B // world
+        shard = [c[rank * Bs:(rank + 1) * Bs].contiguous() for c in ctx_dev]
+        for i in range(3 + 2 * pool):
+            model.loop_device(shard[i % pool], T)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            s0.record(st)
+            for i in range(args.steps):
+                model.loop_device(shard[i % pool], T)
+            s1.record(st)
+        barrier()
+        sms = parallel.max_over_ranks(s0.elapsed_time(s1), dev)
+        strong = {"value": B * T * args.steps / (sms / 1e3), "unit": "tokens/s", "scaling": "strong", "global_batch": B,
+                  "per_gpu_batch": Bs, "ms_per_step": sms / args.steps,
+                  "speedup_vs_one_gpu_line": None, "note": "same metric with the 64-image batch sharded over the GPUs"}
+
     # ---------------------------------------------------------------- training sub-record (BASELINE config 4)
     # The default run also takes a short measurement of the data-parallel training step at the same per-GPU shapes
     # (64 images per GPU, weak scaling), so that the driver's 1/2/4/8-GPU scaling runs record the step that contains
@@ -643,7 +665,7 @@ def main():
                 "data": "synthetic",
                 "config": bench_config(wl, world, pool, pool_mb),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "train": train_rec, "detail": extra}
+                "train": train_rec, "strong_scaling": strong, "detail": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

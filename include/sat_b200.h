@@ -17,7 +17,7 @@
  *     are int32 (model.py:214-216).
  *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); no hidden
  *     synchronisation except in *_host entry points, which return after the results
- *     are in host memory, and in sat_set_weight (one-time repack).
+ *     are in host memory.
  *   - a handle is bound to the CUDA device current at sat_create and is not thread
  *     safe (the reference's driver loop is single threaded: base_model.py:184-212).
  */
@@ -96,7 +96,9 @@ int sat_get_info(sat_handle* h, const char* key, int64_t* value);
  * the TF variable name with or without ":0" (e.g. "lstm/lstm_cell/kernel"); `dev` holds the
  * variable in the reference's layout: dense kernels [in, units] (rows=in, cols=units), biases
  * [units] (rows=1), the LSTM kernel [D+E+H, 4H] with column blocks i,j,f,o, the embedding [V,E].
- * The data is repacked into the library's own storage before the call returns. */
+ * The repack into the library's own storage is queued on `stream` (no host synchronisation: a training loop that
+ * refreshes the decode weights pays one sync, not twenty): `dev` must stay valid until `stream` has passed this
+ * call, and work that uses the weights must be ordered after it (the same stream, or an event). */
 int sat_set_weight(sat_handle* h, const char* tf_var_name, const float* dev, int64_t rows, int64_t cols,
                    void* stream);
 /* number of variables still missing (0 = ready) */

@@ -505,7 +505,6 @@ extern "C" int sat_set_weight(sat_handle* h, const char* tf_var_name, const floa
             return fail(SAT_ERR_INVALID, "%s: expected [%d,%d], got [%lld,%lld]", name.c_str(), h->d.vocabulary_size,
                         h->d.dim_embedding, (long long)rows, (long long)cols);
         CK(cudaMemcpyAsync(h->embedding, dev, (size_t)rows * cols * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        CK(cudaStreamSynchronize(st));
         h->emb_set = true;
         return SAT_OK;
     }
@@ -514,7 +513,6 @@ extern "C" int sat_set_weight(sat_handle* h, const char* tf_var_name, const floa
             return fail(SAT_ERR_INVALID, "%s: expected %d elements, got [%lld,%lld]", name.c_str(), h->att_vec.n,
                         (long long)rows, (long long)cols);
         CK(cudaMemcpyAsync(h->att_vec.dev, dev, (size_t)h->att_vec.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        CK(cudaStreamSynchronize(st));
         h->att_vec.set = true;
         return SAT_OK;
     }
@@ -524,7 +522,6 @@ extern "C" int sat_set_weight(sat_handle* h, const char* tf_var_name, const floa
                 return fail(SAT_ERR_INVALID, "%s: expected [%d,%d], got [%lld,%lld]", name.c_str(), ly->K, ly->n_out,
                             (long long)rows, (long long)cols);
             CK(lin_repack_weight(dev, ly->K, ly->n_out, ly->lstm ? ly->n_out / 4 : 0, ly->wpack, h->opt_layout, st));
-            CK(cudaStreamSynchronize(st));
             ly->w_set = true;
             return SAT_OK;
         }
@@ -534,7 +531,6 @@ extern "C" int sat_set_weight(sat_handle* h, const char* tf_var_name, const floa
                 return fail(SAT_ERR_INVALID, "%s: expected %d elements, got [%lld,%lld]", name.c_str(), ly->n_out,
                             (long long)rows, (long long)cols);
             CK(lin_repack_bias(dev, ly->n_out, ly->lstm ? ly->n_out / 4 : 0, ly->bias, st));
-            CK(cudaStreamSynchronize(st));
             ly->b_set = true;
             return SAT_OK;
         }

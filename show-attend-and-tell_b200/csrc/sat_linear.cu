@@ -470,17 +470,22 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                     __syncwarp();
                     cluster_sync_all();
                 } else {
-                    __syncthreads();
+                    named_bar_sync(2, kLinThreads);   // (with the TMA / MMA warps, which arrive from their own code path)
                 }
                 if (pt == 0) trace_stamp(L.dbg, 8);
             }
             // ---- part 2: one warp = one activation row per iteration (lane u owns outputs 4u..4u+3).  Kept
             // ROLLED and small on purpose: this code runs a handful of times per launch, so its cost is the
             // number of distinct instructions fetched, not arithmetic.
+            // (dry pass: every shared-memory read goes to a 512-byte scratch line of the control block instead of the
+            // pipeline stages, which the TMA is still filling: same instructions, no race with the async writes)
+            const float* const row_base = dry ? reinterpret_cast<const float*>(smem_raw + 512) : tile_s;
+            const int row_mul = dry ? 0 : kTileN;
+            const uint32_t row_addr = dry ? smem_u32(smem_raw + 512) : tile_addr;
             uint32_t peer[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)   // (dry: the own tile stands in for every peer)
-                peer[r] = (splits > 1 && r < splits) ? dsmem_map(tile_addr, (uint32_t)(dry ? split : r)) : tile_addr;
+            for (int r = 0; r < 8; ++r)   // (dry: the own scratch line stands in for every peer)
+                peer[r] = (splits > 1 && r < splits) ? dsmem_map(row_addr, (uint32_t)(dry ? split : r)) : row_addr;
             if (pt == 0 && !dry) trace_stamp(L.dbg, 15);
             const bool long_rows = row_loop && splits == 1 && epi != kEpiLstm && !out_pa && vec_out && !dry &&
                                    hi - lo > 4 * kLinProducers;
@@ -518,9 +523,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 auto fetch = [&](float4 (&dst)[8], int idx) {
                     const int bb = idx >> 5;
                     if (splits == 1) {
-                        dst[0] = *reinterpret_cast<const float4*>(tile_s + bb * kTileN + 4 * u);
+                        dst[0] = *reinterpret_cast<const float4*>(row_base + bb * row_mul + 4 * u);
                     } else {
-                        const uint32_t off = (uint32_t)(bb * kTileN + 4 * u) * 4u;
+                        const uint32_t off = (uint32_t)(bb * row_mul + 4 * u) * 4u;
 #pragma unroll
                         for (int r = 0; r < 8; ++r)
                             if (r < splits) dst[r] = ld_dsmem_f4(peer[r] + off);
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                         cprev = c_in[(size_t)(row0 + bb) * Hh + unit];
                     float4 g;
                     if (splits == 1) {
-                        g = *reinterpret_cast<const float4*>(tile_s + bb * kTileN + 4 * u);
+                        g = *reinterpret_cast<const float4*>(row_base + bb * row_mul + 4 * u);
                     } else {
                         g = cur[0];
 #pragma unroll
@@ -593,7 +598,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 for (int r0 = 0; r0 < rows_here; r0 += kLinProducers / 4) {
                     const int r = r0 + (pt >> 2);
                     const bool live = r < rows_here;
-                    const float4* row_t = reinterpret_cast<const float4*>(tile_s + (live ? r : 0) * kTileN) + part * 8;
+                    const float4* row_t = reinterpret_cast<const float4*>(row_base + (live ? r : 0) * row_mul) + part * 8;
                     // every element becomes an ordered 64-bit key (value bits, then inverted index) and the scan is a
                     // running 64-bit max: two independent chains of 2-instruction steps instead of one chain of
                     // compare / compare / select per element
@@ -696,7 +701,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     }
     if (warp < 2) {   // the TMA / MMA warps join the epilogue's rendezvous
         __syncwarp();
-        if (P.splits > 1) cluster_sync_all(); else __syncthreads();
+        if (P.splits > 1) cluster_sync_all(); else named_bar_sync(2, kLinThreads);
         if (P.splits > 1) cluster_arrive_relaxed();
     }
     if (threadIdx.x == 64) trace_stamp(L.dbg, 9);

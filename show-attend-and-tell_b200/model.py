@@ -162,6 +162,7 @@ class CaptionGenerator(object):
         """weights: {tf_variable_name[:0]: ndarray/tensor} in the reference layouts."""
         torch = self.torch
         given = {(k[:-2] if k.endswith(":0") else k): v for k, v in weights.items()}
+        keep = []
         for name, shp in self._shapes.items():
             if name not in given:
                 continue
@@ -173,8 +174,11 @@ class CaptionGenerator(object):
             if got != tuple(shp) and not vec_ok:
                 raise ValueError("%s: expected shape %s, got %s" % (name, shp, got))
             rows, cols = (shp[0], shp[1]) if len(shp) == 2 else (1, shp[0])
-            torch.cuda.synchronize(self.device)
+            self._sync_in()                     # (the upload / cast above ran on the caller's stream: a stream wait, no host sync)
             self._check(self.lib.sat_set_weight(self._h, name.encode(), self._p(w), rows, cols, self._st()))
+            keep.append(w)                      # the repack is asynchronous: the source lives until the stream is past it
+        if keep:
+            self.stream.synchronize()           # ONE synchronisation per call (it was one per variable)
         return self.lib.sat_weights_missing(self._h)
 
     def load(self, sess=None, model_file=None):

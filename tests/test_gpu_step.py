@@ -303,3 +303,29 @@ def test_config3_as_stated():
     got = m.decode_step(ctx, lw, c, hh, extras=True)
     for k in ("memory", "output", "probs", "logits", "alpha"):
         assert_close(got[k], ref[k], "config 3 step / " + k)
+
+
+def test_real_conv5_3_features():
+    """the decoder on REAL conv5_3 features (tests/golden/vgg_conv5_3.npz: the 14 images the reference ships,
+    through its own VGG16 weights: 94 % zeros, values up to ~290 — far from the relu(N(0,1)) of the other tests, the tanh
+    layers saturate) against the oracle: single step, initialize, and a teacher-forced loop with real caption ids."""
+    z = np.load(os.path.join(GOLD, "vgg_conv5_3.npz"))
+    ctx = z["feats"].astype(np.float32)[:12]
+    sent = z["sentences"][:12, :8].astype(np.int32)
+    ocfg, w, m = make_pair(12, max_caption_length=8)
+    c0r, h0r = R.initialize(ocfg, w, ctx, np.float64)
+    c0, h0 = m.initialize(ctx)
+    assert_close(c0, c0r, "c0 (real features)")
+    assert_close(h0, h0r, "h0 (real features)")
+    rng = np.random.RandomState(6)
+    lw = sent[:, 0]
+    c = rng.uniform(-0.5, 0.5, (12, 512)).astype(np.float32)
+    h = rng.uniform(-0.5, 0.5, (12, 512)).astype(np.float32)
+    ref = R.decode_step(ocfg, w, ctx, lw, c, h, np.float64)
+    got = m.decode_step(ctx, lw, c, h, extras=True)
+    for k in ("memory", "output", "probs", "logits", "alpha"):
+        assert_close(got[k], ref[k], k + " (real features)")
+    _, steps = R.decode_loop(ocfg, w, ctx, 8, sent, np.float32)
+    _, logits = m.decode_loop(ctx, 8, sent, want_logits=True)
+    for t in (0, 3, 7):
+        assert_close(logits[t], steps[t]["logits"], "loop logits step %d (real features)" % t)
