@@ -78,14 +78,13 @@ def init_masks(cfg: R.OracleConfig, seed: int, B: int):
 # ------------------------------------------------------------------ forward with autograd (2-layer modes)
 def forward_torch(cfg: R.OracleConfig, w, contexts, sentences, masks, seed=None,
                   global_mask_sum=None, global_batch=None):
-    """Mirror of ref_step.train_forward on torch float64 tensors (2-layer attend/decode/initialize).
+    """Mirror of ref_step.train_forward on torch float64 tensors (1- and 2-layer attend / decode / initialize).
 
     w: dict name -> torch tensor (requires_grad).  seed=None switches all dropout off.
     global_mask_sum / global_batch: normalisers of the GLOBAL batch when this is one data-parallel shard
     (model.py:316-318 divides by reduce_sum(masks) of the whole batch, :324-326 by batch_size*num_ctx).
     """
     import torch
-    assert cfg.num_attend_layers == 2 and cfg.num_decode_layers == 2 and cfg.num_initalize_layers == 2
     f64 = torch.float64
     B, T = sentences.shape
     L = cfg.num_ctx
@@ -105,19 +104,28 @@ def forward_torch(cfg: R.OracleConfig, w, contexts, sentences, masks, seed=None,
 
     im = init_masks(cfg, seed, B) if seed is not None else {}
     m = drop(ctx.mean(dim=1), im.get("init_mean"), kf)
-    c = dense(drop(dense(m, "initialize/fc_a1", torch.tanh), im.get("init_a"), kf), "initialize/fc_a2")
-    h_state = dense(drop(dense(m, "initialize/fc_b1", torch.tanh), im.get("init_b"), kf), "initialize/fc_b2")
+    if cfg.num_initalize_layers == 1:                      # model.py:362-371
+        c = dense(m, "initialize/fc_a")
+        h_state = dense(m, "initialize/fc_b")
+    else:                                                  # model.py:372-392
+        c = dense(drop(dense(m, "initialize/fc_a1", torch.tanh), im.get("init_a"), kf), "initialize/fc_a2")
+        h_state = dense(drop(dense(m, "initialize/fc_b1", torch.tanh), im.get("init_b"), kf), "initialize/fc_b2")
     h_out = h_state
     word = torch.zeros(B, dtype=torch.long)
     ces, alphas, correct = [], [], []
     ctx2d = ctx.reshape(B * L, -1)
     for t in range(T):
         dm = step_masks(cfg, seed, t, B) if seed is not None else {}
-        t1 = dense(drop(ctx2d, dm.get("att_ctx"), kf), "attend/fc_1a", torch.tanh)
-        t2 = dense(drop(h_out, dm.get("att_out"), kf), "attend/fc_1b", torch.tanh)
-        temp = t1 + t2.repeat_interleave(L, dim=0)
-        temp = drop(temp, dm.get("att_mid"), kf)
-        e = (temp @ w["attend/fc_2/kernel"]).reshape(B, L)
+        if cfg.num_attend_layers == 1:                     # model.py:401-414 (both layers bias-free)
+            l1 = (drop(ctx2d, dm.get("att_ctx"), kf) @ w["attend/fc_a/kernel"]).reshape(B, L)
+            l2 = drop(h_out, dm.get("att_out"), kf) @ w["attend/fc_b/kernel"]
+            e = l1 + l2
+        else:                                              # model.py:415-434
+            t1 = dense(drop(ctx2d, dm.get("att_ctx"), kf), "attend/fc_1a", torch.tanh)
+            t2 = dense(drop(h_out, dm.get("att_out"), kf), "attend/fc_1b", torch.tanh)
+            temp = t1 + t2.repeat_interleave(L, dim=0)
+            temp = drop(temp, dm.get("att_mid"), kf)
+            e = (temp @ w["attend/fc_2/kernel"]).reshape(B, L)
         alpha = torch.softmax(e, dim=1)
         context = (ctx * alpha[:, :, None]).sum(dim=1)
         alphas.append(alpha * mk[:, t:t + 1])
@@ -130,8 +138,11 @@ def forward_torch(cfg: R.OracleConfig, w, contexts, sentences, masks, seed=None,
         h_out = drop(h_raw, dm.get("lstm_out"), kl)
         h_state = drop(h_raw, dm.get("lstm_state"), kl)
         expanded = drop(torch.cat([h_out, context, emb], dim=1), dm.get("dec_in"), kf)
-        td = drop(dense(expanded, "decode/fc_1", torch.tanh), dm.get("dec_mid"), kf)
-        logits = dense(td, "decode/fc_2")
+        if cfg.num_decode_layers == 1:                     # model.py:442-447
+            logits = dense(expanded, "decode/fc")
+        else:                                              # model.py:448-458
+            td = drop(dense(expanded, "decode/fc_1", torch.tanh), dm.get("dec_mid"), kf)
+            logits = dense(td, "decode/fc_2")
         ce = torch.logsumexp(logits, dim=1) - logits[torch.arange(B), sent[:, t]]
         ces.append(ce * mk[:, t])
         pred = logits.argmax(dim=1)

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     unsigned gen0 = 0;
     if (xpre && threadIdx.x == 0) gen0 = ld_acquire_gpu(P.xbar + 1);
     tc_fence_before();
+    __syncwarp();   // (lane 0 of warp 0 / warp 1 come back from their one-thread setup before the aligned barrier)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                     __syncwarp();
                     cluster_sync_all();
                 } else {
-                    named_bar_sync(2, kLinThreads);   // (with the TMA / MMA warps, which arrive from their own code path)
+                    named_bar_sync(1, kLinProducers);   // the tile is complete: only the epilogue warps read it
                 }
                 if (pt == 0) trace_stamp(L.dbg, 8);
             }
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
                 // the embedding row of the chosen word (model.py:272-274), packed, to the next LSTM / decode layers.
                 // Every step of this tail is a round trip on the critical path of the decode step, which is why it
                 // is spread over the CTAs instead of being a serial pass of the last one.
-                unsigned long long* red_s = reinterpret_cast<unsigned long long*>(smem_raw + 520);   // [8] + word
+                unsigned long long* red_s = reinterpret_cast<unsigned long long*>(smem_raw + 256);   // [8] + word (clear of the dry pass's scratch line)
                 if (!dry) {
                     if (pt == 0) trace_stamp(L.dbg, 11);
                     __threadfence();
@@ -699,10 +700,10 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
             }
         }
     }
-    if (warp < 2) {   // the TMA / MMA warps join the epilogue's rendezvous
+    if (warp < 2 && P.splits > 1) {   // the TMA / MMA warps join the cluster rendezvous of the epilogue
         __syncwarp();
-        if (P.splits > 1) cluster_sync_all(); else named_bar_sync(2, kLinThreads);
-        if (P.splits > 1) cluster_arrive_relaxed();
+        cluster_sync_all();
+        cluster_arrive_relaxed();
     }
     if (threadIdx.x == 64) trace_stamp(L.dbg, 9);
     if (P.splits > 1) cluster_wait();   // peers may still be reading this CTA's tile

@@ -267,18 +267,19 @@ __global__ void bias_act_kernel(float* x, const float* b, int rows, int cols, in
     pdl_enter();
     const size_t n = (size_t)rows * cols;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float v = x[i] + b[i % cols];
+        float v = x[i] + (b ? b[i % cols] : 0.f);
         x[i] = act ? tanhf(v) : v;
     }
 }
 // dx = drop(dy) * (1 - y^2) in place on dy (dense [rows, cols]: mask index = linear index): the backward of
 // y = tanh(.) followed by dropout
 __global__ void drop_tanh_bwd_kernel(float* dy, const float* y, size_t n, const unsigned long long* seedp, unsigned long long stream,
-                                     float keep) {
+                                     float keep, size_t per_step) {
     pdl_enter();
     const unsigned long long seed = *seedp;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float d = seed ? dy[i] * drop_scale(seed, stream, i, keep) : dy[i];
+        const size_t ts = per_step ? i / per_step : 0;   // (stacked time steps: see concat3_drop_kernel)
+        const float d = seed ? dy[i] * drop_scale(seed, stream + 16ull * ts, i - ts * per_step, keep) : dy[i];
         dy[i] = d * (1.0f - y[i] * y[i]);
     }
 }
@@ -324,8 +325,11 @@ __global__ void colsum_kernel(float* db, const float* dx, int rows, int cols, co
 }
 // out[r, :] = concat(a[r, :na], b[r, :nb], c[r, :nc]) with dropout on the first `ndrop` columns, mask index
 // r * ndrop + col (= a dropout2d over a dense [rows, ndrop] matrix: one launch instead of three copies + one dropout)
+// rows_per_step > 0: the rows are T stacked time steps of rows_per_step rows each; step t draws its mask from stream
+// `stream + 16 t` with the row index inside the step (what T per-step launches with ST(t, k) would have drawn)
 __global__ void concat3_drop_kernel(float* out, int ldo, const float* a, int na, const float* b, int nb, const float* c, int nc,
-                                    int ndrop, int rows, const unsigned long long* seedp, unsigned long long stream, float keep) {
+                                    int ndrop, int rows, const unsigned long long* seedp, unsigned long long stream, float keep,
+                                    int rows_per_step) {
     pdl_enter();
     const unsigned long long seed = *seedp;
     const int cols = na + nb + nc;
@@ -333,8 +337,21 @@ __global__ void concat3_drop_kernel(float* out, int ldo, const float* a, int na,
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / cols), col = (int)(i - (size_t)r * cols);
         float v = col < na ? a[(size_t)r * na + col] : col < na + nb ? b[(size_t)r * nb + col - na] : c[(size_t)r * nc + col - na - nb];
-        if (seed && col < ndrop) v *= drop_scale(seed, stream, (unsigned long long)r * ndrop + col, keep);
+        if (seed && col < ndrop) {
+            const int ts = rows_per_step ? r / rows_per_step : 0, rl = r - ts * rows_per_step;
+            v *= drop_scale(seed, stream + 16ull * ts, (unsigned long long)rl * ndrop + col, keep);
+        }
         out[(size_t)r * ldo + col] = v;
+    }
+}
+// y = drop(x) for T stacked dense steps of `per_step` elements each (streams as above)
+__global__ void dropout_steps_kernel(float* y, const float* x, size_t n, size_t per_step, const unsigned long long* seedp,
+                                     unsigned long long stream, float keep) {
+    pdl_enter();
+    const unsigned long long seed = *seedp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t ts = i / per_step;
+        y[i] = seed ? x[i] * drop_scale(seed, stream + 16ull * ts, i - ts * per_step, keep) : x[i];
     }
 }
 // the transpose of the above: src[r, :] (dropout on the first ndrop columns) is split into three destinations, each
@@ -718,16 +735,20 @@ __global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_out, const
 }
 // masked cross entropy of one time step + its gradient; one block per row
 constexpr int kCeThreads = 1024;   // one CTA per batch row: the three passes over the V logits are latency bound
+// (rows_per_step > 0: block r is row r % rows_per_step of time step t + r / rows_per_step — all T steps in one launch)
 __global__ void __launch_bounds__(kCeThreads) ce_kernel(const float* logits, float* dlogits, const int32_t* sent, int sent_ld, int t,
-                                                        const float* masks, int V, const float* inv_msum_p, float* loss_acc) {
+                                                        const float* masks, int V, const float* inv_msum_p, float* loss_acc,
+                                                        int rows_per_step) {
     pdl_enter();
     constexpr int NW = kCeThreads / 32;
     const float inv_msum = *inv_msum_p;
     __shared__ float red[NW];
     __shared__ int redi[NW];
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* x = logits + (size_t)b * V;
-    float* d = dlogits + (size_t)b * V;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b = blockIdx.x;
+    if (rows_per_step) { t += b / rows_per_step; b = b % rows_per_step; }
+    const float* x = logits + (size_t)blockIdx.x * V;
+    float* d = dlogits + (size_t)blockIdx.x * V;
     float m = -INFINITY;
     int mi = 0x7fffffff;
     for (int i = threadIdx.x; i < V; i += kCeThreads) {
@@ -893,6 +914,8 @@ __global__ void fill_kernel(float* x, float v, size_t n) {
 // ------------------------------------------------------------------------------------------ state
 enum Var { vEmb = 0, vIa1W, vIa1B, vIa2W, vIa2B, vIb1W, vIb1B, vIb2W, vIb2B, vA1aW, vA1aB, vA1bW, vA1bB, vA2W, vLW, vLB,
            vD1W, vD1B, vD2W, vD2B, kNumVars };
+// names of the 2-layer graph; the 1-layer variants of initialize / attend / decode (model.py:362-371, 401-414, 442-447)
+// reuse the first-layer slots under the reference's names for them and leave the second-layer slots empty (fill_layout)
 const char* kVarNames[kNumVars] = {
     "word_embedding/weights", "initialize/fc_a1/kernel", "initialize/fc_a1/bias", "initialize/fc_a2/kernel",
     "initialize/fc_a2/bias", "initialize/fc_b1/kernel", "initialize/fc_b1/bias", "initialize/fc_b2/kernel",
@@ -907,6 +930,8 @@ struct TrainState {
     size_t off[kNumVars + 1];
     int rows[kNumVars], cols[kNumVars];
     bool regularised[kNumVars];
+    const char* names[kNumVars];
+    int present[kNumVars], num_present = 0;   // slots in use, in enumeration order (sat_train_var)
     // stashes (index [t])
     std::vector<float*> T1, q, hd, alpha, z, lstm_in, acts, c, h_out, h_state, expd, t1, td, dlogits, emb;
     float *ctxd = nullptr, *temp = nullptr, *e = nullptr, *G = nullptr, *logits = nullptr;
@@ -941,6 +966,19 @@ struct TrainState {
     std::vector<float*> dys[4];            // [t] slices of dY_all per layer (decode/fc_2 uses dlogits)
     uint8_t *tc_sx = nullptr, *tc_sw = nullptr;   // packed X_all^T / packed dY_all
     bool tc_stack = false;
+    // decode layers of all T steps at once (teacher forcing: nothing in the recurrence consumes the logits, so the two
+    // layers and their input gradients are [T*B]-row products after / before the time loops instead of 4 T products
+    // of B rows that each stream the whole weight matrix)
+    bool dec_all = false;
+    int all_rt = 0, all_rows = 0;                 // row tile of the stacked rows, rows rounded up to it
+    float *logits_all = nullptr, *dexp_all = nullptr;
+    uint8_t* tc_vx_all = nullptr;
+    // the [B*L]-row products of attend/fc_1a are outside the recurrence (forward: T1[t] needs only ctx and the mask of
+    // step t; backward: nothing waits for dW1a): they run on a second, low-priority stream beside the batch-row work
+    // of the time loops, joined through events (graph edges once the step is captured)
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> ev;          // [0] fork, [1] join, then T x {T1 ready, scorer backward done, dtemp packed}
+    float* dtemp2 = nullptr;              // second d temp buffer: the scorer backward of step t-1 beside the product of step t
     sat_handle* handle = nullptr;
     float* loss_acc = nullptr;   // [0] ce, [1] accuracy, [2] attention, [3] reg, [4] grad norm^2, [5] out-of-vocabulary ids seen
                                  // by the last forward pass ([6] the same, accumulated since sat_train_init)
@@ -966,6 +1004,8 @@ void train_free(void* p) {
     for (void* b : s->all) cudaFree(b);
     for (auto& g : s->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+    if (s->side) cudaStreamDestroy(s->side);
     delete s;
 }
 
@@ -975,35 +1015,55 @@ void train_free(void* p) {
 // the dropout generator on the host: lets a CPU test pin it against the numpy copy in oracle/train_ref.py
 extern "C" float sat_train_rng_uniform(uint64_t seed, uint64_t stream, uint64_t index) { return rng_u24(seed, stream, index); }
 
-extern "C" int sat_train_num_vars(sat_handle* h) {
-    (void)h;
-    return kNumVars;
-}
-
 static void fill_layout(TrainState* s) {
     const sat_dims& d = s->d;
     const int D = d.dim_ctx, E = d.dim_embedding, H = d.num_lstm_units, A = d.dim_attend_layer, Dd = d.dim_decode_layer,
-              I = d.dim_initalize_layer, V = d.vocabulary_size;
-    const int shp[kNumVars][2] = {{V, E}, {D, I}, {1, I}, {I, H}, {1, H}, {D, I}, {1, I}, {I, H}, {1, H}, {D, A}, {1, A}, {H, A},
-                                  {1, A}, {A, 1}, {D + E + H, 4 * H}, {1, 4 * H}, {H + D + E, Dd}, {1, Dd}, {Dd, V}, {1, V}};
+              I = d.dim_initalize_layer, V = d.vocabulary_size, L = d.num_ctx;
+    int shp[kNumVars][2] = {{V, E}, {D, I}, {1, I}, {I, H}, {1, H}, {D, I}, {1, I}, {I, H}, {1, H}, {D, A}, {1, A}, {H, A},
+                            {1, A}, {A, 1}, {D + E + H, 4 * H}, {1, 4 * H}, {H + D + E, Dd}, {1, Dd}, {Dd, V}, {1, V}};
+    for (int i = 0; i < kNumVars; ++i) s->names[i] = kVarNames[i];
+    auto set = [&](int v, const char* name, int r, int c) { s->names[v] = name; shp[v][0] = r; shp[v][1] = c; };
+    if (d.num_initalize_layers == 1) {        // memory = fc_a(mean), output = fc_b(mean)                 model.py:362-371
+        set(vIa1W, "initialize/fc_a/kernel", D, H); set(vIa1B, "initialize/fc_a/bias", 1, H);
+        set(vIb1W, "initialize/fc_b/kernel", D, H); set(vIb1B, "initialize/fc_b/bias", 1, H);
+        set(vIa2W, nullptr, 0, 0); set(vIa2B, nullptr, 0, 0); set(vIb2W, nullptr, 0, 0); set(vIb2B, nullptr, 0, 0);
+    }
+    if (d.num_attend_layers == 1) {           // logits = fc_a(ctx)[BL,1] + fc_b(h)[B,L], both without bias model.py:401-414
+        set(vA1aW, "attend/fc_a/kernel", D, 1); set(vA1bW, "attend/fc_b/kernel", H, L);
+        set(vA1aB, nullptr, 0, 0); set(vA1bB, nullptr, 0, 0); set(vA2W, nullptr, 0, 0);
+    }
+    if (d.num_decode_layers == 1) {           // logits = fc(expanded)                                    model.py:442-447
+        set(vD1W, "decode/fc/kernel", H + D + E, V); set(vD1B, "decode/fc/bias", 1, V);
+        set(vD2W, nullptr, 0, 0); set(vD2B, nullptr, 0, 0);
+    }
     size_t o = 0;
+    s->num_present = 0;
     for (int i = 0; i < kNumVars; ++i) {
         s->off[i] = o;
         s->rows[i] = shp[i][0];
         s->cols[i] = shp[i][1];
         o += ((size_t)shp[i][0] * shp[i][1] + 31) / 32 * 32;
+        if (s->names[i]) s->present[s->num_present++] = i;
         // L2-regularised: embedding + every dense kernel, not the LSTM kernel, not biases (nn.py:33-37)
-        s->regularised[i] = (i == vEmb) || (shp[i][0] > 1 && i != vLW) || i == vA2W;
+        s->regularised[i] = s->names[i] && ((i == vEmb) || (shp[i][0] > 1 && i != vLW));
     }
     s->off[kNumVars] = o;
+}
+
+extern "C" int sat_train_num_vars(sat_handle* h) {
+    if (!h) return kNumVars;
+    TrainState tmp;
+    tmp.d = *sat_handle_dims(h);
+    fill_layout(&tmp);
+    return tmp.num_present;
 }
 
 extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop_rate, float lstm_drop_rate,
                               float attention_loss_factor, float fc_kernel_regularizer_scale) {
     if (!h) return sat_fail(SAT_ERR_INVALID, "null handle");
     const sat_dims* dp = sat_handle_dims(h);
-    if (dp->num_attend_layers != 2 || dp->num_decode_layers != 2 || dp->num_initalize_layers != 2)
-        return sat_fail(SAT_ERR_UNSUPPORTED, "the training step supports the 2-layer attend/decode/initialize graph only");
+    for (int nl : {dp->num_attend_layers, dp->num_decode_layers, dp->num_initalize_layers})
+        if (nl != 1 && nl != 2) return sat_fail(SAT_ERR_UNSUPPORTED, "attend/decode/initialize have 1 or 2 layers (got %d)", nl);
     if (B < 1 || T < 1) return sat_fail(SAT_ERR_INVALID, "bad B/T");
     TCK(cudaSetDevice(sat_handle_device(h)));
     void** slot = sat_handle_train_slot(h);
@@ -1039,13 +1099,24 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
     A1(&s->dalpha, BL); A1(&s->dtemp, BL * A); A1(&s->dq, B * A); A1(&s->dhd, B * H); A1(&s->dbuf, B * (D + E + I + H));
     A1(&s->loss_acc, 8);
     s->handle = h;
-    s->tc_ok = (D % 128 == 0) && (A % 128 == 0) && (BL % 128 == 0);
+    const bool att2 = d.num_attend_layers == 2, dec2 = d.num_decode_layers == 2;
+    s->tc_ok = att2 && (D % 128 == 0) && (A % 128 == 0) && (BL % 128 == 0);
     if (s->tc_ok) {
         float* f = nullptr;   // (sizes in floats: a packed operand takes 4 bytes per element, like fp32)
         A1(&f, BL * D); s->tc_xpa = reinterpret_cast<uint8_t*>(f);
         A1(&f, BL * (A > D ? A : D)); s->tc_wbig = reinterpret_cast<uint8_t*>(f);
         A1(&f, D * A); s->tc_w1a = reinterpret_cast<uint8_t*>(f);
         A1(&s->tc_b1a, A);
+        A1(&s->dtemp2, BL * A);
+        int lo_pri = 0, hi_pri = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        if (rc == SAT_OK && cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo_pri) == cudaSuccess) {
+            s->ev.assign(2 + 3 * (size_t)T, nullptr);
+            for (auto& e : s->ev)
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = sat_fail(SAT_ERR_CUDA, "event creation failed");
+        } else {
+            s->side = nullptr;
+        }
     }
     {
         const size_t XLs = D + E + H, XDs = H + D + E;
@@ -1056,7 +1127,9 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
         for (int i = 0; i < 4; ++i) {
             TrainState::TcLayer& l = s->tcl[i];
             l.var_w = vw[i]; l.var_b = vb[i]; l.K = (int)Ks[i]; l.N = (int)Ns[i];
-            l.fwd = (Ks[i] % 64 == 0) && s->tc_rt <= 256;
+            // (the 1-layer variants of attend / decode stay on the CUDA-core products: they are not the shipped graph)
+            const bool used = i == 1 || (i == 0 ? att2 : dec2);
+            l.fwd = used && (Ks[i] % 64 == 0) && s->tc_rt <= 256;
             l.dx = l.fwd && (Ns[i] % 64 == 0);
             float* f = nullptr;
             const size_t npad = (Ns[i] + 127) / 128 * 128, kpad = (Ks[i] + 127) / 128 * 128;
@@ -1090,8 +1163,22 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
                 xmax = TB * kp > xmax ? TB * kp : xmax;
                 wmax = TB * np > wmax ? TB * np : wmax;
             }
+            s->dec_all = dec2 && s->tc_vk > 0;
+            s->all_rt = TB >= 128 ? 128 : (int)TB;
+            s->all_rows = (int)((TB + s->all_rt - 1) / s->all_rt * s->all_rt);
+            if (s->dec_all)   // packed rows of expanded / td / d td, all T steps
+                for (int i = 2; i < 4; ++i) {
+                    const size_t kp = (Ks[i] + 127) / 128 * 128;
+                    xmax = (size_t)s->all_rows * kp > xmax ? (size_t)s->all_rows * kp : xmax;
+                }
             A1(&f, xmax); s->tc_sx = reinterpret_cast<uint8_t*>(f);
             A1(&f, wmax); s->tc_sw = reinterpret_cast<uint8_t*>(f);
+            if (s->dec_all) {
+                A1(&s->logits_all, TB * V);
+                A1(&s->dexp_all, TB * XDs);
+                A1(&f, (size_t)(s->all_rows + 16) * s->tc_vk); s->tc_vx_all = reinterpret_cast<uint8_t*>(f);
+                if (rc == SAT_OK) cudaMemset(s->tc_vx_all, 0, (size_t)(s->all_rows + 16) * s->tc_vk * 4);
+            }
         }
     }
     float* cells = nullptr;
@@ -1126,8 +1213,9 @@ extern "C" int sat_train_var(sat_handle* h, int32_t i, const char** name, int64_
     TrainState* s = (TrainState*)*sat_handle_train_slot(h);
     if (!s) { tmp.d = *sat_handle_dims(h); fill_layout(&tmp); s = &tmp; }
     if (total) *total = (int64_t)s->off[kNumVars];
-    if (i < 0 || i >= kNumVars) return i == -1 ? SAT_OK : sat_fail(SAT_ERR_INVALID, "variable index %d", i);
-    if (name) *name = kVarNames[i];
+    if (i < 0 || i >= s->num_present) return i == -1 ? SAT_OK : sat_fail(SAT_ERR_INVALID, "variable index %d", i);
+    i = s->present[i];
+    if (name) *name = s->names[i];
     if (offset) *offset = (int64_t)s->off[i];
     if (rows) *rows = s->rows[i];
     if (cols) *cols = s->cols[i];
@@ -1138,7 +1226,7 @@ extern "C" int sat_train_var(sat_handle* h, int32_t i, const char** name, int64_
 // y = act(dropout?(x) W + b)
 static int dense_fwd(cudaStream_t st, const float* x, int rows, int K, const float* W, const float* b, int N, float* y, int act) {
     TCK(sgemm(st, false, false, rows, N, K, x, K, W, N, y, N, false));
-    launch_k(bias_act_kernel, GRID1D((size_t)rows * N), 256, st, y, b, rows, N, act);
+    if (b || act) launch_k(bias_act_kernel, GRID1D((size_t)rows * N), 256, st, y, b, rows, N, act);
     return SAT_OK;
 }
 // given dy (w.r.t. pre-activation): dW += x^T dy, db += colsum(dy), dx = dy W^T (if dx)
@@ -1173,12 +1261,18 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     // ------------------------------------------------------------ initialize (model.py:239-242, 358-393)
     launch_k(mean_L_kernel, dim3((D + 127) / 128, B), 128, st, s->mean, contexts, L, D);
     launch_k(dropout2d_kernel, GRID1D((size_t)B * D), 256, st, s->meand, D, s->mean, D, B, D, seed, INIT + 0, kf, 0);
-    TRET(dense_fwd(st, s->meand, B, D, P(vIa1W), P(vIa1B), I, s->ia1, 1));
-    launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, s->ia1d, I, s->ia1, I, B, I, seed, INIT + 1, kf, 0);
-    TRET(dense_fwd(st, s->ia1d, B, I, P(vIa2W), P(vIa2B), H, s->c0, 0));
-    TRET(dense_fwd(st, s->meand, B, D, P(vIb1W), P(vIb1B), I, s->ib1, 1));
-    launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, s->ib1d, I, s->ib1, I, B, I, seed, INIT + 2, kf, 0);
-    TRET(dense_fwd(st, s->ib1d, B, I, P(vIb2W), P(vIb2B), H, s->h0, 0));
+    const bool init2 = d.num_initalize_layers == 2, att2 = d.num_attend_layers == 2, dec2 = d.num_decode_layers == 2;
+    if (init2) {
+        TRET(dense_fwd(st, s->meand, B, D, P(vIa1W), P(vIa1B), I, s->ia1, 1));
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, s->ia1d, I, s->ia1, I, B, I, seed, INIT + 1, kf, 0);
+        TRET(dense_fwd(st, s->ia1d, B, I, P(vIa2W), P(vIa2B), H, s->c0, 0));
+        TRET(dense_fwd(st, s->meand, B, D, P(vIb1W), P(vIb1B), I, s->ib1, 1));
+        launch_k(dropout2d_kernel, GRID1D((size_t)B * I), 256, st, s->ib1d, I, s->ib1, I, B, I, seed, INIT + 2, kf, 0);
+        TRET(dense_fwd(st, s->ib1d, B, I, P(vIb2W), P(vIb2B), H, s->h0, 0));
+    } else {   // one layer each, no activation (model.py:362-371)
+        TRET(dense_fwd(st, s->meand, B, D, P(vIa1W), P(vIa1B), H, s->c0, 0));
+        TRET(dense_fwd(st, s->meand, B, D, P(vIb1W), P(vIb1B), H, s->h0, 0));
+    }
 
     const bool tc = s->tc_ok && sat_handle_train_tc(s->handle);
     const int lmode = sat_handle_layout_mode(s->handle);
@@ -1200,7 +1294,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             }
         }
     }
-    const bool tcv = tcb && s->tc_vk > 0;
+    const bool tcv = tcb && dec2 && s->tc_vk > 0;
     if (tcv) {   // decode/fc_2's W^T (rows Dd, K = V rounded up) for its input gradient
         sat::PackJob job{P(vD2W), nullptr, V, V, Dd, 128, s->tc_vw, s->tc_vk / 64};
         TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
@@ -1232,10 +1326,30 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         return true;
     };
     int trc = SAT_OK;
+    // second stream for the fc_1a products (SAT_TRAIN_SIDE=0: everything in order on the caller's stream)
+    static const int side_env = []() { const char* e = getenv("SAT_TRAIN_SIDE"); return (e && e[0] == '0') ? 0 : 1; }();
+    auto hand = [&](cudaStream_t from, cudaStream_t to, cudaEvent_t e) -> cudaError_t {   // `to` continues after `from`'s work so far
+        cudaError_t ce = cudaEventRecord(e, from);
+        return ce != cudaSuccess ? ce : cudaStreamWaitEvent(to, e, 0);
+    };
+    auto evT1 = [&](int t) { return s->ev[2 + 3 * t]; };
+    auto evAb = [&](int t) { return s->ev[3 + 3 * t]; };
+    auto evRp = [&](int t) { return s->ev[4 + 3 * t]; };
     const bool stack = tcb && s->tc_stack;   // weight gradients of the four batch-row layers after the time loop
+    static const int dec_all_env = []() { const char* e = getenv("SAT_TRAIN_DEC_ALL"); return (e && e[0] == '0') ? 0 : 1; }();
+    const bool dec_all = stack && tcv && s->dec_all && dec_all_env;   // decode layers of all T steps as [T*B]-row products
+    const int TBr = T * B;
+    auto all_splits = [&](int n_out, int K) {
+        const int tiles = ((n_out + 127) / 128) * (s->all_rows / (s->all_rt > 0 ? s->all_rt : 1));
+        int sp = 1;
+        while (sp * 2 <= 8 && tiles * sp * 2 <= 148 && sp * 2 <= K / 64) sp *= 2;
+        return sp;
+    };
     // scorer: fused one-pass kernels when the rows are float4-addressable (every buffer involved is a cudaMalloc'd
     // [rows, A] matrix or an A-vector, so A % 4 == 0 gives 16-byte alignment)
-    const bool att_fused = (A & 3) == 0 && ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads)) & 15) == 0;
+    const bool att_fused = att2 && (A & 3) == 0 && ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads)) & 15) == 0;
+    const bool side = tc && att_fused && s->side && side_env;
+    cudaStream_t sd = side ? s->side : st;
     int ab_chunks = 1, ab_rows = L, ab_wave = 0;
     {
         const int gx = (A / 4 + kAbCT - 1) / kAbCT;
@@ -1258,13 +1372,27 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         ab_rows = (L + ab_chunks - 1) / ab_chunks;
         ab_chunks = (L + ab_rows - 1) / ab_rows;
     }
+    if (side) {   // T1[t] = tanh(drop_t(ctx) W1a + b1a) for every step, queued ahead on the second stream
+        TCK(hand(st, sd, s->ev[0]));
+        for (int t = 0; t < T; ++t) {
+            sat::PackJob job{contexts, nullptr, D, D, BL, 128, s->tc_xpa};
+            const sat::DropSpec drop{seed, ST(t, 0), kf};
+            TCK(sat::pack_rows_launch(&job, 1, lmode, sd, &drop, PDLK));
+            TRET(sat_dense_packed(s->handle, s->tc_xpa, BL, 128, D, s->tc_w1a, s->tc_b1a, A, sat::kEpiBiasTanh, s->T1[t], A, 0, 1, sd));
+            TCK(cudaEventRecord(evT1(t), sd));
+        }
+    }
     // ------------------------------------------------------------ forward through time (model.py:258-312)
     for (int t = 0; t < T; ++t) {
         const float* h_out_prev = t ? s->h_out[t - 1] : s->h0;
         const float* h_state_prev = t ? s->h_state[t - 1] : s->h0;
         const float* c_prev = t ? s->c[t - 1] : s->c0;
         // attend (model.py:395-436)
-        if (tc) {   // T1 = tanh(drop(ctx) W1a + b1a) on the tcgen05 dense kernel: the context dropout is applied while the
+        if (!att2) {   // one layer: e = drop(ctx) wa [BL] + drop(h) Wb [B, L]
+            launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
+            launch_k(rowdot_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->ctxd, P(vA1aW), BL, D);
+        } else if (side) {
+        } else if (tc) {   // T1 = tanh(drop(ctx) W1a + b1a) on the tcgen05 dense kernel: the context dropout is applied while the
                     // rows are packed (no fp32 dropped copy), bias + tanh fused in the epilogue
             sat::PackJob job{contexts, nullptr, D, D, BL, 128, s->tc_xpa};
             const sat::DropSpec drop{seed, ST(t, 0), kf};
@@ -1275,9 +1403,14 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             TRET(dense_fwd(st, s->ctxd, BL, D, P(vA1aW), P(vA1aB), A, s->T1[t], 1));
         }
         launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
-        if (tc_fwd(0, s->hd[t], sat::kEpiBiasTanh, s->q[t], &trc)) { TRET(trc); }
+        if (!att2) {
+            TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), nullptr, L, s->dalpha, 0));   // (dalpha: backward scratch, free here)
+            launch_k(copy2d_kernel, GRID1D((size_t)BL), 256, st, s->e, L, s->dalpha, L, B, L, 1);
+        } else if (tc_fwd(0, s->hd[t], sat::kEpiBiasTanh, s->q[t], &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
-        if (att_fused) {
+        if (side) TCK(cudaStreamWaitEvent(st, evT1(t), 0));
+        if (!att2) {
+        } else if (att_fused) {
             launch_k(att_logits_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->T1[t], s->q[t], P(vA2W), B, L, A, seed, ST(t, 2), kf);
         } else {
             launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
@@ -1294,21 +1427,44 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         // LSTM with DropoutWrapper (model.py:228-236, 276-279)
         // lstm_in = [ drop_in(concat(z, emb)) | h_state_prev ]
         launch_k(concat3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->lstm_in[t], XL, s->z[t], D, s->emb[t], E, h_state_prev, H, D + E, B,
-                                                                    seed, ST(t, 3), kl);
+                                                                    seed, ST(t, 3), kl, 0);
         if (tc_fwd(1, s->lstm_in[t], sat::kEpiNone, s->acts[t], &trc)) { TRET(trc); }   // (bias and gates: next kernel)
         else TCK(sgemm(st, false, false, B, 4 * H, XL, s->lstm_in[t], XL, P(vLW), 4 * H, s->acts[t], 4 * H, false));
         launch_k(lstm_fwd_kernel, GRID1D((size_t)B * H), 256, st, s->acts[t], P(vLB), c_prev, s->c[t], s->h_out[t], s->h_state[t], B, H, seed,
                  ST(t, 5), ST(t, 4), kl);
         // decode (model.py:282-287, 438-459)
+        if (dec_all) continue;   // (the decode layers of every step follow the loop)
         launch_k(concat3_drop_kernel, GRID1D((size_t)B * XD), 256, st, s->expd[t], XD, s->h_out[t], H, s->z[t], D, s->emb[t], E, XD, B,
-                                                                    seed, ST(t, 6), kf);
-        if (tc_fwd(2, s->expd[t], sat::kEpiBiasTanh, s->t1[t], &trc)) { TRET(trc); }
-        else TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), Dd, s->t1[t], 1));
-        launch_k(dropout2d_kernel, GRID1D((size_t)B * Dd), 256, st, s->td[t], Dd, s->t1[t], Dd, B, Dd, seed, ST(t, 7), kf, 0);
-        if (tc_fwd(3, s->td[t], sat::kEpiBias, s->logits, &trc)) { TRET(trc); }
-        else TRET(dense_fwd(st, s->td[t], B, Dd, P(vD2W), P(vD2B), V, s->logits, 0));
+                                                                    seed, ST(t, 6), kf, 0);
+        if (!dec2) {
+            TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), V, s->logits, 0));
+        } else {
+            if (tc_fwd(2, s->expd[t], sat::kEpiBiasTanh, s->t1[t], &trc)) { TRET(trc); }
+            else TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), Dd, s->t1[t], 1));
+            launch_k(dropout2d_kernel, GRID1D((size_t)B * Dd), 256, st, s->td[t], Dd, s->t1[t], Dd, B, Dd, seed, ST(t, 7), kf, 0);
+            if (tc_fwd(3, s->td[t], sat::kEpiBias, s->logits, &trc)) { TRET(trc); }
+            else TRET(dense_fwd(st, s->td[t], B, Dd, P(vD2W), P(vD2B), V, s->logits, 0));
+        }
         // masked cross entropy + accuracy, and d loss / d logits (model.py:292-305, 316-318, 332-334)
-        launch_k(ce_kernel, B, kCeThreads, st, s->logits, s->dlogits[t], sentences, T, t, masks, V, inv_msum, s->loss_acc);
+        launch_k(ce_kernel, B, kCeThreads, st, s->logits, s->dlogits[t], sentences, T, t, masks, V, inv_msum, s->loss_acc, 0);
+    }
+    if (dec_all) {   // decode of all T steps (model.py:282-305): the per-step stashes are contiguous = [T*B, .] matrices
+        launch_k(concat3_drop_kernel, GRID1D((size_t)TBr * XD), 256, st, s->expd[0], XD, s->h_out[0], H, s->z[0], D, s->emb[0], E, XD, TBr,
+                                                                      seed, ST(0, 6), kf, B);
+        {
+            sat::PackJob job{s->expd[0], nullptr, XD, XD, TBr, s->all_rt, s->tc_sx};
+            TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
+            TRET(sat_dense_packed(s->handle, s->tc_sx, TBr, s->all_rt, XD, s->tcl[2].w, s->tcl[2].b, Dd, sat::kEpiBiasTanh, s->t1[0], Dd, 0,
+                                  all_splits(Dd, XD), st));
+        }
+        launch_k(dropout_steps_kernel, GRID1D((size_t)TBr * Dd), 256, st, s->td[0], s->t1[0], (size_t)TBr * Dd, (size_t)B * Dd, seed, ST(0, 7), kf);
+        {
+            sat::PackJob job{s->td[0], nullptr, Dd, Dd, TBr, s->all_rt, s->tc_sx};
+            TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
+            TRET(sat_dense_packed(s->handle, s->tc_sx, TBr, s->all_rt, Dd, s->tcl[3].w, s->tcl[3].b, V, sat::kEpiBias, s->logits_all, V, 0,
+                                  all_splits(V, Dd), st));
+        }
+        launch_k(ce_kernel, TBr, kCeThreads, st, s->logits_all, s->dlogits[0], sentences, T, 0, masks, V, inv_msum, s->loss_acc, B);
     }
     // attention coverage loss (model.py:320-326) and L2 regulariser (model.py:328)
     launch_k(coverage_loss_kernel, 64, 256, st, s->datt, s->att, BL, s->att_factor, inv_gbl, s->loss_acc);
@@ -1323,6 +1479,18 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     TCK(cudaMemsetAsync(s->dh_out, 0, (size_t)B * H * sizeof(float), st));    // d loss / d h_out[t] from step t+1's attend
     TCK(cudaMemsetAsync(s->dh_state, 0, (size_t)B * H * sizeof(float), st));  // d loss / d h_state[t] from step t+1's LSTM
     TCK(cudaMemsetAsync(s->dc, 0, (size_t)B * H * sizeof(float), st));
+    if (dec_all) {   // d logits -> d td (x tanh', dropout) -> d expanded, for all T steps
+        sat::PackJob job{s->dlogits[0], nullptr, V, V, TBr, s->all_rt, s->tc_vx_all, s->tc_vk / 64};
+        TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
+        TRET(sat_dense_packed(s->handle, s->tc_vx_all, TBr, s->all_rt, s->tc_vk, s->tc_vw, nullptr, Dd, sat::kEpiNone, s->dys[2][0], Dd, 0,
+                              all_splits(Dd, s->tc_vk), st));
+        launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)TBr * Dd), 256, st, s->dys[2][0], s->t1[0], (size_t)TBr * Dd, seed, ST(0, 7), kf,
+                 (size_t)B * Dd);
+        sat::PackJob job2{s->dys[2][0], nullptr, Dd, Dd, TBr, s->all_rt, s->tc_sx};
+        TCK(sat::pack_rows_launch(&job2, 1, lmode, st, nullptr, PDLK));
+        TRET(sat_dense_packed(s->handle, s->tc_sx, TBr, s->all_rt, Dd, s->tcl[2].wT, nullptr, XD, sat::kEpiNone, s->dexp_all, XD, 0,
+                              all_splits(XD, Dd), st));
+    }
     for (int t = T - 1; t >= 0; --t) {
         const float* h_state_prev = t ? s->h_state[t - 1] : s->h0;
         const float* c_prev = t ? s->c[t - 1] : s->c0;
@@ -1332,6 +1500,11 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         float* dG = stack ? s->dys[1][t] : s->dG;
         float* dq = stack ? s->dys[0][t] : s->dq;
         bool vdx = false;
+        const float* dexp = dec_all ? s->dexp_all + (size_t)t * B * XD : s->dexp;
+        if (dec_all) {
+        } else if (!dec2) {
+            TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), V, s->dlogits[t], Gd(vD1W), Gd(vD1B), s->dexp));
+        } else {
         if (tcv) {   // dtd = dlogits W2^T on the tensor cores (ragged K = V: zero-padded last K block)
             sat::PackJob job{s->dlogits[t], nullptr, V, V, B, s->tc_rt, s->tc_vx, s->tc_vk / 64};
             TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
@@ -1342,11 +1515,12 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         if (stack) { if (!vdx) TCK(sgemm(st, false, true, B, Dd, V, s->dlogits[t], V, P(vD2W), V, dtd, Dd, false)); }
         else if (vdx) TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), nullptr));
         else TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), dtd));
-        launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, s->t1[t], (size_t)B * Dd, seed, ST(t, 7), kf);
+        launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, s->t1[t], (size_t)B * Dd, seed, ST(t, 7), kf, (size_t)0);
         if (tc_dx(2, dtd, s->dexp, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
         else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), s->dexp));
+        }
         // drop(dexp) = [dh_out (+=) | dz (=) | demb (=)]
-        launch_k(split3_drop_kernel, GRID1D((size_t)B * XD), 256, st, s->dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, s->demb, E, 0, XD, seed,
+        launch_k(split3_drop_kernel, GRID1D((size_t)B * XD), 256, st, dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, s->demb, E, 0, XD, seed,
                                                                    ST(t, 6), kf);
         // h_out = drop_out(h_raw), h_state = drop_state(h_raw)
         launch_k(lstm_bwd_kernel, GRID1D((size_t)B * H), 256, st, dG, s->dc, s->dh_out, s->dh_state, s->acts[t], s->c[t], c_prev, B, H, seed,
@@ -1360,10 +1534,17 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         // attention: context vector, softmax, scorer
         launch_k(context_bwd_kernel, (BL * 32 + 255) / 256, 256, st, s->dalpha, s->dz, contexts, s->datt, B, L, D, masks, T, t);
         launch_k(softmax_bwd_kernel, (B * 32 + 255) / 256, 256, st, s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
+        if (!att2) {   // de = dalpha [B, L]: dwa += drop(ctx)^T de, dWb += drop(h)^T de, d drop(h) = de Wb^T
+            launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
+            launch_k(colsum_kernel, dim3((D + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aW), s->ctxd, BL, D, s->dalpha);
+            TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), L, s->dalpha, Gd(vA1bW), nullptr, s->dhd));
+        } else {
+        float* const dtemp = (side && (t & 1)) ? s->dtemp2 : s->dtemp;
         if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
             TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));
+            if (side && t + 2 < T) TCK(cudaStreamWaitEvent(st, evRp(t + 2), 0));   // this d temp buffer has been packed
             launch_k(ab_wave ? att_bwd_fused_wave_kernel : att_bwd_fused_kernel, dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B),
-                     kAbRG * kAbCT, st, s->dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A,
+                     kAbRG * kAbCT, st, dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A,
                      ab_rows, seed, ST(t, 2), kf);
         } else {
             launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
@@ -1378,9 +1559,11 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             // packed weight; split-K over an 8-CTA cluster, accumulated into the gradient in the epilogue
             // (the context dropout mask is re-applied while ctx is packed: mask index row * D + column, as in the forward pass)
             const sat::DropSpec drop{seed, ST(t, 0), kf};
-            TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, st, &drop, PDLK));
-            TCK(sat::lin_repack_weight(s->dtemp, BL, A, 0, s->tc_wbig, lmode, st, nullptr, PDLK));
-            TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, st, 1));
+            TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, sd, &drop, PDLK));   // (needs nothing of this step)
+            if (side) TCK(hand(st, sd, evAb(t)));
+            TCK(sat::lin_repack_weight(dtemp, BL, A, 0, s->tc_wbig, lmode, sd, nullptr, PDLK));
+            if (side) TCK(cudaEventRecord(evRp(t), sd));
+            TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, sd, 1));
             if (!att_fused) launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aB), s->dtemp, BL, A, nullptr);
         } else {
             launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
@@ -1389,9 +1572,11 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         launch_k(tanh_bwd_kernel, GRID1D((size_t)B * A), 256, st, dq, s->q[t], (size_t)B * A);
         if (tc_dx(0, dq, s->dhd, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
         else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
+        }
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
         launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
     }
+    if (side) TCK(hand(sd, st, s->ev[1]));   // join: every fc_1a weight-gradient product has been accumulated
     if (stack) {
         // dW += X_all^T dY_all, db += colsum(dY_all) for attend/fc_1b, lstm, decode/fc_1, decode/fc_2 (the repack kernel
         // transposes: X_all [T*B, K] read as a "[K' x n_out'] weight" is the packed operand X_all^T, row tile 128)
@@ -1413,12 +1598,17 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     // h0 is both h_out[-1] (attend of step 0) and h_state[-1] (LSTM of step 0); c0 receives dc
     launch_k(copy2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dh_state, H, B, H, 1);
     float* dmid = s->dbuf + (size_t)B * D;  // [B, I]
+    if (!init2) {
+        TRET(dense_bwd(st, s->meand, B, D, P(vIb1W), H, s->dh_out, Gd(vIb1W), Gd(vIb1B), nullptr));
+        TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), H, s->dc, Gd(vIa1W), Gd(vIa1B), nullptr));
+    } else {
     TRET(dense_bwd(st, s->ib1d, B, I, P(vIb2W), H, s->dh_out, Gd(vIb2W), Gd(vIb2B), dmid));
-    launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ib1, (size_t)B * I, seed, INIT + 2, kf);
+    launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ib1, (size_t)B * I, seed, INIT + 2, kf, (size_t)0);
     TRET(dense_bwd(st, s->meand, B, D, P(vIb1W), I, dmid, Gd(vIb1W), Gd(vIb1B), nullptr));
     TRET(dense_bwd(st, s->ia1d, B, I, P(vIa2W), H, s->dc, Gd(vIa2W), Gd(vIa2B), dmid));
-    launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ia1, (size_t)B * I, seed, INIT + 1, kf);
+    launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ia1, (size_t)B * I, seed, INIT + 1, kf, (size_t)0);
     TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), I, dmid, Gd(vIa1W), Gd(vIa1B), nullptr));
+    }
     TCK(cudaGetLastError());
     TCK(cudaMemcpyAsync(losses, s->loss_acc, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return SAT_OK;

@@ -251,3 +251,36 @@ def test_save_in_the_reference_format_and_resume(tmp_path):
     m3 = sat_b200.CaptionGenerator(m.config)
     assert m3.load(None, path) == 20
     assert m3.decode_loop(ctx, ocfg.max_caption_length).shape == (4, ocfg.max_caption_length)
+
+
+@pytest.mark.parametrize("layers", [(1, 1, 1), (1, 2, 2), (2, 1, 2), (2, 2, 1)])
+@pytest.mark.parametrize("seed", [0, 13])
+def test_one_layer_variants_of_attend_decode_initialize(layers, seed):
+    """config.py:15-19 lets each of initialize / attend / decode have one layer instead of two (model.py:362-371,
+    401-414, 442-447; different variable names and, for attend, no biases and no hidden layer).  Same bars as the
+    shipped graph: losses to 1e-4, every gradient to 2e-4, with dropout off and on; and one optimizer step."""
+    la, ld, li = layers
+    dims = dict(TDIMS, num_attend_layers=la, num_decode_layers=ld, num_initalize_layers=li)
+    ocfg, w, m, ctx, sent, masks = setup(B=4, seed=5, dims=dims)
+    names = set(m.train_state_dict("grads"))
+    assert names == set(w), names ^ set(w)
+    ref_l, ref_g = TR.loss_and_grads(ocfg, w, ctx, sent, masks, seed if seed else None, reg_in_grad=False)
+    losses = m.train_forward_backward(ctx, sent, masks, seed=seed).cpu().numpy()
+    ce, acc, att, reg = [float(x) for x in losses]
+    assert abs(ce - ref_l["cross_entropy_loss"]) < 1e-4 * ref_l["cross_entropy_loss"]
+    assert abs(att - ref_l["attention_loss"]) < 1e-4 * ref_l["attention_loss"] + 1e-9
+    assert abs(reg - ref_l["reg_loss"]) < 1e-4 * ref_l["reg_loss"]
+    grad_check(m, ref_g, 2e-4, floor_rel=1e-3)
+    # clip + Adam on top (reg gradient included), against the oracle's update of every variable
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    _, g = TR.loss_and_grads(ocfg, w64, ctx, sent, masks, 100, reg_in_grad=True)
+    zeros = lambda: {k: np.zeros_like(v) for k, v in w64.items()}
+    new_w, _, _, norm = TR.clip_and_adam(w64, g, zeros(), zeros(), 1, lr=1e-4, clip=5.0)
+    out = m.train_step(ctx, sent, masks, seed=100)
+    assert abs(out["gradient_norm"] - norm) < 2e-4 * norm
+    got = {k: v.detach().cpu().numpy() for k, v in m.train_state_dict("params").items()}
+    for k in w64:
+        np.testing.assert_allclose(got[k].reshape(w64[k].shape), new_w[k], rtol=0, atol=3e-6)
+    # the trained variables drive the decode kernels of the same handle
+    assert m.sync_inference_weights() == 0
+    assert m.decode_loop(ctx, ocfg.max_caption_length).shape == (4, ocfg.max_caption_length)
