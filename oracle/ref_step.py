@@ -12,7 +12,10 @@ ships no tests, golden vectors or known-answer files for this path (SURVEY.md
 the GraphDef the reference itself recorded in
 ``summary/events.out.tfevents.1535421942.CLARK-CL-LI`` (variable names/shapes,
 concat orders, LSTM gate order and forget bias, dropout formula) — see
-``tests/golden/graph_fixture.json`` and ``tests/test_oracle_structure.py``.
+``tests/golden/graph_fixture.json`` and ``tests/test_oracle_structure.py`` — and
+*numerically* only through the scalars of the one training step that file
+recorded (loss identities and brackets, ``tests/test_oracle_recorded_step.py``):
+no tensor of the reference is available to compare with.
 
 Every function cites the reference lines it restates (paths are relative to
 ``/root/reference``).  Arithmetic is numpy; ``dtype`` selects fp32 (the

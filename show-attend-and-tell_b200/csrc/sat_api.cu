@@ -73,6 +73,7 @@ struct GraphEntry {
 struct sat_handle {
     sat_dims d;
     int dev = 0, num_sms = 0, smem_optin = 0;
+    int opt_prologue1 = 1;   // mean of the contexts taken by the packing pass of the projection ("prologue1")
     int opt_gemm = 1, opt_layout = 0, opt_graphs = 1, opt_hoist = 1, opt_coop = 1, opt_xpack = 1;
     int opt_l2_w = 2, opt_l2_t = 1, opt_l2_ctx = 1;  // weights evict_last; both attention streams evict_first
     bool weights_locked = false;
@@ -399,6 +400,7 @@ extern "C" int sat_set_option(sat_handle* h, const char* key, int64_t value) {
         h->opt_layout = (int)value;
     } else if (k == "graphs") h->opt_graphs = (int)value;
     else if (k == "hoist") { h->opt_hoist = (int)value; h->prep_ctx = nullptr; }
+    else if (k == "prologue1") h->opt_prologue1 = (int)value;
     else if (k == "coop") h->opt_coop = (int)value;
     else if (k == "xpack") h->opt_xpack = (int)value;
     else if (k == "pa") h->opt_pa = (int)value;
@@ -736,7 +738,9 @@ int sat_dense_packed(sat_handle* h, const uint8_t* x_pa, int rows, int row_tile,
 
 // --------------------------------------------------------------- contexts
 // attend fc_1a over every location (model.py:417-420): T1 = tanh(ctx2d * W1a + b1a)
-static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStream_t st) {
+// mean_done (optional): the caller also wants the mean over the L locations (initialize); set to true if the packing
+// pass produced it on the way (one pass over the conv features for both)
+static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStream_t st, bool* mean_done = nullptr) {
     if (h->d.num_attend_layers != 2) return SAT_OK;
     h->cur_tag = kTagProj;
     LinProblem P;
@@ -745,8 +749,13 @@ static int project_contexts(sat_handle* h, const float* ctx, int n_img, cudaStre
     if (h->opt_gemm != 0 && h->opt_pa && (h->d.dim_ctx % 64) == 0) {
         // thousands of rows: converting them inside the GEMM's producer warps is latency bound, so the
         // contexts are packed once by a streaming kernel and the GEMM fetches them by TMA
-        PackJob job{ctx, nullptr, h->d.dim_ctx, h->d.dim_ctx, P.rows, P.row_tile, P.xpack};
-        CK(pack_rows_launch(&job, 1, h->opt_layout, st));
+        if (mean_done && h->opt_prologue1 && (h->d.dim_ctx % 128) == 0) {
+            CK(ctx_mean_pack_launch(ctx, h->mean, P.xpack, P.row_tile, h->opt_layout, n_img, h->d.num_ctx, h->d.dim_ctx, st));
+            *mean_done = true;
+        } else {
+            PackJob job{ctx, nullptr, h->d.dim_ctx, h->d.dim_ctx, P.rows, P.row_tile, P.xpack};
+            CK(pack_rows_launch(&job, 1, h->opt_layout, st));
+        }
         h->launches += 1;
         P.seg[0].pa = P.xpack;
     }
@@ -785,16 +794,21 @@ static int prepare_impl(sat_handle* h, const float* ctx, int n_img, float* c0, f
     // the mean of the contexts first: the projection and the initialize layers are then consecutive dense
     // launches, chained by programmatic dependent launch instead of separated by a fully serialised small kernel
     const bool want_init = c0 && h0;
-    if (want_init) {
+    // one pass over the conv features for the mean and the projection operand when the projection runs from packed rows
+    const bool one_pass = want_init && h->opt_hoist && h->opt_prologue1 && h->d.num_attend_layers == 2 && h->opt_gemm != 0 &&
+                          h->opt_pa && (h->d.dim_ctx % 128) == 0;
+    bool mean_done = false;
+    if (want_init && !one_pass) {
         CK(ctx_mean_launch(ctx, h->mean, n_img, h->d.num_ctx, h->d.dim_ctx, st));
         h->launches += 1;
+        mean_done = true;
     }
     if (h->opt_hoist) {
-        RET(project_contexts(h, ctx, n_img, st));
+        RET(project_contexts(h, ctx, n_img, st, one_pass ? &mean_done : nullptr));
         h->prep_ctx = ctx;
         h->prep_ni = n_img;
     }
-    if (want_init) RET(run_initialize(h, ctx, n_img, c0, h0, st, h0_pa, true));
+    if (want_init) RET(run_initialize(h, ctx, n_img, c0, h0, st, h0_pa, mean_done));
     return SAT_OK;
 }
 

@@ -1046,12 +1046,18 @@ cudaError_t att_launch(const AttParams& p, cudaStream_t st) {
 // mean over the L locations (model.py:240): out[i, d] = (1/L) sum_l ctx[i, l, d]
 // One block per (image, 128-feature slab): 8 row groups x 32 float4 columns, rows summed in location order per
 // group and the 8 groups added in fixed order (bit-reproducible); loads of 4 rows are in flight per thread.
-__global__ void __launch_bounds__(256) ctx_mean_kernel(const float* __restrict__ ctx, float* __restrict__ out, int L, int D) {
+// PACK: the same pass also writes every row in the packed-activation layout the context projection (attend/fc_1a)
+// fetches by TMA (one pass over the conv features for the mean AND the projection operand;
+// the summation order — and with it the mean, bit for bit — is that of the plain kernel).
+template <bool PACK>
+__global__ void __launch_bounds__(256) ctx_mean_kernel(const float* __restrict__ ctx, float* __restrict__ out, int L, int D,
+                                                       uint8_t* __restrict__ pa, int row_tile, int mode) {
     constexpr int RG = 8, C4 = 32;
     __shared__ float4 red[RG][C4];
     const int i = blockIdx.y;
     const int c4 = threadIdx.x % C4, rg = threadIdx.x / C4;
     const int d = blockIdx.x * (4 * C4) + 4 * c4;
+    const int kblocks = D >> 6;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (d < D) {
         const float* p = ctx + (size_t)i * L * D + d;
@@ -1065,10 +1071,17 @@ __global__ void __launch_bounds__(256) ctx_mean_kernel(const float* __restrict__
             s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
             s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
             s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
+            if (PACK) {
+                pa_store4(pa, mode, row_tile, kblocks, i * L + l, d, &a.x);
+                pa_store4(pa, mode, row_tile, kblocks, i * L + l + RG, d, &b.x);
+                pa_store4(pa, mode, row_tile, kblocks, i * L + l + 2 * RG, d, &c.x);
+                pa_store4(pa, mode, row_tile, kblocks, i * L + l + 3 * RG, d, &e.x);
+            }
         }
         for (; l < L; l += RG) {
             const float4 a = *reinterpret_cast<const float4*>(p + (size_t)l * D);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            if (PACK) pa_store4(pa, mode, row_tile, kblocks, i * L + l, d, &a.x);
         }
     }
     red[rg][c4] = s;
@@ -1084,7 +1097,16 @@ __global__ void __launch_bounds__(256) ctx_mean_kernel(const float* __restrict__
 
 cudaError_t ctx_mean_launch(const float* ctx, float* out, int NI, int L, int D, cudaStream_t st) {
     dim3 grid((D + 127) / 128, NI);
-    ctx_mean_kernel<<<grid, 256, 0, st>>>(ctx, out, L, D);
+    ctx_mean_kernel<false><<<grid, 256, 0, st>>>(ctx, out, L, D, nullptr, 0, 0);
+    return cudaGetLastError();
+}
+
+// mean + packed rows (row tile `row_tile`, D % 64 == 0) in one pass; rows beyond NI * L of the last row tile are not
+// written (they only feed output rows the projection never stores)
+cudaError_t ctx_mean_pack_launch(const float* ctx, float* out, uint8_t* pa, int row_tile, int layout_mode, int NI, int L, int D,
+                                 cudaStream_t st) {
+    dim3 grid((D + 127) / 128, NI);
+    ctx_mean_kernel<true><<<grid, 256, 0, st>>>(ctx, out, L, D, pa, row_tile, layout_mode);
     return cudaGetLastError();
 }
 

@@ -47,5 +47,7 @@ size_t att_smem_bytes(const AttParams& p);
 size_t att_part_floats(const AttParams& p);
 cudaError_t att_launch(const AttParams& p, cudaStream_t st);
 cudaError_t ctx_mean_launch(const float* ctx, float* out, int NI, int L, int D, cudaStream_t st);
+cudaError_t ctx_mean_pack_launch(const float* ctx, float* out, uint8_t* pa, int row_tile, int layout_mode, int NI, int L, int D,
+                                 cudaStream_t st);
 
 }  // namespace sat

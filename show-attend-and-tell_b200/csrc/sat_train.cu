@@ -388,25 +388,33 @@ __global__ void copy2d_kernel(float* y, int ldy, const float* x, int ldx, int ro
 // Word ids index the embedding table and its gradient: an id outside [0, V) (TF's embedding_lookup / sparse softmax
 // raise InvalidArgument on those) reads as a zero row, contributes no gradient and is counted in *bad (reported by
 // sat_get_info "train_bad_ids"; the facade raises), instead of reading / corrupting neighbouring memory.
+// rows_per_step > 0: rows are T stacked time steps, row r = (step r / rows_per_step, batch row r % rows_per_step), and
+// idx is the [B, T] sentence matrix itself: step t looks up word t-1 of its row (teacher forcing), step 0 word id 0
+__device__ __forceinline__ int step_word(const int32_t* idx, int idx_ld, int r, int rows_per_step) {
+    if (!idx) return 0;
+    if (!rows_per_step) return idx[(size_t)r * idx_ld];
+    const int ts = r / rows_per_step, b = r - ts * rows_per_step;
+    return ts ? idx[(size_t)b * idx_ld + ts - 1] : 0;
+}
 __global__ void gather_rows_kernel(float* y, int ldy, const float* table, int E, const int32_t* idx, int idx_ld, int rows, int V,
-                                   float* bad) {
+                                   float* bad, int rows_per_step) {
     pdl_enter();
     const size_t n = (size_t)rows * E;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / E), c = (int)(i - (size_t)r * E);
-        const int w = idx ? idx[(size_t)r * idx_ld] : 0;
+        const int w = step_word(idx, idx_ld, r, rows_per_step);
         const bool ok = (unsigned)w < (unsigned)V;
         if (!ok && c == 0) atomicAdd(bad, 1.0f);
         y[(size_t)r * ldy + c] = ok ? table[(size_t)w * E + c] : 0.f;
     }
 }
 __global__ void scatter_add_rows_kernel(float* dtable, int E, const int32_t* idx, int idx_ld, const float* dx, int ldx, int rows,
-                                        int V) {
+                                        int V, int rows_per_step) {
     pdl_enter();
     const size_t n = (size_t)rows * E;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / E), c = (int)(i - (size_t)r * E);
-        const int w = idx ? idx[(size_t)r * idx_ld] : 0;
+        const int w = step_word(idx, idx_ld, r, rows_per_step);
         if ((unsigned)w < (unsigned)V) atomicAdd(dtable + (size_t)w * E + c, dx[(size_t)r * ldx + c]);
     }
 }
@@ -483,9 +491,21 @@ __device__ __forceinline__ void att_bwd_fused_body(float* __restrict__ dtemp, fl
                                                    const float* __restrict__ T1, const float* __restrict__ q,
                                                    const float* __restrict__ de, const float* __restrict__ w2, int L, int A,
                                                    int chunk_rows, const unsigned long long* seedp,
-                                                   unsigned long long stream, float keep) {
+                                                   unsigned long long stream, float keep, const float* __restrict__ alpha) {
     pdl_enter();
     __shared__ float4 red[3][kAbRG - 1][kAbCT];
+    // alpha != nullptr: `de` still holds d loss / d alpha and the softmax backward de = alpha (dalpha - sum alpha dalpha)
+    // is taken here (every CTA of image b recomputes the L-term dot product) instead of in a launch of its own
+    float sdot = 0.f;
+    if (alpha) {
+        __shared__ float sd[kAbRG * kAbCT / 32];
+        float p = 0.f;
+        for (int l = threadIdx.x; l < L; l += kAbRG * kAbCT) p = fmaf(alpha[(size_t)blockIdx.z * L + l], de[(size_t)blockIdx.z * L + l], p);
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = p;
+        __syncthreads();
+        for (int w = 0; w < kAbRG * kAbCT / 32; ++w) sdot += sd[w];
+    }
     const unsigned long long seed = *seedp;
     const DropGen gen = drop_gen(seed, stream, keep);
     const int ct = threadIdx.x % kAbCT, rg = threadIdx.x / kAbCT;
@@ -500,7 +520,7 @@ __device__ __forceinline__ void att_bwd_fused_body(float* __restrict__ dtemp, fl
         for (int l = l0 + rg; l < l1; l += kAbRG) {
             const size_t r = (size_t)b * L + l;
             const float4 t = reinterpret_cast<const float4*>(T1)[r * A4 + c4];
-            const float d = de[r];
+            const float d = alpha ? alpha[r] * (de[r] - sdot) : de[r];
             float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
             if (seed) {
                 const unsigned long long i = (r * A4 + c4) << 2;
@@ -542,13 +562,13 @@ __device__ __forceinline__ void att_bwd_fused_body(float* __restrict__ dtemp, fl
 #define ATT_BWD_ARGS                                                                                                      \
     float *__restrict__ dtemp, float *dq, float *dw2, float *db, const float *__restrict__ T1, const float *__restrict__ q, \
         const float *__restrict__ de, const float *__restrict__ w2, int L, int A, int chunk_rows,                         \
-        const unsigned long long *seedp, unsigned long long stream, float keep
+        const unsigned long long *seedp, unsigned long long stream, float keep, const float *__restrict__ alpha
 __global__ void __launch_bounds__(kAbRG* kAbCT) att_bwd_fused_kernel(ATT_BWD_ARGS) {
-    att_bwd_fused_body(dtemp, dq, dw2, db, T1, q, de, w2, L, A, chunk_rows, seedp, stream, keep);
+    att_bwd_fused_body(dtemp, dq, dw2, db, T1, q, de, w2, L, A, chunk_rows, seedp, stream, keep, alpha);
 }
 // the same held to 64 registers (4 CTAs per SM), for the one-resident-wave experiment (SAT_TRAIN_ATTBWD_WAVE=1)
 __global__ void __launch_bounds__(kAbRG* kAbCT, 4) att_bwd_fused_wave_kernel(ATT_BWD_ARGS) {
-    att_bwd_fused_body(dtemp, dq, dw2, db, T1, q, de, w2, L, A, chunk_rows, seedp, stream, keep);
+    att_bwd_fused_body(dtemp, dq, dw2, db, T1, q, de, w2, L, A, chunk_rows, seedp, stream, keep, alpha);
 }
 #undef ATT_BWD_ARGS
 // e[r] = sum_a temp[r, a] * w2[a]       (one warp per row)
@@ -620,6 +640,73 @@ __global__ void __launch_bounds__(256) context_fwd4_kernel(float* __restrict__ z
         for (int l = rg; l < L; l += 8) {
             const float4 v = c[(size_t)l * D4];
             const float w = al[l];
+            a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+        }
+    }
+    if (rg > 0) red[rg - 1][ct] = a;
+    __syncthreads();
+    if (rg == 0 && c4 < D4) {
+#pragma unroll
+        for (int g = 0; g < 7; ++g) {
+            const float4 v = red[g][ct];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        reinterpret_cast<float4*>(z)[(size_t)b * D4 + c4] = a;
+    }
+}
+// softmax over the L scores of image b, then the context vector, in one launch: every CTA of the image (one per 128
+// columns) recomputes the L-term softmax in shared memory (L <= kSmL) and the first one records alpha and the
+// coverage accumulator att[b, l] += alpha[b, l] * mask[b, t] — what softmax_rows_kernel + context_fwd4_kernel do in
+// two dependent launches, of which the first keeps 8 CTAs busy
+constexpr int kSmL = 1024;
+__global__ void __launch_bounds__(256) softmax_context_fwd4_kernel(float* __restrict__ z, float* __restrict__ alpha,
+                                                                    const float* __restrict__ e, const float* __restrict__ ctx,
+                                                                    int L, int D, float* att, const float* masks, int mld, int t) {
+    pdl_enter();
+    __shared__ float4 red[7][32];
+    __shared__ float al_s[kSmL];
+    __shared__ float rs[8];
+    const int ct = threadIdx.x & 31, rg = threadIdx.x >> 5, b = blockIdx.y;
+    const float* x = e + (size_t)b * L;
+    float m = -INFINITY;
+    for (int l = threadIdx.x; l < L; l += 256) m = fmaxf(m, x[l]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (ct == 0) rs[rg] = m;
+    __syncthreads();
+    m = rs[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, rs[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int l = threadIdx.x; l < L; l += 256) {
+        const float v = expf(x[l] - m);
+        al_s[l] = v;
+        sum += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (ct == 0) rs[rg] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += rs[w];
+    const float mk = att ? masks[(size_t)b * mld + t] : 0.f;
+    for (int l = threadIdx.x; l < L; l += 256) {
+        const float a = al_s[l] / sum;
+        al_s[l] = a;
+        if (blockIdx.x == 0) {
+            alpha[(size_t)b * L + l] = a;
+            if (att) att[(size_t)b * L + l] += a * mk;
+        }
+    }
+    __syncthreads();
+    const int D4 = D >> 2, c4 = blockIdx.x * 32 + ct;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < D4) {
+        const float4* c = reinterpret_cast<const float4*>(ctx) + (size_t)b * L * D4 + c4;
+#pragma unroll 4
+        for (int l = rg; l < L; l += 8) {
+            const float4 v = c[(size_t)l * D4];
+            const float w = al_s[l];
             a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
         }
     }
@@ -972,6 +1059,7 @@ struct TrainState {
     bool dec_all = false;
     int all_rt = 0, all_rows = 0;                 // row tile of the stacked rows, rows rounded up to it
     float *logits_all = nullptr, *dexp_all = nullptr;
+    float* demb_all = nullptr;                    // d emb of every step: ONE scatter into the embedding gradient after the loop
     uint8_t* tc_vx_all = nullptr;
     // the [B*L]-row products of attend/fc_1a are outside the recurrence (forward: T1[t] needs only ctx and the mask of
     // step t; backward: nothing waits for dW1a): they run on a second, low-priority stream beside the batch-row work
@@ -1098,6 +1186,7 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
     A1(&s->dc, B * H); A1(&s->dG, B * 4 * H); A1(&s->dlin, B * (D + E + H)); A1(&s->dz, B * D); A1(&s->demb, B * E);
     A1(&s->dalpha, BL); A1(&s->dtemp, BL * A); A1(&s->dq, B * A); A1(&s->dhd, B * H); A1(&s->dbuf, B * (D + E + I + H));
     A1(&s->loss_acc, 8);
+    A1(&s->demb_all, (size_t)T * B * E);
     s->handle = h;
     const bool att2 = d.num_attend_layers == 2, dec2 = d.num_decode_layers == 2;
     s->tc_ok = att2 && (D % 128 == 0) && (A % 128 == 0) && (BL % 128 == 0);
@@ -1335,6 +1424,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     auto evT1 = [&](int t) { return s->ev[2 + 3 * t]; };
     auto evAb = [&](int t) { return s->ev[3 + 3 * t]; };
     auto evRp = [&](int t) { return s->ev[4 + 3 * t]; };
+    static const int fuse_sm = []() { const char* e = getenv("SAT_TRAIN_FUSE_SOFTMAX"); return (e && e[0] == '0') ? 0 : 1; }();
     const bool stack = tcb && s->tc_stack;   // weight gradients of the four batch-row layers after the time loop
     static const int dec_all_env = []() { const char* e = getenv("SAT_TRAIN_DEC_ALL"); return (e && e[0] == '0') ? 0 : 1; }();
     const bool dec_all = stack && tcv && s->dec_all && dec_all_env;   // decode layers of all T steps as [T*B]-row products
@@ -1416,14 +1506,20 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
             launch_k(rowdot_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->temp, P(vA2W), BL, A);
         }
+        const bool ctx4 = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(contexts) & 15) == 0;
+        if (ctx4 && L <= kSmL && fuse_sm)   // softmax + coverage + context vector in one launch
+            launch_k(softmax_context_fwd4_kernel, dim3((D / 4 + 31) / 32, B), 256, st, s->z[t], s->alpha[t], s->e, contexts, L, D, s->att, masks, T, t);
+        else
         launch_k(softmax_rows_kernel, (B * 32 + 255) / 256, 256, st, s->alpha[t], s->e, B, L, s->att, masks, T, t);   // + coverage
-        if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(contexts) & 15) == 0)   // un-dropped ctx
+        if (ctx4 && L <= kSmL && fuse_sm) {
+        } else if (ctx4)   // un-dropped ctx
             launch_k(context_fwd4_kernel, dim3((D / 4 + 31) / 32, B), 256, st, s->z[t], s->alpha[t], contexts, L, D);
         else
             launch_k(context_fwd_kernel, dim3((D + 127) / 128, B), 128, st, s->z[t], s->alpha[t], contexts, B, L, D);
         // embedding of the previous word: 0 at t = 0, then teacher forcing (model.py:254, 310)
-        launch_k(gather_rows_kernel, GRID1D((size_t)B * E), 256, st, s->emb[t], E, P(vEmb), E, t ? sentences + (t - 1) : nullptr, T, B, V,
-                 s->loss_acc + 5);
+        if (t == 0)   // every step's rows at once (teacher forcing: the words are inputs)
+            launch_k(gather_rows_kernel, GRID1D((size_t)T * B * E), 256, st, s->emb[0], E, P(vEmb), E, sentences, T, T * B, V,
+                     s->loss_acc + 5, B);
         // LSTM with DropoutWrapper (model.py:228-236, 276-279)
         // lstm_in = [ drop_in(concat(z, emb)) | h_state_prev ]
         launch_k(concat3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->lstm_in[t], XL, s->z[t], D, s->emb[t], E, h_state_prev, H, D + E, B,
@@ -1479,6 +1575,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     TCK(cudaMemsetAsync(s->dh_out, 0, (size_t)B * H * sizeof(float), st));    // d loss / d h_out[t] from step t+1's attend
     TCK(cudaMemsetAsync(s->dh_state, 0, (size_t)B * H * sizeof(float), st));  // d loss / d h_state[t] from step t+1's LSTM
     TCK(cudaMemsetAsync(s->dc, 0, (size_t)B * H * sizeof(float), st));
+    if (stack && att_fused) TCK(cudaMemsetAsync(s->dys[0][0], 0, (size_t)T * B * A * sizeof(float), st));   // d q of every step
     if (dec_all) {   // d logits -> d td (x tanh', dropout) -> d expanded, for all T steps
         sat::PackJob job{s->dlogits[0], nullptr, V, V, TBr, s->all_rt, s->tc_vx_all, s->tc_vk / 64};
         TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
@@ -1501,6 +1598,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         float* dq = stack ? s->dys[0][t] : s->dq;
         bool vdx = false;
         const float* dexp = dec_all ? s->dexp_all + (size_t)t * B * XD : s->dexp;
+        float* const demb = s->demb_all + (size_t)t * B * E;
         if (dec_all) {
         } else if (!dec2) {
             TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), V, s->dlogits[t], Gd(vD1W), Gd(vD1B), s->dexp));
@@ -1520,7 +1618,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), s->dexp));
         }
         // drop(dexp) = [dh_out (+=) | dz (=) | demb (=)]
-        launch_k(split3_drop_kernel, GRID1D((size_t)B * XD), 256, st, dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, s->demb, E, 0, XD, seed,
+        launch_k(split3_drop_kernel, GRID1D((size_t)B * XD), 256, st, dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, demb, E, 0, XD, seed,
                                                                    ST(t, 6), kf);
         // h_out = drop_out(h_raw), h_state = drop_state(h_raw)
         launch_k(lstm_bwd_kernel, GRID1D((size_t)B * H), 256, st, dG, s->dc, s->dh_out, s->dh_state, s->acts[t], s->c[t], c_prev, B, H, seed,
@@ -1528,12 +1626,12 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         if (tc_dx(1, dG, s->dlin, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), nullptr)); }
         else TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), s->dlin));
         // dlin = [d xd (D+E) | dh_state_prev]
-        launch_k(split3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->dlin, XL, B, s->dz, D, 1, s->demb, E, 1, s->dh_state, H, 0, D + E, seed,
+        launch_k(split3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->dlin, XL, B, s->dz, D, 1, demb, E, 1, s->dh_state, H, 0, D + E, seed,
                                                                    ST(t, 3), kl);
-        launch_k(scatter_add_rows_kernel, GRID1D((size_t)B * E), 256, st, Gd(vEmb), E, t ? sentences + (t - 1) : nullptr, T, s->demb, E, B, V);
         // attention: context vector, softmax, scorer
         launch_k(context_bwd_kernel, (BL * 32 + 255) / 256, 256, st, s->dalpha, s->dz, contexts, s->datt, B, L, D, masks, T, t);
-        launch_k(softmax_bwd_kernel, (B * 32 + 255) / 256, 256, st, s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
+        const bool sm_in_ab = att2 && att_fused && fuse_sm;   // (the fused scorer backward takes the softmax backward itself)
+        if (!sm_in_ab) launch_k(softmax_bwd_kernel, (B * 32 + 255) / 256, 256, st, s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
         if (!att2) {   // de = dalpha [B, L]: dwa += drop(ctx)^T de, dWb += drop(h)^T de, d drop(h) = de Wb^T
             launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
             launch_k(colsum_kernel, dim3((D + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aW), s->ctxd, BL, D, s->dalpha);
@@ -1541,11 +1639,11 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         } else {
         float* const dtemp = (side && (t & 1)) ? s->dtemp2 : s->dtemp;
         if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
-            TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));
+            if (!stack) TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));   // (stacked: zeroed once before the loop)
             if (side && t + 2 < T) TCK(cudaStreamWaitEvent(st, evRp(t + 2), 0));   // this d temp buffer has been packed
             launch_k(ab_wave ? att_bwd_fused_wave_kernel : att_bwd_fused_kernel, dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B),
                      kAbRG * kAbCT, st, dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A,
-                     ab_rows, seed, ST(t, 2), kf);
+                     ab_rows, seed, ST(t, 2), kf, sm_in_ab ? s->alpha[t] : nullptr);
         } else {
             launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
             launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
@@ -1576,6 +1674,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
         launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
     }
+    launch_k(scatter_add_rows_kernel, GRID1D((size_t)T * B * E), 256, st, Gd(vEmb), E, sentences, T, s->demb_all, E, T * B, V, B);
     if (side) TCK(hand(sd, st, s->ev[1]));   // join: every fc_1a weight-gradient product has been accumulated
     if (stack) {
         // dW += X_all^T dY_all, db += colsum(dY_all) for attend/fc_1b, lstm, decode/fc_1, decode/fc_2 (the repack kernel

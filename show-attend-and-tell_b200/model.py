@@ -215,8 +215,8 @@ class CaptionGenerator(object):
         self._flat = torch.zeros(total.value + 8, device=self.device)
         self.grads = self._flat[:total.value]
         self._tail = self._flat[total.value:]
-        self._msum_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
-        self._msum_key = None
+        from .parallel import StepCollective
+        self._dp = StepCollective(self._flat, total.value)
         # optimizer slots (model.py:479-503): Adam m, v; RMSProp rms (starts at ONE like TF's), mg (centered), momentum;
         # Momentum accumulator; SGD none
         kind = getattr(cfg, "optimizer", "Adam")
@@ -395,7 +395,8 @@ class CaptionGenerator(object):
         return int(seed)
 
     def allreduce_gradients(self):
-        """Sum the flat gradient buffer (with its scalar tail) over the ranks: the one collective of a data-parallel step."""
+        """Sum the flat gradient buffer (with its scalar tail) over the ranks (what StepCollective.reduce does inside
+        train_step; kept for callers that drive sat_train_forward_backward / train_apply themselves)."""
         import torch.distributed as dist
         dist.all_reduce(self._flat)
 
@@ -406,8 +407,9 @@ class CaptionGenerator(object):
         (losses [4], squared gradient norm [1]) without reading them back, so that the host can queue the next step
         while this one runs (the reference reads its summary every step; a training loop rarely needs to).
         seed: see _step_seed (None = new dropout masks every step, 0 = dropout off).
-        next_masks (data parallel): the masks of the NEXT batch, if the input pipeline already has them: their sum then
-        rides in this step's gradient collective (default: the same masks tensor is expected again)."""
+        next_masks (data parallel): the masks the NEXT call will be given, if the input pipeline already has them: their
+        sum then rides in this step's gradient collective and the next step starts without a collective of its own
+        (a promise — only the shape is checked; default: the same masks tensor is expected again)."""
         import torch.distributed as dist
         torch = self.torch
         B, T = self._train_BT
@@ -420,19 +422,11 @@ class CaptionGenerator(object):
             # or a batch whose masks were not announced (`next_masks`) — pays a separate 8-byte all-reduce.  Everything
             # stays on the device and in stream order: the host can queue step i+1 while step i runs.
             nxt = mk if next_masks is None else self._dev(next_masks, torch.float32)
-            key = (mk.data_ptr(), mk._version, tuple(mk.shape))
-            if self._msum_key != key:
-                self._msum_dev.copy_(mk.sum(dtype=torch.float64).reshape(1))
-                dist.all_reduce(self._msum_dev)
+            gsum = self._dp.global_mask_sum(mk)
             seed = self._step_seed(seed)
             seed = seed + 0x1000003 * dist.get_rank() if seed else 0   # rank-offset mask streams (0 stays "off")
-            losses = self.train_forward_backward(contexts, sentences, mk, seed, self._msum_dev, B * world)
-            self._tail[:3].copy_(losses[:3])               # CE / accuracy / attention are sums of shard parts
-            self._tail[3:4].copy_(nxt.sum().reshape(1))    # (exact in fp32: at most batch x steps ones per rank)
-            self.allreduce_gradients()                     # the single collective of the step
-            losses = torch.cat([self._tail[:3], losses[3:4]])
-            self._msum_dev.copy_(self._tail[3:4])
-            self._msum_key = (nxt.data_ptr(), nxt._version, tuple(nxt.shape))
+            losses = self.train_forward_backward(contexts, sentences, mk, seed, gsum, B * world)
+            losses = torch.cat([self._dp.reduce(losses, nxt, announced=next_masks is not None), losses[3:4]])   # the single collective of the step
         else:
             seed = self._step_seed(seed)
             msum = self._mask_sum(masks, mk)

@@ -65,3 +65,51 @@ def gather_shards(local, n_total, device=None):
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad)
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
+
+
+class StepCollective(object):
+    """The collective protocol of one data-parallel training step (model.train_step), on any torch device.
+
+    flat = [gradients (n_grad floats) | ce, accuracy, attention sums | sum of the NEXT batch's masks | pad]: ONE
+    all-reduce per step.  The whole-batch mask sum a step needs BEFORE its backward pass (model.py:316-318 divides by
+    it) therefore arrived with the previous step's collective; only the first step of a run, or a batch whose masks
+    were not announced, pays a separate 8-byte all-reduce.  Everything stays on the device and in stream order."""
+
+    def __init__(self, flat, n_grad):
+        import torch
+        self.flat, self.n_grad = flat, int(n_grad)
+        self.tail = flat[self.n_grad:]
+        assert self.tail.numel() >= 4
+        self.mask_sum = torch.zeros(1, dtype=torch.float64, device=flat.device)   # global sum for the batch `key` names
+        self.key = None
+        self.collectives = 0
+
+    @staticmethod
+    def _key(masks):
+        return (masks.data_ptr(), masks._version, tuple(masks.shape))
+
+    def global_mask_sum(self, masks):
+        """Device scalar (float64 [1]): sum of `masks` over all ranks.  No collective if the previous reduce() carried
+        it: either announced explicitly (`next_masks`, a promise about this call's masks: only the shape is checked)
+        or the very same tensor is fed again."""
+        import torch
+        import torch.distributed as dist
+        if self.key not in (self._key(masks), ("announced", tuple(masks.shape))):
+            self.mask_sum.copy_(masks.sum(dtype=torch.float64).reshape(1))
+            dist.all_reduce(self.mask_sum)
+            self.collectives += 1
+        self.key = self._key(masks)
+        return self.mask_sum
+
+    def reduce(self, shard_losses, next_masks, announced=False):
+        """After the backward pass filled flat[:n_grad]: sums gradients and the three shard-additive losses over the
+        ranks and hands over the next batch's mask sum (announced=True: `next_masks` are the masks the NEXT step will
+        be called with, whatever tensor object they arrive in).  Returns the device tensor [ce, accuracy, attention]."""
+        import torch.distributed as dist
+        self.tail[:3].copy_(shard_losses[:3])
+        self.tail[3:4].copy_(next_masks.sum().reshape(1))    # (exact in fp32: at most batch x steps ones per rank)
+        dist.all_reduce(self.flat)
+        self.collectives += 1
+        self.mask_sum.copy_(self.tail[3:4])
+        self.key = ("announced", tuple(next_masks.shape)) if announced else self._key(next_masks)
+        return self.tail[:3]

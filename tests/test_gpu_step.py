@@ -108,6 +108,28 @@ def test_hoisted_and_per_step_projection_agree():
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("B", [4, 64])
+def test_one_pass_prologue_matches_the_three_launch_prologue(B):
+    """the mean over the L locations (model.py:240) is taken by the same pass that packs the
+    conv features for the context projection (attend/fc_1a).  Same summation order and the same bf16 split as the
+    separate kernels: initial state, projection and every token after it are bit-identical."""
+    ocfg, w, m = make_pair(B, num_ctx=196, dim_ctx=512, dim_attend_layer=128, dim_embedding=64, num_lstm_units=64,
+                           dim_initalize_layer=64, dim_decode_layer=64, vocabulary_size=200, max_caption_length=4)
+    ctx = R.synth_contexts(ocfg, B, seed=3)
+    out = {}
+    for one in (1, 0):
+        m.set_option("prologue1", one)
+        c0, h0 = m.initialize(ctx)
+        toks, logits = m.decode_loop(ctx, 4, None, want_logits=True)
+        out[one] = (np.asarray(c0).copy(), np.asarray(h0).copy(), toks.copy(), logits.copy())
+    m.set_option("prologue1", 1)
+    for a, b in zip(out[1], out[0]):
+        assert np.array_equal(a, b)
+    ref_c, ref_h = R.initialize(ocfg, w, ctx, np.float64)
+    assert_close(out[1][0], ref_c, "initial memory")
+    assert_close(out[1][1], ref_h, "initial output")
+
+
 def test_packed_activation_and_prepass_paths_agree():
     """Operands packed by their producer kernels (default) vs the cooperative pre-pass vs per-stage producer
     warps: the same bf16 hi/lo split feeds the same MMAs.  The two conversion paths agree bit for bit; the packed path

@@ -117,6 +117,91 @@ def test_two_rank_gloo_shard_gather_and_max():
         assert tmax == 2.0
 
 
+def _dp_worker(rank, world, port, q):
+    """Two data-parallel training steps over gloo: the oracle stands in for each rank's forward + backward pass, the
+    host protocol (parallel.StepCollective: one collective per step, next batch's mask sum riding with the gradients)
+    is the product code under test."""
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import warnings
+    import torch
+    import torch.distributed as dist
+    from oracle import ref_step as R, train_ref as TR
+    parallel.init_process_group("gloo")
+    cfg = R.OracleConfig(batch_size=4, num_ctx=6, dim_ctx=8, dim_embedding=6, num_lstm_units=8, dim_initalize_layer=6,
+                         dim_attend_layer=6, dim_decode_layer=8, vocabulary_size=20, max_caption_length=4)
+    w = R.init_weights(cfg, seed=2)
+    names = sorted(w)
+    n_grad = sum(w[k].size for k in names)
+    dp = parallel.StepCollective(torch.zeros(n_grad + 8, dtype=torch.float32), n_grad)
+    rng = np.random.RandomState(5)
+    batches = []
+    for it in range(3):
+        ctx = R.synth_contexts(cfg, 4, seed=10 + it)
+        sent = rng.randint(1, 20, (4, 4)).astype(np.int32)
+        lens = rng.randint(1, 5, 4)
+        batches.append((ctx, sent, (np.arange(4)[None, :] < lens[:, None]).astype(np.float32)))
+    lo, hi = parallel.shard_range(4, rank, world)
+    out = []
+    for it in range(2):
+        ctx, sent, masks = batches[it]
+        mk = torch.tensor(masks[lo:hi])
+        nxt = torch.tensor(batches[it + 1][2][lo:hi])
+        gsum = float(dp.global_mask_sum(mk).item())
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            l, g = TR.loss_and_grads(cfg, w, ctx[lo:hi], sent[lo:hi], masks[lo:hi], None, global_mask_sum=gsum,
+                                     global_batch=4, reg_in_grad=False)
+        dp.flat[:n_grad].copy_(torch.tensor(np.concatenate([g[k].ravel() for k in names]), dtype=torch.float32))
+        shard = torch.tensor([l["cross_entropy_loss"], l["accuracy"], l["attention_loss"], 0.0], dtype=torch.float32)
+        glob = dp.reduce(shard, nxt, announced=True)
+        out.append((gsum, dp.flat[:n_grad].numpy().copy(), glob.numpy().copy(), float(dp.mask_sum.item())))
+    q.put((rank, dp.collectives, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_training_step_protocol():
+    import warnings
+    import torch.multiprocessing as mp
+    from oracle import ref_step as R, train_ref as TR
+    ctx_ = mp.get_context("spawn")
+    q = ctx_.Queue()
+    port = _free_port()
+    procs = [ctx_.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # the same two batches on ONE process
+    cfg = R.OracleConfig(batch_size=4, num_ctx=6, dim_ctx=8, dim_embedding=6, num_lstm_units=8, dim_initalize_layer=6,
+                         dim_attend_layer=6, dim_decode_layer=8, vocabulary_size=20, max_caption_length=4)
+    w = R.init_weights(cfg, seed=2)
+    names = sorted(w)
+    rng = np.random.RandomState(5)
+    for it in range(2):
+        ctx = R.synth_contexts(cfg, 4, seed=10 + it)
+        sent = rng.randint(1, 20, (4, 4)).astype(np.int32)
+        lens = rng.randint(1, 5, 4)
+        masks = (np.arange(4)[None, :] < lens[:, None]).astype(np.float32)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            l, g = TR.loss_and_grads(cfg, w, ctx, sent, masks, None, reg_in_grad=False)
+        ref = np.concatenate([g[k].ravel() for k in names])
+        for rank, ncoll, steps in outs:
+            gsum, flat, glob, nxt_sum = steps[it]
+            assert gsum == float(masks.sum())                       # the normaliser every rank used is the global one
+            assert np.abs(flat - ref).max() < 1e-5 * np.abs(ref).max()
+            assert abs(glob[0] - l["cross_entropy_loss"]) < 1e-5 * l["cross_entropy_loss"]
+            assert abs(glob[2] - l["attention_loss"]) < 1e-5 * l["attention_loss"]
+            assert abs(glob[1] - l["accuracy"]) < 1e-6
+    for rank, ncoll, steps in outs:
+        assert ncoll == 3            # mask sum of the first batch + ONE collective per step: the second step needed no extra one
+        assert steps[0][3] == steps[1][0]
+
+
 def test_golden_fixtures_match_current_oracle():
     """tests/golden/step_*.npz were produced by the fp64 oracle; guard against silent drift."""
     here = os.path.join(os.path.dirname(__file__), "golden")
