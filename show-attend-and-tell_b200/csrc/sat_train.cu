@@ -1424,7 +1424,9 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     auto evT1 = [&](int t) { return s->ev[2 + 3 * t]; };
     auto evAb = [&](int t) { return s->ev[3 + 3 * t]; };
     auto evRp = [&](int t) { return s->ev[4 + 3 * t]; };
-    static const int fuse_sm = []() { const char* e = getenv("SAT_TRAIN_FUSE_SOFTMAX"); return (e && e[0] == '0') ? 0 : 1; }();
+    // SAT_TRAIN_FUSE_SOFTMAX: 0 = separate softmax kernels, 2 = only the forward one folded in, 1 / unset = both directions
+    static const int fuse_env = []() { const char* e = getenv("SAT_TRAIN_FUSE_SOFTMAX"); return e ? atoi(e) : 1; }();
+    const bool fuse_sm = fuse_env != 0;
     const bool stack = tcb && s->tc_stack;   // weight gradients of the four batch-row layers after the time loop
     static const int dec_all_env = []() { const char* e = getenv("SAT_TRAIN_DEC_ALL"); return (e && e[0] == '0') ? 0 : 1; }();
     const bool dec_all = stack && tcv && s->dec_all && dec_all_env;   // decode layers of all T steps as [T*B]-row products
@@ -1630,7 +1632,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
                                                                    ST(t, 3), kl);
         // attention: context vector, softmax, scorer
         launch_k(context_bwd_kernel, (BL * 32 + 255) / 256, 256, st, s->dalpha, s->dz, contexts, s->datt, B, L, D, masks, T, t);
-        const bool sm_in_ab = att2 && att_fused && fuse_sm;   // (the fused scorer backward takes the softmax backward itself)
+        const bool sm_in_ab = att2 && att_fused && fuse_env == 1;   // (the fused scorer backward takes the softmax backward itself)
         if (!sm_in_ab) launch_k(softmax_bwd_kernel, (B * 32 + 255) / 256, 256, st, s->dalpha, s->alpha[t], B, L);   // dalpha now holds de
         if (!att2) {   // de = dalpha [B, L]: dwa += drop(ctx)^T de, dWb += drop(h)^T de, d drop(h) = de Wb^T
             launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
