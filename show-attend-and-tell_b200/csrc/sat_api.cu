@@ -289,6 +289,10 @@ extern "C" int sat_create(const sat_dims* dims, sat_handle** out) {
 
     sat_handle* h = new sat_handle();
     h->d = d;
+    // SAT_PDL=0: start with programmatic dependent launch off (option "pdl").  For tools that assume one kernel of a
+    // stream at a time: compute-sanitizer's synccheck reports warps of an early-started kernel as divergent at their
+    // first block barrier (profiles/r02_sanitizer_synccheck.log).
+    if (const char* e = getenv("SAT_PDL")) h->opt_pdl = (e[0] == '0') ? 0 : 1;
     int rc = SAT_OK;
     auto body = [&]() -> int {
         CK(cudaGetDevice(&h->dev));

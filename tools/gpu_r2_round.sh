@@ -10,9 +10,9 @@ timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --workload 4 > gpurun
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --workload 5 > gpurun_out/bench_cfg5.log 2>&1
 timeout 200 python tools/timeline.py --head > gpurun_out/timeline.log 2>&1
 # ---- compute-sanitizer on small shapes (step / loop / beam / train): memcheck, racecheck, synccheck
-SMALL='tests/test_gpu_step.py::test_golden_step_and_loop tests/test_gpu_step.py::test_config1_reference_default_graph tests/test_gpu_beam.py::test_beam_search_small tests/test_gpu_train.py::test_losses_and_gradients_match_autograd tests/test_gpu_train.py::test_adam_update_matches_tf_semantics'
+SMALL="tests/test_gpu_step.py::test_golden_step_and_loop tests/test_gpu_step.py::test_config1_reference_default_graph tests/test_gpu_beam.py::test_beam_search_small tests/test_gpu_train.py::test_losses_and_gradients_match_autograd tests/test_gpu_train.py::test_adam_update_matches_tf_semantics tests/test_gpu_train.py::test_tensor_core_attend_projection_in_training tests/test_gpu_edges.py"
 for tool in memcheck synccheck racecheck; do
-  timeout 420 compute-sanitizer --tool $tool --print-limit 5 python -m pytest $SMALL -m gpu -q -x --timeout 400 > gpurun_out/sanitizer_$tool.log 2>&1
+  timeout 420 compute-sanitizer --tool $tool --print-limit 8 python -m pytest $SMALL -m gpu -q -x --timeout 400 > gpurun_out/sanitizer_$tool.log 2>&1
   echo "exit $?" >> gpurun_out/sanitizer_$tool.log
   grep -E "ERROR SUMMARY|passed|failed|exit" gpurun_out/sanitizer_$tool.log | tail -3
 done
