@@ -1501,7 +1501,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         } else if (tc_fwd(0, s->hd[t], sat::kEpiBiasTanh, s->q[t], &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
         if (side) TCK(cudaStreamWaitEvent(st, evT1(t), 0));
-        if (!att2) {
+        if (!att2) {   // (the 1-layer scores are complete: e = drop(ctx) wa + drop(h) Wb above)
         } else if (att_fused) {
             launch_k(att_logits_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->T1[t], s->q[t], P(vA2W), B, L, A, seed, ST(t, 2), kf);
         } else {
@@ -1509,15 +1509,15 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             launch_k(rowdot_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->temp, P(vA2W), BL, A);
         }
         const bool ctx4 = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(contexts) & 15) == 0;
-        if (ctx4 && L <= kSmL && fuse_sm)   // softmax + coverage + context vector in one launch
+        if (ctx4 && L <= kSmL && fuse_sm) {   // softmax + coverage + context vector in one launch
             launch_k(softmax_context_fwd4_kernel, dim3((D / 4 + 31) / 32, B), 256, st, s->z[t], s->alpha[t], s->e, contexts, L, D, s->att, masks, T, t);
-        else
-        launch_k(softmax_rows_kernel, (B * 32 + 255) / 256, 256, st, s->alpha[t], s->e, B, L, s->att, masks, T, t);   // + coverage
-        if (ctx4 && L <= kSmL && fuse_sm) {
-        } else if (ctx4)   // un-dropped ctx
-            launch_k(context_fwd4_kernel, dim3((D / 4 + 31) / 32, B), 256, st, s->z[t], s->alpha[t], contexts, L, D);
-        else
-            launch_k(context_fwd_kernel, dim3((D + 127) / 128, B), 128, st, s->z[t], s->alpha[t], contexts, B, L, D);
+        } else {
+            launch_k(softmax_rows_kernel, (B * 32 + 255) / 256, 256, st, s->alpha[t], s->e, B, L, s->att, masks, T, t);   // + coverage
+            if (ctx4)   // un-dropped ctx
+                launch_k(context_fwd4_kernel, dim3((D / 4 + 31) / 32, B), 256, st, s->z[t], s->alpha[t], contexts, L, D);
+            else
+                launch_k(context_fwd_kernel, dim3((D + 127) / 128, B), 128, st, s->z[t], s->alpha[t], contexts, B, L, D);
+        }
         // embedding of the previous word: 0 at t = 0, then teacher forcing (model.py:254, 310)
         if (t == 0)   // every step's rows at once (teacher forcing: the words are inputs)
             launch_k(gather_rows_kernel, GRID1D((size_t)T * B * E), 256, st, s->emb[0], E, P(vEmb), E, sentences, T, T * B, V,
@@ -1605,19 +1605,19 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         } else if (!dec2) {
             TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), V, s->dlogits[t], Gd(vD1W), Gd(vD1B), s->dexp));
         } else {
-        if (tcv) {   // dtd = dlogits W2^T on the tensor cores (ragged K = V: zero-padded last K block)
-            sat::PackJob job{s->dlogits[t], nullptr, V, V, B, s->tc_rt, s->tc_vx, s->tc_vk / 64};
-            TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
-            TRET(sat_dense_packed(s->handle, s->tc_vx, B, s->tc_rt, s->tc_vk, s->tc_vw, nullptr, Dd, sat::kEpiNone, dtd, Dd, 0,
-                                  tc_splits(Dd, s->tc_vk), st));
-            vdx = true;
-        }
-        if (stack) { if (!vdx) TCK(sgemm(st, false, true, B, Dd, V, s->dlogits[t], V, P(vD2W), V, dtd, Dd, false)); }
-        else if (vdx) TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), nullptr));
-        else TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), dtd));
-        launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, s->t1[t], (size_t)B * Dd, seed, ST(t, 7), kf, (size_t)0);
-        if (tc_dx(2, dtd, s->dexp, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
-        else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), s->dexp));
+            if (tcv) {   // dtd = dlogits W2^T on the tensor cores (ragged K = V: zero-padded last K block)
+                sat::PackJob job{s->dlogits[t], nullptr, V, V, B, s->tc_rt, s->tc_vx, s->tc_vk / 64};
+                TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
+                TRET(sat_dense_packed(s->handle, s->tc_vx, B, s->tc_rt, s->tc_vk, s->tc_vw, nullptr, Dd, sat::kEpiNone, dtd, Dd, 0,
+                                      tc_splits(Dd, s->tc_vk), st));
+                vdx = true;
+            }
+            if (stack) { if (!vdx) TCK(sgemm(st, false, true, B, Dd, V, s->dlogits[t], V, P(vD2W), V, dtd, Dd, false)); }
+            else if (vdx) TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), nullptr));
+            else TRET(dense_bwd(st, s->td[t], B, Dd, P(vD2W), V, s->dlogits[t], Gd(vD2W), Gd(vD2B), dtd));
+            launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * Dd), 256, st, dtd, s->t1[t], (size_t)B * Dd, seed, ST(t, 7), kf, (size_t)0);
+            if (tc_dx(2, dtd, s->dexp, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), nullptr)); }
+            else TRET(dense_bwd(st, s->expd[t], B, XD, P(vD1W), Dd, dtd, Gd(vD1W), Gd(vD1B), s->dexp));
         }
         // drop(dexp) = [dh_out (+=) | dz (=) | demb (=)]
         launch_k(split3_drop_kernel, GRID1D((size_t)B * XD), 256, st, dexp, XD, B, s->dh_out, H, 1, s->dz, D, 0, demb, E, 0, XD, seed,
@@ -1639,39 +1639,39 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             launch_k(colsum_kernel, dim3((D + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aW), s->ctxd, BL, D, s->dalpha);
             TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), L, s->dalpha, Gd(vA1bW), nullptr, s->dhd));
         } else {
-        float* const dtemp = (side && (t & 1)) ? s->dtemp2 : s->dtemp;
-        if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
-            if (!stack) TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));   // (stacked: zeroed once before the loop)
-            if (side && t + 2 < T) TCK(cudaStreamWaitEvent(st, evRp(t + 2), 0));   // this d temp buffer has been packed
-            launch_k(ab_wave ? att_bwd_fused_wave_kernel : att_bwd_fused_kernel, dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B),
-                     kAbRG * kAbCT, st, dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A,
-                     ab_rows, seed, ST(t, 2), kf, sm_in_ab ? s->alpha[t] : nullptr);
-        } else {
-            launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
-            launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
-            launch_k(att_dtemp_kernel, GRID1D((size_t)BL * A), 256, st, s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
-            launch_k(segsum_kernel, dim3((A + 127) / 128, B), 128, st, dq, s->dtemp, B, L, A);
-            launch_k(tanh_bwd_kernel, GRID1D((size_t)BL * A), 256, st, s->dtemp, s->T1[t], (size_t)BL * A);
-        }
-        if (tc) {
-            // dW1a[D, A] += ctxd^T[D, BL] * dtemp[BL, A]: the weight repack kernel transposes, so ctxd [BL x D] read
-            // as a "[K x n_out] weight" IS the packed activation ctxd^T (row tile 128), and dtemp [BL x A] is the
-            // packed weight; split-K over an 8-CTA cluster, accumulated into the gradient in the epilogue
-            // (the context dropout mask is re-applied while ctx is packed: mask index row * D + column, as in the forward pass)
-            const sat::DropSpec drop{seed, ST(t, 0), kf};
-            TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, sd, &drop, PDLK));   // (needs nothing of this step)
-            if (side) TCK(hand(st, sd, evAb(t)));
-            TCK(sat::lin_repack_weight(dtemp, BL, A, 0, s->tc_wbig, lmode, sd, nullptr, PDLK));
-            if (side) TCK(cudaEventRecord(evRp(t), sd));
-            TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, sd, 1));
-            if (!att_fused) launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aB), s->dtemp, BL, A, nullptr);
-        } else {
-            launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
-            TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));       // contexts are inputs
-        }
-        launch_k(tanh_bwd_kernel, GRID1D((size_t)B * A), 256, st, dq, s->q[t], (size_t)B * A);
-        if (tc_dx(0, dq, s->dhd, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
-        else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
+            float* const dtemp = (side && (t & 1)) ? s->dtemp2 : s->dtemp;
+            if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
+                if (!stack) TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));   // (stacked: zeroed once before the loop)
+                if (side && t + 2 < T) TCK(cudaStreamWaitEvent(st, evRp(t + 2), 0));   // this d temp buffer has been packed
+                launch_k(ab_wave ? att_bwd_fused_wave_kernel : att_bwd_fused_kernel, dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B),
+                         kAbRG * kAbCT, st, dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A,
+                         ab_rows, seed, ST(t, 2), kf, sm_in_ab ? s->alpha[t] : nullptr);
+            } else {
+                launch_k(att_temp_kernel, GRID1D((size_t)BL * A), 256, st, s->temp, s->T1[t], s->q[t], B, L, A, seed, ST(t, 2), kf);
+                launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA2W), s->temp, BL, A, s->dalpha);   // dw2 += temp^T de
+                launch_k(att_dtemp_kernel, GRID1D((size_t)BL * A), 256, st, s->dtemp, s->dalpha, P(vA2W), BL, A, seed, ST(t, 2), kf);
+                launch_k(segsum_kernel, dim3((A + 127) / 128, B), 128, st, dq, s->dtemp, B, L, A);
+                launch_k(tanh_bwd_kernel, GRID1D((size_t)BL * A), 256, st, s->dtemp, s->T1[t], (size_t)BL * A);
+            }
+            if (tc) {
+                // dW1a[D, A] += ctxd^T[D, BL] * dtemp[BL, A]: the weight repack kernel transposes, so ctxd [BL x D] read
+                // as a "[K x n_out] weight" IS the packed activation ctxd^T (row tile 128), and dtemp [BL x A] is the
+                // packed weight; split-K over an 8-CTA cluster, accumulated into the gradient in the epilogue
+                // (the context dropout mask is re-applied while ctx is packed: mask index row * D + column, as in the forward pass)
+                const sat::DropSpec drop{seed, ST(t, 0), kf};
+                TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, sd, &drop, PDLK));   // (needs nothing of this step)
+                if (side) TCK(hand(st, sd, evAb(t)));
+                TCK(sat::lin_repack_weight(dtemp, BL, A, 0, s->tc_wbig, lmode, sd, nullptr, PDLK));
+                if (side) TCK(cudaEventRecord(evRp(t), sd));
+                TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, sd, 1));
+                if (!att_fused) launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aB), s->dtemp, BL, A, nullptr);
+            } else {
+                launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
+                TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));       // contexts are inputs
+            }
+            launch_k(tanh_bwd_kernel, GRID1D((size_t)B * A), 256, st, dq, s->q[t], (size_t)B * A);
+            if (tc_dx(0, dq, s->dhd, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
+            else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
         }
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
         launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
@@ -1703,12 +1703,12 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         TRET(dense_bwd(st, s->meand, B, D, P(vIb1W), H, s->dh_out, Gd(vIb1W), Gd(vIb1B), nullptr));
         TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), H, s->dc, Gd(vIa1W), Gd(vIa1B), nullptr));
     } else {
-    TRET(dense_bwd(st, s->ib1d, B, I, P(vIb2W), H, s->dh_out, Gd(vIb2W), Gd(vIb2B), dmid));
-    launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ib1, (size_t)B * I, seed, INIT + 2, kf, (size_t)0);
-    TRET(dense_bwd(st, s->meand, B, D, P(vIb1W), I, dmid, Gd(vIb1W), Gd(vIb1B), nullptr));
-    TRET(dense_bwd(st, s->ia1d, B, I, P(vIa2W), H, s->dc, Gd(vIa2W), Gd(vIa2B), dmid));
-    launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ia1, (size_t)B * I, seed, INIT + 1, kf, (size_t)0);
-    TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), I, dmid, Gd(vIa1W), Gd(vIa1B), nullptr));
+        TRET(dense_bwd(st, s->ib1d, B, I, P(vIb2W), H, s->dh_out, Gd(vIb2W), Gd(vIb2B), dmid));
+        launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ib1, (size_t)B * I, seed, INIT + 2, kf, (size_t)0);
+        TRET(dense_bwd(st, s->meand, B, D, P(vIb1W), I, dmid, Gd(vIb1W), Gd(vIb1B), nullptr));
+        TRET(dense_bwd(st, s->ia1d, B, I, P(vIa2W), H, s->dc, Gd(vIa2W), Gd(vIa2B), dmid));
+        launch_k(drop_tanh_bwd_kernel, GRID1D((size_t)B * I), 256, st, dmid, s->ia1, (size_t)B * I, seed, INIT + 1, kf, (size_t)0);
+        TRET(dense_bwd(st, s->meand, B, D, P(vIa1W), I, dmid, Gd(vIa1W), Gd(vIa1B), nullptr));
     }
     TCK(cudaGetLastError());
     TCK(cudaMemcpyAsync(losses, s->loss_acc, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
