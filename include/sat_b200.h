@@ -80,6 +80,10 @@ int sat_version(void);
  *                 own into one of two buffer sets, so that it overlaps the decode steps of the previous call [0].
  *                 Contract: the contexts passed to sat_decode_loop are COMPLETE when the call is made (not produced
  *                 by earlier work queued on the same stream).  The pipelined host API does this by itself.
+ *   "prologue1"   1 = the pass that packs the contexts for the hoisted projection also takes their mean over the
+ *                 locations (one pass over the conv features for initialize and attend/fc_1a) [1]
+ *   "chain"       1 = greedy loops at 64-row batches run the three dense layers of a step as phases of ONE persistent
+ *                 launch (sat_chain.cu; an experiment, slower than the default chained launches) [0]
  *   "warm"        1 = idle epilogue warps pre-run the epilogue code to warm the instruction caches [1]
  *   "att_wpc"     1 = warp-per-chunk attention kernel for 512-float rows [1]
  *   "att_sms", "att_occ", "att_warps", "l2_w", "l2_vocab", "l2_t", "l2_ctx", "l2_prefetch": grid / cache-policy knobs
@@ -87,6 +91,7 @@ int sat_version(void);
  *                 "prof_ns_<family>" / "prof_n_<family>"
  *   "trace"       1 / 2 / 3 = in-kernel globaltimer stamps of a dense launch ("trace_at") / of the attention kernel /
  *                 of every launch of a loop (tools/trace*.py, tools/timeline.py)
+ * Environment: SAT_PDL=0 creates handles with "pdl" off (for tools that expect one kernel of a stream at a time).
  * A handle expects the GPU to itself while a loop runs: the fused arg-max of the vocabulary layer ends in a grid-wide
  * rendezvous of its one-wave launch (a stuck rendezvous traps with a message after a few seconds). */
 int sat_set_option(sat_handle* h, const char* key, int64_t value);
@@ -170,7 +175,8 @@ int sat_dense_fwd(sat_handle* h, const float* x, const float* w_tf, const float*
                   int32_t K, int32_t n_out, int32_t act, int32_t splits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Training step (model.py:250-334 losses, :461-511 optimizer; driver base_model.py:39-68).  2-layer graph.
+ * Training step (model.py:250-334 losses, :461-511 optimizer; driver base_model.py:39-68), for the 1- and 2-layer
+ * variants of initialize / attend / decode (config.py:15-19; sat_train_var enumerates the variables of the chosen graph).
  * The trainable variables live in ONE flat fp32 device buffer owned by the caller (parameters), with
  * parallel buffers for the gradient and the two Adam slots; sat_train_var describes the layout
  * (TF variable name, offset in floats, TF shape).  A data-parallel step is
@@ -178,8 +184,13 @@ int sat_dense_fwd(sat_handle* h, const float* x, const float* w_tf, const float*
  * Dropout masks come from a counter-based generator keyed by `seed` (0 = dropout off), so a step is
  * reproducible; ranks must use different seeds.
  * Knobs: sat_set_option "train_tc" 1 = the large products of the step run on the tcgen05 dense kernel [1], 0 = fp32
- * CUDA-core SGEMM everywhere; environment SAT_TRAIN_PDL=0 launches the step's kernels without the programmatic-
- * serialization attribute (read once per process; for A/B timing only, results are identical). */
+ * CUDA-core SGEMM everywhere.  Environment switches, read once per process, for A/B timing (results agree to round-off):
+ * SAT_TRAIN_PDL=0 launches the step's kernels without the programmatic-serialization attribute; SAT_TRAIN_DEC_ALL=0 keeps
+ * the decode layers inside the time loop (default: one stacked product per layer for all T steps); SAT_TRAIN_SIDE=0 keeps
+ * the attend/fc_1a products on the caller's stream (default: a second, low-priority stream of the library's own);
+ * SAT_TRAIN_FUSE_SOFTMAX=0 / 2 un-fuses the softmax kernels (both directions / the backward one only).
+ * Word ids outside [0, vocabulary_size) read as zero rows, contribute no gradient and are counted
+ * (sat_get_info "train_bad_ids"). */
 int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop_rate, float lstm_drop_rate,
                    float attention_loss_factor, float fc_kernel_regularizer_scale);
 int sat_train_num_vars(sat_handle* h);
