@@ -1416,7 +1416,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     };
     int trc = SAT_OK;
     // second stream for the fc_1a products (SAT_TRAIN_SIDE=0: everything in order on the caller's stream)
-    static const int side_env = []() { const char* e = getenv("SAT_TRAIN_SIDE"); return (e && e[0] == '0') ? 0 : 1; }();
+    // (2 / 3: only the forward / only the backward products)
+    static const int side_env = []() { const char* e = getenv("SAT_TRAIN_SIDE"); return e ? atoi(e) : 1; }();
     auto hand = [&](cudaStream_t from, cudaStream_t to, cudaEvent_t e) -> cudaError_t {   // `to` continues after `from`'s work so far
         cudaError_t ce = cudaEventRecord(e, from);
         return ce != cudaSuccess ? ce : cudaStreamWaitEvent(to, e, 0);
@@ -1440,8 +1441,9 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     // scorer: fused one-pass kernels when the rows are float4-addressable (every buffer involved is a cudaMalloc'd
     // [rows, A] matrix or an A-vector, so A % 4 == 0 gives 16-byte alignment)
     const bool att_fused = att2 && (A & 3) == 0 && ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads)) & 15) == 0;
-    const bool side = tc && att_fused && s->side && side_env;
-    cudaStream_t sd = side ? s->side : st;
+    const bool side_any = tc && att_fused && s->side && side_env;
+    const bool side_f = side_any && side_env != 3, side_b = side_any && side_env != 2;
+    cudaStream_t sd = side_f ? s->side : st;
     int ab_chunks = 1, ab_rows = L, ab_wave = 0;
     {
         const int gx = (A / 4 + kAbCT - 1) / kAbCT;
@@ -1464,7 +1466,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         ab_rows = (L + ab_chunks - 1) / ab_chunks;
         ab_chunks = (L + ab_rows - 1) / ab_rows;
     }
-    if (side) {   // T1[t] = tanh(drop_t(ctx) W1a + b1a) for every step, queued ahead on the second stream
+    if (side_f) {   // T1[t] = tanh(drop_t(ctx) W1a + b1a) for every step, queued ahead on the second stream
         TCK(hand(st, sd, s->ev[0]));
         for (int t = 0; t < T; ++t) {
             sat::PackJob job{contexts, nullptr, D, D, BL, 128, s->tc_xpa};
@@ -1483,7 +1485,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         if (!att2) {   // one layer: e = drop(ctx) wa [BL] + drop(h) Wb [B, L]
             launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
             launch_k(rowdot_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->ctxd, P(vA1aW), BL, D);
-        } else if (side) {
+        } else if (side_f) {
         } else if (tc) {   // T1 = tanh(drop(ctx) W1a + b1a) on the tcgen05 dense kernel: the context dropout is applied while the
                     // rows are packed (no fp32 dropped copy), bias + tanh fused in the epilogue
             sat::PackJob job{contexts, nullptr, D, D, BL, 128, s->tc_xpa};
@@ -1500,7 +1502,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             launch_k(copy2d_kernel, GRID1D((size_t)BL), 256, st, s->e, L, s->dalpha, L, B, L, 1);
         } else if (tc_fwd(0, s->hd[t], sat::kEpiBiasTanh, s->q[t], &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
-        if (side) TCK(cudaStreamWaitEvent(st, evT1(t), 0));
+        if (side_f) TCK(cudaStreamWaitEvent(st, evT1(t), 0));
         if (!att2) {   // (the 1-layer scores are complete: e = drop(ctx) wa + drop(h) Wb above)
         } else if (att_fused) {
             launch_k(att_logits_kernel, (BL * 32 + 255) / 256, 256, st, s->e, s->T1[t], s->q[t], P(vA2W), B, L, A, seed, ST(t, 2), kf);
@@ -1577,6 +1579,8 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     TCK(cudaMemsetAsync(s->dh_out, 0, (size_t)B * H * sizeof(float), st));    // d loss / d h_out[t] from step t+1's attend
     TCK(cudaMemsetAsync(s->dh_state, 0, (size_t)B * H * sizeof(float), st));  // d loss / d h_state[t] from step t+1's LSTM
     TCK(cudaMemsetAsync(s->dc, 0, (size_t)B * H * sizeof(float), st));
+    sd = side_b ? s->side : st;
+    if (side_b && !side_f) TCK(hand(st, sd, s->ev[0]));   // (the second stream joins the step here)
     if (stack && att_fused) TCK(cudaMemsetAsync(s->dys[0][0], 0, (size_t)T * B * A * sizeof(float), st));   // d q of every step
     if (dec_all) {   // d logits -> d td (x tanh', dropout) -> d expanded, for all T steps
         sat::PackJob job{s->dlogits[0], nullptr, V, V, TBr, s->all_rt, s->tc_vx_all, s->tc_vk / 64};
@@ -1639,10 +1643,10 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             launch_k(colsum_kernel, dim3((D + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aW), s->ctxd, BL, D, s->dalpha);
             TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), L, s->dalpha, Gd(vA1bW), nullptr, s->dhd));
         } else {
-            float* const dtemp = (side && (t & 1)) ? s->dtemp2 : s->dtemp;
+            float* const dtemp = (side_b && (t & 1)) ? s->dtemp2 : s->dtemp;
             if (att_fused) {   // temp, dw2, dtemp, dq, tanh' and (tensor-core path) db1a in one pass over T1
                 if (!stack) TCK(cudaMemsetAsync(dq, 0, (size_t)B * A * sizeof(float), st));   // (stacked: zeroed once before the loop)
-                if (side && t + 2 < T) TCK(cudaStreamWaitEvent(st, evRp(t + 2), 0));   // this d temp buffer has been packed
+                if (side_b && t + 2 < T) TCK(cudaStreamWaitEvent(st, evRp(t + 2), 0));   // this d temp buffer has been packed
                 launch_k(ab_wave ? att_bwd_fused_wave_kernel : att_bwd_fused_kernel, dim3((A / 4 + kAbCT - 1) / kAbCT, ab_chunks, B),
                          kAbRG * kAbCT, st, dtemp, dq, Gd(vA2W), tc ? Gd(vA1aB) : nullptr, s->T1[t], s->q[t], s->dalpha, P(vA2W), L, A,
                          ab_rows, seed, ST(t, 2), kf, sm_in_ab ? s->alpha[t] : nullptr);
@@ -1660,9 +1664,9 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
                 // (the context dropout mask is re-applied while ctx is packed: mask index row * D + column, as in the forward pass)
                 const sat::DropSpec drop{seed, ST(t, 0), kf};
                 TCK(sat::lin_repack_weight(contexts, BL, D, 0, s->tc_xpa, lmode, sd, &drop, PDLK));   // (needs nothing of this step)
-                if (side) TCK(hand(st, sd, evAb(t)));
+                if (side_b) TCK(hand(st, sd, evAb(t)));
                 TCK(sat::lin_repack_weight(dtemp, BL, A, 0, s->tc_wbig, lmode, sd, nullptr, PDLK));
-                if (side) TCK(cudaEventRecord(evRp(t), sd));
+                if (side_b) TCK(cudaEventRecord(evRp(t), sd));
                 TRET(sat_dense_packed(s->handle, s->tc_xpa, D, 128, BL, s->tc_wbig, nullptr, A, sat::kEpiNone, Gd(vA1aW), A, 1, 8, sd, 1));
                 if (!att_fused) launch_k(colsum_kernel, dim3((A + 127) / 128, (BL + 255) / 256), 128, st, Gd(vA1aB), s->dtemp, BL, A, nullptr);
             } else {
@@ -1677,7 +1681,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
     }
     launch_k(scatter_add_rows_kernel, GRID1D((size_t)T * B * E), 256, st, Gd(vEmb), E, sentences, T, s->demb_all, E, T * B, V, B);
-    if (side) TCK(hand(sd, st, s->ev[1]));   // join: every fc_1a weight-gradient product has been accumulated
+    if (side_b) TCK(hand(sd, st, s->ev[1]));   // join: every fc_1a weight-gradient product has been accumulated
     if (stack) {
         // dW += X_all^T dY_all, db += colsum(dY_all) for attend/fc_1b, lstm, decode/fc_1, decode/fc_2 (the repack kernel
         // transposes: X_all [T*B, K] read as a "[K' x n_out'] weight" is the packed operand X_all^T, row tile 128)
