@@ -329,7 +329,9 @@ __global__ void colsum_kernel(float* db, const float* dx, int rows, int cols, co
 // `stream + 16 t` with the row index inside the step (what T per-step launches with ST(t, k) would have drawn)
 __global__ void concat3_drop_kernel(float* out, int ldo, const float* a, int na, const float* b, int nb, const float* c, int nc,
                                     int ndrop, int rows, const unsigned long long* seedp, unsigned long long stream, float keep,
-                                    int rows_per_step) {
+                                    int rows_per_step, uint8_t* pa, int pa_mode, int pa_row_tile) {
+    // pa (optional): the row also goes out as a packed operand of the tcgen05 dense kernel (row tile pa_row_tile, width
+    // = cols, a multiple of 64): the product that consumes it needs no packing launch of its own
     pdl_enter();
     const unsigned long long seed = *seedp;
     const int cols = na + nb + nc;
@@ -342,6 +344,31 @@ __global__ void concat3_drop_kernel(float* out, int ldo, const float* a, int na,
             v *= drop_scale(seed, stream + 16ull * ts, (unsigned long long)rl * ndrop + col, keep);
         }
         out[(size_t)r * ldo + col] = v;
+        if (pa) sat::pa_store(pa, pa_mode, pa_row_tile, cols >> 6, r, col, v);
+    }
+}
+// y = drop(x) for a dense [rows, cols] matrix, also written as a packed operand (see concat3_drop_kernel)
+__global__ void dropout_pack_kernel(float* y, const float* x, int rows, int cols, const unsigned long long* seedp,
+                                    unsigned long long stream, float keep, uint8_t* pa, int pa_mode, int pa_row_tile) {
+    pdl_enter();
+    const unsigned long long seed = *seedp;
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+        const float v = seed ? x[i] * drop_scale(seed, stream, i, keep) : x[i];
+        y[i] = v;
+        sat::pa_store(pa, pa_mode, pa_row_tile, cols >> 6, r, c, v);
+    }
+}
+// dx = dy * (1 - y^2) in place on dy [rows, cols], also written as a packed operand
+__global__ void tanh_bwd_pack_kernel(float* dy, const float* y, int rows, int cols, uint8_t* pa, int pa_mode, int pa_row_tile) {
+    pdl_enter();
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+        const float v = dy[i] * (1.0f - y[i] * y[i]);
+        dy[i] = v;
+        sat::pa_store(pa, pa_mode, pa_row_tile, cols >> 6, r, c, v);
     }
 }
 // y = drop(x) for T stacked dense steps of `per_step` elements each (streams as above)
@@ -800,7 +827,7 @@ __global__ void lstm_fwd_kernel(float* G, const float* bias, const float* c_prev
 // flowing into c_t from step t+1) -> dG (pre-activation), dc_prev
 __global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_out, const float* dh_state, const float* acts, const float* c,
                                 const float* c_prev, int B, int H, const unsigned long long* seedp, unsigned long long st_out,
-                                unsigned long long st_state, float keep) {
+                                unsigned long long st_state, float keep, uint8_t* pa, int pa_mode, int pa_row_tile) {
     pdl_enter();
     const unsigned long long seed = *seedp;
     const size_t n = (size_t)B * H;
@@ -813,10 +840,19 @@ __global__ void lstm_bwd_kernel(float* dG, float* dc, const float* dh_out, const
                               : dh_out[i] + dh_state[i];
         const float dcc = dh * go * (1.0f - tc * tc) + dc[i];
         float* d = dG + (size_t)b * 4 * H;
-        d[u] = dcc * gj * gi * (1.0f - gi);
-        d[H + u] = dcc * gi * (1.0f - gj * gj);
-        d[2 * H + u] = dcc * c_prev[i] * gf * (1.0f - gf);
-        d[3 * H + u] = dh * tc * go * (1.0f - go);
+        const float di = dcc * gj * gi * (1.0f - gi), dj = dcc * gi * (1.0f - gj * gj), df = dcc * c_prev[i] * gf * (1.0f - gf),
+                    d_o = dh * tc * go * (1.0f - go);
+        d[u] = di;
+        d[H + u] = dj;
+        d[2 * H + u] = df;
+        d[3 * H + u] = d_o;
+        if (pa) {   // d G as the packed operand of the input-gradient product (see concat3_drop_kernel)
+            const int kb = (4 * H) >> 6;
+            sat::pa_store(pa, pa_mode, pa_row_tile, kb, b, u, di);
+            sat::pa_store(pa, pa_mode, pa_row_tile, kb, b, H + u, dj);
+            sat::pa_store(pa, pa_mode, pa_row_tile, kb, b, 2 * H + u, df);
+            sat::pa_store(pa, pa_mode, pa_row_tile, kb, b, 3 * H + u, d_o);
+        }
         dc[i] = dcc * gf;
     }
 }
@@ -1230,6 +1266,8 @@ extern "C" int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop
         float* f = nullptr;
         A1(&f, (size_t)(s->tc_rt + 16) * kmax);
         s->tc_xs = reinterpret_cast<uint8_t*>(f);
+        // (producers that write their rows here directly never touch the padding rows of the tile: zero once)
+        if (rc == SAT_OK) cudaMemset(s->tc_xs, 0, (size_t)(s->tc_rt + 16) * kmax * 4);
         if (s->tcl[3].fwd && V % 8 == 0) {
             s->tc_vk = (int)((V + 63) / 64 * 64);
             const size_t ddp = (Dd + 127) / 128 * 128;
@@ -1414,6 +1452,18 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         *rc = sat_dense_packed(s->handle, s->tc_xs, B, s->tc_rt, l.N, l.wT, nullptr, l.K, sat::kEpiNone, dx, l.K, 0, tc_splits(l.K, l.N), st);
         return true;
     };
+    // the same two products when the producer of x / dy has already written the packed operand into tc_xs
+    static const int fuse_pack_env = []() { const char* e = getenv("SAT_TRAIN_FUSE_PACK"); return (e && e[0] == '0') ? 0 : 1; }();
+    auto pk_fwd_ok = [&](int li) { return tcb && fuse_pack_env && s->tcl[li].fwd; };
+    auto pk_dx_ok = [&](int li) { return tcb && fuse_pack_env && s->tcl[li].dx; };
+    auto tc_fwd_packed = [&](int li, int epi, float* y) -> int {
+        TrainState::TcLayer& l = s->tcl[li];
+        return sat_dense_packed(s->handle, s->tc_xs, B, s->tc_rt, l.K, l.w, l.b, l.N, epi, y, l.N, 0, tc_splits(l.N, l.K), st);
+    };
+    auto tc_dx_packed = [&](int li, float* dx) -> int {
+        TrainState::TcLayer& l = s->tcl[li];
+        return sat_dense_packed(s->handle, s->tc_xs, B, s->tc_rt, l.N, l.wT, nullptr, l.K, sat::kEpiNone, dx, l.K, 0, tc_splits(l.K, l.N), st);
+    };
     int trc = SAT_OK;
     // second stream for the fc_1a products (SAT_TRAIN_SIDE=0: everything in order on the caller's stream)
     // (2 / 3: only the forward / only the backward products)
@@ -1496,10 +1546,15 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
             launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
             TRET(dense_fwd(st, s->ctxd, BL, D, P(vA1aW), P(vA1aB), A, s->T1[t], 1));
         }
-        launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
+        const bool hd_packed = att2 && pk_fwd_ok(0);
+        if (hd_packed)
+            launch_k(dropout_pack_kernel, GRID1D((size_t)B * H), 256, st, s->hd[t], h_out_prev, B, H, seed, ST(t, 1), kf, s->tc_xs, lmode, s->tc_rt);
+        else
+            launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->hd[t], H, h_out_prev, H, B, H, seed, ST(t, 1), kf, 0);
         if (!att2) {
             TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), nullptr, L, s->dalpha, 0));   // (dalpha: backward scratch, free here)
             launch_k(copy2d_kernel, GRID1D((size_t)BL), 256, st, s->e, L, s->dalpha, L, B, L, 1);
+        } else if (hd_packed) { TRET(tc_fwd_packed(0, sat::kEpiBiasTanh, s->q[t]));
         } else if (tc_fwd(0, s->hd[t], sat::kEpiBiasTanh, s->q[t], &trc)) { TRET(trc); }
         else TRET(dense_fwd(st, s->hd[t], B, H, P(vA1bW), P(vA1bB), A, s->q[t], 1));
         if (side_f) TCK(cudaStreamWaitEvent(st, evT1(t), 0));
@@ -1527,15 +1582,16 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
         // LSTM with DropoutWrapper (model.py:228-236, 276-279)
         // lstm_in = [ drop_in(concat(z, emb)) | h_state_prev ]
         launch_k(concat3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->lstm_in[t], XL, s->z[t], D, s->emb[t], E, h_state_prev, H, D + E, B,
-                                                                    seed, ST(t, 3), kl, 0);
-        if (tc_fwd(1, s->lstm_in[t], sat::kEpiNone, s->acts[t], &trc)) { TRET(trc); }   // (bias and gates: next kernel)
+                                                                    seed, ST(t, 3), kl, 0, pk_fwd_ok(1) ? s->tc_xs : nullptr, lmode, s->tc_rt);
+        if (pk_fwd_ok(1)) { TRET(tc_fwd_packed(1, sat::kEpiNone, s->acts[t])); }
+        else if (tc_fwd(1, s->lstm_in[t], sat::kEpiNone, s->acts[t], &trc)) { TRET(trc); }   // (bias and gates: next kernel)
         else TCK(sgemm(st, false, false, B, 4 * H, XL, s->lstm_in[t], XL, P(vLW), 4 * H, s->acts[t], 4 * H, false));
         launch_k(lstm_fwd_kernel, GRID1D((size_t)B * H), 256, st, s->acts[t], P(vLB), c_prev, s->c[t], s->h_out[t], s->h_state[t], B, H, seed,
                  ST(t, 5), ST(t, 4), kl);
         // decode (model.py:282-287, 438-459)
         if (dec_all) continue;   // (the decode layers of every step follow the loop)
         launch_k(concat3_drop_kernel, GRID1D((size_t)B * XD), 256, st, s->expd[t], XD, s->h_out[t], H, s->z[t], D, s->emb[t], E, XD, B,
-                                                                    seed, ST(t, 6), kf, 0);
+                                                                    seed, ST(t, 6), kf, 0, (uint8_t*)nullptr, 0, 0);
         if (!dec2) {
             TRET(dense_fwd(st, s->expd[t], B, XD, P(vD1W), P(vD1B), V, s->logits, 0));
         } else {
@@ -1550,7 +1606,7 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
     }
     if (dec_all) {   // decode of all T steps (model.py:282-305): the per-step stashes are contiguous = [T*B, .] matrices
         launch_k(concat3_drop_kernel, GRID1D((size_t)TBr * XD), 256, st, s->expd[0], XD, s->h_out[0], H, s->z[0], D, s->emb[0], E, XD, TBr,
-                                                                      seed, ST(0, 6), kf, B);
+                                                                      seed, ST(0, 6), kf, B, (uint8_t*)nullptr, 0, 0);
         {
             sat::PackJob job{s->expd[0], nullptr, XD, XD, TBr, s->all_rt, s->tc_sx};
             TCK(sat::pack_rows_launch(&job, 1, lmode, st, nullptr, PDLK));
@@ -1628,8 +1684,11 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
                                                                    ST(t, 6), kf);
         // h_out = drop_out(h_raw), h_state = drop_state(h_raw)
         launch_k(lstm_bwd_kernel, GRID1D((size_t)B * H), 256, st, dG, s->dc, s->dh_out, s->dh_state, s->acts[t], s->c[t], c_prev, B, H, seed,
-                 ST(t, 5), ST(t, 4), kl);
-        if (tc_dx(1, dG, s->dlin, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), nullptr)); }
+                 ST(t, 5), ST(t, 4), kl, pk_dx_ok(1) ? s->tc_xs : (uint8_t*)nullptr, lmode, s->tc_rt);
+        if (pk_dx_ok(1)) {
+            TRET(tc_dx_packed(1, s->dlin));
+            if (!stack) TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), nullptr));
+        } else if (tc_dx(1, dG, s->dlin, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), nullptr)); }
         else TRET(dense_bwd(st, s->lstm_in[t], B, XL, P(vLW), 4 * H, dG, Gd(vLW), Gd(vLB), s->dlin));
         // dlin = [d xd (D+E) | dh_state_prev]
         launch_k(split3_drop_kernel, GRID1D((size_t)B * XL), 256, st, s->dlin, XL, B, s->dz, D, 1, demb, E, 1, s->dh_state, H, 0, D + E, seed,
@@ -1673,9 +1732,15 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
                 launch_k(dropout2d_kernel, GRID1D((size_t)BL * D), 256, st, s->ctxd, D, contexts, D, BL, D, seed, ST(t, 0), kf, 0);
                 TRET(dense_bwd(st, s->ctxd, BL, D, P(vA1aW), A, s->dtemp, Gd(vA1aW), Gd(vA1aB), nullptr));       // contexts are inputs
             }
+            if (pk_dx_ok(0)) {
+                launch_k(tanh_bwd_pack_kernel, GRID1D((size_t)B * A), 256, st, dq, s->q[t], B, A, s->tc_xs, lmode, s->tc_rt);
+                TRET(tc_dx_packed(0, s->dhd));
+                if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr));
+            } else {
             launch_k(tanh_bwd_kernel, GRID1D((size_t)B * A), 256, st, dq, s->q[t], (size_t)B * A);
             if (tc_dx(0, dq, s->dhd, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
             else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
+            }
         }
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
         launch_k(dropout2d_kernel, GRID1D((size_t)B * H), 256, st, s->dh_out, H, s->dhd, H, B, H, seed, ST(t, 1), kf, 0);
