@@ -187,8 +187,10 @@ int sat_dense_fwd(sat_handle* h, const float* x, const float* w_tf, const float*
  * CUDA-core SGEMM everywhere.  Environment switches, read once per process, for A/B timing (results agree to round-off):
  * SAT_TRAIN_PDL=0 launches the step's kernels without the programmatic-serialization attribute; SAT_TRAIN_DEC_ALL=0 keeps
  * the decode layers inside the time loop (default: one stacked product per layer for all T steps); SAT_TRAIN_SIDE=0 keeps
- * the attend/fc_1a products on the caller's stream (default: a second, low-priority stream of the library's own);
- * SAT_TRAIN_FUSE_SOFTMAX=0 / 2 un-fuses the softmax kernels (both directions / the backward one only).
+ * the attend/fc_1a products on the caller's stream (default: a second, low-priority stream of the library's own; 2 / 3:
+ * only the forward / only the backward ones);
+ * SAT_TRAIN_FUSE_SOFTMAX=0 / 2 un-fuses the softmax kernels (both directions / the backward one only); SAT_TRAIN_FUSE_PACK=0
+ * packs the operands of the batch-row products in launches of their own instead of in their producer kernels.
  * Word ids outside [0, vocabulary_size) read as zero rows, contribute no gradient and are counted
  * (sat_get_info "train_bad_ids"). */
 int sat_train_init(sat_handle* h, int32_t B, int32_t T, float fc_drop_rate, float lstm_drop_rate,

@@ -1737,9 +1737,9 @@ static int train_enqueue(TrainState* s, const float* params, float* grads, const
                 TRET(tc_dx_packed(0, s->dhd));
                 if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr));
             } else {
-            launch_k(tanh_bwd_kernel, GRID1D((size_t)B * A), 256, st, dq, s->q[t], (size_t)B * A);
-            if (tc_dx(0, dq, s->dhd, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
-            else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
+                launch_k(tanh_bwd_kernel, GRID1D((size_t)B * A), 256, st, dq, s->q[t], (size_t)B * A);
+                if (tc_dx(0, dq, s->dhd, &trc)) { TRET(trc); if (!stack) TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), nullptr)); }
+                else TRET(dense_bwd(st, s->hd[t], B, H, P(vA1bW), A, dq, Gd(vA1bW), Gd(vA1bB), s->dhd));
             }
         }
         // attend consumed drop(h_out[t-1]): this becomes d h_out[t-1] (the decode part is added next iteration)
