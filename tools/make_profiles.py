@@ -55,7 +55,7 @@ if os.path.exists(tp):
         agg.setdefault((k, g), []).append(u)
     tot = sum(u for _, _, u in one)
     with open(os.path.join(P, tag + "_train_launches_summary.csv"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 6000 -c 3000 python bench.py --steps 1 --warmup 1 --no-cpu --workload 4\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 5000 -c 3000 (tools/gpu_train_list.sh 5000 3000) python bench.py --steps 1 --warmup 1 --no-cpu --workload 4\n")
         f.write("# training step, config 4 (B=64 L=196 D=512 H=1024 V=10000 T=20): the %d launches of ONE step (between two adam_kernel "
                 "launches), %.1f us in total; cold-cache and serialised (the real step overlaps launch latencies)\n" % (len(one), tot))
         f.write("kernel,grid,launches,mean_us,total_us,share_of_total\n")
