@@ -87,16 +87,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) att_fused_kernel(const __g
     const long long NR = (long long)p.NI * L;
     const int r_begin = att_rbegin(NR, P, c), r_end = att_rbegin(NR, P, c + 1);
 
-    // barrier setup by the lanes of warp 0 in parallel (slot s by lane s): no one-thread section ahead of the aligned
-    // block barrier (compute-sanitizer's synccheck reports such a warp as divergent at the barrier)
-    if (threadIdx.x == 0) { trace_stamp(p.dbg, 0); tl_begin(p.tl); }
-    if (threadIdx.x < 32) {
-        for (int s = threadIdx.x; s < p.nslots; s += 32) {
+    if (threadIdx.x == 0) {
+        trace_stamp(p.dbg, 0);
+        tl_begin(p.tl);
+        for (int s = 0; s < p.nslots; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kAttConsumerWarps);
         }
         fence_mbar_init();
-        __syncwarp();
     }
     __syncthreads();
     if (p.pdl) { pdl_wait(); pdl_launch_dependents(); }   // q / word of this step come from the predecessor
@@ -607,14 +605,14 @@ __global__ void __launch_bounds__(10 * 32, 1) att_wpc_kernel(const __grid_consta
     const long long NR = (long long)p.NI * L;
     const int r_begin = att_rbegin(NR, P, c), r_end = att_rbegin(NR, P, c + 1);
 
-    if (threadIdx.x == 0) { trace_stamp(p.dbg, 0); tl_begin(p.tl); }
-    if (threadIdx.x < 32) {   // (slot s by lane s, see att_fused_kernel)
-        for (int s = threadIdx.x; s < p.nslots; s += 32) {
+    if (threadIdx.x == 0) {
+        trace_stamp(p.dbg, 0);
+        tl_begin(p.tl);
+        for (int s = 0; s < p.nslots; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         fence_mbar_init();
-        __syncwarp();
     }
     __syncthreads();
 

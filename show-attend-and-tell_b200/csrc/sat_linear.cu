@@ -123,18 +123,16 @@ __global__ void __launch_bounds__(kLinThreads, 1) lin_umma_kernel(const __grid_c
     while ((int)tmem_cols < N) tmem_cols <<= 1;
 
     // ---- one-time setup
-    // barrier setup by the lanes of warp 0 in parallel (stage s by lane s, the accumulator barrier by lane S): no
-    // one-thread section ahead of the aligned block barrier below
-    if (threadIdx.x == 0) { trace_stamp(L.dbg, 0); tl_begin(L.tl); }
-    if (warp == 0) {
-        if (lane < S) {
-            mbar_init(&full_w[lane], 1);
-            mbar_init(&full_x[lane], xtma ? 1 : kLinProducers);
-            mbar_init(&empty[lane], 1);
+    if (threadIdx.x == 0) {
+        trace_stamp(L.dbg, 0);
+        tl_begin(L.tl);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_w[s], 1);
+            mbar_init(&full_x[s], xtma ? 1 : kLinProducers);
+            mbar_init(&empty[s], 1);
         }
-        if (lane == S) mbar_init(tmem_full, 1);
+        mbar_init(tmem_full, 1);
         fence_mbar_init();
-        __syncwarp();
     }
     if (warp == 1) {
         tmem_alloc(tmem_ptr, tmem_cols);
